@@ -1,0 +1,166 @@
+/*
+ * swne_nmf.h -- C-ABI of the B200-native NMF hot path of SWNE (libswne_nmf.so).
+ *
+ * This is the boundary a maintainer of yanwu2014/swne binds from the package's Rcpp layer
+ * (src/swne_cpp_funcs.cpp + src/RcppExports.cpp) and that this repo binds with
+ * ctypes (swne_b200/_capi.py).  Plain pointers and sizes only; no C++ or torch types; nothing throws
+ * across the boundary.  Every entry point returns an int status (SWNE_OK == 0) and leaves a message for
+ * swne_nmf_last_error().  All host matrices use R's memory layout (column-major):
+ *     A : n x m (genes x cells)   A[i + n*j]
+ *     W : n x k                   W[i + n*f]
+ *     H : k x m                   H[f + k*j]
+ * The library owns all device memory inside the opaque handle and keeps no host pointer after a call
+ * returns.  One handle drives one GPU; multi-GPU runs use one process (or thread) per GPU, cells
+ * (columns of A and H) sharded across ranks, see swne_nmf_comm_init.
+ *
+ * Reference interfaces replaced (file:line in /root/reference):
+ *   swne_nmf_fit*            <- NNLM::nnmf(...) as called at R/nmf.R:117, R/nmf.R:129, R/nmf.R:167-168,
+ *                               i.e. .Call("NNLM_c_nnmf", A, k, Wi, Hi, Wm, Hm, alpha, beta, max_iter,
+ *                               rel_tol, n_threads, verbose, show_warning, inner_max_iter,
+ *                               inner_rel_tol, method, trace)  
+ *   swne_nmf_set_matrix_csc* <- the dgCMatrix slot access pattern of src/swne_cpp_funcs.cpp:27-31
+ *   swne_nnlm                <- NNLM::nnlm(...) as called at R/nmf.R:223 and R/nmf.R:247
+ *   swne_nnsvd_init          <- nnsvd_init, R/nmf.R:12-47 (svd call at :20)
+ *   swne_zero_replace        <- R/nmf.R:121-127 (thresholding only; the runif draws stay with the caller)
+ *   swne_sample_coords       <- get_sample_coords, R/swne_plotting.R:70-84
+ *   swne_factor_distance     <- the k x k distance of get_factor_coords, R/swne_plotting.R:43-52
+ *   swne_recon_error         <- the error block of FindNumFactors, R/nmf.R:170-179 (+ kl_div :71-75)
+ */
+#ifndef SWNE_NMF_H
+#define SWNE_NMF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWNE_NMF_ABI_VERSION 1
+
+/* status codes */
+#define SWNE_OK 0
+#define SWNE_WARN_NOT_CONVERGED 1 /* NNLM: "Target tolerance not reached. Try a larger max.iter." */
+#define SWNE_ERR_BAD_ARG -1       /* negative / non-finite input, k out of range, masks, bad enum */
+#define SWNE_ERR_CUDA -2
+#define SWNE_ERR_NCCL -3
+#define SWNE_ERR_NO_MATRIX -4     /* fit called before set_matrix */
+#define SWNE_ERR_UNSUPPORTED -5
+#define SWNE_ERR_INTERRUPTED -6   /* progress callback asked to stop (Rcpp::checkUserInterrupt) */
+
+#define SWNE_LOSS_MSE 0 /* NNLM method code 1: scd + mse */
+#define SWNE_LOSS_MKL 1 /* NNLM method code 3: scd + mkl */
+
+/* which implementation of the two skinny contractions W'A and A H' the mse path uses */
+#define SWNE_ENGINE_AUTO 0
+#define SWNE_ENGINE_SIMT 1   /* fp32 CUDA-core kernels, three launches per half step */
+#define SWNE_ENGINE_TC 2     /* fused one-pass tcgen05 kernel on split-fp16 (fp32-emulating) operands */
+
+#define SWNE_MAX_K 64
+
+typedef struct swne_nmf_handle_s *swne_nmf_handle_t;
+
+typedef struct swne_nmf_params {
+    int k;                 /* number of factors, 1..SWNE_MAX_K (RunNMF itself enforces k >= 3) */
+    double alpha[3];       /* penalties on W: [L2, angle, L1]  (RunNMF's scalar alpha -> alpha[0]) */
+    double beta[3];        /* penalties on H: [L2, angle, L1] */
+    int loss;              /* SWNE_LOSS_MSE | SWNE_LOSS_MKL */
+    int max_iter;          /* 500 RunNMF, 250 FindNumFactors */
+    double rel_tol;        /* 1e-4; a negative value disables the convergence test (fixed #iterations) */
+    int inner_max_iter;    /* <=0 -> NNLM default: 50 (mse) / 1 (mkl) */
+    double inner_rel_tol;  /* <=0 -> 1e-9 */
+    int trace;             /* <=0 -> NNLM default 100/inner_max_iter; error block every `trace` iterations */
+    int verbose;           /* 0 silent, 2 prints the per-trace table to stderr */
+    int engine;            /* SWNE_ENGINE_* */
+    int full_traces;       /* 1: also evaluate the loss that is not being optimised (mkl in an mse fit)
+                              at every trace point, as NNLM does; 0: only in the final error block */
+    int profile;           /* 1: bracket every kernel family with CUDA events (disables graph replay) */
+} swne_nmf_params_t;
+
+#define SWNE_PROF_SLOTS 8
+typedef struct swne_nmf_result {
+    int n_iteration;       /* outer iterations performed */
+    int n_trace;           /* number of valid entries in the trace arrays */
+    int not_converged;     /* 1 when |rel_err| > rel_tol at exit */
+    int engine_used;       /* SWNE_ENGINE_SIMT | SWNE_ENGINE_TC */
+    double loop_ms;        /* CUDA-event time of the iteration loop on the library's stream */
+    double upload_ms;      /* host->device time of W0/H0 (and A for the one-shot calls) */
+    double download_ms;    /* device->host time of W/H */
+    long long gpu_launches;/* kernels launched inside the loop */
+    /* profile==1: per kernel family summed event time and launch count.
+       slot 0 pass/contract-H, 1 solve-H, 2 contract-W, 3 solve-W, 4 gram/loss, 5 mkl update, 6 allreduce */
+    double prof_ms[SWNE_PROF_SLOTS];
+    long long prof_launches[SWNE_PROF_SLOTS];
+} swne_nmf_result_t;
+
+/* called on the calling thread after every error block; return non-zero to stop (user interrupt) */
+typedef int (*swne_nmf_progress_fn)(void *user, int iteration, double mse, double mkl, double target,
+                                    double rel_err);
+
+const char *swne_nmf_last_error(void);
+int swne_nmf_abi_version(void);
+int swne_nmf_device_count(int *count);
+void swne_nmf_default_params(swne_nmf_params_t *p, int k);
+
+int swne_nmf_create(swne_nmf_handle_t *out, int device);
+int swne_nmf_destroy(swne_nmf_handle_t h);
+int swne_nmf_set_progress(swne_nmf_handle_t h, swne_nmf_progress_fn fn, void *user);
+
+/* ---- multi-GPU: cells sharded over ranks, one ncclAllReduce of {A H' (n x k), H H' (k x k), loss
+ * partials} per outer iteration.  id is an ncclUniqueId (128 bytes) made by rank 0 and sent to the
+ * other ranks by the caller (torch.distributed / MPI / R parallel). */
+int swne_nmf_comm_unique_id(void *id128);
+int swne_nmf_comm_init(swne_nmf_handle_t h, const void *id128, int rank, int nranks);
+
+/* ---- the data matrix (this rank's cells).  m is the LOCAL number of cells. Values must be finite and
+ * >= 0 (RunNMF R/nmf.R:98,106). The matrix stays resident until replaced, so several fits
+ * (FindNumFactors) reuse one upload. */
+int swne_nmf_set_matrix_dense_f64(swne_nmf_handle_t h, const double *A, int n, int m);
+int swne_nmf_set_matrix_dense_f32(swne_nmf_handle_t h, const float *A, int n, int m);
+/* dgCMatrix slots: p (m+1), i (nnz, 0-based row = gene), x (nnz) */
+int swne_nmf_set_matrix_csc_f64(swne_nmf_handle_t h, const int *p, const int *i, const double *x, int n, int m);
+int swne_nmf_set_matrix_csc_f32(swne_nmf_handle_t h, const int *p, const int *i, const float *x, int n, int m);
+/* A already in HBM (fp32, cell-major = R column-major, leading dimension n): no copy is made on the
+ * host; used by bench.py for the HBM-resident measurement. */
+int swne_nmf_set_matrix_dense_f32_device(swne_nmf_handle_t h, const float *dA, int n, int m);
+/* replaces the resident matrix by a full random permutation of its entries (FindNumFactors'
+ * A.rand <- matrix(sample(A), ...), R/nmf.R:165); perm is a host permutation of 0..n*m-1 */
+int swne_nmf_matrix_info(swne_nmf_handle_t h, int *n, int *m, long long *nnz, double *sum, double *sumsq);
+
+/* ---- the fit.  W (n x k) and H (k x m_local) hold the init on entry (NNLM's init=list(W,H)) and the
+ * result on return.  Trace arrays hold trace_len >= ceil(max_iter/trace)+1 doubles (may be NULL). */
+int swne_nmf_fit(swne_nmf_handle_t h, const swne_nmf_params_t *p, double *W, double *H,
+                 double *mse, double *mkl, double *target_loss, double *average_epochs, int trace_len,
+                 swne_nmf_result_t *res);
+/* one-shot forms with the NNLM_c_nnmf argument list (A uploaded inside the call) */
+int swne_nmf_fit_dense_f64(swne_nmf_handle_t h, const swne_nmf_params_t *p, const double *A, int n, int m,
+                           double *W, double *H, double *mse, double *mkl, double *target_loss,
+                           double *average_epochs, int trace_len, swne_nmf_result_t *res);
+int swne_nmf_fit_csc_f64(swne_nmf_handle_t h, const swne_nmf_params_t *p, const int *cp, const int *ci,
+                         const double *cx, int n, int m, double *W, double *H, double *mse, double *mkl,
+                         double *target_loss, double *average_epochs, int trace_len, swne_nmf_result_t *res);
+
+/* ---- NNLM::nnlm on the resident matrix: side 0 solves H (k x m) given W (ProjectSamples),
+ * side 1 solves W (n x k) given H (ProjectFeatures on the fitted genes).  coef holds the init. */
+int swne_nnlm(swne_nmf_handle_t h, int side, int k, const double *X, double *coef, const double *alpha3,
+              int loss, int max_iter, double rel_tol, long long *sweeps);
+
+/* ---- seeding */
+/* NNDSVD of the resident matrix from a randomized truncated SVD (oversample p, q power iterations). */
+int swne_nnsvd_init(swne_nmf_handle_t h, int k, int oversample, int power_iters, uint64_t seed,
+                    double *W, double *H, double *singular_values);
+/* x < eps -> 0 in place; returns the number of zeros so the caller can draw its runif()s */
+int swne_zero_replace(double *x, size_t len, double eps, const double *fill, size_t n_fill, size_t *n_zero);
+
+/* ---- consumers of H */
+int swne_sample_coords(swne_nmf_handle_t h, const double *H, int k, int m, const double *H_coords /* k x 2 col-major */,
+                       double alpha_exp, int n_pull, double *out /* m x 2 col-major */);
+/* distance: 0 cosine (1 - cos), 1 pearson sqrt(2(1-r)), 2 euclidean; out k x k */
+int swne_factor_distance(swne_nmf_handle_t h, const double *H, int k, int m, int distance, double *out);
+/* mean((W H - A)^2) and mean(kl_div(W H, A)) on the resident matrix (FindNumFactors error block) */
+int swne_recon_error(swne_nmf_handle_t h, const double *W, const double *H, int k, double *mse, double *kl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWNE_NMF_H */

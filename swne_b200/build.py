@@ -1,0 +1,78 @@
+"""Builds swne_b200/libswne_nmf.so (sm_100a only) with nvcc: one object per KP instantiation, in parallel.
+
+    python -m swne_b200.build [--force]
+
+The .so is built in-tree (git-ignored, shipped to the GPU box by gpurun).  No torch involved: the
+library links only libcudart (static) and libdl: NCCL is dlopen'ed and the driver entry point for TMA
+descriptors is fetched with cudaGetDriverEntryPoint, so the .so also loads on a box without a GPU driver.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libswne_nmf.so")
+KPS = (8, 16, 24, 32, 40, 48, 56, 64)
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC"]
+
+
+def _sources():
+    out = []
+    for root, _, files in os.walk(CSRC):
+        out += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".h"))]
+    out.append(os.path.join(HERE, "..", "include", "swne_nmf.h"))
+    return sorted(out)
+
+
+def _digest():
+    h = hashlib.sha256()
+    for p in _sources():
+        h.update(p.encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def build(force=False, verbose=False):
+    stamp = os.path.join(OBJ, "digest.txt")
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    jobs = []
+    objs = []
+    main_o = os.path.join(OBJ, "swne_nmf.o")
+    jobs.append([NVCC] + FLAGS + ["-c", os.path.join(CSRC, "swne_nmf.cu"), "-o", main_o])
+    objs.append(main_o)
+    for kp in KPS:
+        o = os.path.join(OBJ, "kernels_kp%d.o" % kp)
+        jobs.append([NVCC] + FLAGS + ["-DKP_VALUE=%d" % kp, "-c", os.path.join(CSRC, "kernels_kp.cu"), "-o", o])
+        objs.append(o)
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        outs = list(ex.map(_run, jobs))
+    if verbose:
+        for o in outs:
+            if o.strip():
+                print(o)
+    _run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"])
+    with open(stamp, "w") as f:
+        f.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

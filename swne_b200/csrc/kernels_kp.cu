@@ -1,0 +1,58 @@
+// kernels_kp.cu -- instantiates the KP-templated kernels for one KP (-DKP_VALUE=8|16|...|64).
+#include "kernels_simt.cuh"
+#include "kp_ops.h"
+
+#ifndef KP_VALUE
+#error "compile with -DKP_VALUE=<multiple of 8 up to 64>"
+#endif
+
+namespace swne {
+namespace {
+constexpr int KP = KP_VALUE;
+
+void gram_l(const float *X, int rows, double *G64, double *colsum64, cudaStream_t st)
+{
+    gram_kernel<KP><<<(rows + 255) / 256, 256, 0, st>>>(X, rows, G64, colsum64);
+}
+void contract_cells_l(const float *A, size_t ldA, int n, int m, const float *Wt, float *C, cudaStream_t st)
+{
+    contract_cells_kernel<KP><<<(m + 63) / 64, 128, 0, st>>>(A, ldA, n, m, Wt, C);
+}
+void contract_genes_l(const float *A, size_t ldA, int n, int m, const float *H, float *B, int cpc, int chunks, cudaStream_t st)
+{
+    dim3 grid((n + 63) / 64, chunks);
+    contract_genes_kernel<KP><<<grid, 128, 0, st>>>(A, ldA, n, m, H, B, cpc);
+}
+void solve_l(float *X, const float *C, const float *G, const float *G0, float l1, int k, int cols, int max_iter, float rel_tol,
+             unsigned long long *sweeps, double *loss_part, cudaStream_t st)
+{
+    scd_ls_solve_kernel<KP><<<(cols + 127) / 128, 128, 0, st>>>(X, C, G, G0, l1, k, cols, max_iter, rel_tol, sweeps, loss_part);
+}
+void kl_l(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y, const float *sumY, float b0,
+          float b1, float b2, int k, int cols, int max_iter, float rel_tol, unsigned long long *sweeps, double *kl_part,
+          double *sq_part, int err, cudaStream_t st)
+{
+    scd_kl_kernel<KP><<<(cols + 3) / 4, 128, 0, st>>>(ptr, idx, val, ajt, X, Y, sumY, b0, b1, b2, k, cols, max_iter, rel_tol,
+                                                      sweeps, kl_part, sq_part, err);
+}
+void kl_trace_l(const int *cptr, const int *cidx, const float *cval, const float *H, const float *Wt, int k, int m,
+                double *kl_part, cudaStream_t st)
+{
+    kl_trace_kernel<KP><<<(m + 3) / 4, 128, 0, st>>>(cptr, cidx, cval, H, Wt, k, m, kl_part);
+}
+void recon_error_l(const float *A, size_t ldA, int n, int m, const float *Wt, const float *H, int k, double *out2, int grid,
+                   cudaStream_t st)
+{
+    recon_error_kernel<KP><<<grid, 256, 0, st>>>(A, ldA, n, m, Wt, H, k, out2);
+}
+void right_multiply_l(float *X, size_t rows, const float *T, int l, cudaStream_t st)
+{
+    right_multiply_kernel<KP><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(X, rows, T, l);
+}
+}  // namespace
+
+#define KP_OPS_NAME2(v) kp_ops_table_##v
+#define KP_OPS_NAME(v) KP_OPS_NAME2(v)
+extern const KpOps KP_OPS_NAME(KP_VALUE) = {gram_l, contract_cells_l, contract_genes_l, solve_l, kl_l, kl_trace_l,
+                                            recon_error_l, right_multiply_l};
+}  // namespace swne

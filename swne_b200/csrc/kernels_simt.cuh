@@ -1,0 +1,477 @@
+// kernels_simt.cuh -- fp32 CUDA-core kernels of the NMF hot path (engine SWNE_ENGINE_SIMT) plus the
+// ingest / layout / bookkeeping kernels every engine shares.
+//
+// Device layouts (all fp32 unless noted):
+//   dA  [m][ldA]  cell-major: row j = the n gene values of cell j   (== R's column-major n x m)
+//   dWt [n][KP]   gene-major: row g = the k factor loadings of gene g, zero padded to KP
+//   dH  [m][KP]   cell-major: row j = the k factor scores of cell j, zero padded to KP
+// KP = k rounded up to a multiple of 8 (<= 64).  Gram matrices are KP x KP, symmetric.
+//
+// What each kernel restates (NNLM restated):
+//   contract_cells_kernel  : Wt * A[:,j]      inside update()           (H side)
+//   contract_genes_kernel  : H  * At[:,g]     inside update()           (W side, no A.t() copy)
+//   gram_kernel            : G = X X'         inside update()
+//   scd_ls_solve_kernel    : mu = G h - X a (+L1); scd_ls_update(h, G, mu, 50, 1e-9)
+//   scd_kl_kernel          : scd_kl_update (sparse aware: zero entries of A add exactly 0 to a2 and b)
+#pragma once
+#include "common.cuh"
+
+namespace swne {
+
+// ----------------------------------------------------------------------------------------------
+// Gram: G64[KP*KP] += X'X, colsum64[KP] += column sums, X [rows][KP].  256 threads, 256 rows / block
+// ----------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(256) gram_kernel(const float *__restrict__ X, int rows, double *__restrict__ G64,
+                                                   double *__restrict__ colsum64)
+{
+    constexpr int ROWS = 64;
+    constexpr int PAIRS = (KP * KP + 255) / 256;
+    __shared__ float xs[ROWS][KP + 1];
+    float acc[PAIRS];
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q) acc[q] = 0.f;
+    float cs = 0.f;
+    const int row_begin = blockIdx.x * 256;
+    const int row_end = min(rows, row_begin + 256);
+    for (int r0 = row_begin; r0 < row_end; r0 += ROWS) {
+        const int nr = min(ROWS, row_end - r0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < ROWS * KP; t += 256) {
+            const int r = t / KP, f = t % KP;
+            xs[r][f] = (r < nr) ? X[(size_t)(r0 + r) * KP + f] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PAIRS; ++q) {
+            const int pr = threadIdx.x + q * 256;
+            if (pr < KP * KP) {
+                const int a = pr / KP, b = pr % KP;
+                float s = 0.f;
+#pragma unroll 8
+                for (int r = 0; r < ROWS; ++r) s += xs[r][a] * xs[r][b];
+                acc[q] += s;
+            }
+        }
+        if (threadIdx.x < KP) {
+            float s = 0.f;
+            for (int r = 0; r < ROWS; ++r) s += xs[r][threadIdx.x];
+            cs += s;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q) {
+        const int pr = threadIdx.x + q * 256;
+        if (pr < KP * KP) atomicAdd(&G64[pr], (double)acc[q]);
+    }
+    if (threadIdx.x < KP) atomicAdd(&colsum64[threadIdx.x], (double)cs);
+}
+
+// ----------------------------------------------------------------------------------------------
+// C[m][KP] = A[m][n] * Wt[n][KP]        (H side: c_j = Wt a_j for a tile of 64 cells)
+// 128 threads; thread (ty = t/8, tx = t%8) owns cells ty*4..+4 and factors tx*FPT..+FPT
+// ----------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(128) contract_cells_kernel(const float *__restrict__ A, size_t ldA, int n, int m,
+                                                             const float *__restrict__ Wt, float *__restrict__ C)
+{
+    constexpr int FPT = KP / 8, TM = 64, TK = 32;
+    __shared__ float as[TM][TK + 1];
+    __shared__ float ws[TK][KP];
+    const int t = threadIdx.x, ty = t >> 3, tx = t & 7, lane = t & 31, wid = t >> 5;
+    const int cell0 = blockIdx.x * TM;
+    float acc[4][FPT];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int f = 0; f < FPT; ++f) acc[a][f] = 0.f;
+    for (int g0 = 0; g0 < n; g0 += TK) {
+        __syncthreads();
+        // A tile: each warp loads 16 cell rows x 32 genes (128 B coalesced per row)
+#pragma unroll 4
+        for (int r = wid; r < TM; r += 4) {
+            const int cell = cell0 + r, g = g0 + lane;
+            as[r][lane] = (cell < m && g < n) ? __ldg(A + (size_t)cell * ldA + g) : 0.f;
+        }
+        for (int q = t; q < TK * KP; q += 128) {
+            const int g = g0 + q / KP;
+            ws[q / KP][q % KP] = (g < n) ? Wt[(size_t)g * KP + q % KP] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < TK; ++kk) {
+            float av[4], wv[FPT];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) av[a] = as[ty * 4 + a][kk];
+#pragma unroll
+            for (int f = 0; f < FPT; ++f) wv[f] = ws[kk][tx * FPT + f];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int f = 0; f < FPT; ++f) acc[a][f] = fmaf(av[a], wv[f], acc[a][f]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int cell = cell0 + ty * 4 + a;
+        if (cell < m)
+#pragma unroll
+            for (int f = 0; f < FPT; ++f) C[(size_t)cell * KP + tx * FPT + f] = acc[a][f];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// B[n][KP] += A[cells]' * H[cells][KP]   (W side: b_g = H At[:,g]); split over cell chunks, fp32 atomics
+// grid (gene tiles of 64, cell chunks); 128 threads; thread (ty, tx) owns genes ty*4..+4, factors tx*FPT..
+// ----------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(128) contract_genes_kernel(const float *__restrict__ A, size_t ldA, int n, int m,
+                                                             const float *__restrict__ H, float *__restrict__ B,
+                                                             int cells_per_chunk)
+{
+    constexpr int FPT = KP / 8, TG = 64, TK = 32;
+    __shared__ __align__(16) float as[TK][TG + 4];
+    __shared__ __align__(16) float hs[TK][KP];
+    const int t = threadIdx.x, ty = t >> 3, tx = t & 7;
+    const int gene0 = blockIdx.x * TG;
+    const int c_begin = blockIdx.y * cells_per_chunk, c_end = min(m, c_begin + cells_per_chunk);
+    float acc[4][FPT];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int f = 0; f < FPT; ++f) acc[a][f] = 0.f;
+    for (int c0 = c_begin; c0 < c_end; c0 += TK) {
+        __syncthreads();
+        // 32 cells x 64 genes: half warp per cell row (256 B contiguous)
+        for (int q = t; q < TK * TG; q += 128) {
+            const int r = q / TG, gi = q % TG;
+            const int cell = c0 + r, g = gene0 + gi;
+            as[r][gi] = (cell < c_end && g < n) ? __ldg(A + (size_t)cell * ldA + g) : 0.f;
+        }
+        for (int q = t; q < TK * KP; q += 128) {
+            const int cell = c0 + q / KP;
+            hs[q / KP][q % KP] = (cell < c_end) ? H[(size_t)cell * KP + q % KP] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < TK; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&as[kk][ty * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            float hv[FPT];
+#pragma unroll
+            for (int f = 0; f < FPT; ++f) hv[f] = hs[kk][tx * FPT + f];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int f = 0; f < FPT; ++f) acc[a][f] = fmaf(av[a], hv[f], acc[a][f]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int g = gene0 + ty * 4 + a;
+        if (g < n)
+#pragma unroll
+            for (int f = 0; f < FPT; ++f) atomicAdd(&B[(size_t)g * KP + tx * FPT + f], acc[a][f]);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// SCD least squares: one thread per column, h and mu in registers, G broadcast from shared memory.
+// Semantics of scd_ls_update kept: coordinate order 0..k-1, clamp at 0, skip when unchanged,
+// continue while any coordinate's relative change 2|d|/(new+old+tiny) exceeds rel_tol, cap max_iter,
+// warm start from the previous iterate.
+// ----------------------------------------------------------------------------------------------
+template <int KP>
+__device__ __forceinline__ int scd_ls_thread(float (&h)[KP], float (&mu)[KP], const float *__restrict__ sG,
+                                             const float *__restrict__ sInvD, int k, int max_iter, float rel_tol)
+{
+    int t = 0;
+    bool again = true;
+    // asm volatile loads: without them the compiler hoists all KP*KP loop-invariant loads of G out of
+    // the sweep loop and spills them to local memory
+    const unsigned sg_addr = (unsigned)__cvta_generic_to_shared(sG);
+    for (; t < max_iter && again; ++t) {
+        again = false;
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk) {
+            if (kk < k) {
+                float tmp = fmaf(-mu[kk], sInvD[kk], h[kk]);
+                tmp = fmaxf(tmp, 0.f);
+                const float d = tmp - h[kk];
+                if (d != 0.f) {
+#pragma unroll
+                    for (int r = 0; r < KP / 4; ++r) {
+                        float4 g;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w)
+                                     : "r"(sg_addr + (unsigned)((kk * KP + 4 * r) * 4)));
+                        mu[4 * r + 0] = fmaf(d, g.x, mu[4 * r + 0]);
+                        mu[4 * r + 1] = fmaf(d, g.y, mu[4 * r + 1]);
+                        mu[4 * r + 2] = fmaf(d, g.z, mu[4 * r + 2]);
+                        mu[4 * r + 3] = fmaf(d, g.w, mu[4 * r + 3]);
+                    }
+                    // e = 2|d| / (tmp + h + tiny) > rel_tol, division free
+                    again |= (2.f * fabsf(d) > rel_tol * (tmp + h[kk] + TINY_NUM_F));
+                    h[kk] = tmp;
+                }
+            }
+        }
+    }
+    return t;
+}
+
+// X [cols][KP] in/out (warm start), C [cols][KP] = the contraction (Wt a_j), G penalised Gram,
+// G0 plain Gram (only when loss_part != nullptr), l1 = the L1 penalty added to mu.
+template <int KP>
+__global__ void __launch_bounds__(128) scd_ls_solve_kernel(float *__restrict__ X, const float *__restrict__ C,
+                                                           const float *__restrict__ G, const float *__restrict__ G0,
+                                                           float l1, int k, int cols, int max_iter, float rel_tol,
+                                                           unsigned long long *sweeps, double *loss_part)
+{
+    __shared__ __align__(16) float sG[KP * KP];
+    __shared__ __align__(16) float sG0[KP * KP];
+    __shared__ float sInvD[KP];
+    __shared__ double scratch[32];
+    for (int t = threadIdx.x; t < KP * KP; t += blockDim.x) {
+        sG[t] = G[t];
+        sG0[t] = G0 ? G0[t] : 0.f;
+    }
+    for (int t = threadIdx.x; t < KP; t += blockDim.x) sInvD[t] = (t < k) ? 1.f / G[t * KP + t] : 0.f;
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int it = 0;
+    double lp = 0.0;
+    if (j < cols) {
+        float h[KP], mu[KP];
+        const float4 *hp = reinterpret_cast<const float4 *>(X + (size_t)j * KP);
+        const float4 *cp = reinterpret_cast<const float4 *>(C + (size_t)j * KP);
+#pragma unroll
+        for (int r = 0; r < KP / 4; ++r) {
+            const float4 v = hp[r];
+            h[4 * r] = v.x; h[4 * r + 1] = v.y; h[4 * r + 2] = v.z; h[4 * r + 3] = v.w;
+            const float4 c = cp[r];
+            mu[4 * r] = l1 - c.x; mu[4 * r + 1] = l1 - c.y; mu[4 * r + 2] = l1 - c.z; mu[4 * r + 3] = l1 - c.w;
+        }
+#pragma unroll 1
+        for (int q = 0; q < k; ++q) {
+            const float hq = X[(size_t)j * KP + q];
+            const float4 *g4 = reinterpret_cast<const float4 *>(sG + q * KP);
+#pragma unroll
+            for (int r = 0; r < KP / 4; ++r) {
+                const float4 g = g4[r];
+                mu[4 * r + 0] = fmaf(hq, g.x, mu[4 * r + 0]);
+                mu[4 * r + 1] = fmaf(hq, g.y, mu[4 * r + 1]);
+                mu[4 * r + 2] = fmaf(hq, g.z, mu[4 * r + 2]);
+                mu[4 * r + 3] = fmaf(hq, g.w, mu[4 * r + 3]);
+            }
+        }
+        it = scd_ls_thread<KP>(h, mu, sG, sInvD, k, max_iter, rel_tol);
+        float4 *op = reinterpret_cast<float4 *>(X + (size_t)j * KP);
+#pragma unroll
+        for (int r = 0; r < KP / 4; ++r) op[r] = make_float4(h[4 * r], h[4 * r + 1], h[4 * r + 2], h[4 * r + 3]);
+        if (loss_part) {
+            // h' G0 h - 2 h' c ; mu is dead, reuse it for t = G0 h
+#pragma unroll
+            for (int r = 0; r < KP; ++r) mu[r] = 0.f;
+#pragma unroll 1
+            for (int q = 0; q < k; ++q) {
+                const float hq = X[(size_t)j * KP + q];  // just written by this thread
+                const float4 *g4 = reinterpret_cast<const float4 *>(sG0 + q * KP);
+#pragma unroll
+                for (int r = 0; r < KP / 4; ++r) {
+                    const float4 g = g4[r];
+                    mu[4 * r + 0] = fmaf(hq, g.x, mu[4 * r + 0]);
+                    mu[4 * r + 1] = fmaf(hq, g.y, mu[4 * r + 1]);
+                    mu[4 * r + 2] = fmaf(hq, g.z, mu[4 * r + 2]);
+                    mu[4 * r + 3] = fmaf(hq, g.w, mu[4 * r + 3]);
+                }
+            }
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < KP / 4; ++r) {
+                const float4 c = cp[r];
+                s = fmaf(h[4 * r + 0], mu[4 * r + 0] - 2.f * c.x, s);
+                s = fmaf(h[4 * r + 1], mu[4 * r + 1] - 2.f * c.y, s);
+                s = fmaf(h[4 * r + 2], mu[4 * r + 2] - 2.f * c.z, s);
+                s = fmaf(h[4 * r + 3], mu[4 * r + 3] - 2.f * c.w, s);
+            }
+            lp = (double)s;
+        }
+    }
+    const double tot_it = block_sum((double)it, scratch);
+    if (threadIdx.x == 0) atomicAdd(sweeps, (unsigned long long)(tot_it + 0.5));
+    if (loss_part) {
+        const double tot = block_sum(lp, scratch);
+        if (threadIdx.x == 0) atomicAdd(loss_part, tot);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// SCD KL update, sparse aware, one warp per column.  (scd_kl_update)
+//   ptr/idx/val : the sparse view whose "columns" are the columns being solved
+//   X  [cols][KP] in/out;  Y [rows][KP] the fixed factor (row r = factors of entity r);  sumY[KP]
+//   ajt : nnz scratch (A-hat on the support).  err != 0: add sum a log(ahat+tiny) and sum a^2-2 a ahat
+// ----------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(128) scd_kl_kernel(const int *__restrict__ ptr, const int *__restrict__ idx,
+                                                     const float *__restrict__ val, float *__restrict__ ajt,
+                                                     float *__restrict__ X, const float *__restrict__ Y,
+                                                     const float *__restrict__ sumY, float b0, float b1, float b2, int k,
+                                                     int cols, int max_iter, float rel_tol, unsigned long long *sweeps,
+                                                     double *kl_part, double *sq_part, int err)
+{
+    __shared__ float sh[4][KP];
+    __shared__ double scratch[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int j = blockIdx.x * 4 + wid;
+    int it = 0;
+    double klp = 0.0, sqp = 0.0;
+    if (j < cols) {
+        float *h = sh[wid];
+        for (int f = lane; f < KP; f += 32) h[f] = X[(size_t)j * KP + f];
+        __syncwarp();
+        float sumH = 0.f;
+        for (int f = 0; f < k; ++f) sumH += h[f];
+        const int b = ptr[j], e = ptr[j + 1];
+        for (int q = b + lane; q < e; q += 32) {
+            const float *y = Y + (size_t)idx[q] * KP;
+            float s = 0.f;
+            for (int f = 0; f < k; ++f) s = fmaf(y[f], h[f], s);
+            ajt[q] = s;
+        }
+        __syncwarp();
+        bool again = true;
+        for (; it < max_iter && again; ++it) {
+            again = false;
+            for (int kk = 0; kk < k; ++kk) {
+                float a2 = 0.f, bb = 0.f;
+                for (int q = b + lane; q < e; q += 32) {
+                    const float w = Y[(size_t)idx[q] * KP + kk];
+                    const float mu = w / (ajt[q] + TINY_NUM_F);
+                    const float av = val[q];
+                    a2 = fmaf(av * mu, mu, a2);
+                    bb = fmaf(av, mu, bb);
+                }
+                a2 = warp_sum(a2); bb = warp_sum(bb);
+                const float hk = h[kk];
+                bb -= sumY[kk];
+                a2 += b0;
+                bb += a2 * hk - b2 - b1 * (sumH - hk);
+                float tmp = bb / (a2 + TINY_NUM_F);
+                if (!(tmp > 0.f)) tmp = 0.f;
+                if (tmp != hk) {
+                    const float d = tmp - hk;
+                    for (int q = b + lane; q < e; q += 32) ajt[q] = fmaf(d, Y[(size_t)idx[q] * KP + kk], ajt[q]);
+                    again |= (2.f * fabsf(d) > rel_tol * (tmp + hk + TINY_NUM_F));
+                    sumH += d;
+                    __syncwarp();
+                    if (lane == 0) h[kk] = tmp;
+                    __syncwarp();
+                }
+            }
+        }
+        for (int f = lane; f < KP; f += 32) X[(size_t)j * KP + f] = h[f];
+        if (err) {
+            for (int q = b + lane; q < e; q += 32) {
+                const double av = (double)val[q], ah = (double)ajt[q];
+                klp += av * log(ah + TINY_NUM_D);
+                sqp += av * av - 2.0 * av * ah;
+            }
+        }
+    }
+    const double tot_it = block_sum((lane == 0) ? (double)it : 0.0, scratch);
+    if (threadIdx.x == 0) atomicAdd(sweeps, (unsigned long long)(tot_it + 0.5));
+    if (err) {
+        const double t1 = block_sum(klp, scratch);
+        if (threadIdx.x == 0) atomicAdd(kl_part, t1);
+        const double t2 = block_sum(sqp, scratch);
+        if (threadIdx.x == 0) atomicAdd(sq_part, t2);
+    }
+}
+
+// A-hat on the support only: kl_part += sum_nz a log(ahat + tiny)   (mkl trace of an mse fit)
+template <int KP>
+__global__ void __launch_bounds__(128) kl_trace_kernel(const int *__restrict__ cptr, const int *__restrict__ cidx,
+                                                       const float *__restrict__ cval, const float *__restrict__ H,
+                                                       const float *__restrict__ Wt, int k, int m, double *kl_part)
+{
+    __shared__ float sh[4][KP];
+    __shared__ double scratch[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int j = blockIdx.x * 4 + wid;
+    double klp = 0.0;
+    if (j < m) {
+        for (int f = lane; f < KP; f += 32) sh[wid][f] = H[(size_t)j * KP + f];
+        __syncwarp();
+        for (int q = cptr[j] + lane; q < cptr[j + 1]; q += 32) {
+            const float *w = Wt + (size_t)cidx[q] * KP;
+            float s = 0.f;
+            for (int f = 0; f < k; ++f) s = fmaf(w[f], sh[wid][f], s);
+            klp += (double)cval[q] * log((double)s + TINY_NUM_D);
+        }
+    }
+    const double t1 = block_sum(klp, scratch);
+    if (threadIdx.x == 0) atomicAdd(kl_part, t1);
+}
+
+// ----------------------------------------------------------------------------------------------
+// dense reconstruction errors of FindNumFactors (R/nmf.R:170-179): sum (ahat - a)^2 and
+// sum kl_div(ahat, a) with kl_div(x,y) = x log(x/y) - x + y on x+1e-12, y+1e-12 (R/nmf.R:71-75)
+// one block per cell, threads over genes
+// ----------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(256) recon_error_kernel(const float *__restrict__ A, size_t ldA, int n, int m,
+                                                          const float *__restrict__ Wt, const float *__restrict__ H, int k,
+                                                          double *out2)
+{
+    __shared__ float sh[KP];
+    __shared__ double scratch[32];
+    double se = 0.0, kl = 0.0;
+    for (int j = blockIdx.x; j < m; j += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < KP) sh[threadIdx.x] = H[(size_t)j * KP + threadIdx.x];
+        __syncthreads();
+        for (int g = threadIdx.x; g < n; g += blockDim.x) {
+            const float4 *w4 = reinterpret_cast<const float4 *>(Wt + (size_t)g * KP);
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < KP / 4; ++r) {
+                const float4 w = w4[r];
+                s = fmaf(w.x, sh[4 * r], s); s = fmaf(w.y, sh[4 * r + 1], s);
+                s = fmaf(w.z, sh[4 * r + 2], s); s = fmaf(w.w, sh[4 * r + 3], s);
+            }
+            const double a = (double)A[(size_t)j * ldA + g], ah = (double)s;
+            se += (ah - a) * (ah - a);
+            const double x = ah + 1e-12, y = a + 1e-12;
+            kl += x * log(x / y) - x + y;
+        }
+    }
+    const double t1 = block_sum(se, scratch);
+    if (threadIdx.x == 0) atomicAdd(&out2[0], t1);
+    const double t2 = block_sum(kl, scratch);
+    if (threadIdx.x == 0) atomicAdd(&out2[1], t2);
+}
+
+// X [rows][KP] <- X * T (T l x l, row-major double, applied in fp32)
+template <int KP>
+__global__ void right_multiply_kernel(float *X, size_t rows, const float *__restrict__ T, int l)
+{
+    __shared__ float sT[KP * KP];
+    for (int t = threadIdx.x; t < KP * KP; t += blockDim.x) sT[t] = T[t];
+    __syncthreads();
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float x[KP], y[KP];
+#pragma unroll
+    for (int f = 0; f < KP; ++f) { x[f] = X[r * KP + f]; y[f] = 0.f; }
+#pragma unroll
+    for (int a = 0; a < KP; ++a)
+        if (a < l)
+#pragma unroll
+            for (int b = 0; b < KP; ++b) y[b] = fmaf(x[a], sT[a * KP + b], y[b]);
+#pragma unroll
+    for (int f = 0; f < KP; ++f) X[r * KP + f] = y[f];
+}
+
+
+}  // namespace swne

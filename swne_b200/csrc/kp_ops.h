@@ -1,0 +1,31 @@
+// kp_ops.h -- launch table of the kernels that are templated on KP (k padded to a multiple of 8).
+// Each KP is compiled in its own translation unit (kernels_kp.cu with -DKP_VALUE=...) so the build
+// parallelises over cores; swne_nmf.cu picks the table with kp_ops(KP).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace swne {
+
+struct FitScalars;
+
+struct KpOps {
+    void (*gram)(const float *X, int rows, double *G64, double *colsum64, cudaStream_t st);
+    void (*contract_cells)(const float *A, size_t ldA, int n, int m, const float *Wt, float *C, cudaStream_t st);
+    void (*contract_genes)(const float *A, size_t ldA, int n, int m, const float *H, float *B, int cells_per_chunk, int chunks,
+                           cudaStream_t st);
+    void (*solve)(float *X, const float *C, const float *G, const float *G0, float l1, int k, int cols, int max_iter,
+                  float rel_tol, unsigned long long *sweeps, double *loss_part, cudaStream_t st);
+    void (*kl)(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y, const float *sumY,
+               float b0, float b1, float b2, int k, int cols, int max_iter, float rel_tol, unsigned long long *sweeps,
+               double *kl_part, double *sq_part, int err, cudaStream_t st);
+    void (*kl_trace)(const int *cptr, const int *cidx, const float *cval, const float *H, const float *Wt, int k, int m,
+                     double *kl_part, cudaStream_t st);
+    void (*recon_error)(const float *A, size_t ldA, int n, int m, const float *Wt, const float *H, int k, double *out2, int grid,
+                        cudaStream_t st);
+    void (*right_multiply)(float *X, size_t rows, const float *T, int l, cudaStream_t st);
+};
+
+const KpOps *kp_ops(int KP);  // nullptr when KP is not one of 8,16,...,64
+
+}  // namespace swne

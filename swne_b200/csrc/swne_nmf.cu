@@ -1,0 +1,1315 @@
+// swne_nmf.cu -- C-ABI (include/swne_nmf.h) and host orchestration of the B200-native NMF hot path.
+//
+// Host-side restatement of NNLM's c_nnmf outer loop (reference call sites
+// /root/reference/R/nmf.R:117,129,167-168) driving the CUDA kernels in kernels_simt.cuh (fp32 CUDA-core
+// engine) and pass_tc.cuh (fused tcgen05 engine).  No CPU fallback: every numerical step runs on the GPU.
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>  // types only; the functions are resolved with dlopen so a 1-GPU user needs no NCCL
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_misc.cuh"
+#include "kp_ops.h"
+#include "linalg_small.h"
+#include "pass_tc.cuh"
+
+namespace swne {
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+struct ArgError { int code; };
+#define FAIL(code, ...)               \
+    do {                              \
+        swne::set_error(__VA_ARGS__); \
+        throw swne::ArgError{code};   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static void load_nccl()
+{
+    if (g_nccl.lib) return;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *lib = nullptr;
+    for (const char *nm : names) {
+        lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) FAIL(SWNE_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define LOADSYM(field, name)                                             \
+    g_nccl.field = (decltype(g_nccl.field))dlsym(lib, name);             \
+    if (!g_nccl.field) FAIL(SWNE_ERR_NCCL, "NCCL symbol %s missing", name)
+    LOADSYM(GetUniqueId, "ncclGetUniqueId");
+    LOADSYM(CommInitRank, "ncclCommInitRank");
+    LOADSYM(CommDestroy, "ncclCommDestroy");
+    LOADSYM(AllReduce, "ncclAllReduce");
+    LOADSYM(GroupStart, "ncclGroupStart");
+    LOADSYM(GroupEnd, "ncclGroupEnd");
+    LOADSYM(GetErrorString, "ncclGetErrorString");
+#undef LOADSYM
+    g_nccl.lib = lib;
+}
+#define NCCL_CHECK(expr)                                                                              \
+    do {                                                                                              \
+        ncclResult_t _r = (expr);                                                                     \
+        if (_r != ncclSuccess) FAIL(SWNE_ERR_NCCL, "NCCL error at %s:%d: %s", __FILE__, __LINE__,     \
+                                    g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?");         \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t count)
+    {
+        if (count <= cap) return;
+        release();
+        CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+        cap = count;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+    }
+};
+
+struct SparseView {
+    bool ready = false;
+    DevBuf<int> cptr, cidx, gptr, gidx;
+    DevBuf<float> cval, gval, ajt;
+};
+
+}  // namespace swne
+
+struct swne_nmf_handle_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    // resident matrix (this rank's cells)
+    int n = 0, m = 0;
+    size_t ldA = 0;
+    float *dA = nullptr;
+    bool own_A = false;
+    swne::DevBuf<float> A_store;
+    swne::MatStats stats{};          // local
+    swne::SparseView sp;
+    swne::TcMatrix tc;               // split-fp16 copy + TMA descriptors for the tcgen05 engine
+    // communicator
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    // per fit workspaces (grown on demand)
+    swne::DevBuf<float> Wt, H, C, B, G, G0, cs32;
+    swne::DevBuf<double> G64w, G64h, stage;
+    swne::DevBuf<swne::MatStats> dstats;
+    swne::DevBuf<swne::FitScalars> dscal;
+    swne::DevBuf<double> red;        // packed all-reduce buffer of doubles
+    void *pinned = nullptr;          // host mirror of scalars + Grams
+    size_t pinned_bytes = 0;
+    swne_nmf_progress_fn progress = nullptr;
+    void *progress_user = nullptr;
+};
+
+namespace swne {
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        CUDA_CHECK(cudaSetDevice(dev));
+    }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+extern const KpOps kp_ops_table_8, kp_ops_table_16, kp_ops_table_24, kp_ops_table_32, kp_ops_table_40, kp_ops_table_48,
+    kp_ops_table_56, kp_ops_table_64;
+const KpOps *kp_ops(int KP)
+{
+    switch (KP) {
+        case 8: return &kp_ops_table_8;
+        case 16: return &kp_ops_table_16;
+        case 24: return &kp_ops_table_24;
+        case 32: return &kp_ops_table_32;
+        case 40: return &kp_ops_table_40;
+        case 48: return &kp_ops_table_48;
+        case 56: return &kp_ops_table_56;
+        case 64: return &kp_ops_table_64;
+        default: return nullptr;
+    }
+}
+
+static int kp_of(int k) { return std::max(8, round_up(k, 8)); }
+
+static const KpOps &ops_of(int KPv)
+{
+    const KpOps *o = kp_ops(KPv);
+    if (!o) FAIL(SWNE_ERR_BAD_ARG, "k out of range");
+    return *o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// matrix ingest
+// ------------------------------------------------------------------------------------------------
+static void check_stats(swne_nmf_handle_s *h)
+{
+    CUDA_CHECK(cudaMemcpyAsync(&h->stats, h->dstats.p, sizeof(MatStats), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (h->stats.bad & 4u) { h->n = h->m = 0; FAIL(SWNE_ERR_BAD_ARG, "CSC row index out of range"); }
+    if (h->stats.bad & 1u) { h->n = h->m = 0; FAIL(SWNE_ERR_BAD_ARG, "The input matrix contains negative elements !"); }
+    if (h->stats.bad & 2u) { h->n = h->m = 0; FAIL(SWNE_ERR_BAD_ARG, "The input matrix contains non-finite elements (NA/NaN/Inf); masks and missing values are not supported"); }
+}
+
+static void begin_matrix(swne_nmf_handle_s *h, int n, int m, bool alloc)
+{
+    if (n < 1 || m < 1) FAIL(SWNE_ERR_BAD_ARG, "matrix must have at least one row and one column");
+    h->sp.ready = false;
+    h->tc.ready = false;
+    h->n = n; h->m = m;
+    h->ldA = round_up_sz((size_t)n, 4);
+    if (alloc) {
+        h->A_store.reserve((size_t)m * h->ldA);
+        h->dA = h->A_store.p;
+        h->own_A = true;
+    }
+    h->dstats.reserve(1);
+    CUDA_CHECK(cudaMemsetAsync(h->dstats.p, 0, sizeof(MatStats), h->stream));
+}
+
+template <typename T>
+static void set_dense(swne_nmf_handle_s *h, const T *A, int n, int m)
+{
+    if (!A) FAIL(SWNE_ERR_BAD_ARG, "A is NULL");
+    begin_matrix(h, n, m, true);
+    const size_t rows_per_chunk = std::max<size_t>(1, ((size_t)256 << 20) / ((size_t)n * sizeof(T)));
+    DevBuf<T> stagebuf;
+    stagebuf.reserve(std::min<size_t>(rows_per_chunk, m) * (size_t)n);
+    for (size_t r0 = 0; r0 < (size_t)m; r0 += rows_per_chunk) {
+        const size_t nr = std::min(rows_per_chunk, (size_t)m - r0);
+        CUDA_CHECK(cudaMemcpyAsync(stagebuf.p, A + r0 * n, nr * n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+        const int grid = (int)std::min<size_t>(nr, (size_t)h->sm_count * 8);
+        ingest_dense_kernel<T><<<grid, 256, 0, h->stream>>>(stagebuf.p, (size_t)n, h->dA + r0 * h->ldA, h->ldA, n, (int)nr,
+                                                            h->dstats.p);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    }
+    stagebuf.release();
+    check_stats(h);
+}
+
+template <typename T>
+static void set_csc(swne_nmf_handle_s *h, const int *p, const int *idx, const T *x, int n, int m)
+{
+    if (!p || (!idx && p[m] > 0) || (!x && p[m] > 0)) FAIL(SWNE_ERR_BAD_ARG, "CSC slot pointer is NULL");
+    for (int j = 0; j < m; ++j)
+        if (p[j + 1] < p[j]) FAIL(SWNE_ERR_BAD_ARG, "CSC column pointer is not non-decreasing");
+    begin_matrix(h, n, m, true);
+    CUDA_CHECK(cudaMemsetAsync(h->dA, 0, (size_t)m * h->ldA * sizeof(float), h->stream));
+    DevBuf<int> dp, di;
+    DevBuf<T> dx;
+    dp.reserve((size_t)m + 1);
+    CUDA_CHECK(cudaMemcpyAsync(dp.p, p, ((size_t)m + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    // upload the nonzeros in column chunks of <= 64M entries
+    const long long chunk_nnz = 64ll << 20;
+    int c0 = 0;
+    while (c0 < m) {
+        int c1 = c0 + 1;
+        while (c1 < m && (long long)p[c1 + 1] - p[c0] <= chunk_nnz) ++c1;
+        const size_t cnt = (size_t)(p[c1] - p[c0]);
+        if (cnt) {
+            di.reserve(cnt); dx.reserve(cnt);
+            CUDA_CHECK(cudaMemcpyAsync(di.p, idx + p[c0], cnt * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+            CUDA_CHECK(cudaMemcpyAsync(dx.p, x + p[c0], cnt * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+            const int cols = c1 - c0;
+            const int grid = std::min((cols + 7) / 8, h->sm_count * 8);
+            ingest_csc_kernel<T><<<grid, 256, 0, h->stream>>>(dp.p, di.p, dx.p, h->dA + (size_t)c0 * h->ldA, h->ldA, n, c0,
+                                                              cols, p[c0], h->dstats.p);
+            CUDA_CHECK(cudaGetLastError());
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        }
+        c0 = c1;
+    }
+    // the implicit zeros contribute (0+tiny) log(0+tiny) each to the KL constant
+    check_stats(h);
+    const double zeros = (double)n * (double)m - (double)h->stats.nnz;
+    h->stats.klc += zeros * (TINY_NUM_D * log(TINY_NUM_D));
+    dp.release(); di.release(); dx.release();
+}
+
+static void ensure_sparse(swne_nmf_handle_s *h)
+{
+    if (h->sp.ready) return;
+    SparseView &sp = h->sp;
+    const int n = h->n, m = h->m;
+    cudaStream_t st = h->stream;
+    DevBuf<int> cnt;
+    // by cell
+    cnt.reserve((size_t)m);
+    sp.cptr.reserve((size_t)m + 1);
+    count_nz_by_cell_kernel<<<std::min((m + 7) / 8, h->sm_count * 16), 256, 0, st>>>(h->dA, h->ldA, n, m, cnt.p);
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(cnt.p, sp.cptr.p, m);
+    int nnz = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&nnz, sp.cptr.p + m, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    sp.cidx.reserve((size_t)nnz); sp.cval.reserve((size_t)nnz);
+    sp.gidx.reserve((size_t)nnz); sp.gval.reserve((size_t)nnz); sp.ajt.reserve((size_t)nnz);
+    fill_by_cell_kernel<<<std::min((m + 7) / 8, h->sm_count * 16), 256, 0, st>>>(h->dA, h->ldA, n, m, sp.cptr.p, sp.cidx.p,
+                                                                                sp.cval.p);
+    // by gene
+    const int chunk = 1024, nchunks = (m + chunk - 1) / chunk;
+    DevBuf<int> cnt2, tot;
+    cnt2.reserve((size_t)nchunks * n); tot.reserve((size_t)n);
+    sp.gptr.reserve((size_t)n + 1);
+    dim3 grid((n + 127) / 128, nchunks);
+    count_nz_by_gene_kernel<<<grid, 128, 0, st>>>(h->dA, h->ldA, n, m, chunk, cnt2.p);
+    chunk_offsets_kernel<<<(n + 127) / 128, 128, 0, st>>>(cnt2.p, nchunks, n, tot.p);
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(tot.p, sp.gptr.p, n);
+    fill_by_gene_kernel<<<grid, 128, 0, st>>>(h->dA, h->ldA, n, m, chunk, cnt2.p, sp.gptr.p, sp.gidx.p, sp.gval.p);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cnt.release(); cnt2.release(); tot.release();
+    sp.ready = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// profiling helper: event pairs per kernel family
+// ------------------------------------------------------------------------------------------------
+struct Prof {
+    bool on = false;
+    cudaStream_t st = nullptr;
+    struct Rec { int slot; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    long long launches[SWNE_PROF_SLOTS] = {0};
+    long long total_launches = 0;
+    void begin(int slot)
+    {
+        if (!on) return;
+        Rec r{slot, nullptr, nullptr};
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, st);
+        recs.push_back(r);
+    }
+    void end(int slot, int n_launch)
+    {
+        launches[slot] += n_launch;
+        total_launches += n_launch;
+        if (!on) return;
+        cudaEventRecord(recs.back().b, st);
+    }
+    void finish(swne_nmf_result_t *res)
+    {
+        for (int s = 0; s < SWNE_PROF_SLOTS; ++s) { res->prof_ms[s] = 0; res->prof_launches[s] = launches[s]; }
+        res->gpu_launches = total_launches;
+        for (auto &r : recs) {
+            float ms = 0.f;
+            cudaEventSynchronize(r.b);
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            res->prof_ms[r.slot] += ms;
+            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        }
+        recs.clear();
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// building blocks
+// ------------------------------------------------------------------------------------------------
+static void launch_gram(swne_nmf_handle_s *h, int KPv, const float *X, int rows, double *G64 /* KP*KP + KP */)
+{
+    CUDA_CHECK(cudaMemsetAsync(G64, 0, sizeof(double) * (size_t)(KPv * KPv + KPv), h->stream));
+    ops_of(KPv).gram(X, rows, G64, G64 + KPv * KPv, h->stream);
+    CUDA_CHECK(cudaGetLastError());
+}
+static void launch_finalize_gram(swne_nmf_handle_s *h, int k, int KPv, const double *G64, float *G, float *G0, float *cs32,
+                                 double p0, double p1)
+{
+    finalize_gram_kernel<<<(KPv * KPv + 255) / 256, 256, 0, h->stream>>>(G64, G, G0, cs32, G64 + KPv * KPv, k, KPv, p0, p1);
+    CUDA_CHECK(cudaGetLastError());
+}
+static void launch_contract_cells(swne_nmf_handle_s *h, int KPv, const float *Wt, float *C)
+{
+    ops_of(KPv).contract_cells(h->dA, h->ldA, h->n, h->m, Wt, C, h->stream);
+    CUDA_CHECK(cudaGetLastError());
+}
+static void launch_contract_genes(swne_nmf_handle_s *h, int KPv, const float *H, float *B)
+{
+    CUDA_CHECK(cudaMemsetAsync(B, 0, sizeof(float) * (size_t)h->n * KPv, h->stream));
+    const int gx = (h->n + 63) / 64;
+    // enough chunks to fill the machine ~4x over, each at least 256 cells
+    int chunks = std::max(1, std::min((h->m + 255) / 256, (h->sm_count * 8 + gx - 1) / gx));
+    int cpc = round_up((h->m + chunks - 1) / chunks, 32);
+    chunks = (h->m + cpc - 1) / cpc;
+    ops_of(KPv).contract_genes(h->dA, h->ldA, h->n, h->m, H, B, cpc, chunks, h->stream);
+    CUDA_CHECK(cudaGetLastError());
+}
+static void launch_solve(swne_nmf_handle_s *h, int k, int KPv, float *X, const float *C, const float *G, const float *G0,
+                         float l1, int cols, int max_iter, float rel_tol, unsigned long long *sweeps, double *loss_part)
+{
+    ops_of(KPv).solve(X, C, G, G0, l1, k, cols, max_iter, rel_tol, sweeps, loss_part, h->stream);
+    CUDA_CHECK(cudaGetLastError());
+}
+static void launch_kl(swne_nmf_handle_s *h, int k, int KPv, const int *ptr, const int *idx, const float *val, float *X,
+                      const float *Y, const float *sumY, const double *pen, int cols, int max_iter, float rel_tol,
+                      unsigned long long *sweeps, FitScalars *sc, int err)
+{
+    ops_of(KPv).kl(ptr, idx, val, h->sp.ajt.p, X, Y, sumY, (float)pen[0], (float)pen[1], (float)pen[2], k, cols, max_iter,
+                   rel_tol, sweeps, &sc->kl_part, &sc->sq_part, err, h->stream);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+static void upload_factor_cellmajor(swne_nmf_handle_s *h, const double *src, float *dst, int k, int KPv, size_t cols)
+{
+    h->stage.reserve(cols * (size_t)k);
+    CUDA_CHECK(cudaMemcpyAsync(h->stage.p, src, cols * k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const size_t tot = cols * (size_t)KPv;
+    factor_in_cellmajor_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->stage.p, dst, k, KPv, cols);
+    CUDA_CHECK(cudaGetLastError());
+}
+static void download_factor_cellmajor(swne_nmf_handle_s *h, const float *src, double *dst, int k, int KPv, size_t cols)
+{
+    h->stage.reserve(cols * (size_t)k);
+    const size_t tot = cols * (size_t)k;
+    factor_out_cellmajor_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(src, h->stage.p, k, KPv, cols);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(dst, h->stage.p, tot * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+static void upload_factor_colmajor(swne_nmf_handle_s *h, const double *src, float *dst, int k, int KPv, int n)
+{
+    h->stage.reserve((size_t)n * k);
+    CUDA_CHECK(cudaMemcpyAsync(h->stage.p, src, (size_t)n * k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const size_t tot = (size_t)n * KPv;
+    factor_in_colmajor_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->stage.p, dst, k, KPv, n);
+    CUDA_CHECK(cudaGetLastError());
+}
+static void download_factor_colmajor(swne_nmf_handle_s *h, const float *src, double *dst, int k, int KPv, int n)
+{
+    h->stage.reserve((size_t)n * k);
+    const size_t tot = (size_t)n * k;
+    factor_out_colmajor_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(src, h->stage.p, k, KPv, n);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(dst, h->stage.p, tot * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
+static void allreduce(swne_nmf_handle_s *h, float *f, size_t nf, double *d, size_t nd)
+{
+    if (h->nranks <= 1) return;
+    NCCL_CHECK(g_nccl.GroupStart());
+    if (nf) NCCL_CHECK(g_nccl.AllReduce(f, f, nf, ncclFloat32, ncclSum, h->comm, h->stream));
+    if (nd) NCCL_CHECK(g_nccl.AllReduce(d, d, nd, ncclFloat64, ncclSum, h->comm, h->stream));
+    NCCL_CHECK(g_nccl.GroupEnd());
+}
+
+static void validate_init(const double *x, size_t len, const char *name)
+{
+    for (size_t i = 0; i < len; ++i)
+        if (!(x[i] >= 0.0) || isinf(x[i])) FAIL(SWNE_ERR_BAD_ARG, "init %s has negative or non-finite entries", name);
+}
+
+// host mirror read back at every error block
+struct HostTrace {
+    FitScalars sc;
+    double G64w[SWNE_MAX_K * SWNE_MAX_K + SWNE_MAX_K];  // W'W and column sums of W
+    double G64h[SWNE_MAX_K * SWNE_MAX_K + SWNE_MAX_K];  // H H' and row sums of H (global)
+};
+
+// ------------------------------------------------------------------------------------------------
+// the fit (c_nnmf)
+// ------------------------------------------------------------------------------------------------
+static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W, double *H, double *mse_tr, double *mkl_tr,
+                    double *terr_tr, double *epo_tr, int trace_len, swne_nmf_result_t *res)
+{
+    if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident: call swne_nmf_set_matrix_* first");
+    if (!pp || !W || !H) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    swne_nmf_params_t p = *pp;
+    const int k = p.k, n = h->n, m = h->m;
+    if (k < 1 || k > SWNE_MAX_K) FAIL(SWNE_ERR_BAD_ARG, "k must be in 1..%d", SWNE_MAX_K);
+    if (p.loss != SWNE_LOSS_MSE && p.loss != SWNE_LOSS_MKL) FAIL(SWNE_ERR_BAD_ARG, "loss must be mse or mkl");
+    if (p.max_iter < 1) FAIL(SWNE_ERR_BAD_ARG, "max_iter must be >= 1");
+    for (int q = 0; q < 3; ++q)
+        if (!(p.alpha[q] >= 0.0) || !(p.beta[q] >= 0.0)) FAIL(SWNE_ERR_BAD_ARG, "penalties must be >= 0");
+    if (p.inner_max_iter <= 0) p.inner_max_iter = (p.loss == SWNE_LOSS_MSE) ? 50 : 1;
+    if (p.inner_rel_tol <= 0.0) p.inner_rel_tol = 1e-9;
+    if (p.trace <= 0) p.trace = std::max(1, 100 / p.inner_max_iter);
+    const int need_len = (p.max_iter + p.trace - 1) / p.trace + 1;
+    if ((mse_tr || mkl_tr || terr_tr || epo_tr) && trace_len < need_len)
+        FAIL(SWNE_ERR_BAD_ARG, "trace arrays need ceil(max_iter/trace)+1 = %d entries", need_len);
+    if (p.loss == SWNE_LOSS_MKL && h->nranks > 1) FAIL(SWNE_ERR_UNSUPPORTED, "mkl loss is single-GPU only");
+    validate_init(W, (size_t)n * k, "W");
+    validate_init(H, (size_t)k * m, "H");
+
+    const int KPv = kp_of(k);
+    const int GS = KPv * KPv + KPv;  // Gram + column sums
+    cudaStream_t st = h->stream;
+    memset(res, 0, sizeof(*res));
+
+    int engine = p.engine;
+    if (p.loss == SWNE_LOSS_MKL) engine = SWNE_ENGINE_SIMT;
+    if (engine == SWNE_ENGINE_AUTO) engine = tc_supported(h->n, h->m, k) ? SWNE_ENGINE_TC : SWNE_ENGINE_SIMT;
+    if (engine == SWNE_ENGINE_TC && !tc_supported(h->n, h->m, k))
+        FAIL(SWNE_ERR_UNSUPPORTED, "tcgen05 engine does not support this shape (n=%d, k=%d)", n, k);
+    res->engine_used = engine;
+
+    // ---- workspaces
+    h->Wt.reserve((size_t)n * KPv); h->H.reserve((size_t)m * KPv);
+    h->C.reserve((size_t)m * KPv); h->B.reserve((size_t)n * KPv);
+    h->G.reserve((size_t)KPv * KPv); h->G0.reserve((size_t)KPv * KPv); h->cs32.reserve((size_t)KPv);
+    h->G64w.reserve(GS); h->G64h.reserve(GS);
+    h->dscal.reserve(1); h->red.reserve(8);
+    if (!h->pinned) {
+        CUDA_CHECK(cudaMallocHost(&h->pinned, sizeof(HostTrace)));
+        h->pinned_bytes = sizeof(HostTrace);
+    }
+    HostTrace *ht = (HostTrace *)h->pinned;
+    if (p.loss == SWNE_LOSS_MKL || p.full_traces) ensure_sparse(h);
+    if (engine == SWNE_ENGINE_TC) tc_prepare(h->tc, h->dA, h->ldA, n, m, KPv, h->sm_count, st);
+
+    // ---- global constants (all-reduced once)
+    double gl[5] = {h->stats.sum, h->stats.sumsq, h->stats.klc, (double)h->stats.nnz, (double)m};
+    if (h->nranks > 1) {
+        CUDA_CHECK(cudaMemcpyAsync(h->red.p, gl, sizeof(gl), cudaMemcpyHostToDevice, st));
+        allreduce(h, nullptr, 0, h->red.p, 5);
+        CUDA_CHECK(cudaMemcpyAsync(gl, h->red.p, sizeof(gl), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    const double sumsqA = gl[1], klcA = gl[2], m_glob = gl[4];
+    const double N = (double)n * m_glob;
+
+    // ---- upload the init
+    cudaEvent_t e0, e1, e2, e3;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    cudaEventRecord(e0, st);
+    upload_factor_colmajor(h, W, h->Wt.p, k, KPv, n);
+    CUDA_CHECK(cudaStreamSynchronize(st));  // stage buffer is reused
+    upload_factor_cellmajor(h, H, h->H.p, k, KPv, (size_t)m);
+    CUDA_CHECK(cudaMemsetAsync(h->dscal.p, 0, sizeof(FitScalars), st));
+    cudaEventRecord(e1, st);
+
+    Prof prof;
+    prof.on = p.profile != 0;
+    prof.st = st;
+    const float inner_tol = (float)p.inner_rel_tol;
+    const bool mse = p.loss == SWNE_LOSS_MSE;
+
+    // H0 H0' (W update of iteration 0 needs it)
+    prof.begin(4);
+    launch_gram(h, KPv, h->H.p, m, h->G64h.p);
+    prof.end(4, 1);
+    if (h->nranks > 1) allreduce(h, nullptr, 0, h->G64h.p, GS);
+    bool have_B = false;  // the fused pass leaves A H' of the *new* H behind for the next W update
+
+    double rel_err = p.rel_tol + 1.0, terr_last = 1e99;
+    int i = 0, i_e = 0;
+    int rc = SWNE_OK;
+
+    auto error_block = [&](bool final_block) {
+        // W'W is current (computed before the H update); H H' and the loss partials are current
+        if (!mse || !(p.full_traces || final_block)) {
+            // nothing extra
+        } else {
+            ensure_sparse(h);
+            prof.begin(4);
+            ops_of(KPv).kl_trace(h->sp.cptr.p, h->sp.cidx.p, h->sp.cval.p, h->H.p, h->Wt.p, k, m, &h->dscal.p->kl_part, st);
+            CUDA_CHECK(cudaGetLastError());
+            prof.end(4, 1);
+            if (h->nranks > 1) allreduce(h, nullptr, 0, &h->dscal.p->kl_part, 1);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(&ht->sc, h->dscal.p, sizeof(FitScalars), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(ht->G64w, h->G64w.p, sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(ht->G64h, h->G64h.p, sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        double w2 = 0, wg = 0, w1 = 0, h2 = 0, hg = 0, h1 = 0, wwhh = 0, sum_ahat = 0;
+        for (int a = 0; a < k; ++a) {
+            for (int b = 0; b < k; ++b) {
+                const double gw = ht->G64w[a * KPv + b], gh = ht->G64h[a * KPv + b];
+                wg += gw; hg += gh; wwhh += gw * gh;
+                if (a == b) { w2 += gw; h2 += gh; }
+            }
+            const double cw = ht->G64w[KPv * KPv + a], ch = ht->G64h[KPv * KPv + a];
+            w1 += cw; h1 += ch; sum_ahat += cw * ch;
+        }
+        double mse_v, mkl_v;
+        const double nan_v = nan("");
+        if (mse) {
+            mse_v = (sumsqA + ht->sc.loss_part) / N;
+            mkl_v = (p.full_traces || final_block) ? (klcA - ht->sc.kl_part + sum_ahat) / N : nan_v;
+        } else {
+            mse_v = (ht->sc.sq_part + wwhh) / N;
+            mkl_v = (klcA - ht->sc.kl_part + sum_ahat) / N;
+        }
+        double terr = mse ? 0.5 * mse_v : mkl_v;
+        if (p.alpha[0] != p.alpha[1]) terr += 0.5 * (p.alpha[0] - p.alpha[1]) * w2 / N;
+        if (p.beta[0] != p.beta[1]) terr += 0.5 * (p.beta[0] - p.beta[1]) * h2 / N;
+        if (p.alpha[1] != 0.0) terr += 0.5 * p.alpha[1] * wg / N;
+        if (p.beta[1] != 0.0) terr += 0.5 * p.beta[1] * hg / N;
+        if (p.alpha[2] != 0.0) terr += p.alpha[2] * w1 / N;
+        if (p.beta[2] != 0.0) terr += p.beta[2] * h1 / N;
+        const double epochs = (double)(ht->sc.sweeps_w + ht->sc.sweeps_h) / ((double)n + m_glob);
+        if (mse_tr) mse_tr[i_e] = mse_v;
+        if (mkl_tr) mkl_tr[i_e] = mkl_v;
+        if (terr_tr) terr_tr[i_e] = terr;
+        if (epo_tr) epo_tr[i_e] = epochs;
+        rel_err = 2.0 * (terr_last - terr) / (terr_last + terr + TINY_NUM_D);
+        terr_last = terr;
+        if (p.verbose >= 2) fprintf(stderr, "%6d | %12.6g %12.6g %12.6g | %10.3g | %8.2f\n", i + 1, mse_v, mkl_v, terr, rel_err, epochs);
+        ++i_e;
+        // sweeps restart after every block (total_raw_iter = 0)
+        CUDA_CHECK(cudaMemsetAsync(&h->dscal.p->sweeps_w, 0, 2 * sizeof(unsigned long long), st));
+        if (h->progress && h->progress(h->progress_user, i + 1, mse_v, mkl_v, terr, rel_err)) rc = SWNE_ERR_INTERRUPTED;
+    };
+
+    cudaEventRecord(e2, st);
+    for (; i < p.max_iter && fabs(rel_err) > p.rel_tol && rc == SWNE_OK; ++i) {
+        // loss partials restart every iteration (only the last one before a block is read)
+        CUDA_CHECK(cudaMemsetAsync(h->dscal.p, 0, 3 * sizeof(double), st));
+        if (mse) {
+            // ---------------- W update: A' ~ H' Wt
+            if (!have_B) {
+                prof.begin(2);
+                launch_contract_genes(h, KPv, h->H.p, h->B.p);
+                prof.end(2, 1);
+                if (h->nranks > 1) { prof.begin(6); allreduce(h, h->B.p, (size_t)n * KPv, nullptr, 0); prof.end(6, 1); }
+            }
+            prof.begin(3);
+            launch_finalize_gram(h, k, KPv, h->G64h.p, h->G.p, nullptr, nullptr, p.alpha[0], p.alpha[1]);
+            launch_solve(h, k, KPv, h->Wt.p, h->B.p, h->G.p, nullptr, (float)p.alpha[2], n, p.inner_max_iter, inner_tol,
+                         &h->dscal.p->sweeps_w, nullptr);
+            prof.end(3, 2);
+            // ---------------- H update: A ~ Wt' H
+            prof.begin(4);
+            launch_gram(h, KPv, h->Wt.p, n, h->G64w.p);
+            launch_finalize_gram(h, k, KPv, h->G64w.p, h->G.p, h->G0.p, nullptr, p.beta[0], p.beta[1]);
+            prof.end(4, 2);
+            if (engine == SWNE_ENGINE_TC) {
+                prof.begin(0);
+                tc_pass(h->tc, h->Wt.p, h->H.p, h->G.p, h->G0.p, (float)p.beta[2], k, p.inner_max_iter, inner_tol, h->B.p,
+                        h->G64h.p, h->dscal.p, st);
+                prof.end(0, tc_pass_launches());
+                have_B = true;
+                if (h->nranks > 1) {
+                    prof.begin(6);
+                    allreduce(h, h->B.p, (size_t)n * KPv, h->G64h.p, GS);
+                    allreduce(h, nullptr, 0, &h->dscal.p->loss_part, 1);
+                    prof.end(6, 2);
+                }
+            } else {
+                prof.begin(0);
+                launch_contract_cells(h, KPv, h->Wt.p, h->C.p);
+                prof.end(0, 1);
+                prof.begin(1);
+                launch_solve(h, k, KPv, h->H.p, h->C.p, h->G.p, h->G0.p, (float)p.beta[2], m, p.inner_max_iter, inner_tol,
+                             &h->dscal.p->sweeps_h, &h->dscal.p->loss_part);
+                prof.end(1, 1);
+                prof.begin(4);
+                launch_gram(h, KPv, h->H.p, m, h->G64h.p);
+                prof.end(4, 1);
+                if (h->nranks > 1) {
+                    prof.begin(6);
+                    allreduce(h, nullptr, 0, h->G64h.p, GS);
+                    allreduce(h, nullptr, 0, &h->dscal.p->loss_part, 1);
+                    prof.end(6, 2);
+                }
+            }
+        } else {
+            // ---------------- mkl: W update on the by-gene view, H update on the by-cell view
+            prof.begin(5);
+            launch_finalize_gram(h, k, KPv, h->G64h.p, h->G.p, nullptr, h->cs32.p, 0.0, 0.0);
+            launch_kl(h, k, KPv, h->sp.gptr.p, h->sp.gidx.p, h->sp.gval.p, h->Wt.p, h->H.p, h->cs32.p, p.alpha, n,
+                      p.inner_max_iter, inner_tol, &h->dscal.p->sweeps_w, h->dscal.p, 0);
+            prof.end(5, 2);
+            prof.begin(4);
+            launch_gram(h, KPv, h->Wt.p, n, h->G64w.p);
+            launch_finalize_gram(h, k, KPv, h->G64w.p, h->G.p, nullptr, h->cs32.p, 0.0, 0.0);
+            prof.end(4, 2);
+            prof.begin(5);
+            launch_kl(h, k, KPv, h->sp.cptr.p, h->sp.cidx.p, h->sp.cval.p, h->H.p, h->Wt.p, h->cs32.p, p.beta, m,
+                      p.inner_max_iter, inner_tol, &h->dscal.p->sweeps_h, h->dscal.p, 1);
+            prof.end(5, 1);
+            prof.begin(4);
+            launch_gram(h, KPv, h->H.p, m, h->G64h.p);
+            prof.end(4, 1);
+        }
+        if (i % p.trace == 0) error_block(false);
+    }
+    if (i > 0 && (i - 1) % p.trace != 0 && rc == SWNE_OK) {
+        --i;  // error_block reports iteration i+1
+        error_block(true);
+        ++i;
+    } else if (mse && !p.full_traces && i_e > 0 && rc == SWNE_OK && mkl_tr) {
+        // final state coincides with the last block: fill in its mkl
+        ensure_sparse(h);
+        CUDA_CHECK(cudaMemsetAsync(&h->dscal.p->kl_part, 0, sizeof(double), st));
+        ops_of(KPv).kl_trace(h->sp.cptr.p, h->sp.cidx.p, h->sp.cval.p, h->H.p, h->Wt.p, k, m, &h->dscal.p->kl_part, st);
+        CUDA_CHECK(cudaGetLastError());
+        if (h->nranks > 1) allreduce(h, nullptr, 0, &h->dscal.p->kl_part, 1);
+        CUDA_CHECK(cudaMemcpyAsync(&ht->sc, h->dscal.p, sizeof(FitScalars), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        double sum_ahat = 0;
+        for (int a = 0; a < k; ++a) sum_ahat += ht->G64w[KPv * KPv + a] * ht->G64h[KPv * KPv + a];
+        mkl_tr[i_e - 1] = (klcA - ht->sc.kl_part + sum_ahat) / N;
+    }
+    cudaEventRecord(e3, st);
+
+    // ---- results
+    download_factor_colmajor(h, h->Wt.p, W, k, KPv, n);
+    download_factor_cellmajor(h, h->H.p, H, k, KPv, (size_t)m);
+    cudaEvent_t e4;
+    cudaEventCreate(&e4);
+    cudaEventRecord(e4, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1); res->upload_ms = ms;
+    cudaEventElapsedTime(&ms, e2, e3); res->loop_ms = ms;
+    cudaEventElapsedTime(&ms, e3, e4); res->download_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3); cudaEventDestroy(e4);
+    prof.finish(res);
+    res->n_iteration = i;
+    res->n_trace = i_e;
+    res->not_converged = (rel_err > p.rel_tol) ? 1 : 0;
+    if (rc != SWNE_OK) { set_error("interrupted by the progress callback"); return rc; }
+    return res->not_converged ? SWNE_WARN_NOT_CONVERGED : SWNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nnlm: one update() on the resident matrix
+// ------------------------------------------------------------------------------------------------
+static int nnlm_impl(swne_nmf_handle_s *h, int side, int k, const double *X, double *coef, const double *alpha3, int loss,
+                     int max_iter, double rel_tol, long long *sweeps)
+{
+    if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident");
+    if (!X || !coef) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    if (k < 1 || k > SWNE_MAX_K) FAIL(SWNE_ERR_BAD_ARG, "k must be in 1..%d", SWNE_MAX_K);
+    if (side != 0 && side != 1) FAIL(SWNE_ERR_BAD_ARG, "side must be 0 (solve H) or 1 (solve W)");
+    if (side == 1 && h->nranks > 1) FAIL(SWNE_ERR_UNSUPPORTED, "nnlm side 1 is single-GPU only");
+    if (max_iter <= 0) max_iter = 10000;
+    if (rel_tol <= 0) rel_tol = 1e-12;
+    double pen[3] = {0, 0, 0};
+    if (alpha3) for (int q = 0; q < 3; ++q) pen[q] = alpha3[q];
+    const int n = h->n, m = h->m, KPv = kp_of(k), GS = KPv * KPv + KPv;
+    cudaStream_t st = h->stream;
+    h->Wt.reserve((size_t)n * KPv); h->H.reserve((size_t)m * KPv);
+    h->C.reserve((size_t)std::max(n, m) * KPv);
+    h->G.reserve((size_t)KPv * KPv); h->G0.reserve((size_t)KPv * KPv); h->cs32.reserve((size_t)KPv);
+    h->G64w.reserve(GS); h->dscal.reserve(1);
+    CUDA_CHECK(cudaMemsetAsync(h->dscal.p, 0, sizeof(FitScalars), st));
+    float *fixed, *solve;
+    int fixed_rows, cols;
+    if (side == 0) {
+        validate_init(X, (size_t)n * k, "x"); validate_init(coef, (size_t)k * m, "coefficients");
+        upload_factor_colmajor(h, X, h->Wt.p, k, KPv, n);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        upload_factor_cellmajor(h, coef, h->H.p, k, KPv, (size_t)m);
+        fixed = h->Wt.p; solve = h->H.p; fixed_rows = n; cols = m;
+    } else {
+        validate_init(X, (size_t)k * m, "x"); validate_init(coef, (size_t)n * k, "coefficients");
+        upload_factor_cellmajor(h, X, h->H.p, k, KPv, (size_t)m);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        upload_factor_colmajor(h, coef, h->Wt.p, k, KPv, n);
+        fixed = h->H.p; solve = h->Wt.p; fixed_rows = m; cols = n;
+    }
+    launch_gram(h, KPv, fixed, fixed_rows, h->G64w.p);
+    if (loss == SWNE_LOSS_MSE) {
+        launch_finalize_gram(h, k, KPv, h->G64w.p, h->G.p, nullptr, nullptr, pen[0], pen[1]);
+        if (side == 0) launch_contract_cells(h, KPv, fixed, h->C.p);
+        else launch_contract_genes(h, KPv, fixed, h->C.p);
+        launch_solve(h, k, KPv, solve, h->C.p, h->G.p, nullptr, (float)pen[2], cols, max_iter, (float)rel_tol,
+                     &h->dscal.p->sweeps_h, nullptr);
+    } else if (loss == SWNE_LOSS_MKL) {
+        ensure_sparse(h);
+        launch_finalize_gram(h, k, KPv, h->G64w.p, h->G.p, nullptr, h->cs32.p, 0.0, 0.0);
+        if (side == 0)
+            launch_kl(h, k, KPv, h->sp.cptr.p, h->sp.cidx.p, h->sp.cval.p, solve, fixed, h->cs32.p, pen, cols, max_iter,
+                      (float)rel_tol, &h->dscal.p->sweeps_h, h->dscal.p, 0);
+        else
+            launch_kl(h, k, KPv, h->sp.gptr.p, h->sp.gidx.p, h->sp.gval.p, solve, fixed, h->cs32.p, pen, cols, max_iter,
+                      (float)rel_tol, &h->dscal.p->sweeps_h, h->dscal.p, 0);
+    } else {
+        FAIL(SWNE_ERR_BAD_ARG, "loss must be mse or mkl");
+    }
+    FitScalars sc;
+    CUDA_CHECK(cudaMemcpyAsync(&sc, h->dscal.p, sizeof(sc), cudaMemcpyDeviceToHost, st));
+    if (side == 0) download_factor_cellmajor(h, solve, coef, k, KPv, (size_t)m);
+    else download_factor_colmajor(h, solve, coef, k, KPv, n);
+    if (sweeps) *sweeps = (long long)sc.sweeps_h;
+    return SWNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NNDSVD from a randomized truncated SVD of the resident matrix (R/nmf.R:12-47)
+//   A (n x m) = U S V'.  Range finder on the gene side: Y = A Omega (n x l), power iterations with
+//   CholeskyQR2 re-orthonormalisation, then the small problem B = Q'A (l x m) through its Gram.
+// ------------------------------------------------------------------------------------------------
+__global__ void fill_gaussian_kernel(float *x, size_t rows, int l, int KP, uint64_t seed)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * (size_t)KP) return;
+    const int f = (int)(t % KP);
+    float v = 0.f;
+    if (f < l) {
+        // splitmix64 -> two uniforms -> Box-Muller
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (t + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+        const float u1 = ((float)(uint32_t)(z >> 40) + 1.f) * (1.f / 16777217.f);
+        const float u2 = (float)(uint32_t)(z & 0xFFFFFFu) * (1.f / 16777216.f);
+        v = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+    }
+    x[t] = v;
+}
+// X <- X R^{-1} with R'R = X'X (Cholesky QR), twice
+static void cholesky_qr2(swne_nmf_handle_s *h, int KPv, int l, float *X, int rows, double *G64dev, float *Tdev)
+{
+    std::vector<double> G(KPv * KPv + KPv), R(l * l), Ri(l * l);
+    std::vector<float> T(KPv * KPv);
+    for (int pass = 0; pass < 2; ++pass) {
+        launch_gram(h, KPv, X, rows, G64dev);
+        if (h->nranks > 1 && rows == h->m) allreduce(h, nullptr, 0, G64dev, KPv * KPv + KPv);
+        CUDA_CHECK(cudaMemcpyAsync(G.data(), G64dev, sizeof(double) * G.size(), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        std::vector<double> Gs(l * l);
+        for (int a = 0; a < l; ++a)
+            for (int b = 0; b < l; ++b) Gs[a * l + b] = G[a * KPv + b];
+        if (!small_cholesky_upper(Gs.data(), l, R.data())) FAIL(SWNE_ERR_BAD_ARG, "randomized SVD: rank deficient sketch (k too large for this matrix?)");
+        small_upper_inverse(R.data(), l, Ri.data());
+        std::fill(T.begin(), T.end(), 0.f);
+        for (int a = 0; a < l; ++a)
+            for (int b = 0; b < l; ++b) T[a * KPv + b] = (float)Ri[a * l + b];
+        CUDA_CHECK(cudaMemcpyAsync(Tdev, T.data(), sizeof(float) * T.size(), cudaMemcpyHostToDevice, h->stream));
+        ops_of(KPv).right_multiply(X, (size_t)rows, Tdev, l, h->stream);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    }
+}
+
+static int nnsvd_impl(swne_nmf_handle_s *h, int k, int oversample, int power_iters, uint64_t seed, double *W, double *H,
+                      double *sv)
+{
+    if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident");
+    if (!W || !H) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    if (h->nranks > 1) FAIL(SWNE_ERR_UNSUPPORTED, "nnsvd init is single-GPU only (seed on one rank, then scatter H)");
+    const int n = h->n, m = h->m;
+    if (k < 1 || k > std::min(n, m)) FAIL(SWNE_ERR_BAD_ARG, "k must be in 1..min(n,m)");
+    if (oversample < 0) oversample = 10;
+    if (power_iters < 0) power_iters = 4;
+    int l = std::min(std::min(n, m), k + oversample);
+    if (l > SWNE_MAX_K) l = SWNE_MAX_K;
+    if (k > l) FAIL(SWNE_ERR_BAD_ARG, "k must be <= %d", SWNE_MAX_K);
+    const int KPv = kp_of(l), GS = KPv * KPv + KPv;
+    cudaStream_t st = h->stream;
+    h->Wt.reserve((size_t)n * KPv); h->H.reserve((size_t)m * KPv);
+    h->G.reserve((size_t)KPv * KPv); h->G64w.reserve(GS);
+    float *Y = h->Wt.p, *Z = h->H.p;  // Y [n][KP] gene side, Z [m][KP] cell side
+    const size_t totz = (size_t)m * KPv;
+    fill_gaussian_kernel<<<(unsigned)((totz + 255) / 256), 256, 0, st>>>(Z, (size_t)m, l, KPv, seed);
+    CUDA_CHECK(cudaGetLastError());
+    launch_contract_genes(h, KPv, Z, Y);                    // Y = A Omega
+    cholesky_qr2(h, KPv, l, Y, n, h->G64w.p, h->G.p);
+    for (int q = 0; q < power_iters; ++q) {
+        launch_contract_cells(h, KPv, Y, Z);                // Z = A' Q
+        cholesky_qr2(h, KPv, l, Z, m, h->G64w.p, h->G.p);
+        launch_contract_genes(h, KPv, Z, Y);                // Y = A Z
+        cholesky_qr2(h, KPv, l, Y, n, h->G64w.p, h->G.p);
+    }
+    launch_contract_cells(h, KPv, Y, Z);                    // Z = A' Q  (m x l) = B'
+    launch_gram(h, KPv, Z, m, h->G64w.p);                   // B B' = Z'Z
+    std::vector<double> G(GS);
+    CUDA_CHECK(cudaMemcpyAsync(G.data(), h->G64w.p, sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    std::vector<double> S(l * l), evec(l * l), eval(l);
+    for (int a = 0; a < l; ++a)
+        for (int b = 0; b < l; ++b) S[a * l + b] = G[a * KPv + b];
+    small_jacobi_eigh(S.data(), l, eval.data(), evec.data());  // descending, evec columns
+    // U = Q Uhat (n x l), V = Z Uhat S^-1 (m x l): right-multiply on device
+    std::vector<float> T(KPv * KPv, 0.f);
+    for (int a = 0; a < l; ++a)
+        for (int b = 0; b < l; ++b) T[a * KPv + b] = (float)evec[a * l + b];
+    CUDA_CHECK(cudaMemcpyAsync(h->G.p, T.data(), sizeof(float) * T.size(), cudaMemcpyHostToDevice, st));
+    ops_of(KPv).right_multiply(Y, (size_t)n, h->G.p, l, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int a = 0; a < l; ++a)
+        for (int b = 0; b < l; ++b) {
+            const double s = sqrt(std::max(eval[b], 0.0));
+            T[a * KPv + b] = (s > 0) ? (float)(evec[a * l + b] / s) : 0.f;
+        }
+    CUDA_CHECK(cudaMemcpyAsync(h->G.p, T.data(), sizeof(float) * T.size(), cudaMemcpyHostToDevice, st));
+    ops_of(KPv).right_multiply(Z, (size_t)m, h->G.p, l, st);
+    CUDA_CHECK(cudaGetLastError());
+    // NNDSVD split on the host in double (O((n+m) k))
+    std::vector<double> U((size_t)n * l), V((size_t)m * l);
+    download_factor_colmajor(h, Y, U.data(), l, KPv, n);          // U[i + n f]
+    {
+        std::vector<double> Vt((size_t)m * l);
+        download_factor_cellmajor(h, Z, Vt.data(), l, KPv, (size_t)m);  // [cell][f]
+        for (size_t j = 0; j < (size_t)m; ++j)
+            for (int f = 0; f < l; ++f) V[j + (size_t)m * f] = Vt[j * l + f];
+    }
+    for (int f = 0; f < k; ++f) {
+        const double s = sqrt(std::max(eval[f], 0.0));
+        if (sv) sv[f] = s;
+        const double *u = &U[(size_t)n * f], *v = &V[(size_t)m * f];
+        if (f == 0) {
+            for (int i = 0; i < n; ++i) W[i] = sqrt(s) * fabs(u[i]);
+            for (int j = 0; j < m; ++j) H[(size_t)j * k] = sqrt(s) * fabs(v[j]);
+            continue;
+        }
+        double nup = 0, nun = 0, nvp = 0, nvn = 0;
+        for (int i = 0; i < n; ++i) { if (u[i] >= 0) nup += u[i] * u[i]; else nun += u[i] * u[i]; }
+        for (int j = 0; j < m; ++j) { if (v[j] >= 0) nvp += v[j] * v[j]; else nvn += v[j] * v[j]; }
+        nup = sqrt(nup); nun = sqrt(nun); nvp = sqrt(nvp); nvn = sqrt(nvn);
+        const double termp = nup * nvp, termn = nun * nvn;
+        if (termp >= termn) {
+            const double c = sqrt(s * termp);
+            for (int i = 0; i < n; ++i) W[i + (size_t)n * f] = (u[i] >= 0) ? c * u[i] / nup : 0.0;
+            for (int j = 0; j < m; ++j) H[f + (size_t)j * k] = (v[j] >= 0) ? c * v[j] / nvp : 0.0;
+        } else {
+            const double c = sqrt(s * termn);
+            for (int i = 0; i < n; ++i) W[i + (size_t)n * f] = (u[i] < 0) ? -c * u[i] / nun : 0.0;
+            for (int j = 0; j < m; ++j) H[f + (size_t)j * k] = (v[j] < 0) ? -c * v[j] / nvn : 0.0;
+        }
+    }
+    return SWNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// consumers of H
+// ------------------------------------------------------------------------------------------------
+__global__ void gram64_kernel(const double *__restrict__ H, int k, int m, double *__restrict__ G /* k*k + k */)
+{
+    // one block per pair chunk: thread (a,b) strides over cells; small k, setup-time kernel
+    const int pr = blockIdx.x;  // pair index or k*k + a for column sums
+    const int a = pr / k, b = pr % k;
+    __shared__ double scratch[32];
+    double s = 0.0;
+    if (pr < k * k) {
+        for (int j = threadIdx.x; j < m; j += blockDim.x) s += H[(size_t)j * k + a] * H[(size_t)j * k + b];
+    } else {
+        const int c = pr - k * k;
+        for (int j = threadIdx.x; j < m; j += blockDim.x) s += H[(size_t)j * k + c];
+    }
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) G[pr] = s;
+}
+
+static int sample_coords_impl(swne_nmf_handle_s *h, const double *H, int k, int m, const double *coords, double alpha,
+                              int n_pull, double *out)
+{
+    if (!H || !coords || !out) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    if (k < 1 || k > 64 || m < 1) FAIL(SWNE_ERR_BAD_ARG, "bad k or m");
+    // R/swne_plotting.R:71-72
+    if (n_pull > 0 && n_pull < 3) n_pull = 3;
+    if (n_pull <= 0 || n_pull > k) n_pull = k;
+    cudaStream_t st = h->stream;
+    DevBuf<double> dH, dC, dO;
+    dH.reserve((size_t)k * m); dC.reserve(2 * k); dO.reserve(2 * (size_t)m);
+    CUDA_CHECK(cudaMemcpyAsync(dH.p, H, sizeof(double) * (size_t)k * m, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(dC.p, coords, sizeof(double) * 2 * k, cudaMemcpyHostToDevice, st));
+    sample_coords_kernel<<<(m + 127) / 128, 128, 2 * k * sizeof(double), st>>>(dH.p, k, m, dC.p, alpha, n_pull, dO.p);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(out, dO.p, sizeof(double) * 2 * (size_t)m, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    dH.release(); dC.release(); dO.release();
+    return SWNE_OK;
+}
+
+static int factor_distance_impl(swne_nmf_handle_s *h, const double *H, int k, int m, int distance, double *out)
+{
+    if (!H || !out) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    if (k < 1 || k > 64 || m < 1) FAIL(SWNE_ERR_BAD_ARG, "bad k or m");
+    if (distance < 0 || distance > 2) FAIL(SWNE_ERR_BAD_ARG, "distance must be 0 cosine, 1 pearson or 2 euclidean");
+    cudaStream_t st = h->stream;
+    DevBuf<double> dH, dG;
+    dH.reserve((size_t)k * m); dG.reserve(k * k + k);
+    CUDA_CHECK(cudaMemcpyAsync(dH.p, H, sizeof(double) * (size_t)k * m, cudaMemcpyHostToDevice, st));
+    gram64_kernel<<<k * k + k, 256, 0, st>>>(dH.p, k, m, dG.p);
+    CUDA_CHECK(cudaGetLastError());
+    std::vector<double> G(k * k + k);
+    CUDA_CHECK(cudaMemcpyAsync(G.data(), dG.p, sizeof(double) * G.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    dH.release(); dG.release();
+    for (int a = 0; a < k; ++a)
+        for (int b = 0; b < k; ++b) {
+            const double gab = G[a * k + b], gaa = G[a * k + a], gbb = G[b * k + b];
+            double d;
+            if (distance == 0) {
+                d = 1.0 - gab / sqrt(gaa * gbb);
+            } else if (distance == 1) {
+                const double ma = G[k * k + a] / m, mb = G[k * k + b] / m;
+                const double cov = gab - m * ma * mb, va = gaa - m * ma * ma, vb = gbb - m * mb * mb;
+                d = sqrt(std::max(0.0, 2.0 * (1.0 - cov / sqrt(va * vb))));
+            } else {
+                d = sqrt(std::max(0.0, gaa + gbb - 2.0 * gab));
+            }
+            out[a + (size_t)k * b] = d;
+        }
+    return SWNE_OK;
+}
+
+static int recon_error_impl(swne_nmf_handle_s *h, const double *W, const double *H, int k, double *mse, double *kl)
+{
+    if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident");
+    if (!W || !H) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    if (k < 1 || k > SWNE_MAX_K) FAIL(SWNE_ERR_BAD_ARG, "k out of range");
+    const int n = h->n, m = h->m, KPv = kp_of(k);
+    cudaStream_t st = h->stream;
+    h->Wt.reserve((size_t)n * KPv); h->H.reserve((size_t)m * KPv); h->red.reserve(8);
+    upload_factor_colmajor(h, W, h->Wt.p, k, KPv, n);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    upload_factor_cellmajor(h, H, h->H.p, k, KPv, (size_t)m);
+    CUDA_CHECK(cudaMemsetAsync(h->red.p, 0, 2 * sizeof(double), st));
+    const int grid = std::min(m, h->sm_count * 8);
+    ops_of(KPv).recon_error(h->dA, h->ldA, n, m, h->Wt.p, h->H.p, k, h->red.p, grid, st);
+    CUDA_CHECK(cudaGetLastError());
+    if (h->nranks > 1) allreduce(h, nullptr, 0, h->red.p, 2);
+    double r[2];
+    CUDA_CHECK(cudaMemcpyAsync(r, h->red.p, sizeof(r), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    double mg = (double)m;
+    if (h->nranks > 1) {
+        double gl = (double)m;
+        CUDA_CHECK(cudaMemcpyAsync(h->red.p, &gl, sizeof(double), cudaMemcpyHostToDevice, st));
+        allreduce(h, nullptr, 0, h->red.p, 1);
+        CUDA_CHECK(cudaMemcpyAsync(&mg, h->red.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    const double N = (double)n * mg;
+    if (mse) *mse = r[0] / N;
+    if (kl) *kl = r[1] / N;
+    return SWNE_OK;
+}
+
+}  // namespace swne
+
+// ==================================================================================================
+// extern "C"
+// ==================================================================================================
+using namespace swne;
+
+#define API_BEGIN try {
+#define API_END                                            \
+    }                                                      \
+    catch (const swne::ArgError &e) { return e.code; }     \
+    catch (const swne::CudaError &) { return SWNE_ERR_CUDA; } \
+    catch (const std::bad_alloc &) { swne::set_error("host allocation failed"); return SWNE_ERR_CUDA; } \
+    catch (...) { swne::set_error("unknown C++ exception"); return SWNE_ERR_CUDA; }
+
+extern "C" {
+
+const char *swne_nmf_last_error(void) { return g_err; }
+int swne_nmf_abi_version(void) { return SWNE_NMF_ABI_VERSION; }
+
+int swne_nmf_device_count(int *count)
+{
+    API_BEGIN
+    if (!count) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    CUDA_CHECK(cudaGetDeviceCount(count));
+    return SWNE_OK;
+    API_END
+}
+
+void swne_nmf_default_params(swne_nmf_params_t *p, int k)
+{
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->k = k;
+    p->loss = SWNE_LOSS_MSE;
+    p->max_iter = 500;
+    p->rel_tol = 1e-4;
+    p->inner_max_iter = 0;
+    p->inner_rel_tol = 1e-9;
+    p->trace = 0;
+    p->verbose = 0;
+    p->engine = SWNE_ENGINE_AUTO;
+    p->full_traces = 0;
+    p->profile = 0;
+}
+
+int swne_nmf_create(swne_nmf_handle_t *out, int device)
+{
+    API_BEGIN
+    if (!out) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    int cnt = 0;
+    CUDA_CHECK(cudaGetDeviceCount(&cnt));
+    if (cnt < 1) FAIL(SWNE_ERR_CUDA, "no CUDA device visible: libswne_nmf has no CPU fallback");
+    if (device < 0 || device >= cnt) FAIL(SWNE_ERR_BAD_ARG, "device %d out of range (0..%d)", device, cnt - 1);
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) FAIL(SWNE_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    swne_nmf_handle_s *h = new swne_nmf_handle_s();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    *out = h;
+    return SWNE_OK;
+    API_END
+}
+
+int swne_nmf_destroy(swne_nmf_handle_t h)
+{
+    API_BEGIN
+    if (!h) return SWNE_OK;
+    DeviceGuard g(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    h->A_store.release();
+    h->sp.cptr.release(); h->sp.cidx.release(); h->sp.gptr.release(); h->sp.gidx.release();
+    h->sp.cval.release(); h->sp.gval.release(); h->sp.ajt.release();
+    tc_release(h->tc);
+    h->Wt.release(); h->H.release(); h->C.release(); h->B.release(); h->G.release(); h->G0.release(); h->cs32.release();
+    h->G64w.release(); h->G64h.release(); h->stage.release(); h->dstats.release(); h->dscal.release(); h->red.release();
+    if (h->pinned) cudaFreeHost(h->pinned);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return SWNE_OK;
+    API_END
+}
+
+int swne_nmf_set_progress(swne_nmf_handle_t h, swne_nmf_progress_fn fn, void *user)
+{
+    if (!h) { set_error("NULL handle"); return SWNE_ERR_BAD_ARG; }
+    h->progress = fn; h->progress_user = user;
+    return SWNE_OK;
+}
+
+int swne_nmf_comm_unique_id(void *id128)
+{
+    API_BEGIN
+    if (!id128) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    load_nccl();
+    ncclUniqueId id;
+    NCCL_CHECK(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return SWNE_OK;
+    API_END
+}
+
+int swne_nmf_comm_init(swne_nmf_handle_t h, const void *id128, int rank, int nranks)
+{
+    API_BEGIN
+    if (!h || !id128) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) FAIL(SWNE_ERR_BAD_ARG, "bad rank/nranks");
+    DeviceGuard g(h->device);
+    if (nranks == 1) { h->rank = 0; h->nranks = 1; return SWNE_OK; }
+    load_nccl();
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NCCL_CHECK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    h->rank = rank; h->nranks = nranks;
+    return SWNE_OK;
+    API_END
+}
+
+#define HANDLE_GUARD(h)                                               \
+    if (!(h)) FAIL(SWNE_ERR_BAD_ARG, "NULL handle");                  \
+    DeviceGuard _guard((h)->device)
+
+int swne_nmf_set_matrix_dense_f64(swne_nmf_handle_t h, const double *A, int n, int m)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    set_dense<double>(h, A, n, m);
+    return SWNE_OK;
+    API_END
+}
+int swne_nmf_set_matrix_dense_f32(swne_nmf_handle_t h, const float *A, int n, int m)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    set_dense<float>(h, A, n, m);
+    return SWNE_OK;
+    API_END
+}
+int swne_nmf_set_matrix_csc_f64(swne_nmf_handle_t h, const int *p, const int *i, const double *x, int n, int m)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    set_csc<double>(h, p, i, x, n, m);
+    return SWNE_OK;
+    API_END
+}
+int swne_nmf_set_matrix_csc_f32(swne_nmf_handle_t h, const int *p, const int *i, const float *x, int n, int m)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    set_csc<float>(h, p, i, x, n, m);
+    return SWNE_OK;
+    API_END
+}
+int swne_nmf_set_matrix_dense_f32_device(swne_nmf_handle_t h, const float *dA, int n, int m)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    if (!dA) FAIL(SWNE_ERR_BAD_ARG, "A is NULL");
+    cudaPointerAttributes attr;
+    CUDA_CHECK(cudaPointerGetAttributes(&attr, dA));
+    if (attr.type != cudaMemoryTypeDevice) FAIL(SWNE_ERR_BAD_ARG, "A is not a device pointer");
+    if (n % 4 == 0 && ((uintptr_t)dA & 15) == 0) {
+        begin_matrix(h, n, m, false);
+        h->A_store.release();
+        h->dA = const_cast<float *>(dA);   // borrowed: the caller keeps it alive and unchanged
+        h->own_A = false;
+    } else {
+        begin_matrix(h, n, m, true);
+        CUDA_CHECK(cudaMemsetAsync(h->dA, 0, (size_t)m * h->ldA * sizeof(float), h->stream));
+        CUDA_CHECK(cudaMemcpy2DAsync(h->dA, h->ldA * sizeof(float), dA, (size_t)n * sizeof(float), (size_t)n * sizeof(float), m,
+                                     cudaMemcpyDeviceToDevice, h->stream));
+    }
+    const int grid = std::min(m, h->sm_count * 8);
+    ingest_dense_kernel<float><<<grid, 256, 0, h->stream>>>(h->dA, h->ldA, nullptr, h->ldA, n, m, h->dstats.p);
+    CUDA_CHECK(cudaGetLastError());
+    check_stats(h);
+    return SWNE_OK;
+    API_END
+}
+
+int swne_nmf_matrix_info(swne_nmf_handle_t h, int *n, int *m, long long *nnz, double *sum, double *sumsq)
+{
+    API_BEGIN
+    if (!h) FAIL(SWNE_ERR_BAD_ARG, "NULL handle");
+    if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident");
+    if (n) *n = h->n;
+    if (m) *m = h->m;
+    if (nnz) *nnz = (long long)h->stats.nnz;
+    if (sum) *sum = h->stats.sum;
+    if (sumsq) *sumsq = h->stats.sumsq;
+    return SWNE_OK;
+    API_END
+}
+
+int swne_nmf_fit(swne_nmf_handle_t h, const swne_nmf_params_t *p, double *W, double *H, double *mse, double *mkl,
+                 double *target_loss, double *average_epochs, int trace_len, swne_nmf_result_t *res)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    swne_nmf_result_t local;
+    return fit_impl(h, p, W, H, mse, mkl, target_loss, average_epochs, trace_len, res ? res : &local);
+    API_END
+}
+
+int swne_nmf_fit_dense_f64(swne_nmf_handle_t h, const swne_nmf_params_t *p, const double *A, int n, int m, double *W,
+                           double *H, double *mse, double *mkl, double *target_loss, double *average_epochs,
+                           int trace_len, swne_nmf_result_t *res)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, h->stream);
+    set_dense<double>(h, A, n, m);
+    cudaEventRecord(b, h->stream);
+    swne_nmf_result_t local;
+    swne_nmf_result_t *r = res ? res : &local;
+    const int rc = fit_impl(h, p, W, H, mse, mkl, target_loss, average_epochs, trace_len, r);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    r->upload_ms += ms;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return rc;
+    API_END
+}
+
+int swne_nmf_fit_csc_f64(swne_nmf_handle_t h, const swne_nmf_params_t *p, const int *cp, const int *ci, const double *cx,
+                         int n, int m, double *W, double *H, double *mse, double *mkl, double *target_loss,
+                         double *average_epochs, int trace_len, swne_nmf_result_t *res)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    set_csc<double>(h, cp, ci, cx, n, m);
+    swne_nmf_result_t local;
+    return fit_impl(h, p, W, H, mse, mkl, target_loss, average_epochs, trace_len, res ? res : &local);
+    API_END
+}
+
+int swne_nnlm(swne_nmf_handle_t h, int side, int k, const double *X, double *coef, const double *alpha3, int loss,
+              int max_iter, double rel_tol, long long *sweeps)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    return nnlm_impl(h, side, k, X, coef, alpha3, loss, max_iter, rel_tol, sweeps);
+    API_END
+}
+
+int swne_nnsvd_init(swne_nmf_handle_t h, int k, int oversample, int power_iters, uint64_t seed, double *W, double *H,
+                    double *singular_values)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    return nnsvd_impl(h, k, oversample, power_iters, seed, W, H, singular_values);
+    API_END
+}
+
+int swne_zero_replace(double *x, size_t len, double eps, const double *fill, size_t n_fill, size_t *n_zero)
+{
+    API_BEGIN
+    if (!x && len) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    size_t z = 0;
+    for (size_t i = 0; i < len; ++i) {
+        if (x[i] < eps) x[i] = 0.0;
+        if (x[i] == 0.0) {
+            if (fill) {
+                if (z >= n_fill) FAIL(SWNE_ERR_BAD_ARG, "fill vector shorter than the number of zeros");
+                x[i] = fill[z];
+            }
+            ++z;
+        }
+    }
+    if (n_zero) *n_zero = z;
+    return SWNE_OK;
+    API_END
+}
+
+int swne_sample_coords(swne_nmf_handle_t h, const double *H, int k, int m, const double *H_coords, double alpha_exp,
+                       int n_pull, double *out)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    return sample_coords_impl(h, H, k, m, H_coords, alpha_exp, n_pull, out);
+    API_END
+}
+
+int swne_factor_distance(swne_nmf_handle_t h, const double *H, int k, int m, int distance, double *out)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    return factor_distance_impl(h, H, k, m, distance, out);
+    API_END
+}
+
+int swne_recon_error(swne_nmf_handle_t h, const double *W, const double *H, int k, double *mse, double *kl)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    return recon_error_impl(h, W, H, k, mse, kl);
+    API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,385 @@
+"""Host-side mirror of SWNE's NMF front-end (/root/reference/R/nmf.R) over the C-ABI.
+
+Same names, argument meaning and error behaviour as the R functions so the parity tests read like tests
+of the reference: RunNMF (R/nmf.R:96-134), FindNumFactors (:157-205), nnsvd_init (:12-47), ica_init
+(:56-66), kl_div (:71-75), ProjectFeatures (:222-225), ProjectSamples (:241-249), and nnmf / nnlm for the
+NNLM calls themselves.  All numerics run in libswne_nmf.so on the GPU; this file
+only validates, seeds and marshals.  Matrices follow R: A is genes x cells (n x m), W n x k, H k x m.
+"""
+import ctypes
+import time
+
+import numpy as np
+
+from . import _capi as C
+
+
+def _is_csc(A):
+    return hasattr(A, "indptr") and hasattr(A, "indices") and hasattr(A, "data") and getattr(A, "format", "") == "csc"
+
+
+class NMFHandle:
+    """One GPU's resident matrix + workspaces (swne_nmf_handle_t).  Reuse it across fits (FindNumFactors)."""
+
+    def __init__(self, device=0):
+        self._lib = C.load()
+        self._h = ctypes.c_void_p()
+        C.check(self._lib.swne_nmf_create(ctypes.byref(self._h), int(device)))
+        self.device = device
+        self.n = self.m = 0
+        self.rank, self.nranks = 0, 1
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            self._lib.swne_nmf_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- communicator (cells sharded across ranks)
+    @staticmethod
+    def unique_id():
+        buf = ctypes.create_string_buffer(128)
+        C.check(C.load().swne_nmf_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, nranks):
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        C.check(self._lib.swne_nmf_comm_init(self._h, buf, int(rank), int(nranks)))
+        self.rank, self.nranks = rank, nranks
+
+    # ---- matrix
+    def set_matrix(self, A):
+        """A: numpy (n x m, any float dtype), scipy.sparse CSC (dgCMatrix analogue), or a torch CUDA
+        float32 tensor of shape (m, n) (cell-major == R column-major n x m) that is used in place."""
+        if _is_csc(A):
+            n, m = A.shape
+            p = np.ascontiguousarray(A.indptr, dtype=np.int32)
+            i = np.ascontiguousarray(A.indices, dtype=np.int32)
+            if A.data.dtype == np.float32:
+                x = np.ascontiguousarray(A.data)
+                C.check(self._lib.swne_nmf_set_matrix_csc_f32(self._h, C.iptr(p), C.iptr(i), C.fptr(x), n, m))
+            else:
+                x = np.ascontiguousarray(A.data, dtype=np.float64)
+                C.check(self._lib.swne_nmf_set_matrix_csc_f64(self._h, C.iptr(p), C.iptr(i), C.dptr(x), n, m))
+        elif hasattr(A, "data_ptr") and hasattr(A, "is_cuda"):
+            if not A.is_cuda or A.dim() != 2 or str(A.dtype) != "torch.float32" or not A.is_contiguous():
+                raise ValueError("device matrix must be a contiguous CUDA float32 tensor of shape (cells, genes)")
+            m, n = A.shape
+            self._keep = A  # borrowed by the library
+            C.check(self._lib.swne_nmf_set_matrix_dense_f32_device(self._h, ctypes.c_void_p(A.data_ptr()), n, m))
+        else:
+            A = np.asarray(A)
+            if A.ndim != 2:
+                raise ValueError("A must be a matrix")
+            n, m = A.shape
+            if A.dtype == np.float32:
+                Af = np.asfortranarray(A)
+                C.check(self._lib.swne_nmf_set_matrix_dense_f32(self._h, C.fptr(Af), n, m))
+            else:
+                Af = np.asfortranarray(A, dtype=np.float64)
+                C.check(self._lib.swne_nmf_set_matrix_dense_f64(self._h, C.dptr(Af), n, m))
+        self.n, self.m = n, m
+
+    def matrix_info(self):
+        n, m = ctypes.c_int(), ctypes.c_int()
+        nnz = ctypes.c_longlong()
+        s, s2 = ctypes.c_double(), ctypes.c_double()
+        C.check(self._lib.swne_nmf_matrix_info(self._h, ctypes.byref(n), ctypes.byref(m), ctypes.byref(nnz),
+                                               ctypes.byref(s), ctypes.byref(s2)))
+        return dict(n=n.value, m=m.value, nnz=nnz.value, sum=s.value, sumsq=s2.value)
+
+    # ---- NNLM::nnmf on the resident matrix
+    def fit(self, k, W0, H0, alpha=0.0, beta=0.0, loss="mse", max_iter=500, rel_tol=1e-4, inner_max_iter=0,
+            inner_rel_tol=1e-9, trace=0, verbose=0, engine="auto", full_traces=False, profile=False,
+            show_warning=False):
+        if loss not in C.LOSS:
+            raise ValueError("loss must be 'mse' or 'mkl'")
+        if self.n == 0:
+            raise C.SwneError(C.SWNE_ERR_NO_MATRIX, "set_matrix first")
+        n, m = self.n, self.m
+        W = np.asfortranarray(np.array(W0, dtype=np.float64, copy=True))
+        H = np.asfortranarray(np.array(H0, dtype=np.float64, copy=True))
+        if W.shape != (n, k) or H.shape != (k, m):
+            raise ValueError("init shapes must be W %s and H %s" % ((n, k), (k, m)))
+        p = C.Params()
+        self._lib.swne_nmf_default_params(ctypes.byref(p), int(k))
+        p.alpha[:] = list(C.pad3(alpha)); p.beta[:] = list(C.pad3(beta))
+        p.loss = C.LOSS[loss]; p.max_iter = int(max_iter); p.rel_tol = float(rel_tol)
+        p.inner_max_iter = int(inner_max_iter); p.inner_rel_tol = float(inner_rel_tol); p.trace = int(trace)
+        p.verbose = int(verbose); p.engine = C.ENGINE[engine]; p.full_traces = int(bool(full_traces))
+        p.profile = int(bool(profile))
+        imi = p.inner_max_iter if p.inner_max_iter > 0 else (50 if loss == "mse" else 1)
+        tr = p.trace if p.trace > 0 else max(1, 100 // imi)
+        L = -(-int(max_iter) // tr) + 1
+        mse = np.zeros(L); mkl = np.zeros(L); terr = np.zeros(L); epo = np.zeros(L)
+        res = C.Result()
+        t0 = time.perf_counter()
+        code = C.check(self._lib.swne_nmf_fit(self._h, ctypes.byref(p), C.dptr(W), C.dptr(H), C.dptr(mse), C.dptr(mkl),
+                                             C.dptr(terr), C.dptr(epo), L, ctypes.byref(res)))
+        wall = time.perf_counter() - t0
+        if code == C.SWNE_WARN_NOT_CONVERGED and show_warning:
+            import warnings
+            warnings.warn("Target tolerance not reached. Try a larger max.iter.")
+        t = res.n_trace
+        out = NNMF(W=np.array(W), H=np.array(H), mse=mse[:t].copy(), mkl=mkl[:t].copy(), target_loss=terr[:t].copy(),
+                   average_epochs=epo[:t].copy(), n_iteration=res.n_iteration, run_time=wall,
+                   options=dict(method="scd", loss=loss, alpha=C.pad3(alpha), beta=C.pad3(beta), max_iter=max_iter,
+                                rel_tol=rel_tol, inner_max_iter=imi, inner_rel_tol=inner_rel_tol, trace=tr,
+                                engine=C.ENGINE_NAME[res.engine_used]),
+                   not_converged=bool(res.not_converged),
+                   stats=dict(loop_ms=res.loop_ms, upload_ms=res.upload_ms, download_ms=res.download_ms,
+                              gpu_launches=res.gpu_launches, prof_ms=list(res.prof_ms),
+                              prof_launches=list(res.prof_launches)))
+        return out
+
+    # ---- NNLM::nnlm on the resident matrix
+    def nnlm(self, side, X, init=None, alpha=0.0, loss="mse", max_iter=10000, rel_tol=1e-12):
+        """side 0: coefficients H (k x m) for fixed W = X (n x k); side 1: W (n x k) for fixed H = X (k x m)."""
+        n, m = self.n, self.m
+        X = np.asfortranarray(X, dtype=np.float64)
+        k = X.shape[1] if side == 0 else X.shape[0]
+        shape = (k, m) if side == 0 else (n, k)
+        if X.shape != ((n, k) if side == 0 else (k, m)):
+            raise ValueError("x has the wrong shape")
+        # NNLM seeds nnlm with runif * 0.01 (R RNG); a deterministic constant start is used instead
+        coef = np.asfortranarray(np.full(shape, 0.005) if init is None else np.array(init, dtype=np.float64, copy=True))
+        al = C.pad3(alpha)
+        sw = ctypes.c_longlong()
+        C.check(self._lib.swne_nnlm(self._h, int(side), int(k), C.dptr(X), C.dptr(coef), C.dptr(al), C.LOSS[loss],
+                                    int(max_iter), float(rel_tol), ctypes.byref(sw)))
+        return dict(coefficients=np.array(coef), n_iteration=sw.value)
+
+    def nnsvd_init(self, k, oversample=10, power_iters=4, seed=1):
+        n, m = self.n, self.m
+        W = np.zeros((n, k), order="F"); H = np.zeros((k, m), order="F"); sv = np.zeros(k)
+        C.check(self._lib.swne_nnsvd_init(self._h, int(k), int(oversample), int(power_iters), int(seed), C.dptr(W),
+                                          C.dptr(H), C.dptr(sv)))
+        return W, H, sv
+
+    def recon_error(self, W, H):
+        W = np.asfortranarray(W, dtype=np.float64); H = np.asfortranarray(H, dtype=np.float64)
+        mse, kl = ctypes.c_double(), ctypes.c_double()
+        C.check(self._lib.swne_recon_error(self._h, C.dptr(W), C.dptr(H), int(W.shape[1]), ctypes.byref(mse), ctypes.byref(kl)))
+        return mse.value, kl.value
+
+    def sample_coords(self, H, H_coords, alpha=1.0, n_pull=None):
+        H = np.asfortranarray(H, dtype=np.float64); Hc = np.asfortranarray(H_coords, dtype=np.float64)
+        k, m = H.shape
+        out = np.zeros((m, 2), order="F")
+        C.check(self._lib.swne_sample_coords(self._h, C.dptr(H), k, m, C.dptr(Hc), float(alpha),
+                                             0 if n_pull is None else int(n_pull), C.dptr(out)))
+        return out
+
+    def factor_distance(self, H, distance="cosine"):
+        d = distance.lower()
+        if d in ("cor", "correlation"):
+            d = "pearson"
+        if d in ("mutual", "information", "mutual information", "ic"):
+            raise C.SwneError(C.SWNE_ERR_UNSUPPORTED, "IC (randomised KDE mutual information) is not on the device path")
+        if d not in ("pearson", "cosine", "euclidean"):
+            raise ValueError("Distance must be one of: pearson, IC, cosine, euclidean")
+        H = np.asfortranarray(H, dtype=np.float64)
+        k, m = H.shape
+        out = np.zeros((k, k), order="F")
+        C.check(self._lib.swne_factor_distance(self._h, C.dptr(H), k, m, {"cosine": 0, "pearson": 1, "euclidean": 2}[d],
+                                               C.dptr(out)))
+        return out
+
+
+class NNMF(dict):
+    """The 'nnmf' list NNLM returns: W, H, mse, mkl, target.loss, average.epochs, n.iteration, run.time, options."""
+
+    __getattr__ = dict.__getitem__
+
+
+_default = {}
+
+
+def default_handle(device=0):
+    if device not in _default:
+        _default[device] = NMFHandle(device)
+    return _default[device]
+
+
+# ------------------------------------------------------------------------------------------------
+# seeding
+# ------------------------------------------------------------------------------------------------
+def nnsvd_init(A, k, handle=None, **kw):
+    """nnsvd_init (R/nmf.R:12-47): NNDSVD of A from a GPU randomized truncated SVD (the R code's
+    svd(A, k, k, LINPACK=T) is rejected by modern R; NNDSVD is invariant to the sign of singular pairs)."""
+    h = handle or default_handle()
+    if handle is None or h.n == 0:
+        h.set_matrix(A)
+    W, H, _ = h.nnsvd_init(k, **kw)
+    return dict(W=W, H=H)
+
+
+def _icafast(X, nc, maxit=100, tol=1e-6):
+    """ica::icafast(alg='par', fun='logcosh') -- host side ('ica stays host')."""
+    X = np.asarray(X, dtype=np.float64)
+    nobs = X.shape[0]
+    X = X - X.mean(axis=0, keepdims=True)
+    vals, vecs = np.linalg.eigh(X.T @ X / nobs)
+    vals, vecs = vals[::-1][:nc], vecs[:, ::-1][:, :nc]
+    Mprt = np.sqrt(vals)[:, None] * vecs.T
+    Xw = X @ (vecs / np.sqrt(vals)[None, :])
+    R = np.eye(nc)
+    it, vtol = 0, 1.0
+    while vtol > tol and it < maxit:
+        g = np.tanh(Xw @ R)
+        Rn = Xw.T @ g / nobs - R * np.mean(1.0 - g * g, axis=0)[None, :]
+        u, _, vt = np.linalg.svd(Rn)
+        Rn = u @ vt
+        vtol = 1.0 - np.min(np.abs(np.sum(R * Rn, axis=0)))
+        R = Rn
+        it += 1
+    M = R.T @ Mprt
+    ix = np.argsort(-np.sum(M * M, axis=1), kind="stable")
+    return Xw @ R[:, ix], M[ix].T
+
+
+def ica_init(A, k, ica_fast=False):
+    """ica_init (R/nmf.R:56-66)."""
+    A = np.asarray(A, dtype=np.float64)
+    if ica_fast:
+        Ac = A - A.mean(axis=1, keepdims=True)
+        u, _, _ = np.linalg.svd(Ac.T, full_matrices=False)
+        S, _ = _icafast(u[:, :50], k, maxit=50, tol=1e-4)
+        return dict(W=Ac @ S, H=S.T)
+    S, M = _icafast(A.T, k, maxit=50, tol=1e-4)
+    return dict(W=M, H=S.T)
+
+
+def zero_replace(init, A_mean, rng, zero_eps=1e-6):
+    """R/nmf.R:121-127: entries < 1e-6 -> 0, zeros -> runif(0, mean(A)/100).  The thresholding runs in the
+    C-ABI (swne_zero_replace); the uniform draws come from the caller's generator, as R's come from R."""
+    lib = C.load()
+    out = {}
+    for key in ("W", "H"):
+        x = np.asfortranarray(np.array(init[key], dtype=np.float64, copy=True))
+        nz = ctypes.c_size_t()
+        C.check(lib.swne_zero_replace(C.dptr(x), x.size, float(zero_eps), None, 0, ctypes.byref(nz)))
+        fill = np.ascontiguousarray(rng.uniform(0.0, A_mean / 100.0, size=nz.value))
+        C.check(lib.swne_zero_replace(C.dptr(x), x.size, float(zero_eps), C.dptr(fill), fill.size, ctypes.byref(nz)))
+        out[key] = x
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the R front-end
+# ------------------------------------------------------------------------------------------------
+def nnmf(A, k, alpha=0.0, beta=0.0, init=None, loss="mse", max_iter=500, rel_tol=1e-4, n_threads=1, verbose=0,
+         inner_max_iter=0, inner_rel_tol=1e-9, trace=0, seed=None, handle=None, **kw):
+    """NNLM::nnmf(A, k, alpha, beta, method='scd', loss, init, max.iter, rel.tol, ...).  n_threads is
+    accepted and ignored.  Without init, W and H start at U(0,1)*0.01 as in NNLM (numpy generator)."""
+    h = handle or default_handle()
+    if A is not None:
+        h.set_matrix(A)
+    n, m = h.n, h.m
+    if init is None:
+        rng = np.random.default_rng(seed)
+        W0 = rng.uniform(size=(n, k)) * 0.01; H0 = rng.uniform(size=(k, m)) * 0.01
+    else:
+        W0, H0 = init["W"], init["H"]
+    return h.fit(k, W0, H0, alpha=alpha, beta=beta, loss=loss, max_iter=max_iter, rel_tol=rel_tol,
+                 inner_max_iter=inner_max_iter, inner_rel_tol=inner_rel_tol, trace=trace, verbose=verbose, **kw)
+
+
+def RunNMF(A, k, alpha=0, init="ica", n_cores=1, loss="mse", max_iter=500, ica_fast=False, seed=None, handle=None,
+           **kw):
+    """RunNMF(A, k, alpha, init, n.cores, loss, max.iter, ica.fast) -- R/nmf.R:96-134.  Same checks and
+    error messages; returns the nnmf list with factor names factor_1..factor_k."""
+    dense = None if _is_csc(A) else np.asarray(A)
+    if (A.data.min() if _is_csc(A) and A.data.size else (dense.min() if dense is not None else 0)) < 0:
+        raise ValueError("The input matrix contains negative elements !")
+    if k < 3:
+        raise ValueError("k must be greater than or equal to 3 to create a viable SWNE plot")
+    if init not in ("ica", "nnsvd", "random"):
+        raise ValueError("Invalid initialization method")
+    if loss not in ("mse", "mkl"):
+        raise ValueError("loss must be 'mse' or 'mkl'")
+    h = handle or default_handle()
+    h.set_matrix(A)
+    rng = np.random.default_rng(seed)
+    if init == "random":
+        nmf_init = None
+    else:
+        if init == "ica":
+            nmf_init = ica_init(A.toarray() if _is_csc(A) else dense, k, ica_fast=ica_fast)
+        else:
+            W0, H0, _ = h.nnsvd_init(k, seed=int(rng.integers(1, 2**31)))
+            nmf_init = dict(W=W0, H=H0)
+        info = h.matrix_info()
+        nmf_init = zero_replace(nmf_init, info["sum"] / (float(info["n"]) * info["m"]), rng)
+    res = nnmf(None, k, alpha=alpha, init=nmf_init, loss=loss, max_iter=max_iter, n_threads=n_cores,
+               seed=None if seed is None else seed + 1, handle=h, **kw)
+    res["factor_names"] = ["factor_%d" % (i + 1) for i in range(k)]
+    return res
+
+
+def kl_div(x, y, pseudocount=1e-12):
+    """kl_div, R/nmf.R:71-75."""
+    x = x + pseudocount; y = y + pseudocount
+    return x * np.log(x / y) - x + y
+
+
+def FindNumFactors(A, k_range=(2, 4, 6, 8, 10, 12), n_cores=1, do_plot=False, seed=None, loss="mse", max_iter=250,
+                   inits=None, A_rand=None, handle=None, **kw):
+    """FindNumFactors -- R/nmf.R:157-205 including its quirks: the fits always use mse and random init
+    (SURVEY fact 6); `loss` only selects the error metric.  `inits[k] = (W0, H0, W0r, H0r)` and `A_rand`
+    may be injected (parity tests); otherwise numpy draws them (R's sample()/runif cannot be reproduced)."""
+    if loss not in ("mse", "mkl"):
+        raise ValueError("Invalid loss function")
+    k_range = list(k_range)
+    if len(k_range) < 3:
+        raise ValueError("k.range sequence must have at least 3 values")
+    A = np.asarray(A.toarray() if _is_csc(A) else A)
+    n, m = A.shape
+    if m > 20000:
+        print("Warning: This function can be slow for very large datasets")
+    rng = np.random.default_rng(seed)
+    if A_rand is None:
+        A_rand = rng.permutation(A.ravel(order="F")).reshape((n, m), order="F")
+    h = handle or default_handle()
+    k_err = np.zeros((2, len(k_range)))
+    for which, mat in enumerate((A, A_rand)):
+        h.set_matrix(mat)
+        for c, k in enumerate(k_range):
+            if inits is not None:
+                W0, H0 = inits[k][2 * which], inits[k][2 * which + 1]
+            else:
+                W0 = rng.uniform(size=(n, k)) * 0.01; H0 = rng.uniform(size=(k, m)) * 0.01
+            z = h.fit(k, W0, H0, loss="mse", max_iter=max_iter, **kw)
+            mse, kl = h.recon_error(z.W, z.H)
+            k_err[which, c] = mse if loss == "mse" else kl
+    err_del = k_err[:, :-1] - k_err[:, 1:]
+    diff = err_del[0] - err_del[1]
+    neg = np.nonzero(diff < 0)[0]
+    min_idx = int(neg[0]) if neg.size else int(np.argmin(diff)) + 1
+    return dict(err=diff, k=k_range[min_idx], k_err=k_err)
+
+
+def ProjectFeatures(newdata, H, alpha=(0, 0, 0), loss="mse", n_cores=1, handle=None):
+    """ProjectFeatures (R/nmf.R:222-225): nnlm(t(H), t(newdata)) -> W (features x factors) for newdata."""
+    h = handle or default_handle()
+    h.set_matrix(newdata)
+    return h.nnlm(1, H, alpha=alpha, loss=loss)["coefficients"]
+
+
+def ProjectSamples(newdata, W, alpha=(0, 0, 0), loss="mse", n_cores=1, handle=None):
+    """ProjectSamples (R/nmf.R:241-249) with features.use already applied by the caller."""
+    h = handle or default_handle()
+    h.set_matrix(newdata)
+    return h.nnlm(0, W, alpha=alpha, loss=loss)["coefficients"]

@@ -1,0 +1,205 @@
+"""CPU tests of the oracle itself (the reference has no tests: SURVEY.md section 4).  The restatement is
+pinned by independent cross-checks -- scipy NNLS (KKT of every half step), monotone target loss, direct
+vs Gram-identity mse, NNDSVD invariants -- and by the committed golden fixtures (regression pin)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import scipy.optimize
+
+from helpers import max_rel, rel_fro, seeded_init, small_matrix
+from oracle import (factor_distance_ref, find_num_factors_ref, get_factor_coords_ref, get_sample_coords_ref,
+                    ica_init_ref, nnlm_ref, nnmf_ref, nnsvd_init_ref, run_nmf_ref, sammon_ref, zero_replace_ref)
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_nnlm_matches_scipy_nnls():
+    A = small_matrix(40, 25, 3, 1)
+    rng = np.random.default_rng(0)
+    W = rng.gamma(0.5, 1.0, size=(40, 6))
+    r = nnlm_ref(W, A)                       # 10000 sweeps / 1e-12 like NNLM::nnlm
+    for j in range(A.shape[1]):
+        x, _ = scipy.optimize.nnls(W, A[:, j])
+        assert np.max(np.abs(x - r["coefficients"][:, j])) < 1e-8
+
+
+def test_last_h_update_is_nnls_solution():
+    A = small_matrix(50, 30, 3, 2)
+    W0, H0 = seeded_init(A, 4, 2)
+    r = nnmf_ref(A, 4, W0, H0, max_iter=40, inner_max_iter=2000, inner_rel_tol=1e-14, rel_tol=-1)
+    for j in range(0, 30, 5):
+        x, _ = scipy.optimize.nnls(r["W"], A[:, j])
+        assert np.max(np.abs(x - r["H"][:, j])) < 1e-7
+
+
+@pytest.mark.parametrize("loss,pen", [("mse", {}), ("mkl", {}), ("mse", dict(alpha=[0.05, 0.01, 0.01], beta=[0.02, 0.0, 0.03])),
+                                      ("mkl", dict(beta=[0, 0, 0.1]))])
+def test_target_loss_is_monotone(loss, pen):
+    A = small_matrix(60, 80, 4, 3)
+    W0, H0 = seeded_init(A, 5, 3)
+    r = nnmf_ref(A, 5, W0, H0, loss=loss, max_iter=40, trace=1, rel_tol=-1, **pen)
+    t = r["target_loss"]
+    assert len(t) == 40 and r["n_iteration"] == 40
+    assert np.all(np.diff(t) <= 1e-12 * np.abs(t[:-1]) + 1e-15)
+
+
+def test_error_block_matches_direct_and_gram_identity():
+    A = small_matrix(45, 70, 4, 4)
+    W0, H0 = seeded_init(A, 5, 4)
+    r = nnmf_ref(A, 5, W0, H0, max_iter=7, trace=3, rel_tol=-1)
+    # blocks at i = 0, 3, 6 -> 3 entries; the last one is the final state ((7-1) % 3 == 0: no extra block)
+    assert len(r["mse"]) == 3
+    W, H = r["W"], r["H"]
+    direct = np.mean((A - W @ H) ** 2)
+    gram = (np.sum(A * A) - 2 * np.sum(H * (W.T @ A)) + np.sum((W.T @ W) * (H @ H.T))) / A.size
+    assert abs(direct - r["mse"][-1]) < 1e-14 and abs(gram - direct) < 1e-12
+    assert abs(r["target_loss"][-1] - 0.5 * direct) < 1e-15
+    Ah = W @ H
+    mkl = np.mean((A + 1e-16) * np.log(A + 1e-16) - A) + np.mean(-(A + 1e-16) * np.log(Ah + 1e-16) + Ah)
+    assert abs(mkl - r["mkl"][-1]) < 1e-12
+
+
+def test_final_block_added_when_last_iteration_is_off_trace():
+    A = small_matrix(30, 40, 3, 5)
+    W0, H0 = seeded_init(A, 3, 5)
+    r = nnmf_ref(A, 3, W0, H0, max_iter=6, trace=4, rel_tol=-1)   # blocks at i=0,4 + final
+    assert len(r["mse"]) == 3 and r["n_iteration"] == 6
+
+
+def test_convergence_rule_and_warning():
+    A = small_matrix(60, 80, 4, 6)
+    W0, H0 = seeded_init(A, 5, 6)
+    r = nnmf_ref(A, 5, W0, H0, max_iter=500)                      # NNLM defaults: rel.tol 1e-4, trace 2
+    assert r["n_iteration"] < 500 and not r["not_converged"]
+    t = r["target_loss"]
+    assert abs(2 * (t[-2] - t[-1]) / (t[-2] + t[-1] + 1e-16)) <= 1e-4
+    r2 = nnmf_ref(A, 5, W0, H0, max_iter=3)
+    assert r2["not_converged"]
+
+
+def test_penalty_terms():
+    A = small_matrix(30, 40, 3, 7)
+    W0, H0 = seeded_init(A, 4, 7)
+    al, be = [0.3, 0.1, 0.2], [0.05, 0.02, 0.07]
+    r = nnmf_ref(A, 4, W0, H0, alpha=al, beta=be, max_iter=5, trace=1, rel_tol=-1)
+    W, H, N = r["W"], r["H"], A.size
+    pen = (0.5 * (al[0] - al[1]) * np.sum(W * W) + 0.5 * al[1] * np.sum(W @ np.ones((4, 4)) * W) + al[2] * W.sum()
+           + 0.5 * (be[0] - be[1]) * np.sum(H * H) + 0.5 * be[1] * np.sum(H.sum(0) ** 2) + be[2] * H.sum()) / N
+    assert abs(r["target_loss"][-1] - (0.5 * r["mse"][-1] + pen)) < 1e-13
+    # scalar alpha = L2 on W only
+    r3 = nnmf_ref(A, 4, W0, H0, alpha=0.5, max_iter=3, trace=1, rel_tol=-1)
+    assert abs(r3["target_loss"][-1] - 0.5 * r3["mse"][-1] - 0.25 * np.sum(r3["W"] ** 2) / N) < 1e-13
+
+
+def test_nndsvd_invariants():
+    A = small_matrix(50, 70, 4, 8)
+    W, H = nnsvd_init_ref(A, 6)
+    assert W.shape == (50, 6) and H.shape == (6, 70) and W.min() >= 0 and H.min() >= 0
+    U, S, Vt = np.linalg.svd(A, full_matrices=False)
+    assert np.allclose(W[:, 0], np.sqrt(S[0]) * np.abs(U[:, 0])) and np.allclose(H[0], np.sqrt(S[0]) * np.abs(Vt[0]))
+    # rank-1 blocks reproduce the dominant sign part of each singular pair
+    for i in range(1, 6):
+        blk = np.outer(W[:, i], H[i])
+        full = S[i] * np.outer(U[:, i], Vt[i])
+        pos = np.outer(np.maximum(U[:, i], 0), np.maximum(Vt[i], 0)) * S[i]
+        neg = np.outer(np.maximum(-U[:, i], 0), np.maximum(-Vt[i], 0)) * S[i]
+        tgt = pos if np.linalg.norm(pos) >= np.linalg.norm(neg) else neg
+        assert rel_fro(blk, tgt) < 1e-10 and np.linalg.norm(blk) <= np.linalg.norm(full) + 1e-12
+    frac_zero = np.mean(W == 0)
+    assert 0.2 < frac_zero < 0.7
+
+
+def test_zero_replace():
+    rng = np.random.default_rng(0)
+    W = np.array([[0.0, 5e-7], [2e-6, 1.0]]); H = np.array([[0.0, 3.0]])
+    W2, H2 = zero_replace_ref(W, H, 2.0, rng)
+    assert np.all(W2 > 0) and np.all(H2 > 0)
+    assert W2[0, 0] <= 0.02 and W2[0, 1] <= 0.02 and W2[1, 0] == 2e-6 and W2[1, 1] == 1.0 and H2[0, 1] == 3.0
+
+
+def test_ica_init_shapes_and_whitening():
+    A = small_matrix(40, 120, 4, 9)
+    W, H = ica_init_ref(A, 4)
+    assert W.shape == (40, 4) and H.shape == (4, 120)
+    S = H.T
+    assert np.allclose(S.T @ S / 120, np.eye(4), atol=1e-8)      # sources are white
+    Ac = A.T - A.T.mean(axis=0, keepdims=True)
+    # M S' reconstructs the rank-4 PCA approximation of the centred data
+    U, s, Vt = np.linalg.svd(Ac, full_matrices=False)
+    assert rel_fro(S @ W.T, (U[:, :4] * s[:4]) @ Vt[:4]) < 1e-8
+
+
+def test_run_nmf_ref_checks():
+    A = small_matrix(30, 40, 3, 10)
+    with pytest.raises(ValueError, match="negative"):
+        run_nmf_ref(-A, 3)
+    with pytest.raises(ValueError, match="k must be greater"):
+        run_nmf_ref(A, 2)
+    with pytest.raises(ValueError, match="Invalid initialization"):
+        run_nmf_ref(A, 3, init="foo")
+    r = run_nmf_ref(A, 3, init="nnsvd", max_iter=20)
+    assert r["W"].shape == (30, 3) and r["H"].min() >= 0
+
+
+def test_find_num_factors_ref_picks_structure():
+    A = small_matrix(60, 120, 4, 11, density_scale=2.0)
+    rng = np.random.default_rng(1)
+    A_rand = rng.permutation(A.ravel()).reshape(A.shape)
+    ks = [2, 3, 4, 5, 6, 7]
+    inits = {k: (rng.uniform(size=(60, k)) * 0.01, rng.uniform(size=(k, 120)) * 0.01,
+                 rng.uniform(size=(60, k)) * 0.01, rng.uniform(size=(k, 120)) * 0.01) for k in ks}
+    r = find_num_factors_ref(A, ks, inits, A_rand, max_iter=60)
+    assert r["k"] in ks and len(r["err"]) == len(ks) - 1
+    assert np.all(np.diff(r["k_err"][0]) < 1e-9)                  # more factors never fit worse
+    with pytest.raises(ValueError):
+        find_num_factors_ref(A, [2, 3], inits, A_rand)
+
+
+def test_sample_coords_ref():
+    rng = np.random.default_rng(3)
+    H = rng.gamma(0.5, 1.0, size=(5, 20)); coords = rng.uniform(size=(5, 2))
+    out = get_sample_coords_ref(H, coords, alpha=1.0, n_pull=None)
+    assert np.allclose(out, (H / H.sum(0)).T @ coords)            # n_pull = k: plain weighted mean
+    out3 = get_sample_coords_ref(H, coords, alpha=2.0, n_pull=1)  # n_pull < 3 -> 3
+    j = 4
+    ix = np.argsort(-H[:, j])[:3]
+    w = H[ix, j] ** 2
+    assert np.allclose(out3[j], (w / w.sum()) @ coords[ix])
+
+
+def test_factor_distance_and_sammon():
+    rng = np.random.default_rng(4)
+    H = rng.gamma(0.5, 1.0, size=(6, 200))
+    D = factor_distance_ref(H, "cosine")
+    assert np.allclose(np.diag(D), 0, atol=1e-12) and np.allclose(D, D.T)
+    assert np.allclose(factor_distance_ref(H, "cor"), np.sqrt(2 * (1 - np.corrcoef(H))))
+    # sammon of a planar configuration recovers its distances
+    P = rng.uniform(size=(7, 2))
+    Dp = np.sqrt(((P[:, None] - P[None]) ** 2).sum(-1))
+    Y = sammon_ref(Dp)
+    Dy = np.sqrt(((Y[:, None] - Y[None]) ** 2).sum(-1))
+    assert np.max(np.abs(Dy - Dp)) < 1e-3
+    C = get_factor_coords_ref(H)
+    assert C.min() == 0.0 and C.max() == 1.0 and C.shape == (6, 2)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "m*.npz"))))
+def test_oracle_reproduces_golden(path):
+    g = np.load(path)
+    r = nnmf_ref(g["A"], int(g["k"]), g["W0"], g["H0"], alpha=g["alpha"], beta=g["beta"], loss=str(g["loss"]),
+                 max_iter=int(g["max_iter"]), trace=int(g["trace"]), rel_tol=-1.0, n_threads=2)
+    assert max_rel(r["target_loss"], g["target_loss"]) < 1e-10
+    assert rel_fro(r["W"], g["W"]) < 1e-8 and rel_fro(r["H"], g["H"]) < 1e-8
+
+
+def test_oracle_self_noise_floor_mse():
+    """summation order (thread count) must not matter for the contractive mse fit (SURVEY H3 contrast)."""
+    A = small_matrix(60, 80, 4, 12)
+    W0, H0 = seeded_init(A, 5, 12)
+    a = nnmf_ref(A, 5, W0, H0, max_iter=30, rel_tol=-1, n_threads=1)
+    # permute genes: same problem, different summation order inside every contraction
+    p = np.random.default_rng(0).permutation(60)
+    b = nnmf_ref(A[p], 5, W0[p], H0, max_iter=30, rel_tol=-1, n_threads=3)
+    assert rel_fro(b["W"], a["W"][p]) < 1e-9 and rel_fro(b["H"], a["H"]) < 1e-9
