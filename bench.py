@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py -- RunNMF iterations/s on BASELINE.json's configuration 3 (3 000 genes x 100 000 cells, k=30,
+mse), synthetic NB-count data, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one outer NMF iteration (W update + H update + loss bookkeeping).  N > 1 shards the SAME
+workload's cells across ranks (strong scaling; one NCCL all-reduce of A H', H H' and the loss partial per
+iteration).  Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of NNLM::nnmf
+(oracle/, "port": the real NNLM cannot be built here) on the host cores, on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "RunNMF iterations/s (3000 genes x 100000 cells, k=30, mse)"
+UNIT = "iterations/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=10)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def cpu_oracle_leg(n, m_full, k, kt, scale, seed, cells, iters, threads=0):
+    """times the oracle (restated NNLM, fp64, OpenMP) on the first `cells` cells of the workload."""
+    from oracle import load_oracle, nnmf_ref
+    from swne_b200 import synth
+    lib = load_oracle()
+    cores = lib.oracle_num_threads() if threads <= 0 else threads
+    A = synth.make_matrix_np(n, cells, kt, scale, seed, dtype=np.float64)
+    W0, H0 = synth.random_init(n, cells, k, 0)
+    nnmf_ref(A, k, W0, H0, max_iter=1, rel_tol=-1.0, trace=1, n_threads=cores)      # warm the threads / page in
+    t0 = time.perf_counter()
+    r = nnmf_ref(A, k, W0, H0, max_iter=iters, rel_tol=-1.0, trace=2, n_threads=cores)
+    dt = time.perf_counter() - t0
+    it_s_sample = r["n_iteration"] / dt
+    scaled = it_s_sample * cells / m_full           # cost is linear in the number of cells
+    sample = "first %d of %d cells, %d iterations, %.1f s wall; value scaled by %d/%d (linear in cells)" % (
+        cells, m_full, iters, dt, cells, m_full)
+    return scaled, cores, sample, dt
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cells = args.cells or 10000
+    iters = max(1, args.steps)
+    n, m, k = cfg["n"], cfg["m"], cfg["k"]
+    t0 = time.perf_counter()
+    val, cores, sample, dt = cpu_oracle_leg(n, m, k, cfg["kt"], cfg["scale"], cfg["seed"], cells, iters)
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": iters, "warmup": args.warmup,
+            "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "cfg3: 3000 genes x 100000 cells, k=30, mse, random init U(0,1)*0.01", "sample_cells": cells},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line))
+
+
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as td
+    from swne_b200 import NMFHandle, synth
+    from swne_b200.dist import init_comm, shard_bounds
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, m, k = cfg["n"], args.cells or cfg["m"], cfg["k"]
+    b = shard_bounds(m, world)
+    m_loc = b[rank + 1] - b[rank]
+    # synthetic shard, generated on the device (same generator family on every rank, rank-dependent stream)
+    dA = synth.make_matrix_torch(n, m_loc, cfg["kt"], cfg["scale"], cfg["seed"] + 1000 * rank)
+    torch.cuda.synchronize()
+    h = NMFHandle(local)
+    if world > 1:
+        init_comm(h)
+    h.set_matrix(dA)
+    W0, H0 = synth.random_init(n, m_loc, k, 0)           # W0 identical on all ranks (same seed), H0 per shard
+    if world > 1:
+        H0 = synth.random_init(n, m_loc, k, 100 + rank)[1]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up: W outer iterations from the random start; the timed run continues from that state
+    warm = h.fit(k, W0, H0, max_iter=max(args.warmup, 3), rel_tol=-1.0, engine=args.engine)
+    barrier()
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        r = h.fit(k, warm.W, warm.H, max_iter=args.steps, rel_tol=-1.0, engine=args.engine)
+        barrier()
+        wall = time.perf_counter() - t0
+        # keep the GPU under the same load while nvidia-smi catches a few more samples
+        if len(clk.samples) < 5:
+            h.fit(k, r.W, r.H, max_iter=max(args.steps, 20), rel_tol=-1.0, engine=args.engine)
+    loop_ms = maxr(r.stats["loop_ms"])
+    ms_per_step = loop_ms / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- roofline of the dominant kernel, measured live with CUDA events on the library's stream
+    pr = h.fit(k, r.W, r.H, max_iter=min(args.steps, 10), rel_tol=-1.0, engine=args.engine, profile=True)
+    prof_ms, prof_n = pr.stats["prof_ms"], pr.stats["prof_launches"]
+    engine = pr.options["engine"]
+    peak, peak_src = peaks()
+    a_bytes = 4.0 * n * m_loc
+    if engine == "tc":
+        dom = 0
+        alg_bytes = a_bytes + 4.0 * k * (2 * m_loc + 2 * n)
+        dom_name = "fused pass (W'A -> H solve -> A H', H H')"
+    else:
+        dom = 0 if prof_ms[0] >= prof_ms[2] else 2
+        alg_bytes = a_bytes + 4.0 * k * (m_loc + n)
+        dom_name = "contract_cells (W'A)" if dom == 0 else "contract_genes (A H')"
+    dom_ms = prof_ms[dom] / max(prof_n[dom], 1)
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    iters_prof = pr.n_iteration
+    shares = {nm: round(ms / max(sum(prof_ms), 1e-9), 4) for nm, ms in zip(
+        ("contract_H_or_pass", "solve_H", "contract_W", "solve_W", "gram_loss", "mkl_update", "allreduce", "other"), prof_ms)}
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": dom_name, "kernel_ms": dom_ms, "peak_source": peak_src,
+                "iteration_frac_of_hbm_roofline": ((a_bytes + 4.0 * k * (2 * m_loc + 2 * n)) / (ms_per_step * 1e-3) / 1e9) / peak,
+                "profiled_ms_per_iteration": sum(prof_ms) / max(iters_prof, 1), "family_share": shares}
+
+    # ---- end to end through the C-ABI with HOST buffers: upload A (pinned fp32), W0/H0, K iterations, download
+    e2e = None
+    if not args.no_e2e:
+        hostA = torch.empty((m_loc, n), dtype=torch.float32, pin_memory=True)
+        hostA.copy_(dA)
+        An = hostA.numpy().T          # (n, m) Fortran-ordered view of the pinned buffer: R's column-major layout
+        barrier()
+        t0 = time.perf_counter()
+        h.set_matrix(An)
+        re = h.fit(k, warm.W, warm.H, max_iter=args.steps, rel_tol=-1.0, engine=args.engine)
+        barrier()
+        e2e_s = maxr(time.perf_counter() - t0)
+        h2d = An.nbytes + 8.0 * (n * k + k * m_loc)
+        d2h = 8.0 * (n * k + k * m_loc)
+        e2e = {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+               "d2h_bytes_per_step": d2h / args.steps, "wall_s": e2e_s,
+               "note": "one RunNMF-style fit of K iterations: A (fp32, pinned host), W0, H0 uploaded once, W and H read back"}
+        h.set_matrix(dA)
+
+    # ---- time to tolerance with NNLM's stopping rule from the same random start (reported, not the headline)
+    ttt = None
+    if not args.no_tol:
+        barrier()
+        t0 = time.perf_counter()
+        rt = h.fit(k, W0, H0, max_iter=500, rel_tol=1e-4, engine=args.engine)
+        barrier()
+        ttt = {"iterations": rt.n_iteration, "loop_s": maxr(rt.stats["loop_ms"]) / 1e3, "wall_s": maxr(time.perf_counter() - t0),
+               "final_target_loss": float(rt.target_loss[-1]), "converged": not rt.not_converged}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        val, cores, sample, _ = cpu_oracle_leg(n, m, k, cfg["kt"], cfg["scale"], cfg["seed"], min(args.cpu_cells, m), args.cpu_iters)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "cfg3: 3000 genes x %d cells, k=%d, mse, random init U(0,1)*0.01, timed from the state after the warm-up iterations" % (m, k),
+                           "cells_per_gpu": m_loc, "engine": engine, "l2": "input (%.2f GB per GPU) larger than L2" % (a_bytes / 1e9),
+                           "parallelism": "cells sharded over %d GPU(s)" % world},
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(r.stats["gpu_launches"]),
+                "roofline": roofline, "cpu_baseline": cpu, "time_to_tolerance": ttt,
+                "timed_region": {"wall_s_incl_upload_download": wall, "loop_ms_cuda_events_max_over_ranks": loop_ms,
+                                 "final_target_loss": float(r.target_loss[-1])}}
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--cells", type=int, default=0, help="override the number of cells (debug / bounded CPU sample)")
+    ap.add_argument("--cpu-cells", type=int, default=10000)
+    ap.add_argument("--cpu-iters", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tol", action="store_true")
+    args = ap.parse_args()
+    from swne_b200 import synth
+    cfg = dict(synth.CONFIGS["cfg3"])
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

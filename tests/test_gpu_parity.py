@@ -1,0 +1,295 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle on the same
+seeded inputs and against the committed golden fixtures.  Bars (BASELINE.json north_star): per-iteration
+reconstruction loss within 1e-4 relative, final W/H within 1e-3 relative Frobenius (fp32 vs the fp64 oracle)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse
+
+from helpers import max_rel, rel_fro, seeded_init, small_matrix
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LOSS_TOL = 1e-4     # relative, per trace entry
+FACTOR_TOL = 1e-3   # relative Frobenius of final W and H
+
+
+def _check_against(res, ref, loss_tol=LOSS_TOL, factor_tol=FACTOR_TOL, key="target_loss"):
+    assert res["n_iteration"] == ref["n_iteration"]
+    assert len(res[key]) == len(ref[key])
+    assert max_rel(res[key], ref[key]) < loss_tol
+    assert rel_fro(res["W"], ref["W"]) < factor_tol
+    assert rel_fro(res["H"], ref["H"]) < factor_tol
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "mse*.npz"))))
+def test_golden_mse(handle, path):
+    g = np.load(path)
+    handle.set_matrix(g["A"])
+    r = handle.fit(int(g["k"]), g["W0"], g["H0"], alpha=g["alpha"], beta=g["beta"], loss="mse",
+                   max_iter=int(g["max_iter"]), trace=int(g["trace"]), rel_tol=-1.0, full_traces=True)
+    _check_against(r, g)
+    assert max_rel(r["mse"], g["mse"]) < LOSS_TOL
+    assert max_rel(r["mkl"], g["mkl"]) < LOSS_TOL
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "mkl*.npz"))))
+def test_golden_mkl(handle, path):
+    g = np.load(path)
+    handle.set_matrix(g["A"])
+    r = handle.fit(int(g["k"]), g["W0"], g["H0"], alpha=g["alpha"], beta=g["beta"], loss="mkl",
+                   max_iter=int(g["max_iter"]), trace=int(g["trace"]), rel_tol=-1.0)
+    # the KL coordinate step is ill-conditioned where a row collapses: loss at the bar, W/H looser
+    _check_against(r, g, factor_tol=2e-2)
+    assert max_rel(r["mse"], g["mse"]) < 1e-3
+
+
+@pytest.mark.parametrize("n,m,kt,k,seed", [(200, 300, 5, 5, 1), (2000, 3000, 9, 16, 1), (301, 517, 6, 30, 2), (128, 257, 6, 40, 3)])
+def test_mse_vs_oracle(handle, n, m, kt, k, seed):
+    from oracle import nnmf_ref
+    A = small_matrix(n, m, kt, seed)
+    W0, H0 = seeded_init(A, k, seed)
+    iters = 20
+    ref = nnmf_ref(A, k, W0, H0, max_iter=iters, trace=1, rel_tol=-1.0)
+    handle.set_matrix(A)
+    r = handle.fit(k, W0, H0, max_iter=iters, trace=1, rel_tol=-1.0, engine="simt")
+    _check_against(r, ref)
+    assert r["H"].min() >= 0 and r["W"].min() >= 0
+    assert max_rel(r["average_epochs"], ref["average_epochs"]) < 0.35      # fp32 stagnates earlier than fp64
+
+
+def test_mse_default_stopping_rule_matches(handle):
+    from oracle import nnmf_ref
+    A = small_matrix(300, 500, 6, 4)
+    W0, H0 = seeded_init(A, 8, 4)
+    ref = nnmf_ref(A, 8, W0, H0)                       # NNLM defaults: 500 / 1e-4 / trace 2
+    handle.set_matrix(A)
+    r = handle.fit(8, W0, H0)
+    assert abs(r["n_iteration"] - ref["n_iteration"]) <= 2   # the stopping test sits on a 1e-4 threshold
+    assert abs(r["target_loss"][-1] - ref["target_loss"][-1]) / ref["target_loss"][-1] < 1e-4
+    assert not r["not_converged"]
+
+
+def test_mse_penalties_vs_oracle(handle):
+    from oracle import nnmf_ref
+    A = small_matrix(200, 300, 5, 5)
+    W0, H0 = seeded_init(A, 6, 5)
+    kw = dict(alpha=[0.05, 0.02, 0.01], beta=[0.03, 0.01, 0.02], max_iter=25, trace=1, rel_tol=-1.0)
+    ref = nnmf_ref(A, 6, W0, H0, **kw)
+    handle.set_matrix(A)
+    r = handle.fit(6, W0, H0, **kw)
+    _check_against(r, ref)
+    # RunNMF's scalar alpha is an L2 penalty on W
+    ref2 = nnmf_ref(A, 6, W0, H0, alpha=0.1, max_iter=10, trace=1, rel_tol=-1.0)
+    r2 = handle.fit(6, W0, H0, alpha=0.1, max_iter=10, trace=1, rel_tol=-1.0)
+    _check_against(r2, ref2)
+
+
+def test_mkl_vs_oracle_with_self_noise(handle):
+    """mkl parity is reported next to the oracle's own summation-order noise on the same input."""
+    from oracle import nnmf_ref
+    A = small_matrix(200, 300, 5, 6)
+    W0, H0 = seeded_init(A, 6, 6)
+    kw = dict(loss="mkl", beta=[0, 0, 0.1], max_iter=30, trace=1, rel_tol=-1.0)
+    ref = nnmf_ref(A, 6, W0, H0, **kw)
+    p = np.random.default_rng(0).permutation(200)
+    ref_perm = nnmf_ref(A[p], 6, W0[p], H0, **kw)
+    noise = max(rel_fro(ref_perm["W"], ref["W"][p]), rel_fro(ref_perm["H"], ref["H"]), 1e-7)
+    handle.set_matrix(A)
+    r = handle.fit(6, W0, H0, **kw)
+    assert max_rel(r["target_loss"], ref["target_loss"]) < LOSS_TOL
+    assert max_rel(r["mkl"], ref["mkl"]) < LOSS_TOL
+    tol = max(FACTOR_TOL, 1e4 * noise)     # fp32 (6e-8) vs the oracle's fp64 (1e-16) perturbation, same amplification
+    assert rel_fro(r["W"], ref["W"]) < tol and rel_fro(r["H"], ref["H"]) < tol
+
+
+def test_csc_input_equals_dense(handle):
+    A = small_matrix(150, 220, 5, 7)
+    W0, H0 = seeded_init(A, 5, 7)
+    handle.set_matrix(A)
+    info_d = handle.matrix_info()
+    rd = handle.fit(5, W0, H0, max_iter=10, trace=1, rel_tol=-1.0)
+    S = scipy.sparse.csc_matrix(A)
+    handle.set_matrix(S)
+    info_s = handle.matrix_info()
+    rs = handle.fit(5, W0, H0, max_iter=10, trace=1, rel_tol=-1.0)
+    assert info_d["nnz"] == info_s["nnz"] == S.nnz
+    assert abs(info_d["sumsq"] - info_s["sumsq"]) < 1e-9 * info_d["sumsq"]
+    assert np.array_equal(rd["H"], rs["H"]) and np.array_equal(rd["W"], rs["W"])
+    assert max_rel(rs["mse"], rd["mse"]) < 1e-12
+    # float32 CSC, an empty column and an empty matrix row
+    S32 = S.astype(np.float32).tolil(); S32[:, 3] = 0; S32[5, :] = 0
+    S32 = S32.tocsc()
+    handle.set_matrix(S32)
+    r32 = handle.fit(5, W0, H0, max_iter=5, trace=1, rel_tol=-1.0)
+    handle.set_matrix(np.asfortranarray(S32.toarray()))
+    rdd = handle.fit(5, W0, H0, max_iter=5, trace=1, rel_tol=-1.0)
+    assert np.array_equal(r32["H"], rdd["H"])
+
+
+def test_float32_and_device_resident_inputs(handle):
+    import torch
+    A = small_matrix(120, 200, 4, 8)
+    W0, H0 = seeded_init(A, 4, 8)
+    handle.set_matrix(A.astype(np.float32))
+    r32 = handle.fit(4, W0, H0, max_iter=8, trace=1, rel_tol=-1.0)
+    dA = torch.from_numpy(np.ascontiguousarray(A.astype(np.float32).T)).cuda()      # (cells, genes)
+    handle.set_matrix(dA)
+    rdev = handle.fit(4, W0, H0, max_iter=8, trace=1, rel_tol=-1.0)
+    assert np.array_equal(r32["W"], rdev["W"]) and np.array_equal(r32["H"], rdev["H"])
+    handle.set_matrix(A)       # release the borrowed tensor
+
+
+def test_nnlm_vs_oracle(handle):
+    from oracle import nnlm_ref
+    g = np.load(os.path.join(GOLD, "aux.npz"))
+    handle.set_matrix(g["A"])
+    r = handle.nnlm(0, g["W"], init=np.full((5, 90), 0.005))
+    assert rel_fro(r["coefficients"], g["nnlm_coef"]) < FACTOR_TOL
+    # W side (ProjectFeatures): solve genes given H
+    A = g["A"]
+    rng = np.random.default_rng(2)
+    H = rng.gamma(0.5, 1.0, size=(5, 90))
+    ref = nnlm_ref(H.T, A.T, init=np.full((5, 60), 0.005))        # coefficients k x genes
+    r = handle.nnlm(1, H, init=np.full((60, 5), 0.005))
+    assert rel_fro(r["coefficients"], ref["coefficients"].T) < FACTOR_TOL
+    # mkl projection
+    refk = nnlm_ref(g["W"], A, loss="mkl", init=np.full((5, 90), 0.005), max_iter=200)
+    rk = handle.nnlm(0, g["W"], init=np.full((5, 90), 0.005), loss="mkl", max_iter=200)
+    assert rel_fro(rk["coefficients"], refk["coefficients"]) < 5e-3
+
+
+def test_project_features_and_samples(handle):
+    from oracle import nnlm_ref
+    from swne_b200 import ProjectFeatures, ProjectSamples
+    A = small_matrix(80, 120, 4, 9)
+    rng = np.random.default_rng(1)
+    W = rng.gamma(0.5, 1.0, size=(80, 4)); H = rng.gamma(0.5, 1.0, size=(4, 120))
+    Hs = ProjectSamples(A, W, handle=handle)
+    Wf = ProjectFeatures(A, H, handle=handle)
+    assert rel_fro(Hs, nnlm_ref(W, A)["coefficients"]) < FACTOR_TOL
+    assert rel_fro(Wf, nnlm_ref(H.T, A.T)["coefficients"].T) < FACTOR_TOL
+
+
+def test_nnsvd_init_vs_lapack(handle):
+    from oracle import nnsvd_init_ref
+    A = small_matrix(300, 500, 6, 10, density_scale=2.0)
+    Wr, Hr = nnsvd_init_ref(A, 6)
+    handle.set_matrix(A)
+    W, H, sv = handle.nnsvd_init(6, oversample=10, power_iters=6, seed=3)
+    S = np.linalg.svd(A, compute_uv=False)[:6]
+    assert max_rel(sv, S) < 1e-4
+    assert W.min() >= 0 and H.min() >= 0
+    # leading (well separated) factors match the LAPACK-based NNDSVD
+    for f in range(6):
+        gap = (S[f] - S[f + 1]) / S[f] if f + 1 < len(S) else 1.0
+        if f == 0 or gap > 0.05:
+            assert rel_fro(W[:, f], Wr[:, f]) < 2e-2 and rel_fro(H[f], Hr[f]) < 2e-2
+    # and it seeds an equally good fit
+    from oracle import nnmf_ref
+    ref = nnmf_ref(A, 6, *seeded_init(A, 6, 10), max_iter=30, rel_tol=-1.0)
+    rng = np.random.default_rng(0)
+    from oracle import zero_replace_ref
+    W0, H0 = zero_replace_ref(W, H, A.mean(), rng)
+    r = handle.fit(6, W0, H0, max_iter=30, rel_tol=-1.0)
+    assert r["target_loss"][-1] < 1.02 * ref["target_loss"][-1]
+
+
+def test_sample_coords_and_distances_vs_golden(handle):
+    g = np.load(os.path.join(GOLD, "aux.npz"))
+    sc = handle.sample_coords(g["H"], g["coords"], alpha=1.3, n_pull=3)
+    ok = ~np.isnan(g["sample_coords"][:, 0])
+    assert np.max(np.abs(sc[ok] - g["sample_coords"][ok])) < 1e-12
+    assert np.all(np.isnan(sc[~ok]))                         # an all-zero cell is 0/0 in R too
+    Hnz = g["H"][:, ok]
+    from oracle import factor_distance_ref
+    for name in ("cosine", "pearson", "euclidean"):
+        assert np.max(np.abs(handle.factor_distance(Hnz, name) - factor_distance_ref(Hnz, name))) < 1e-10
+    with pytest.raises(Exception):
+        handle.factor_distance(Hnz, "IC")
+
+
+def test_embed_swne_vs_oracle(handle):
+    from oracle import get_factor_coords_ref, get_sample_coords_ref
+    from swne_b200 import EmbedSWNE
+    rng = np.random.default_rng(6)
+    H = rng.gamma(0.4, 1.0, size=(7, 400))
+    e = EmbedSWNE(H, alpha_exp=1.5, n_pull=4, handle=handle)
+    Hc = get_factor_coords_ref(H)
+    assert np.max(np.abs(e["H_coords"] - Hc)) < 1e-6
+    assert np.max(np.abs(e["sample_coords"] - get_sample_coords_ref(H, e["H_coords"], 1.5, 4))) < 1e-12
+
+
+def test_find_num_factors_vs_oracle(handle):
+    from oracle import find_num_factors_ref
+    from swne_b200 import FindNumFactors
+    A = small_matrix(120, 200, 4, 11, density_scale=2.0)
+    rng = np.random.default_rng(1)
+    A_rand = np.asfortranarray(rng.permutation(A.ravel()).reshape(A.shape))
+    ks = [2, 3, 4, 5, 6]
+    inits = {k: (rng.uniform(size=(120, k)) * 0.01, rng.uniform(size=(k, 200)) * 0.01,
+                 rng.uniform(size=(120, k)) * 0.01, rng.uniform(size=(k, 200)) * 0.01) for k in ks}
+    ref = find_num_factors_ref(A, ks, inits, A_rand, max_iter=40)
+    r = FindNumFactors(A, ks, inits=inits, A_rand=A_rand, max_iter=40, handle=handle)
+    assert max_rel(r["k_err"], ref["k_err"]) < 2e-3          # different stopping iteration is possible at the 1e-4 rule
+    assert r["k"] == ref["k"]
+    rk = FindNumFactors(A, ks, inits=inits, A_rand=A_rand, max_iter=40, loss="mkl", handle=handle)
+    refk = find_num_factors_ref(A, ks, inits, A_rand, max_iter=40, loss="mkl")
+    assert max_rel(rk["k_err"], refk["k_err"]) < 5e-3
+
+
+def test_run_nmf_front_end(handle):
+    from swne_b200 import RunNMF
+    from swne_b200._capi import SwneError
+    A = small_matrix(100, 150, 4, 12)
+    for init in ("nnsvd", "ica", "random"):
+        r = RunNMF(A, 4, init=init, max_iter=30, seed=1, handle=handle)
+        assert r["W"].shape == (100, 4) and r["H"].shape == (4, 150) and r["factor_names"][0] == "factor_1"
+        assert np.all(np.diff(r["target_loss"]) <= 1e-6 * r["target_loss"][:-1])
+    with pytest.raises(ValueError, match="negative"):
+        RunNMF(-A, 4, handle=handle)
+    with pytest.raises(ValueError, match="k must be greater"):
+        RunNMF(A, 2, handle=handle)
+    with pytest.raises(ValueError, match="Invalid initialization"):
+        RunNMF(A, 4, init="svd", handle=handle)
+    B = A.copy(); B[3, 4] = np.nan
+    with pytest.raises(SwneError):
+        handle.set_matrix(B)
+    handle.set_matrix(A)
+    with pytest.raises(SwneError):
+        handle.fit(4, -np.ones((100, 4)), np.ones((4, 150)))
+    with pytest.raises(SwneError):
+        handle.fit(70, np.ones((100, 70)), np.ones((70, 150)))     # k > SWNE_MAX_K
+    rk = RunNMF(A, 4, init="nnsvd", loss="mkl", max_iter=20, seed=1, handle=handle)
+    assert np.all(np.diff(rk["target_loss"]) <= 1e-5 * np.abs(rk["target_loss"][:-1]))
+
+
+def test_full_size_properties_cfg3(handle):
+    """BASELINE config 3 shape (3000 x 100000, k=30): size-independent properties instead of an oracle run:
+    monotone target loss, H/W nonnegative, KKT of the last H update, Gram-identity loss equals the direct
+    residual."""
+    import torch
+    from swne_b200 import synth
+    c = synth.CONFIGS["cfg3"]
+    dA = synth.make_matrix_torch(c["n"], c["m"], c["kt"], c["scale"], c["seed"])
+    handle.set_matrix(dA)
+    info = handle.matrix_info()
+    assert 0.05 < info["nnz"] / (c["n"] * c["m"]) < 0.4
+    W0, H0 = synth.random_init(c["n"], c["m"], c["k"], 0)
+    r = handle.fit(c["k"], W0, H0, max_iter=12, trace=1, rel_tol=-1.0)
+    t = r["target_loss"]
+    assert np.all(np.diff(t) <= 1e-6 * t[:-1]) and r["W"].min() >= 0 and r["H"].min() >= 0
+    mse_direct, _ = handle.recon_error(r["W"], r["H"])
+    assert abs(mse_direct - r["mse"][-1]) / mse_direct < 1e-4
+    # KKT of the H update on a sample of cells: grad >= -tol where h == 0, |grad| small where h > 0
+    W = torch.from_numpy(r["W"]).cuda()
+    idx = torch.arange(0, c["m"], 997, device="cuda")
+    a = dA[idx].double()                         # cells x genes
+    Hs = torch.from_numpy(np.ascontiguousarray(r["H"][:, idx.cpu().numpy()])).cuda()
+    grad = (W.T @ W) @ Hs - W.T @ a.T
+    scale = (W.T @ a.T).abs().max()
+    assert (grad[Hs > 0].abs().max() / scale) < 5e-3
+    assert (grad[Hs == 0].min() / scale) > -5e-3
+    handle.set_matrix(np.zeros((4, 4)) + 1.0)    # drop the borrowed tensor

@@ -1,0 +1,121 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every declared symbol, fails loudly without a
+GPU (no CPU fallback), the host-side logic (sammon, icafast, sharding) matches the oracle, and the N>1
+cell-sharded algorithm equals the unsharded one (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import rel_fro, seeded_init, small_matrix
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from swne_b200 import _capi
+    lib = _capi.load()
+    header = open(os.path.join(ROOT, "include", "swne_nmf.h")).read()
+    declared = set(re.findall(r"\b(swne_[a-z0-9_]+)\s*\(", header))
+    declared -= {"swne_nmf_progress_fn"}
+    assert declared == set(_capi.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.swne_nmf_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    from swne_b200 import _capi
+    lib = _capi.load()
+    p = _capi.Params()
+    lib.swne_nmf_default_params(ctypes.byref(p), 7)
+    assert p.k == 7 and p.max_iter == 500 and abs(p.rel_tol - 1e-4) < 1e-20 and abs(p.inner_rel_tol - 1e-9) < 1e-20
+    assert p.loss == 0 and p.engine == 0 and list(p.alpha) == [0, 0, 0]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from swne_b200 import NMFHandle
+    from swne_b200._capi import SwneError
+    with pytest.raises(SwneError) as e:
+        NMFHandle(0)
+    assert e.value.code == -2
+
+
+def test_zero_replace_host_entry():
+    from swne_b200 import zero_replace
+    rng = np.random.default_rng(0)
+    init = dict(W=np.array([[0.0, 5e-7], [2e-6, 1.0]]), H=np.array([[0.0, 3.0]]))
+    out = zero_replace(init, 2.0, rng)
+    assert np.all(out["W"] > 0) and out["W"][1, 1] == 1.0 and out["W"][1, 0] == 2e-6 and out["H"][0, 1] == 3.0
+    assert out["W"][0, 0] <= 0.02 and out["H"][0, 0] <= 0.02
+
+
+def test_host_sammon_and_ica_match_oracle():
+    from oracle import ica_init_ref, sammon_ref
+    from swne_b200 import ica_init, sammon
+    rng = np.random.default_rng(4)
+    P = rng.uniform(size=(8, 2))
+    D = np.sqrt(((P[:, None] - P[None]) ** 2).sum(-1)) + 0.05 * (1 - np.eye(8))
+    assert np.max(np.abs(sammon(D) - sammon_ref(D))) < 1e-9
+    A = small_matrix(40, 120, 4, 9)
+    a, (W, H) = ica_init(A, 4), ica_init_ref(A, 4)
+    assert rel_fro(a["W"], W) < 1e-9 and rel_fro(a["H"], H) < 1e-9
+
+
+def test_shard_bounds():
+    from swne_b200.dist import shard_bounds, shard_bounds_nnz
+    assert shard_bounds(10, 4) == [0, 3, 6, 8, 10]
+    assert shard_bounds(3, 4) == [0, 1, 2, 3, 3]
+    b = shard_bounds_nnz(np.array([0, 5, 5, 9, 20, 21, 30]), 3)
+    assert b[0] == 0 and b[-1] == 6 and b == sorted(b)
+
+
+def test_bench_reference_arm_runs():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cells", "2000"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as td
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from helpers import small_matrix, seeded_init
+from swne_b200.dist import shard_bounds
+from sharded_model import sharded_nnmf_mse
+td.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+A = small_matrix(50, 81, 4, 3); W0, H0 = seeded_init(A, 5, 3)
+b = shard_bounds(81, 2); r = td.get_rank()
+W, H, terr = sharded_nnmf_mse(A[:, b[r]:b[r+1]], W0, H0[:, b[r]:b[r+1]], 12, A.shape[1])
+np.savez(sys.argv[4] + ".%d.npz" % r, W=W, H=H, terr=terr)
+td.destroy_process_group()
+'''
+
+
+def test_sharded_algorithm_equals_unsharded_gloo(tmp_path):
+    """world_size-2 gloo run of the cell-sharded schedule (local H update, all-reduce of A H', H H' and the
+    loss partial, replicated W update) against the unsharded oracle."""
+    from oracle import nnmf_ref
+    port = 29000 + os.getpid() % 2000
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), str(tmp_path / "out")]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    A = small_matrix(50, 81, 4, 3); W0, H0 = seeded_init(A, 5, 3)
+    ref = nnmf_ref(A, 5, W0, H0, max_iter=12, trace=1, rel_tol=-1.0)
+    r0, r1 = np.load(str(tmp_path / "out") + ".0.npz"), np.load(str(tmp_path / "out") + ".1.npz")
+    assert np.array_equal(r0["W"], r1["W"])                              # W is replicated bit for bit
+    assert rel_fro(r0["W"], ref["W"]) < 1e-9
+    assert rel_fro(np.concatenate([r0["H"], r1["H"]], axis=1), ref["H"]) < 1e-9
+    assert np.max(np.abs(r0["terr"] - ref["target_loss"]) / ref["target_loss"]) < 1e-10
