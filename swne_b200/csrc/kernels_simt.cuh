@@ -361,7 +361,8 @@ __global__ void __launch_bounds__(128) scd_kl_kernel(const int *__restrict__ ptr
                 if (!(tmp > 0.f)) tmp = 0.f;
                 if (tmp != hk) {
                     const float d = tmp - hk;
-                    for (int q = b + lane; q < e; q += 32) ajt[q] = fmaf(d, Y[(size_t)idx[q] * KP + kk], ajt[q]);
+                    // exact arithmetic keeps ajt >= 0 (d >= -h_kk); fp32 rounding may not: clamp
+                    for (int q = b + lane; q < e; q += 32) ajt[q] = fmaxf(fmaf(d, Y[(size_t)idx[q] * KP + kk], ajt[q]), 0.f);
                     again |= (2.f * fabsf(d) > rel_tol * (tmp + hk + TINY_NUM_F));
                     sumH += d;
                     __syncwarp();
@@ -372,8 +373,14 @@ __global__ void __launch_bounds__(128) scd_kl_kernel(const int *__restrict__ ptr
         }
         for (int f = lane; f < KP; f += 32) X[(size_t)j * KP + f] = h[f];
         if (err) {
+            __syncwarp();
+            // A-hat recomputed from the final h: the incrementally updated ajt keeps fp32 residue where the
+            // exact value is 0, and log(ahat + 1e-16) is sensitive exactly there
             for (int q = b + lane; q < e; q += 32) {
-                const double av = (double)val[q], ah = (double)ajt[q];
+                const float *y = Y + (size_t)idx[q] * KP;
+                float s = 0.f;
+                for (int f = 0; f < k; ++f) s = fmaf(y[f], h[f], s);
+                const double av = (double)val[q], ah = (double)s;
                 klp += av * log(ah + TINY_NUM_D);
                 sqp += av * av - 2.0 * av * ah;
             }

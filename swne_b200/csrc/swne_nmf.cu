@@ -653,7 +653,8 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             prof.end(4, 2);
             prof.begin(5);
             launch_kl(h, k, KPv, h->sp.cptr.p, h->sp.cidx.p, h->sp.cval.p, h->H.p, h->Wt.p, h->cs32.p, p.beta, m,
-                      p.inner_max_iter, inner_tol, &h->dscal.p->sweeps_h, h->dscal.p, 1);
+                      p.inner_max_iter, inner_tol, &h->dscal.p->sweeps_h, h->dscal.p,
+                      (i % p.trace == 0 || i == p.max_iter - 1) ? 1 : 0);
             prof.end(5, 1);
             prof.begin(4);
             launch_gram(h, KPv, h->H.p, m, h->G64h.p);

@@ -206,7 +206,7 @@ def test_sample_coords_and_distances_vs_golden(handle):
     Hnz = g["H"][:, ok]
     from oracle import factor_distance_ref
     for name in ("cosine", "pearson", "euclidean"):
-        assert np.max(np.abs(handle.factor_distance(Hnz, name) - factor_distance_ref(Hnz, name))) < 1e-10
+        assert np.max(np.abs(handle.factor_distance(Hnz, name) - factor_distance_ref(Hnz, name))) < 1e-7  # corrcoef leaves sqrt(2e-16) on the diagonal
     with pytest.raises(Exception):
         handle.factor_distance(Hnz, "IC")
 
