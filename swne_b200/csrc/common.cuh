@@ -63,8 +63,8 @@ __device__ __forceinline__ double block_sum(double v, double *s_scratch /* >= 32
 struct MatStats {
     double sum, sumsq, klc;          // sum a, sum a^2, sum (a+tiny) log(a+tiny) - a
     unsigned long long nnz;
-    unsigned int bad;                // bit0 negative, bit1 non finite
-    unsigned int pad;
+    unsigned int bad;                // bit0 negative, bit1 non finite, bit2 CSC index out of range
+    unsigned int max_bits;           // float bits of the largest entry (entries are >= 0)
 };
 
 // device-side scalars of one fit; copied to the host at every error block

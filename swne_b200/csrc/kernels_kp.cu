@@ -12,7 +12,8 @@ constexpr int KP = KP_VALUE;
 
 void gram_l(const float *X, int rows, double *G64, double *colsum64, cudaStream_t st)
 {
-    gram_kernel<KP><<<(rows + 255) / 256, 256, 0, st>>>(X, rows, G64, colsum64);
+    const int grid = rows < 296 * 64 ? (rows + 63) / 64 : 296;
+    gram_kernel<KP><<<grid, 256, 0, st>>>(X, rows, G64, colsum64);
 }
 void contract_cells_l(const float *A, size_t ldA, int n, int m, const float *Wt, float *C, cudaStream_t st)
 {

@@ -18,6 +18,7 @@ __global__ void ingest_dense_kernel(const T *__restrict__ src, size_t src_ld, fl
     double s = 0, s2 = 0, kc = 0;
     unsigned long long nz = 0;
     unsigned int bad = 0;
+    float mx = 0.f;
     for (int r = blockIdx.x; r < rows; r += gridDim.x) {
         const T *sp = src + (size_t)r * src_ld;
         float *dp = dst ? dst + (size_t)r * dst_ld : nullptr;
@@ -26,6 +27,7 @@ __global__ void ingest_dense_kernel(const T *__restrict__ src, size_t src_ld, fl
             if (!(v >= 0.0)) bad |= (v < 0.0) ? 1u : 2u;
             if (isinf(v)) bad |= 2u;
             if (dp) dp[i] = (float)v;
+            mx = fmaxf(mx, (float)v);
             s += v; s2 += v * v;
             if (v != 0.0) { ++nz; }
             kc += (v + TINY_NUM_D) * log(v + TINY_NUM_D) - v;
@@ -35,6 +37,8 @@ __global__ void ingest_dense_kernel(const T *__restrict__ src, size_t src_ld, fl
     double r0 = block_sum(s, scratch), r1 = block_sum(s2, scratch), r2 = block_sum(kc, scratch);
     double r3 = block_sum((double)nz, scratch);
     bad = __syncthreads_or(bad);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(&st->max_bits, __float_as_uint(mx));
     if (threadIdx.x == 0) {
         atomicAdd(&st->sum, r0); atomicAdd(&st->sumsq, r1); atomicAdd(&st->klc, r2);
         atomicAdd(&st->nnz, (unsigned long long)(r3 + 0.5));
@@ -53,6 +57,7 @@ __global__ void ingest_csc_kernel(const int *__restrict__ p, const int *__restri
     double s = 0, s2 = 0, kc = 0;
     unsigned long long nz = 0;
     unsigned int bad = 0;
+    float mx = 0.f;
     for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < cols; j += gridDim.x * wpb) {
         const int b = p[col0 + j] - base, e = p[col0 + j + 1] - base;
         for (int q = b + lane; q < e; q += 32) {
@@ -62,6 +67,7 @@ __global__ void ingest_csc_kernel(const int *__restrict__ p, const int *__restri
             if (!(v >= 0.0)) bad |= (v < 0.0) ? 1u : 2u;
             if (isinf(v)) bad |= 2u;
             dst[(size_t)j * dst_ld + g] = (float)v;
+            mx = fmaxf(mx, (float)v);
             s += v; s2 += v * v;
             if (v != 0.0) { ++nz; kc += (v + TINY_NUM_D) * log(v + TINY_NUM_D) - v; }
         }
@@ -69,6 +75,8 @@ __global__ void ingest_csc_kernel(const int *__restrict__ p, const int *__restri
     double r0 = block_sum(s, scratch), r1 = block_sum(s2, scratch), r2 = block_sum(kc, scratch);
     double r3 = block_sum((double)nz, scratch);
     bad = __syncthreads_or(bad);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(&st->max_bits, __float_as_uint(mx));
     if (threadIdx.x == 0) {
         atomicAdd(&st->sum, r0); atomicAdd(&st->sumsq, r1); atomicAdd(&st->klc, r2);
         atomicAdd(&st->nnz, (unsigned long long)(r3 + 0.5));

@@ -19,7 +19,7 @@
 namespace swne {
 
 // ----------------------------------------------------------------------------------------------
-// Gram: G64[KP*KP] += X'X, colsum64[KP] += column sums, X [rows][KP].  256 threads, 256 rows / block
+// Gram: G64[KP*KP] += X'X, colsum64[KP] += column sums, X [rows][KP].  256 threads, grid <= 2 x #SM
 // ----------------------------------------------------------------------------------------------
 template <int KP>
 __global__ void __launch_bounds__(256) gram_kernel(const float *__restrict__ X, int rows, double *__restrict__ G64,
@@ -32,8 +32,10 @@ __global__ void __launch_bounds__(256) gram_kernel(const float *__restrict__ X, 
 #pragma unroll
     for (int q = 0; q < PAIRS; ++q) acc[q] = 0.f;
     float cs = 0.f;
-    const int row_begin = blockIdx.x * 256;
-    const int row_end = min(rows, row_begin + 256);
+    // contiguous row range per block; few blocks so that the fp64 atomics at the end stay cheap
+    const int per = ((rows + gridDim.x - 1) / gridDim.x + ROWS - 1) / ROWS * ROWS;
+    const int row_begin = blockIdx.x * per;
+    const int row_end = min(rows, row_begin + per);
     for (int r0 = row_begin; r0 < row_end; r0 += ROWS) {
         const int nr = min(ROWS, row_end - r0);
         __syncthreads();

@@ -468,8 +468,6 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     validate_init(W, (size_t)n * k, "W");
     validate_init(H, (size_t)k * m, "H");
 
-    const int KPv = kp_of(k);
-    const int GS = KPv * KPv + KPv;  // Gram + column sums
     cudaStream_t st = h->stream;
     memset(res, 0, sizeof(*res));
 
@@ -479,6 +477,8 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     if (engine == SWNE_ENGINE_TC && !tc_supported(h->n, h->m, k))
         FAIL(SWNE_ERR_UNSUPPORTED, "tcgen05 engine does not support this shape (n=%d, k=%d)", n, k);
     res->engine_used = engine;
+    const int KPv = (engine == SWNE_ENGINE_TC) ? TC_KP : kp_of(k);
+    const int GS = KPv * KPv + KPv;  // Gram + column sums
 
     // ---- workspaces
     h->Wt.reserve((size_t)n * KPv); h->H.reserve((size_t)m * KPv);
@@ -492,7 +492,8 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     }
     HostTrace *ht = (HostTrace *)h->pinned;
     if (p.loss == SWNE_LOSS_MKL || p.full_traces) ensure_sparse(h);
-    if (engine == SWNE_ENGINE_TC) tc_prepare(h->tc, h->dA, h->ldA, n, m, KPv, h->sm_count, st);
+    if (engine == SWNE_ENGINE_TC)
+        tc_prepare(h->tc, h->dA, h->ldA, n, m, (double)__builtin_bit_cast(float, h->stats.max_bits), h->sm_count, st);
 
     // ---- global constants (all-reduced once)
     double gl[5] = {h->stats.sum, h->stats.sumsq, h->stats.klc, (double)h->stats.nnz, (double)m};
@@ -526,7 +527,15 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     launch_gram(h, KPv, h->H.p, m, h->G64h.p);
     prof.end(4, 1);
     if (h->nranks > 1) allreduce(h, nullptr, 0, h->G64h.p, GS);
-    bool have_B = false;  // the fused pass leaves A H' of the *new* H behind for the next W update
+    bool have_B = false;  // the tcgen05 pass leaves A H' of the *new* H behind for the next W update
+    if (engine == SWNE_ENGINE_TC) {
+        prof.begin(0);
+        CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
+        tc_pass(h->tc, 1, h->Wt.p, h->H.p, h->G.p, h->G.p, 0.f, k, p.inner_max_iter, 0.f, h->B.p, h->dscal.p, st);
+        prof.end(0, tc_pass_launches(1));
+        if (h->nranks > 1) allreduce(h, h->B.p, (size_t)n * KPv, nullptr, 0);
+        have_B = true;
+    }
 
     double rel_err = p.rel_tol + 1.0, terr_last = 1e99;
     int i = 0, i_e = 0;
@@ -612,10 +621,13 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             prof.end(4, 2);
             if (engine == SWNE_ENGINE_TC) {
                 prof.begin(0);
-                tc_pass(h->tc, h->Wt.p, h->H.p, h->G.p, h->G0.p, (float)p.beta[2], k, p.inner_max_iter, inner_tol, h->B.p,
-                        h->G64h.p, h->dscal.p, st);
-                prof.end(0, tc_pass_launches());
-                have_B = true;
+                CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
+                tc_pass(h->tc, 0, h->Wt.p, h->H.p, h->G.p, h->G0.p, (float)p.beta[2], k, p.inner_max_iter, inner_tol, h->B.p,
+                        h->dscal.p, st);
+                prof.end(0, tc_pass_launches(0));
+                prof.begin(4);
+                launch_gram(h, KPv, h->H.p, m, h->G64h.p);
+                prof.end(4, 1);
                 if (h->nranks > 1) {
                     prof.begin(6);
                     allreduce(h, h->B.p, (size_t)n * KPv, h->G64h.p, GS);
