@@ -24,10 +24,13 @@ void contract_genes_l(const float *A, size_t ldA, int n, int m, const float *H, 
     dim3 grid((n + 63) / 64, chunks);
     contract_genes_kernel<KP><<<grid, 128, 0, st>>>(A, ldA, n, m, H, B, cpc);
 }
-void solve_l(float *X, const float *C, const float *G, const float *G0, float l1, int k, int cols, int max_iter, float rel_tol,
+void solve_l(float *X, const float *C, const float *pack, float l1, int k, int cols, int max_iter, float rel_tol,
              unsigned long long *sweeps, double *loss_part, cudaStream_t st)
 {
-    scd_ls_solve_kernel<KP><<<(cols + 127) / 128, 128, 0, st>>>(X, C, G, G0, l1, k, cols, max_iter, rel_tol, sweeps, loss_part);
+    cudaMemcpyToSymbolAsync(c_gram, pack, sizeof(float) * 2 * KP * KP, 0, cudaMemcpyDeviceToDevice, st);
+    // few columns (the W side): one warp per block spreads the latency-bound solves over all SMs
+    const int bs = cols <= 148 * 64 ? 32 : 128;
+    scd_ls_solve_kernel<KP><<<(cols + bs - 1) / bs, bs, 0, st>>>(X, C, pack, l1, k, cols, max_iter, rel_tol, sweeps, loss_part);
 }
 void kl_l(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y, const float *sumY, float b0,
           float b1, float b2, int k, int cols, int max_iter, float rel_tol, unsigned long long *sweeps, double *kl_part,

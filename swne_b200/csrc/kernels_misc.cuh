@@ -5,6 +5,14 @@
 
 namespace swne {
 
+// device-side zero fill (a kernel, so it stays on the compute queue between the kernels it separates)
+__global__ void zero_fill_kernel(uint4 *p16, size_t n16, uint32_t *tail, int ntail)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        p16[i] = make_uint4(0, 0, 0, 0);
+    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // ingest
 // ----------------------------------------------------------------------------------------------
@@ -115,27 +123,41 @@ __global__ void factor_out_colmajor_kernel(const float *__restrict__ src, double
     dst[t] = (double)src[(size_t)i * KP + f];
 }
 
-// builds the penalised fp32 Gram the solver uses from the fp64 sums:
-//   G = G0 + (p0 - p1) I + p1 11' + tiny I   (update()), rows/cols >= k zeroed
-__global__ void finalize_gram_kernel(const double *__restrict__ G64, float *__restrict__ G, float *__restrict__ G0,
-                                     float *__restrict__ colsum32, const double *__restrict__ colsum64,
-                                     int k, int KP, double p0, double p1)
+// builds the GramPack the solvers use from the fp64 sums (one block):
+//   G = G0 + (p0 - p1) I + p1 11' + tiny I   (update()), D = sqrt(diag G),
+//   pack = [ G' = G / (D D') with unit diagonal | G0 | D | 1/D | column sums ], rows/cols >= k zeroed
+__global__ void finalize_gram_kernel(const double *__restrict__ G64, float *__restrict__ pack, int k, int KP, double p0,
+                                     double p1)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < KP * KP) {
-        const int a = t / KP, b = t % KP;
-        double g = 0.0, g0 = 0.0;
-        if (a < k && b < k) {
-            g0 = G64[t];
-            g = g0;
-            if (p0 != p1 && a == b) g += p0 - p1;
+    __shared__ float sInv[64];
+    const double *colsum64 = G64 + KP * KP;
+    for (int t = threadIdx.x; t < KP; t += blockDim.x) {
+        double g = 1.0;
+        if (t < k) {
+            g = G64[t * KP + t];
+            if (p0 != p1) g += p0 - p1;
             if (p1 != 0.0) g += p1;
-            if (a == b) g += TINY_NUM_D;
+            g += TINY_NUM_D;
         }
-        G[t] = (float)g;
-        if (G0) G0[t] = (float)g0;
+        const float d = sqrtf((float)g);
+        pack[2 * KP * KP + t] = d;
+        pack[2 * KP * KP + KP + t] = 1.f / d;
+        sInv[t] = 1.f / d;
+        pack[2 * KP * KP + 2 * KP + t] = (t < k) ? (float)colsum64[t] : 0.f;
     }
-    if (t < KP && colsum32) colsum32[t] = (t < k) ? (float)colsum64[t] : 0.f;
+    __syncthreads();
+    for (int t = threadIdx.x; t < KP * KP; t += blockDim.x) {
+        const int a = t / KP, b = t % KP;
+        float gs = 0.f, g0 = 0.f;
+        if (a < k && b < k) {
+            g0 = (float)G64[t];
+            double g = G64[t];
+            if (p1 != 0.0) g += p1;
+            gs = (a == b) ? 1.f : (float)g * sInv[a] * sInv[b];
+        }
+        pack[t] = gs;
+        pack[KP * KP + t] = g0;
+    }
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -183,119 +183,167 @@ __global__ void __launch_bounds__(128) contract_genes_kernel(const float *__rest
 // continue while any coordinate's relative change 2|d|/(new+old+tiny) exceeds rel_tol, cap max_iter,
 // warm start from the previous iterate.
 // ----------------------------------------------------------------------------------------------
+// Unit-diagonal form: with d_k = sqrt(G_kk), h' = d o h, mu' = mu / d and G' = G / (d d') the update
+//   h_k <- max(0, h_k - mu_k / G_kk)   becomes   h'_k <- max(0, h'_k - mu'_k),   mu' += delta' * G'[:,k]
+// (same iterates up to rounding; the relative-change test is invariant).  It removes one multiply and one
+// load from the dependent chain of every coordinate step.
+//
+// Where G' lives: in the __constant__ bank.  Every thread of a warp needs the same KP floats per coordinate
+// step; from shared memory that is 8 broadcast LDS.128 per warp-step and the SM-wide shared-memory pipe
+// saturates at ~19 SM-cycles per warp-step (tools/micro/solver_bench.cu, measured on B200).  Constant-bank
+// operands arrive through the per-SMSP uniform datapath (LDCU.128 -> FFMA2 with uniform operands) and the
+// sweep becomes FMA-issue bound at ~11 SM-cycles per warp-step.
+//
+// GramPack (device, floats): [0,KP^2) G' unit-diagonal scaled | [KP^2,2KP^2) plain G0 | D[KP] | invD[KP] | colsum[KP]
+constexpr int GRAM_KP_MAX = 64;
+static __constant__ float c_gram[2 * GRAM_KP_MAX * GRAM_KP_MAX];   // per translation unit: G' then G0, row stride KP
+
+__host__ __device__ constexpr int gram_pack_floats(int KP) { return 2 * KP * KP + 3 * KP; }
+
+// One sweep block: coordinates kb*8 .. kb*8+7, branch free so the compiler can pipeline the shared-memory
+// loads of the next coordinate under the FMAs of the current one.  An unchanged coordinate has d == 0 and
+// the update is a no-op, which is exactly scd_ls_update's "if (tmp != h)" skip; padded coordinates
+// (kk >= k: h = 0, mu >= 0, zero row of G') are no-ops too.  mu is held as float2 pairs and updated with
+// the packed FFMA2 of sm_100 (two fp32 FMAs per issue slot).
+template <int KP, bool ANY_CHANGE>
+__device__ __forceinline__ void scd_ls_block8(float (&h)[KP], float2 (&mu)[KP / 2], int kb, float rel_tol, unsigned &changed)
+{
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int kk = kb * 8 + u;
+        float4 g[KP / 4];
+#pragma unroll
+        for (int r = 0; r < KP / 4; ++r)
+            g[r] = make_float4(c_gram[kk * KP + 4 * r], c_gram[kk * KP + 4 * r + 1], c_gram[kk * KP + 4 * r + 2],
+                               c_gram[kk * KP + 4 * r + 3]);
+        const float mk = (kk & 1) ? mu[kk / 2].y : mu[kk / 2].x;
+        const float tmp = fmaxf(h[kk] - mk, 0.f);
+        const float d = tmp - h[kk];
+        const float2 d2 = make_float2(d, d);
+#pragma unroll
+        for (int r = 0; r < KP / 4; ++r) {
+            mu[2 * r + 0] = __ffma2_rn(d2, make_float2(g[r].x, g[r].y), mu[2 * r + 0]);
+            mu[2 * r + 1] = __ffma2_rn(d2, make_float2(g[r].z, g[r].w), mu[2 * r + 1]);
+        }
+        if (ANY_CHANGE) changed |= __float_as_uint(d);   // d is +0 exactly when unchanged
+        else changed |= (2.f * fabsf(d) > rel_tol * (tmp + h[kk] + TINY_NUM_F)) ? 1u : 0u;
+        h[kk] = tmp;
+    }
+}
+
+// h, mu in the scaled variables; G' is read from c_gram.  returns #sweeps
 template <int KP>
-__device__ __forceinline__ int scd_ls_thread(float (&h)[KP], float (&mu)[KP], const float *__restrict__ sG,
-                                             const float *__restrict__ sInvD, int k, int max_iter, float rel_tol)
+__device__ __forceinline__ int scd_ls_thread(float (&h)[KP], float2 (&mu)[KP / 2], int k, int max_iter, float rel_tol)
 {
     int t = 0;
-    bool again = true;
-    // asm volatile loads: without them the compiler hoists all KP*KP loop-invariant loads of G out of
-    // the sweep loop and spills them to local memory
-    const unsigned sg_addr = (unsigned)__cvta_generic_to_shared(sG);
-    for (; t < max_iter && again; ++t) {
-        again = false;
+    unsigned changed = 1u;
+    // with rel_tol below fp32 resolution "relative change > rel_tol" is the same as "changed at all"
+    if (rel_tol < 2.9e-8f) {
+        for (; t < max_iter && changed; ++t) {
+            changed = 0u;
 #pragma unroll
-        for (int kk = 0; kk < KP; ++kk) {
-            if (kk < k) {
-                float tmp = fmaf(-mu[kk], sInvD[kk], h[kk]);
-                tmp = fmaxf(tmp, 0.f);
-                const float d = tmp - h[kk];
-                if (d != 0.f) {
+            for (int kb = 0; kb < KP / 8; ++kb)
+                if (kb * 8 < k) scd_ls_block8<KP, true>(h, mu, kb, rel_tol, changed);
+        }
+    } else {
+        for (; t < max_iter && changed; ++t) {
+            changed = 0u;
 #pragma unroll
-                    for (int r = 0; r < KP / 4; ++r) {
-                        float4 g;
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                     : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w)
-                                     : "r"(sg_addr + (unsigned)((kk * KP + 4 * r) * 4)));
-                        mu[4 * r + 0] = fmaf(d, g.x, mu[4 * r + 0]);
-                        mu[4 * r + 1] = fmaf(d, g.y, mu[4 * r + 1]);
-                        mu[4 * r + 2] = fmaf(d, g.z, mu[4 * r + 2]);
-                        mu[4 * r + 3] = fmaf(d, g.w, mu[4 * r + 3]);
-                    }
-                    // e = 2|d| / (tmp + h + tiny) > rel_tol, division free
-                    again |= (2.f * fabsf(d) > rel_tol * (tmp + h[kk] + TINY_NUM_F));
-                    h[kk] = tmp;
-                }
-            }
+            for (int kb = 0; kb < KP / 8; ++kb)
+                if (kb * 8 < k) scd_ls_block8<KP, false>(h, mu, kb, rel_tol, changed);
         }
     }
     return t;
 }
 
-// X [cols][KP] in/out (warm start), C [cols][KP] = the contraction (Wt a_j), G penalised Gram,
-// G0 plain Gram (only when loss_part != nullptr), l1 = the L1 penalty added to mu.
+// mu' += sum_q h'_q G'[q,:]  with h'_q = X[q] * D[q]   (G' from the constant bank, q uniform)
+template <int KP>
+__device__ __forceinline__ void scd_mu_init(float2 (&mu)[KP / 2], const float *__restrict__ xrow, const float *sD, int k)
+{
+#pragma unroll 1
+    for (int q = 0; q < k; ++q) {
+        const float hq = xrow[q] * sD[q];
+        const float2 h2 = make_float2(hq, hq);
+#pragma unroll
+        for (int r = 0; r < KP / 4; ++r) {
+            mu[2 * r] = __ffma2_rn(h2, make_float2(c_gram[q * KP + 4 * r], c_gram[q * KP + 4 * r + 1]), mu[2 * r]);
+            mu[2 * r + 1] = __ffma2_rn(h2, make_float2(c_gram[q * KP + 4 * r + 2], c_gram[q * KP + 4 * r + 3]), mu[2 * r + 1]);
+        }
+    }
+}
+// t = G0 x  (plain Gram, second half of c_gram)
+template <int KP>
+__device__ __forceinline__ void scd_g0_times(float2 (&t)[KP / 2], const float *__restrict__ xrow, int k)
+{
+#pragma unroll
+    for (int r = 0; r < KP / 2; ++r) t[r] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int q = 0; q < k; ++q) {
+        const float hq = xrow[q];
+        const float2 h2 = make_float2(hq, hq);
+        const float *g0 = c_gram + KP * KP + q * KP;
+#pragma unroll
+        for (int r = 0; r < KP / 4; ++r) {
+            t[2 * r] = __ffma2_rn(h2, make_float2(g0[4 * r], g0[4 * r + 1]), t[2 * r]);
+            t[2 * r + 1] = __ffma2_rn(h2, make_float2(g0[4 * r + 2], g0[4 * r + 3]), t[2 * r + 1]);
+        }
+    }
+}
+
+// X [cols][KP] in/out (warm start), C [cols][KP] = the contraction (Wt a_j); the Grams come from c_gram
+// (uploaded from `pack` by the launcher) and pack's D / invD; l1 = the L1 penalty added to mu.
+// blockDim.x = 32 (few columns: one warp per SM keeps the latency-bound W side spread out) or 128.
 template <int KP>
 __global__ void __launch_bounds__(128) scd_ls_solve_kernel(float *__restrict__ X, const float *__restrict__ C,
-                                                           const float *__restrict__ G, const float *__restrict__ G0,
-                                                           float l1, int k, int cols, int max_iter, float rel_tol,
-                                                           unsigned long long *sweeps, double *loss_part)
+                                                           const float *__restrict__ pack, float l1, int k, int cols,
+                                                           int max_iter, float rel_tol, unsigned long long *sweeps,
+                                                           double *loss_part)
 {
-    __shared__ __align__(16) float sG[KP * KP];
-    __shared__ __align__(16) float sG0[KP * KP];
-    __shared__ float sInvD[KP];
+    __shared__ float sD[KP], sInvD[KP];
     __shared__ double scratch[32];
-    for (int t = threadIdx.x; t < KP * KP; t += blockDim.x) {
-        sG[t] = G[t];
-        sG0[t] = G0 ? G0[t] : 0.f;
+    for (int t = threadIdx.x; t < KP; t += blockDim.x) {
+        sD[t] = pack[2 * KP * KP + t];
+        sInvD[t] = pack[2 * KP * KP + KP + t];
     }
-    for (int t = threadIdx.x; t < KP; t += blockDim.x) sInvD[t] = (t < k) ? 1.f / G[t * KP + t] : 0.f;
     __syncthreads();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     int it = 0;
     double lp = 0.0;
     if (j < cols) {
-        float h[KP], mu[KP];
-        const float4 *hp = reinterpret_cast<const float4 *>(X + (size_t)j * KP);
+        float h[KP];
+        float2 mu[KP / 2];
+        float *xrow = X + (size_t)j * KP;
+        const float4 *hp = reinterpret_cast<const float4 *>(xrow);
         const float4 *cp = reinterpret_cast<const float4 *>(C + (size_t)j * KP);
 #pragma unroll
         for (int r = 0; r < KP / 4; ++r) {
             const float4 v = hp[r];
-            h[4 * r] = v.x; h[4 * r + 1] = v.y; h[4 * r + 2] = v.z; h[4 * r + 3] = v.w;
+            h[4 * r] = v.x * sD[4 * r]; h[4 * r + 1] = v.y * sD[4 * r + 1];
+            h[4 * r + 2] = v.z * sD[4 * r + 2]; h[4 * r + 3] = v.w * sD[4 * r + 3];
             const float4 c = cp[r];
-            mu[4 * r] = l1 - c.x; mu[4 * r + 1] = l1 - c.y; mu[4 * r + 2] = l1 - c.z; mu[4 * r + 3] = l1 - c.w;
+            mu[2 * r] = make_float2((l1 - c.x) * sInvD[4 * r], (l1 - c.y) * sInvD[4 * r + 1]);
+            mu[2 * r + 1] = make_float2((l1 - c.z) * sInvD[4 * r + 2], (l1 - c.w) * sInvD[4 * r + 3]);
         }
-#pragma unroll 1
-        for (int q = 0; q < k; ++q) {
-            const float hq = X[(size_t)j * KP + q];
-            const float4 *g4 = reinterpret_cast<const float4 *>(sG + q * KP);
+        scd_mu_init<KP>(mu, xrow, sD, k);
+        it = scd_ls_thread<KP>(h, mu, k, max_iter, rel_tol);
+        float4 *op = reinterpret_cast<float4 *>(xrow);
 #pragma unroll
-            for (int r = 0; r < KP / 4; ++r) {
-                const float4 g = g4[r];
-                mu[4 * r + 0] = fmaf(hq, g.x, mu[4 * r + 0]);
-                mu[4 * r + 1] = fmaf(hq, g.y, mu[4 * r + 1]);
-                mu[4 * r + 2] = fmaf(hq, g.z, mu[4 * r + 2]);
-                mu[4 * r + 3] = fmaf(hq, g.w, mu[4 * r + 3]);
-            }
+        for (int r = 0; r < KP / 4; ++r) {
+            h[4 * r] *= sInvD[4 * r]; h[4 * r + 1] *= sInvD[4 * r + 1];
+            h[4 * r + 2] *= sInvD[4 * r + 2]; h[4 * r + 3] *= sInvD[4 * r + 3];
+            op[r] = make_float4(h[4 * r], h[4 * r + 1], h[4 * r + 2], h[4 * r + 3]);
         }
-        it = scd_ls_thread<KP>(h, mu, sG, sInvD, k, max_iter, rel_tol);
-        float4 *op = reinterpret_cast<float4 *>(X + (size_t)j * KP);
-#pragma unroll
-        for (int r = 0; r < KP / 4; ++r) op[r] = make_float4(h[4 * r], h[4 * r + 1], h[4 * r + 2], h[4 * r + 3]);
         if (loss_part) {
-            // h' G0 h - 2 h' c ; mu is dead, reuse it for t = G0 h
-#pragma unroll
-            for (int r = 0; r < KP; ++r) mu[r] = 0.f;
-#pragma unroll 1
-            for (int q = 0; q < k; ++q) {
-                const float hq = X[(size_t)j * KP + q];  // just written by this thread
-                const float4 *g4 = reinterpret_cast<const float4 *>(sG0 + q * KP);
-#pragma unroll
-                for (int r = 0; r < KP / 4; ++r) {
-                    const float4 g = g4[r];
-                    mu[4 * r + 0] = fmaf(hq, g.x, mu[4 * r + 0]);
-                    mu[4 * r + 1] = fmaf(hq, g.y, mu[4 * r + 1]);
-                    mu[4 * r + 2] = fmaf(hq, g.z, mu[4 * r + 2]);
-                    mu[4 * r + 3] = fmaf(hq, g.w, mu[4 * r + 3]);
-                }
-            }
+            // h' G0 h - 2 h' c ; mu is dead, reuse it for t = G0 h  (xrow was just written by this thread)
+            scd_g0_times<KP>(mu, xrow, k);
             float s = 0.f;
 #pragma unroll
             for (int r = 0; r < KP / 4; ++r) {
                 const float4 c = cp[r];
-                s = fmaf(h[4 * r + 0], mu[4 * r + 0] - 2.f * c.x, s);
-                s = fmaf(h[4 * r + 1], mu[4 * r + 1] - 2.f * c.y, s);
-                s = fmaf(h[4 * r + 2], mu[4 * r + 2] - 2.f * c.z, s);
-                s = fmaf(h[4 * r + 3], mu[4 * r + 3] - 2.f * c.w, s);
+                s = fmaf(h[4 * r + 0], mu[2 * r].x - 2.f * c.x, s);
+                s = fmaf(h[4 * r + 1], mu[2 * r].y - 2.f * c.y, s);
+                s = fmaf(h[4 * r + 2], mu[2 * r + 1].x - 2.f * c.z, s);
+                s = fmaf(h[4 * r + 3], mu[2 * r + 1].y - 2.f * c.w, s);
             }
             lp = (double)s;
         }

@@ -14,8 +14,9 @@ struct KpOps {
     void (*contract_cells)(const float *A, size_t ldA, int n, int m, const float *Wt, float *C, cudaStream_t st);
     void (*contract_genes)(const float *A, size_t ldA, int n, int m, const float *H, float *B, int cells_per_chunk, int chunks,
                            cudaStream_t st);
-    void (*solve)(float *X, const float *C, const float *G, const float *G0, float l1, int k, int cols, int max_iter,
-                  float rel_tol, unsigned long long *sweeps, double *loss_part, cudaStream_t st);
+    // pack: GramPack of this side (see kernels_simt.cuh); its Grams are copied into the constant bank first
+    void (*solve)(float *X, const float *C, const float *pack, float l1, int k, int cols, int max_iter, float rel_tol,
+                  unsigned long long *sweeps, double *loss_part, cudaStream_t st);
     void (*kl)(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y, const float *sumY,
                float b0, float b1, float b2, int k, int cols, int max_iter, float rel_tol, unsigned long long *sweeps,
                double *kl_part, double *sq_part, int err, cudaStream_t st);

@@ -35,10 +35,13 @@ constexpr int TC_GROUP = 32;          // cells per TMA box / work granule
 constexpr int TC_A_STAGE = TC_TILE * TC_CHUNK * 2;      // 16 KB
 constexpr int TC_W_STAGE = 64 * TC_CHUNK * 2;           // 8 KB  (rows 0..31 W_hi, 32..63 W_lo)
 constexpr int TC_BOX_BYTES = TC_GROUP * TC_CHUNK * 2;   // 4 KB
-constexpr int TC_H_SUB = TC_KP * 64 * 2;                // 4 KB: [32 factors][64 cells] fp16, K-major
-constexpr int TC_H_TILE = 4 * TC_H_SUB;                 // hi k-half 0/1, lo k-half 0/1
-constexpr int TC_MT_PER_PASS = 12;                      // 128-gene accumulators per gene sub-pass (12 * 32 = 384 TMEM columns)
-constexpr int TC_THREADS = 64 + 256;
+constexpr int TC_H_SUB = TC_KP * 64 * 2;                // 4 KB: [32 factors][64 cells] 16-bit, K-major
+constexpr int TC_H_TILE = 4 * TC_H_SUB;                 // hi (bf16) k-half 0/1, lo (fp16) k-half 0/1
+constexpr int TC_CBUF = 8;                              // C accumulators (32 TMEM columns each) in flight
+constexpr int TC_MT_PER_PASS = 8;                       // 128-gene accumulators per gene sub-pass (8 * 32 TMEM columns)
+constexpr int TC_SOLVER_WARPS = 12;
+constexpr int TC_THREADS = (4 + TC_SOLVER_WARPS) * 32;  // warps: 0 TMA, 1 MMA, 2 H-tile loader, 3 idle, 4.. solvers
+constexpr int TC_MAX_TILES = 256;                       // tiles per CTA (one mbarrier each)
 
 struct TcSmem {
     // offsets from the 1024-aligned base
@@ -46,28 +49,31 @@ struct TcSmem {
     static constexpr int a_lo = a_hi + TC_STAGES * TC_A_STAGE;
     static constexpr int w = a_lo + TC_STAGES * TC_A_STAGE;
     static constexpr int h = w + TC_STAGES * TC_W_STAGE;
-    static constexpr int g = h + 2 * TC_H_TILE;
-    static constexpr int g0 = g + TC_KP * TC_KP * 4;
-    static constexpr int invd = g0 + TC_KP * TC_KP * 4;
-    static constexpr int bars = invd + TC_KP * 4;
-    static constexpr int n_bars = 2 * TC_STAGES + 2 + 2 + 2 + 2 + 2;
+    static constexpr int dvec = h + 2 * TC_H_TILE;       // sqrt(diag), 1/sqrt(diag)
+    static constexpr int bars = dvec + 2 * TC_KP * 4;
+    static constexpr int n_bars = 2 * TC_STAGES + 2 * TC_CBUF + 2 + 2 + 2 + TC_MAX_TILES;
     static constexpr int misc = bars + n_bars * 8;
     static constexpr int total = misc + 64;
 };
 
 struct TcPassParams {
     int n, m, k;
-    int n_chunks;            // gene chunks per tile (even, >= ceil(n/64))
+    int n_chunks;            // gene chunks per tile in phase 1 (even, >= ceil(n/64))
     int n_mtiles;            // ceil(n/128)
     int mode;                // 0: phase 1 + solve + phase 3; 1: phase 3 only (A H' of the given H)
-    const float *G, *G0;     // penalised / plain Gram of W (KP x KP)
+    const float *pack;       // GramPack of W'W (D / invD read here; the Grams themselves sit in c_gram)
     float l1;
     int max_iter;
     float rel_tol;
     float *H;                // [m][32] fp32 in/out
     float *B;                // [n][32] fp32, accumulated with red.add (zeroed by the caller)
+    uint8_t *Himg;           // [grid][tiles_per_cta][TC_H_TILE] split 16-bit images of the H tiles
+    int tiles_per_cta;
     FitScalars *scal;
     const int *w_exp;        // device: W was scaled by 2^w_exp before the split
+    const int *hmax_prev;    // device: float bits of max(H) before this pass (sets the fp16 scale of the H images)
+    int *hmax_next;          // device: atomicMax of the float bits of the new H
+    int *overflow;           // device: set when a scaled H entry left the fp16 range
     int a_exp;               // A was scaled by 2^a_exp before the split
     int groups_total;        // ceil(m / 32)
 };
@@ -148,9 +154,10 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_byte
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): f16 x f16 -> f32
-__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, int b_mn_major)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, int b_mn_major, int b_is_bf16 = 0)
 {
-    return (1u << 4) /* C = F32 */ | (0u << 7) /* A = F16 */ | (0u << 10) /* B = F16 */ | ((uint32_t)a_mn_major << 15) |
+    return (1u << 4) /* C = F32 */ | (0u << 7) /* A = F16 */ | ((uint32_t)b_is_bf16 << 10) /* B = F16 | BF16 */ |
+           ((uint32_t)a_mn_major << 15) |
            ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
@@ -160,6 +167,14 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 
 // ------------------------------------------------------------------------------------------------
 // the pass kernel
+//
+//   warp 0      TMA producer: phase 1 streams (A_hi, A_lo, W) chunks of every tile, phase 3 streams (A_hi, A_lo)
+//               for one third of the genes at a time
+//   warp 1      MMA issuer (one lane): phase 1 C[t] = A W' into one of 8 TMEM accumulators; phase 3 D += A' H
+//   warp 2      H-tile loader: copies the split 16-bit image of a solved tile from global scratch to smem
+//   warps 4-15  solvers: take (tile, lane-quarter) jobs from four queues, read C from TMEM, run the SCD solve,
+//               write H, the loss partial and the tile image; afterwards drain D into B
+// Phase 3 of tile t only needs tile t's solve, so the second stream over A overlaps the remaining solves.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
@@ -178,50 +193,48 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     const int cell_end = min(p.m, (g_begin + g_count) * TC_GROUP);
     const int n_tiles = (cell_end - cell_begin + TC_TILE - 1) / TC_TILE;
     const int n_pass = (p.n_mtiles + TC_MT_PER_PASS - 1) / TC_MT_PER_PASS;
+    uint8_t *my_img = p.Himg + (size_t)blockIdx.x * p.tiles_per_cta * TC_H_TILE;
 
     // ---- barriers
     const uint32_t bar0 = sbase + TcSmem::bars;
     auto FULL = [&](int s) { return bar0 + 8u * s; };
     auto EMPTY = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
     auto CFULL = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + b); };
-    auto CEMPTY = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + 2 + b); };
-    auto HFULL = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + 4 + b); };
-    auto HEMPTY = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + 6 + b); };
-    const uint32_t DFULL = bar0 + 8u * (2 * TC_STAGES + 8), DEMPTY = bar0 + 8u * (2 * TC_STAGES + 9);
+    auto CEMPTY = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + TC_CBUF + b); };
+    constexpr int B2 = 2 * TC_STAGES + 2 * TC_CBUF;
+    auto HFULL = [&](int b) { return bar0 + 8u * (B2 + b); };
+    auto HEMPTY = [&](int b) { return bar0 + 8u * (B2 + 2 + b); };
+    const uint32_t DFULL = bar0 + 8u * (B2 + 4), DEMPTY = bar0 + 8u * (B2 + 5);
+    auto TDONE = [&](int t) { return bar0 + 8u * (B2 + 6 + t); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcSmem::misc);
-    int *s_hmax = reinterpret_cast<int *>(smem + TcSmem::misc + 8);
+    int *s_next = reinterpret_cast<int *>(smem + TcSmem::misc + 16);   // per-quarter job counters
 
     // zero the A stages once: rows of a partial tile that TMA never writes must hold finite values
     for (int i = threadIdx.x; i < (2 * TC_STAGES * TC_A_STAGE) / 16; i += blockDim.x)
         reinterpret_cast<uint4 *>(smem + TcSmem::a_hi)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(CFULL(b), 1); mbar_init(CEMPTY(b), 128);
-            mbar_init(HFULL(b), 256); mbar_init(HEMPTY(b), 1);
-        }
-        mbar_init(DFULL, 1); mbar_init(DEMPTY, 256);
-        *s_hmax = 0;
+        for (int b = 0; b < TC_CBUF; ++b) { mbar_init(CFULL(b), 1); mbar_init(CEMPTY(b), 128); }
+        for (int b = 0; b < 2; ++b) { mbar_init(HFULL(b), 1); mbar_init(HEMPTY(b), 1); }
+        mbar_init(DFULL, 1); mbar_init(DEMPTY, TC_SOLVER_WARPS * 32);
+        for (int t = 0; t < n_tiles; ++t) mbar_init(TDONE(t), 128);
+        for (int q = 0; q < 4; ++q) s_next[q] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (warp >= 2) {
-        float *sG = reinterpret_cast<float *>(smem + TcSmem::g), *sG0 = reinterpret_cast<float *>(smem + TcSmem::g0);
-        float *sInvD = reinterpret_cast<float *>(smem + TcSmem::invd);
-        for (int t = threadIdx.x - 64; t < TC_KP * TC_KP; t += 256) { sG[t] = p.G[t]; sG0[t] = p.G0[t]; }
-        for (int t = threadIdx.x - 64; t < TC_KP; t += 256) sInvD[t] = (t < p.k) ? 1.f / p.G[t * TC_KP + t] : 0.f;
-    }
-    // generic-proxy zero fill must be visible to the async proxy (TMA / UMMA reads)
+    float *sD = reinterpret_cast<float *>(smem + TcSmem::dvec), *sInvD = sD + TC_KP;
+    if (p.mode == 0 && threadIdx.x < 2 * TC_KP) sD[threadIdx.x] = p.pack[2 * TC_KP * TC_KP + threadIdx.x];
+    // generic-proxy zero fill must be visible to the async proxy (TMA / UMMA)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tmem_c = tmem;             // columns [0,128): two C accumulators of 64 columns
-    const uint32_t tmem_d = tmem + 128;       // columns [128,512): twelve 128 x 32 accumulators
+    const uint32_t tmem_c = tmem;                       // columns [0,256): eight C accumulators
+    const uint32_t tmem_d = tmem + TC_CBUF * 32;        // columns [256,512): eight 128 x 32 accumulators
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
@@ -267,16 +280,15 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
-            constexpr uint32_t ID_P1_N64 = idesc_f16(128, 64, 0, 0);
-            constexpr uint32_t ID_P1_N32 = idesc_f16(128, 32, 0, 0);
-            constexpr uint32_t ID_P3 = idesc_f16(128, 32, 1, 0);
+            constexpr uint32_t ID_P1 = idesc_f16(128, 32, 0, 0, 0);
+            constexpr uint32_t ID_P3 = idesc_f16(128, 32, 1, 0, 0);
             int stage = 0, phase = 0;
             if (p.mode == 0) {
                 for (int t = 0; t < n_tiles; ++t) {
-                    const int b = t & 1;
-                    mbar_wait(CEMPTY(b), ((t >> 1) & 1) ^ 1);
+                    const int b = t % TC_CBUF;
+                    mbar_wait(CEMPTY(b), ((t / TC_CBUF) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t dC = tmem_c + b * 64;
+                    const uint32_t dC = tmem_c + b * 32;
                     for (int ch = 0; ch < p.n_chunks; ++ch) {
                         mbar_wait(FULL(stage), phase);
                         tc_fence_after();
@@ -285,9 +297,11 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                         const uint32_t ws = sbase + TcSmem::w + stage * TC_W_STAGE;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t dw = desc_sw128(ws + ks * 32, 16, 1024);
-                            tc_mma_f16(dC, desc_sw128(ahi + ks * 32, 16, 1024), dw, ID_P1_N64, (ch | ks) != 0);
-                            tc_mma_f16(dC, desc_sw128(alo + ks * 32, 16, 1024), dw, ID_P1_N32, 1);
+                            const uint64_t da_hi = desc_sw128(ahi + ks * 32, 16, 1024);
+                            const uint64_t dw_hi = desc_sw128(ws + ks * 32, 16, 1024);
+                            tc_mma_f16(dC, da_hi, dw_hi, ID_P1, (ch | ks) != 0);
+                            tc_mma_f16(dC, da_hi, desc_sw128(ws + 32 * 128 + ks * 32, 16, 1024), ID_P1, 1);
+                            tc_mma_f16(dC, desc_sw128(alo + ks * 32, 16, 1024), dw_hi, ID_P1, 1);
                         }
                         tc_commit(EMPTY(stage));
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -335,153 +349,138 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                 tc_commit(DFULL);
             }
         }
-    } else {
-        // =========================== solver / loader / drain warps ===========================
-        const int sw = warp - 2;                 // 0..7
-        const int grp = sw >> 2;                 // solver group: handles tiles t with (t & 1) == grp
+    } else if (warp == 2) {
+        // =========================== H tile loader ===========================
+        int use = 0;
+        for (int ps = 0; ps < n_pass; ++ps) {
+            for (int t = 0; t < n_tiles; ++t, ++use) {
+                const int hb = use & 1;
+                mbar_wait(TDONE(t), 0);
+                mbar_wait(HEMPTY(hb), ((use >> 1) & 1) ^ 1);
+                const uint4 *src = reinterpret_cast<const uint4 *>(my_img + (size_t)t * TC_H_TILE);
+                uint4 *dst = reinterpret_cast<uint4 *>(smem + TcSmem::h + hb * TC_H_TILE);
+#pragma unroll 8
+                for (int i = lane; i < TC_H_TILE / 16; i += 32) dst[i] = __ldcg(src + i);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(HFULL(hb));
+            }
+        }
+    } else if (warp >= 4) {
+        // =========================== solver warps ===========================
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-        const float *sG = reinterpret_cast<const float *>(smem + TcSmem::g);
-        const float *sG0 = reinterpret_cast<const float *>(smem + TcSmem::g0);
-        const float *sInvD = reinterpret_cast<const float *>(smem + TcSmem::invd);
+        const float descale = exp2f(-(float)(p.a_exp + *p.w_exp));
+        // fp16 scale of the H images: the previous max(H) maps to [8, 16), which leaves a factor 4096 of growth
+        // before fp16 overflows (flagged, never silent) while entries down to 1e-9 of the max keep their value
+        int h_exp = 0;
+        {
+            const float hm = __int_as_float(*p.hmax_prev);
+            if (hm > 0.f) {
+                int e;
+                frexpf(hm, &e);
+                h_exp = max(-100, min(100, 4 - e));
+            }
+        }
+        const float hscale = exp2f((float)h_exp);
         float hmax = 0.f;
-        if (p.mode == 0) {
-            const float descale = exp2f(-(float)(p.a_exp + *p.w_exp));
-            double lp = 0.0;
-            unsigned long long its = 0;
-            for (int t = grp; t < n_tiles; t += 2) {
-                const int b = t & 1;
-                mbar_wait(CFULL(b), (t >> 1) & 1);
+        bool ovf = false;
+        double lp = 0.0;
+        unsigned long long its = 0;
+        for (;;) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&s_next[quarter], 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= n_tiles) break;
+            const int lc = quarter * 32 + lane;                      // cell within the tile
+            const int cell = cell_begin + t * TC_TILE + lc;
+            const bool valid = cell < cell_end;
+            float h[32];
+            float *hrow = p.H + (size_t)(valid ? cell : cell_begin) * TC_KP;
+            if (p.mode == 0) {
+                const int b = t % TC_CBUF;
+                mbar_wait(CFULL(b), (t / TC_CBUF) & 1);
                 tc_fence_after();
-                float c[32], mu[32];
-                const uint32_t taddr = tmem_c + b * 64 + ((uint32_t)(quarter * 32) << 16);
-                tc_ld32(taddr, c);
-                tc_ld32(taddr + 32, mu);
+                float c[32];
+                float2 mu[16];
+                tc_ld32(tmem_c + b * 32 + ((uint32_t)(quarter * 32) << 16), c);
                 tc_fence_before();
                 mbar_arrive(CEMPTY(b));
-                const int cell = cell_begin + t * TC_TILE + quarter * 32 + lane;
-                if (cell < cell_end) {
-                    float h[32];
-                    float *hrow = p.H + (size_t)cell * TC_KP;
+                if (valid) {
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
                         const float4 v = reinterpret_cast<const float4 *>(hrow)[r];
-                        h[4 * r] = v.x; h[4 * r + 1] = v.y; h[4 * r + 2] = v.z; h[4 * r + 3] = v.w;
+                        h[4 * r] = v.x * sD[4 * r]; h[4 * r + 1] = v.y * sD[4 * r + 1];
+                        h[4 * r + 2] = v.z * sD[4 * r + 2]; h[4 * r + 3] = v.w * sD[4 * r + 3];
                     }
 #pragma unroll
-                    for (int f = 0; f < 32; ++f) {
-                        c[f] = (c[f] + mu[f]) * descale;
-                        mu[f] = p.l1 - c[f];
-                    }
-#pragma unroll 1
-                    for (int q = 0; q < p.k; ++q) {
-                        const float hq = hrow[q];
-                        const float4 *g4 = reinterpret_cast<const float4 *>(sG + q * TC_KP);
+                    for (int f = 0; f < 32; ++f) c[f] *= descale;
 #pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            const float4 g = g4[r];
-                            mu[4 * r + 0] = fmaf(hq, g.x, mu[4 * r + 0]);
-                            mu[4 * r + 1] = fmaf(hq, g.y, mu[4 * r + 1]);
-                            mu[4 * r + 2] = fmaf(hq, g.z, mu[4 * r + 2]);
-                            mu[4 * r + 3] = fmaf(hq, g.w, mu[4 * r + 3]);
-                        }
-                    }
-                    its += scd_ls_thread<TC_KP>(h, mu, sG, sInvD, p.k, p.max_iter, p.rel_tol);
+                    for (int r = 0; r < 16; ++r)
+                        mu[r] = make_float2((p.l1 - c[2 * r]) * sInvD[2 * r], (p.l1 - c[2 * r + 1]) * sInvD[2 * r + 1]);
+                    scd_mu_init<TC_KP>(mu, hrow, sD, p.k);
+                    its += scd_ls_thread<TC_KP>(h, mu, p.k, p.max_iter, p.rel_tol);
 #pragma unroll
-                    for (int r = 0; r < 8; ++r)
+                    for (int r = 0; r < 8; ++r) {
+                        h[4 * r] *= sInvD[4 * r]; h[4 * r + 1] *= sInvD[4 * r + 1];
+                        h[4 * r + 2] *= sInvD[4 * r + 2]; h[4 * r + 3] *= sInvD[4 * r + 3];
                         reinterpret_cast<float4 *>(hrow)[r] = make_float4(h[4 * r], h[4 * r + 1], h[4 * r + 2], h[4 * r + 3]);
-                    // loss partial h' G0 h - 2 h' c  (mu reused for G0 h)
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) mu[r] = 0.f;
-#pragma unroll 1
-                    for (int q = 0; q < p.k; ++q) {
-                        const float hq = hrow[q];
-                        const float4 *g4 = reinterpret_cast<const float4 *>(sG0 + q * TC_KP);
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            const float4 g = g4[r];
-                            mu[4 * r + 0] = fmaf(hq, g.x, mu[4 * r + 0]);
-                            mu[4 * r + 1] = fmaf(hq, g.y, mu[4 * r + 1]);
-                            mu[4 * r + 2] = fmaf(hq, g.z, mu[4 * r + 2]);
-                            mu[4 * r + 3] = fmaf(hq, g.w, mu[4 * r + 3]);
-                        }
                     }
+                    // loss partial h' G0 h - 2 h' c  (mu reused for G0 h)
+                    scd_g0_times<TC_KP>(mu, hrow, p.k);
                     float s = 0.f;
 #pragma unroll
-                    for (int f = 0; f < 32; ++f) {
-                        s = fmaf(h[f], mu[f] - 2.f * c[f], s);
-                        hmax = fmaxf(hmax, h[f]);
-                    }
+                    for (int f = 0; f < 32; ++f) s = fmaf(h[f], ((f & 1) ? mu[f / 2].y : mu[f / 2].x) - 2.f * c[f], s);
                     lp += (double)s;
+                } else {
+#pragma unroll
+                    for (int f = 0; f < 32; ++f) h[f] = 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) v = reinterpret_cast<const float4 *>(hrow)[r];
+                    h[4 * r] = v.x; h[4 * r + 1] = v.y; h[4 * r + 2] = v.z; h[4 * r + 3] = v.w;
                 }
             }
+            // ---- split fp16 image of this cell's column of the tile: x = h * 2^h_exp, hi = fp16(x), lo = fp16(x - hi);
+            // K-major [factor][cell] sub-tiles of 64 cells, 128 B rows, swizzle-128B by hand
+            uint8_t *img = my_img + (size_t)t * TC_H_TILE + (lc >> 6) * TC_H_SUB;
+            const int cc = lc & 63;
+#pragma unroll
+            for (int f = 0; f < 32; ++f) {
+                hmax = fmaxf(hmax, h[f]);
+                float x = h[f] * hscale;
+                if (x > 60000.f) { x = 60000.f; ovf = true; }
+                const __half hi = __float2half_rn(x);
+                const __half lo = __float2half_rn(x - __half2float(hi));
+                const int off = f * 128 + ((((cc >> 3) ^ (f & 7)) << 4) | ((cc & 7) << 1));
+                *reinterpret_cast<__half *>(img + off) = hi;
+                *reinterpret_cast<__half *>(img + 2 * TC_H_SUB + off) = lo;
+            }
+            __threadfence();
+            mbar_arrive(TDONE(t));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+        if (lane == 0) atomicMax(p.hmax_next, __float_as_int(hmax));
+        if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicOr(p.overflow, 1);
+        if (p.mode == 0) {
             lp = warp_sum(lp);
-            double itd = warp_sum((double)its);
+            const double itd = warp_sum((double)its);
             if (lane == 0) {
                 atomicAdd(&p.scal->loss_part, lp);
                 atomicAdd(&p.scal->sweeps_h, (unsigned long long)(itd + 0.5));
             }
-        } else {
-            // phase 3 only: the scale comes from a max scan over my cells' H rows
-            for (int i = threadIdx.x - 64; i < (cell_end - cell_begin) * TC_KP; i += 256)
-                hmax = fmaxf(hmax, p.H[(size_t)cell_begin * TC_KP + i]);
         }
-        // ---- per-CTA H scale: a power of two that brings the largest entry of my cells to ~2^14
-        atomicMax(s_hmax, __float_as_int(hmax));
-        __threadfence_block();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float hm = __int_as_float(*s_hmax);
-        int h_exp = 0;
-        if (hm > 0.f) {
-            int e;
-            frexpf(hm, &e);  // hm = f * 2^e, f in [0.5, 1)
-            h_exp = 14 - e;
-        }
-        h_exp = max(-100, min(100, h_exp));
-        const float hscale = exp2f((float)h_exp);
+        // ---- drain each gene sub-pass: D (128 genes x 32) -> red.add into B
         const float bdescale = exp2f(-(float)(p.a_exp + h_exp));
-
-        // ---- phase 3: H tile loader (all 256 threads) and accumulator drain
-        const int ltid = threadIdx.x - 64;
-        const int lcell = ltid & 127, fhalf = ltid >> 7;   // this thread converts factors fhalf*16 .. +16 of one cell
-        int use = 0;
+        const int sgrp = (warp - 4) >> 2;        // 0..2: which M-tiles of the sub-pass this warp drains
         for (int ps = 0; ps < n_pass; ++ps) {
             const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
-            for (int t = 0; t < n_tiles; ++t, ++use) {
-                const int hb = use & 1;
-                mbar_wait(HEMPTY(hb), ((use >> 1) & 1) ^ 1);
-                const int cell = cell_begin + t * TC_TILE + lcell;
-                float v[16];
-                if (cell < cell_end) {
-                    const float4 *src = reinterpret_cast<const float4 *>(p.H + (size_t)cell * TC_KP + fhalf * 16);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float4 x = src[r];
-                        v[4 * r] = x.x; v[4 * r + 1] = x.y; v[4 * r + 2] = x.z; v[4 * r + 3] = x.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) v[r] = 0.f;
-                }
-                // K-major [factor][cell] fp16 sub-tiles of 64 cells, 128 B rows, swizzle-128B applied by hand
-                uint8_t *tile = smem + TcSmem::h + hb * TC_H_TILE + (lcell >> 6) * TC_H_SUB;
-                const int cc = lcell & 63;
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const int f = fhalf * 16 + r;
-                    const float x = v[r] * hscale;
-                    const __half hi = __float2half_rn(x);
-                    const __half lo = __float2half_rn(x - __half2float(hi));
-                    const int off = f * 128 + ((((cc >> 3) ^ (f & 7)) << 4) | ((cc & 7) << 1));
-                    *reinterpret_cast<__half *>(tile + off) = hi;
-                    *reinterpret_cast<__half *>(tile + 2 * TC_H_SUB + off) = lo;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(HFULL(hb));
-            }
-            // ---- drain this gene sub-pass: D (128 genes x 32) -> red.add into B
             mbar_wait(DFULL, ps & 1);
             tc_fence_after();
-            for (int mt = mt0 + grp; mt < mt1; mt += 2) {
+            for (int mt = mt0 + sgrp; mt < mt1; mt += TC_SOLVER_WARPS / 4) {
                 float d[32];
                 tc_ld32(tmem_d + (mt - mt0) * 32 + ((uint32_t)(quarter * 32) << 16), d);
                 const int gene = mt * 128 + quarter * 32 + lane;
@@ -559,7 +558,9 @@ struct TcMatrix {
     bool ready = false;
     int n = 0, m = 0, n_pad = 0, a_exp = 0, sm_count = 148;
     __half *Ahi = nullptr, *Alo = nullptr, *Wst = nullptr;
-    int *dev_ints = nullptr;   // [0] W max bits, [1] w_exp, [2] scratch max bits
+    int *dev_ints = nullptr;   // [0] W max bits, [1] w_exp, [2] max(H) bits before the pass, [3] after, [4] overflow flag
+    uint8_t *Himg = nullptr;   // split 16-bit H tile images, [grid][tiles_per_cta][TC_H_TILE]
+    int grid = 0, tiles_per_cta = 0;
     CUtensorMap map_ahi, map_alo, map_w;
     const float *src = nullptr;
 };
@@ -602,7 +603,7 @@ static inline void tc_make_map(CUtensorMap *map, void *base, uint64_t inner, uin
 static inline bool tc_supported(int n, int m, int k)
 {
     // shape limits of this engine: k <= 32; smaller problems than one wave gain nothing
-    return k >= 1 && k <= TC_KP && n >= 64 && m >= 128;
+    return k >= 1 && k <= TC_KP && n >= 64 && m >= 128 && (long long)m <= 148ll * TC_MAX_TILES * TC_TILE / 2;
 }
 
 static inline void tc_release(TcMatrix &tc)
@@ -611,6 +612,7 @@ static inline void tc_release(TcMatrix &tc)
     if (tc.Alo) cudaFree(tc.Alo);
     if (tc.Wst) cudaFree(tc.Wst);
     if (tc.dev_ints) cudaFree(tc.dev_ints);
+    if (tc.Himg) cudaFree(tc.Himg);
     tc = TcMatrix();
 }
 
@@ -625,8 +627,15 @@ static inline void tc_prepare(TcMatrix &tc, const float *dA, size_t ldA, int n, 
     CUDA_CHECK(cudaMalloc(&tc.Ahi, cnt * sizeof(__half)));
     CUDA_CHECK(cudaMalloc(&tc.Alo, cnt * sizeof(__half)));
     CUDA_CHECK(cudaMalloc(&tc.Wst, (size_t)64 * tc.n_pad * sizeof(__half)));
-    CUDA_CHECK(cudaMalloc(&tc.dev_ints, 4 * sizeof(int)));
-    CUDA_CHECK(cudaMemsetAsync(tc.dev_ints, 0, 4 * sizeof(int), st));
+    CUDA_CHECK(cudaMalloc(&tc.dev_ints, 8 * sizeof(int)));
+    {
+        const int groups = (m + TC_GROUP - 1) / TC_GROUP;
+        tc.grid = std::min(sm_count, groups);
+        const int max_groups = (groups + tc.grid - 1) / tc.grid;
+        tc.tiles_per_cta = (max_groups * TC_GROUP + TC_TILE - 1) / TC_TILE;
+        CUDA_CHECK(cudaMalloc(&tc.Himg, (size_t)tc.grid * tc.tiles_per_cta * TC_H_TILE));
+    }
+    CUDA_CHECK(cudaMemsetAsync(tc.dev_ints, 0, 8 * sizeof(int), st));
     tc.a_exp = 0;
     if (a_max > 0) {
         int e;
@@ -655,21 +664,40 @@ static inline void tc_update_w(TcMatrix &tc, const float *Wt, cudaStream_t st)
 
 // one pass.  mode 0: H update (phase 1 + solve) followed by B = A H' of the new H; mode 1: B = A H' only.
 // B must be zeroed by the caller.  launches: 1 (+3 for the W split in mode 0)
-static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, const float *G, const float *G0, float l1, int k,
-                           int max_iter, float rel_tol, float *B, FitScalars *scal, cudaStream_t st)
+static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, const float *pack, float l1, int k, int max_iter,
+                           float rel_tol, float *B, FitScalars *scal, cudaStream_t st)
 {
-    if (mode == 0) tc_update_w(tc, Wt, st);
+    if (mode == 0)
+        CUDA_CHECK(cudaMemcpyToSymbolAsync(c_gram, pack, sizeof(float) * 2 * TC_KP * TC_KP, 0, cudaMemcpyDeviceToDevice, st));
+    if (mode == 0) {
+        tc_update_w(tc, Wt, st);
+        // max(H) of the previous pass becomes the scale reference of this one
+        CUDA_CHECK(cudaMemcpyAsync(tc.dev_ints + 2, tc.dev_ints + 3, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    } else {
+        CUDA_CHECK(cudaMemsetAsync(tc.dev_ints + 2, 0, sizeof(int), st));
+        tc_absmax_kernel<<<148, 256, 0, st>>>(H, (size_t)tc.m * TC_KP, tc.dev_ints + 2);
+    }
+    CUDA_CHECK(cudaMemsetAsync(tc.dev_ints + 3, 0, sizeof(int), st));
     TcPassParams p;
     p.n = tc.n; p.m = tc.m; p.k = k;
     p.n_mtiles = (tc.n + 127) / 128;
     p.n_chunks = 2 * p.n_mtiles;
     p.mode = mode;
-    p.G = G; p.G0 = G0; p.l1 = l1; p.max_iter = max_iter; p.rel_tol = rel_tol;
+    p.pack = pack; p.l1 = l1; p.max_iter = max_iter; p.rel_tol = rel_tol;
     p.H = H; p.B = B; p.scal = scal;
     p.w_exp = tc.dev_ints + 1;
+    p.hmax_prev = tc.dev_ints + 2;
+    p.hmax_next = tc.dev_ints + 3;
+    p.overflow = tc.dev_ints + 4;
     p.a_exp = tc.a_exp;
     p.groups_total = (tc.m + TC_GROUP - 1) / TC_GROUP;
-    const int grid = std::min(tc.sm_count, p.groups_total);
+    p.Himg = tc.Himg;
+    p.tiles_per_cta = tc.tiles_per_cta;
+    const int grid = tc.grid;
+    if (tc.tiles_per_cta > TC_MAX_TILES) {
+        set_error("tcgen05 engine: too many cells per SM");
+        throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};
+    }
     tc_pass_kernel<<<grid, TC_THREADS, TcSmem::total + 1024, st>>>(tc.map_ahi, tc.map_alo, tc.map_w, p);
     CUDA_CHECK(cudaGetLastError());
 }

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "common.cuh"
@@ -128,7 +129,7 @@ struct swne_nmf_handle_s {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     // per fit workspaces (grown on demand)
-    swne::DevBuf<float> Wt, H, C, B, G, G0, cs32;
+    swne::DevBuf<float> Wt, H, C, B, G, pack;   // pack: GramPack (kernels_simt.cuh); G: small scratch of the rSVD
     swne::DevBuf<double> G64w, G64h, stage;
     swne::DevBuf<swne::MatStats> dstats;
     swne::DevBuf<swne::FitScalars> dscal;
@@ -310,11 +311,19 @@ struct Prof {
     std::vector<Rec> recs;
     long long launches[SWNE_PROF_SLOTS] = {0};
     long long total_launches = 0;
+    std::vector<cudaEvent_t> pool;
+    size_t pool_next = 0;
+    cudaEvent_t get()
+    {
+        if (pool_next == pool.size()) {
+            for (int i = 0; i < 256; ++i) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        }
+        return pool[pool_next++];
+    }
     void begin(int slot)
     {
         if (!on) return;
-        Rec r{slot, nullptr, nullptr};
-        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        Rec r{slot, get(), get()};
         cudaEventRecord(r.a, st);
         recs.push_back(r);
     }
@@ -334,27 +343,37 @@ struct Prof {
             cudaEventSynchronize(r.b);
             cudaEventElapsedTime(&ms, r.a, r.b);
             res->prof_ms[r.slot] += ms;
-            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
         }
         recs.clear();
+        for (auto e : pool) cudaEventDestroy(e);
+        pool.clear(); pool_next = 0;
     }
 };
 
 // ------------------------------------------------------------------------------------------------
 // building blocks
 // ------------------------------------------------------------------------------------------------
+// zero `bytes` (multiple of 4, pointer 16-byte aligned) with a kernel
+static void dev_zero(void *ptr, size_t bytes, cudaStream_t st)
+{
+    const size_t n16 = bytes / 16;
+    const int ntail = (int)((bytes % 16) / 4);
+    const int grid = (int)std::min<size_t>(std::max<size_t>(1, (n16 + 255) / 256), 296);
+    zero_fill_kernel<<<grid, 256, 0, st>>>((uint4 *)ptr, n16, (uint32_t *)((char *)ptr + n16 * 16), ntail);
+    CUDA_CHECK(cudaGetLastError());
+}
 static void launch_gram(swne_nmf_handle_s *h, int KPv, const float *X, int rows, double *G64 /* KP*KP + KP */)
 {
-    CUDA_CHECK(cudaMemsetAsync(G64, 0, sizeof(double) * (size_t)(KPv * KPv + KPv), h->stream));
+    dev_zero(G64, sizeof(double) * (size_t)(KPv * KPv + KPv), h->stream);
     ops_of(KPv).gram(X, rows, G64, G64 + KPv * KPv, h->stream);
     CUDA_CHECK(cudaGetLastError());
 }
-static void launch_finalize_gram(swne_nmf_handle_s *h, int k, int KPv, const double *G64, float *G, float *G0, float *cs32,
-                                 double p0, double p1)
+static void launch_finalize_gram(swne_nmf_handle_s *h, int k, int KPv, const double *G64, float *pack, double p0, double p1)
 {
-    finalize_gram_kernel<<<(KPv * KPv + 255) / 256, 256, 0, h->stream>>>(G64, G, G0, cs32, G64 + KPv * KPv, k, KPv, p0, p1);
+    finalize_gram_kernel<<<1, 256, 0, h->stream>>>(G64, pack, k, KPv, p0, p1);
     CUDA_CHECK(cudaGetLastError());
 }
+static float *pack_colsum(float *pack, int KPv) { return pack + 2 * KPv * KPv + 2 * KPv; }
 static void launch_contract_cells(swne_nmf_handle_s *h, int KPv, const float *Wt, float *C)
 {
     ops_of(KPv).contract_cells(h->dA, h->ldA, h->n, h->m, Wt, C, h->stream);
@@ -371,10 +390,10 @@ static void launch_contract_genes(swne_nmf_handle_s *h, int KPv, const float *H,
     ops_of(KPv).contract_genes(h->dA, h->ldA, h->n, h->m, H, B, cpc, chunks, h->stream);
     CUDA_CHECK(cudaGetLastError());
 }
-static void launch_solve(swne_nmf_handle_s *h, int k, int KPv, float *X, const float *C, const float *G, const float *G0,
-                         float l1, int cols, int max_iter, float rel_tol, unsigned long long *sweeps, double *loss_part)
+static void launch_solve(swne_nmf_handle_s *h, int k, int KPv, float *X, const float *C, const float *pack, float l1, int cols,
+                         int max_iter, float rel_tol, unsigned long long *sweeps, double *loss_part)
 {
-    ops_of(KPv).solve(X, C, G, G0, l1, k, cols, max_iter, rel_tol, sweeps, loss_part, h->stream);
+    ops_of(KPv).solve(X, C, pack, l1, k, cols, max_iter, rel_tol, sweeps, loss_part, h->stream);
     CUDA_CHECK(cudaGetLastError());
 }
 static void launch_kl(swne_nmf_handle_s *h, int k, int KPv, const int *ptr, const int *idx, const float *val, float *X,
@@ -483,7 +502,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     // ---- workspaces
     h->Wt.reserve((size_t)n * KPv); h->H.reserve((size_t)m * KPv);
     h->C.reserve((size_t)m * KPv); h->B.reserve((size_t)n * KPv);
-    h->G.reserve((size_t)KPv * KPv); h->G0.reserve((size_t)KPv * KPv); h->cs32.reserve((size_t)KPv);
+    h->pack.reserve((size_t)gram_pack_floats(KPv));
     h->G64w.reserve(GS); h->G64h.reserve(GS);
     h->dscal.reserve(1); h->red.reserve(8);
     if (!h->pinned) {
@@ -519,6 +538,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     Prof prof;
     prof.on = p.profile != 0;
     prof.st = st;
+    if (prof.on) { prof.get(); prof.pool_next = 0; }
     const float inner_tol = (float)p.inner_rel_tol;
     const bool mse = p.loss == SWNE_LOSS_MSE;
 
@@ -531,7 +551,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     if (engine == SWNE_ENGINE_TC) {
         prof.begin(0);
         CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
-        tc_pass(h->tc, 1, h->Wt.p, h->H.p, h->G.p, h->G.p, 0.f, k, p.inner_max_iter, 0.f, h->B.p, h->dscal.p, st);
+        tc_pass(h->tc, 1, h->Wt.p, h->H.p, nullptr, 0.f, k, p.inner_max_iter, 0.f, h->B.p, h->dscal.p, st);
         prof.end(0, tc_pass_launches(1));
         if (h->nranks > 1) allreduce(h, h->B.p, (size_t)n * KPv, nullptr, 0);
         have_B = true;
@@ -610,24 +630,24 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
                 if (h->nranks > 1) { prof.begin(6); allreduce(h, h->B.p, (size_t)n * KPv, nullptr, 0); prof.end(6, 1); }
             }
             prof.begin(3);
-            launch_finalize_gram(h, k, KPv, h->G64h.p, h->G.p, nullptr, nullptr, p.alpha[0], p.alpha[1]);
-            launch_solve(h, k, KPv, h->Wt.p, h->B.p, h->G.p, nullptr, (float)p.alpha[2], n, p.inner_max_iter, inner_tol,
+            launch_finalize_gram(h, k, KPv, h->G64h.p, h->pack.p, p.alpha[0], p.alpha[1]);
+            launch_solve(h, k, KPv, h->Wt.p, h->B.p, h->pack.p, (float)p.alpha[2], n, p.inner_max_iter, inner_tol,
                          &h->dscal.p->sweeps_w, nullptr);
             prof.end(3, 2);
             // ---------------- H update: A ~ Wt' H
             prof.begin(4);
             launch_gram(h, KPv, h->Wt.p, n, h->G64w.p);
-            launch_finalize_gram(h, k, KPv, h->G64w.p, h->G.p, h->G0.p, nullptr, p.beta[0], p.beta[1]);
+            launch_finalize_gram(h, k, KPv, h->G64w.p, h->pack.p, p.beta[0], p.beta[1]);
             prof.end(4, 2);
             if (engine == SWNE_ENGINE_TC) {
                 prof.begin(0);
                 CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
-                tc_pass(h->tc, 0, h->Wt.p, h->H.p, h->G.p, h->G0.p, (float)p.beta[2], k, p.inner_max_iter, inner_tol, h->B.p,
+                tc_pass(h->tc, 0, h->Wt.p, h->H.p, h->pack.p, (float)p.beta[2], k, p.inner_max_iter, inner_tol, h->B.p,
                         h->dscal.p, st);
                 prof.end(0, tc_pass_launches(0));
-                prof.begin(4);
+                prof.begin(7);
                 launch_gram(h, KPv, h->H.p, m, h->G64h.p);
-                prof.end(4, 1);
+                prof.end(7, 1);
                 if (h->nranks > 1) {
                     prof.begin(6);
                     allreduce(h, h->B.p, (size_t)n * KPv, h->G64h.p, GS);
@@ -639,7 +659,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
                 launch_contract_cells(h, KPv, h->Wt.p, h->C.p);
                 prof.end(0, 1);
                 prof.begin(1);
-                launch_solve(h, k, KPv, h->H.p, h->C.p, h->G.p, h->G0.p, (float)p.beta[2], m, p.inner_max_iter, inner_tol,
+                launch_solve(h, k, KPv, h->H.p, h->C.p, h->pack.p, (float)p.beta[2], m, p.inner_max_iter, inner_tol,
                              &h->dscal.p->sweeps_h, &h->dscal.p->loss_part);
                 prof.end(1, 1);
                 prof.begin(4);
@@ -655,16 +675,16 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         } else {
             // ---------------- mkl: W update on the by-gene view, H update on the by-cell view
             prof.begin(5);
-            launch_finalize_gram(h, k, KPv, h->G64h.p, h->G.p, nullptr, h->cs32.p, 0.0, 0.0);
-            launch_kl(h, k, KPv, h->sp.gptr.p, h->sp.gidx.p, h->sp.gval.p, h->Wt.p, h->H.p, h->cs32.p, p.alpha, n,
+            launch_finalize_gram(h, k, KPv, h->G64h.p, h->pack.p, 0.0, 0.0);
+            launch_kl(h, k, KPv, h->sp.gptr.p, h->sp.gidx.p, h->sp.gval.p, h->Wt.p, h->H.p, pack_colsum(h->pack.p, KPv), p.alpha, n,
                       p.inner_max_iter, inner_tol, &h->dscal.p->sweeps_w, h->dscal.p, 0);
             prof.end(5, 2);
             prof.begin(4);
             launch_gram(h, KPv, h->Wt.p, n, h->G64w.p);
-            launch_finalize_gram(h, k, KPv, h->G64w.p, h->G.p, nullptr, h->cs32.p, 0.0, 0.0);
+            launch_finalize_gram(h, k, KPv, h->G64w.p, h->pack.p, 0.0, 0.0);
             prof.end(4, 2);
             prof.begin(5);
-            launch_kl(h, k, KPv, h->sp.cptr.p, h->sp.cidx.p, h->sp.cval.p, h->H.p, h->Wt.p, h->cs32.p, p.beta, m,
+            launch_kl(h, k, KPv, h->sp.cptr.p, h->sp.cidx.p, h->sp.cval.p, h->H.p, h->Wt.p, pack_colsum(h->pack.p, KPv), p.beta, m,
                       p.inner_max_iter, inner_tol, &h->dscal.p->sweeps_h, h->dscal.p,
                       (i % p.trace == 0 || i == p.max_iter - 1) ? 1 : 0);
             prof.end(5, 1);
@@ -732,7 +752,7 @@ static int nnlm_impl(swne_nmf_handle_s *h, int side, int k, const double *X, dou
     cudaStream_t st = h->stream;
     h->Wt.reserve((size_t)n * KPv); h->H.reserve((size_t)m * KPv);
     h->C.reserve((size_t)std::max(n, m) * KPv);
-    h->G.reserve((size_t)KPv * KPv); h->G0.reserve((size_t)KPv * KPv); h->cs32.reserve((size_t)KPv);
+    h->pack.reserve((size_t)gram_pack_floats(KPv));
     h->G64w.reserve(GS); h->dscal.reserve(1);
     CUDA_CHECK(cudaMemsetAsync(h->dscal.p, 0, sizeof(FitScalars), st));
     float *fixed, *solve;
@@ -752,19 +772,19 @@ static int nnlm_impl(swne_nmf_handle_s *h, int side, int k, const double *X, dou
     }
     launch_gram(h, KPv, fixed, fixed_rows, h->G64w.p);
     if (loss == SWNE_LOSS_MSE) {
-        launch_finalize_gram(h, k, KPv, h->G64w.p, h->G.p, nullptr, nullptr, pen[0], pen[1]);
+        launch_finalize_gram(h, k, KPv, h->G64w.p, h->pack.p, pen[0], pen[1]);
         if (side == 0) launch_contract_cells(h, KPv, fixed, h->C.p);
         else launch_contract_genes(h, KPv, fixed, h->C.p);
-        launch_solve(h, k, KPv, solve, h->C.p, h->G.p, nullptr, (float)pen[2], cols, max_iter, (float)rel_tol,
+        launch_solve(h, k, KPv, solve, h->C.p, h->pack.p, (float)pen[2], cols, max_iter, (float)rel_tol,
                      &h->dscal.p->sweeps_h, nullptr);
     } else if (loss == SWNE_LOSS_MKL) {
         ensure_sparse(h);
-        launch_finalize_gram(h, k, KPv, h->G64w.p, h->G.p, nullptr, h->cs32.p, 0.0, 0.0);
+        launch_finalize_gram(h, k, KPv, h->G64w.p, h->pack.p, 0.0, 0.0);
         if (side == 0)
-            launch_kl(h, k, KPv, h->sp.cptr.p, h->sp.cidx.p, h->sp.cval.p, solve, fixed, h->cs32.p, pen, cols, max_iter,
+            launch_kl(h, k, KPv, h->sp.cptr.p, h->sp.cidx.p, h->sp.cval.p, solve, fixed, pack_colsum(h->pack.p, KPv), pen, cols, max_iter,
                       (float)rel_tol, &h->dscal.p->sweeps_h, h->dscal.p, 0);
         else
-            launch_kl(h, k, KPv, h->sp.gptr.p, h->sp.gidx.p, h->sp.gval.p, solve, fixed, h->cs32.p, pen, cols, max_iter,
+            launch_kl(h, k, KPv, h->sp.gptr.p, h->sp.gidx.p, h->sp.gval.p, solve, fixed, pack_colsum(h->pack.p, KPv), pen, cols, max_iter,
                       (float)rel_tol, &h->dscal.p->sweeps_h, h->dscal.p, 0);
     } else {
         FAIL(SWNE_ERR_BAD_ARG, "loss must be mse or mkl");
@@ -1097,7 +1117,7 @@ int swne_nmf_destroy(swne_nmf_handle_t h)
     h->sp.cptr.release(); h->sp.cidx.release(); h->sp.gptr.release(); h->sp.gidx.release();
     h->sp.cval.release(); h->sp.gval.release(); h->sp.ajt.release();
     tc_release(h->tc);
-    h->Wt.release(); h->H.release(); h->C.release(); h->B.release(); h->G.release(); h->G0.release(); h->cs32.release();
+    h->Wt.release(); h->H.release(); h->C.release(); h->B.release(); h->G.release(); h->pack.release();
     h->G64w.release(); h->G64h.release(); h->stage.release(); h->dstats.release(); h->dscal.release(); h->red.release();
     if (h->pinned) cudaFreeHost(h->pinned);
     cudaStreamDestroy(h->stream);

@@ -60,6 +60,25 @@ def test_mse_vs_oracle(handle, n, m, kt, k, seed):
     assert max_rel(r["average_epochs"], ref["average_epochs"]) < 0.35      # fp32 stagnates earlier than fp64
 
 
+@pytest.mark.parametrize("n,m,kt,k,seed", [(256, 384, 5, 8, 1), (2000, 3000, 9, 16, 1), (3000, 4500, 9, 30, 2), (301, 517, 6, 30, 2),
+                                           (1000, 4133, 6, 3, 4)])
+def test_tcgen05_engine_vs_oracle(handle, n, m, kt, k, seed):
+    """the fused TMA/tcgen05 pass (split-fp16 3-product contractions) against the fp64 oracle"""
+    from oracle import nnmf_ref
+    A = small_matrix(n, m, kt, seed)
+    W0, H0 = seeded_init(A, k, seed)
+    iters = 15
+    ref = nnmf_ref(A, k, W0, H0, max_iter=iters, trace=1, rel_tol=-1.0)
+    handle.set_matrix(A)
+    r = handle.fit(k, W0, H0, max_iter=iters, trace=1, rel_tol=-1.0, engine="tc")
+    assert r.options["engine"] == "tc"
+    _check_against(r, ref)
+    assert r["H"].min() >= 0 and r["W"].min() >= 0
+    # penalties go through the same pass
+    kw = dict(alpha=[0.05, 0.02, 0.01], beta=[0.03, 0.01, 0.02], max_iter=8, trace=1, rel_tol=-1.0)
+    _check_against(handle.fit(k, W0, H0, engine="tc", **kw), nnmf_ref(A, k, W0, H0, **kw))
+
+
 def test_mse_default_stopping_rule_matches(handle):
     from oracle import nnmf_ref
     A = small_matrix(300, 500, 6, 4)
@@ -110,11 +129,12 @@ def test_csc_input_equals_dense(handle):
     W0, H0 = seeded_init(A, 5, 7)
     handle.set_matrix(A)
     info_d = handle.matrix_info()
-    rd = handle.fit(5, W0, H0, max_iter=10, trace=1, rel_tol=-1.0)
+    # the CUDA-core engine is run-to-run deterministic at this size (one cell chunk, no atomics race)
+    rd = handle.fit(5, W0, H0, max_iter=10, trace=1, rel_tol=-1.0, engine="simt")
     S = scipy.sparse.csc_matrix(A)
     handle.set_matrix(S)
     info_s = handle.matrix_info()
-    rs = handle.fit(5, W0, H0, max_iter=10, trace=1, rel_tol=-1.0)
+    rs = handle.fit(5, W0, H0, max_iter=10, trace=1, rel_tol=-1.0, engine="simt")
     assert info_d["nnz"] == info_s["nnz"] == S.nnz
     assert abs(info_d["sumsq"] - info_s["sumsq"]) < 1e-9 * info_d["sumsq"]
     assert np.array_equal(rd["H"], rs["H"]) and np.array_equal(rd["W"], rs["W"])
@@ -123,10 +143,12 @@ def test_csc_input_equals_dense(handle):
     S32 = S.astype(np.float32).tolil(); S32[:, 3] = 0; S32[5, :] = 0
     S32 = S32.tocsc()
     handle.set_matrix(S32)
-    r32 = handle.fit(5, W0, H0, max_iter=5, trace=1, rel_tol=-1.0)
+    r32 = handle.fit(5, W0, H0, max_iter=5, trace=1, rel_tol=-1.0, engine="simt")
+    r32t = handle.fit(5, W0, H0, max_iter=5, trace=1, rel_tol=-1.0, engine="tc")
     handle.set_matrix(np.asfortranarray(S32.toarray()))
-    rdd = handle.fit(5, W0, H0, max_iter=5, trace=1, rel_tol=-1.0)
+    rdd = handle.fit(5, W0, H0, max_iter=5, trace=1, rel_tol=-1.0, engine="simt")
     assert np.array_equal(r32["H"], rdd["H"])
+    assert rel_fro(r32t["H"], rdd["H"]) < 1e-4 and rel_fro(r32t["W"], rdd["W"]) < 1e-4
 
 
 def test_float32_and_device_resident_inputs(handle):
@@ -134,10 +156,10 @@ def test_float32_and_device_resident_inputs(handle):
     A = small_matrix(120, 200, 4, 8)
     W0, H0 = seeded_init(A, 4, 8)
     handle.set_matrix(A.astype(np.float32))
-    r32 = handle.fit(4, W0, H0, max_iter=8, trace=1, rel_tol=-1.0)
+    r32 = handle.fit(4, W0, H0, max_iter=8, trace=1, rel_tol=-1.0, engine="simt")
     dA = torch.from_numpy(np.ascontiguousarray(A.astype(np.float32).T)).cuda()      # (cells, genes)
     handle.set_matrix(dA)
-    rdev = handle.fit(4, W0, H0, max_iter=8, trace=1, rel_tol=-1.0)
+    rdev = handle.fit(4, W0, H0, max_iter=8, trace=1, rel_tol=-1.0, engine="simt")
     assert np.array_equal(r32["W"], rdev["W"]) and np.array_equal(r32["H"], rdev["H"])
     handle.set_matrix(A)       # release the borrowed tensor
 
