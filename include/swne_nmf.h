@@ -72,8 +72,9 @@ typedef struct swne_nmf_params {
     int trace;             /* <=0 -> NNLM default 100/inner_max_iter; error block every `trace` iterations */
     int verbose;           /* 0 silent, 2 prints the per-trace table to stderr */
     int engine;            /* SWNE_ENGINE_* */
-    int full_traces;       /* 1: also evaluate the loss that is not being optimised (mkl in an mse fit)
-                              at every trace point, as NNLM does; 0: only in the final error block */
+    int full_traces;       /* the loss that is not being optimised (mkl in an mse fit) is evaluated
+                              1: at every trace point, as NNLM does; 0: only in the final error block;
+                              -1: never (NaN in the mkl trace) */
     int profile;           /* 1: bracket every kernel family with CUDA events (disables graph replay) */
 } swne_nmf_params_t;
 

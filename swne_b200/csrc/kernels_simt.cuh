@@ -205,7 +205,7 @@ __host__ __device__ constexpr int gram_pack_floats(int KP) { return 2 * KP * KP 
 // the update is a no-op, which is exactly scd_ls_update's "if (tmp != h)" skip; padded coordinates
 // (kk >= k: h = 0, mu >= 0, zero row of G') are no-ops too.  mu is held as float2 pairs and updated with
 // the packed FFMA2 of sm_100 (two fp32 FMAs per issue slot).
-template <int KP, bool ANY_CHANGE>
+template <int KP, bool ANY_CHANGE, bool PACKED = true>
 __device__ __forceinline__ void scd_ls_block8(float (&h)[KP], float2 (&mu)[KP / 2], int kb, float rel_tol, unsigned &changed)
 {
 #pragma unroll
@@ -220,10 +220,20 @@ __device__ __forceinline__ void scd_ls_block8(float (&h)[KP], float2 (&mu)[KP / 
         const float tmp = fmaxf(h[kk] - mk, 0.f);
         const float d = tmp - h[kk];
         const float2 d2 = make_float2(d, d);
+        if (PACKED) {
 #pragma unroll
-        for (int r = 0; r < KP / 4; ++r) {
-            mu[2 * r + 0] = __ffma2_rn(d2, make_float2(g[r].x, g[r].y), mu[2 * r + 0]);
-            mu[2 * r + 1] = __ffma2_rn(d2, make_float2(g[r].z, g[r].w), mu[2 * r + 1]);
+            for (int r = 0; r < KP / 4; ++r) {
+                mu[2 * r + 0] = __ffma2_rn(d2, make_float2(g[r].x, g[r].y), mu[2 * r + 0]);
+                mu[2 * r + 1] = __ffma2_rn(d2, make_float2(g[r].z, g[r].w), mu[2 * r + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < KP / 4; ++r) {
+                mu[2 * r + 0].x = fmaf(d, g[r].x, mu[2 * r + 0].x);
+                mu[2 * r + 0].y = fmaf(d, g[r].y, mu[2 * r + 0].y);
+                mu[2 * r + 1].x = fmaf(d, g[r].z, mu[2 * r + 1].x);
+                mu[2 * r + 1].y = fmaf(d, g[r].w, mu[2 * r + 1].y);
+            }
         }
         if (ANY_CHANGE) changed |= __float_as_uint(d);   // d is +0 exactly when unchanged
         else changed |= (2.f * fabsf(d) > rel_tol * (tmp + h[kk] + TINY_NUM_F)) ? 1u : 0u;
@@ -232,7 +242,7 @@ __device__ __forceinline__ void scd_ls_block8(float (&h)[KP], float2 (&mu)[KP / 
 }
 
 // h, mu in the scaled variables; G' is read from c_gram.  returns #sweeps
-template <int KP>
+template <int KP, bool PACKED = true>
 __device__ __forceinline__ int scd_ls_thread(float (&h)[KP], float2 (&mu)[KP / 2], int k, int max_iter, float rel_tol)
 {
     int t = 0;
@@ -243,17 +253,86 @@ __device__ __forceinline__ int scd_ls_thread(float (&h)[KP], float2 (&mu)[KP / 2
             changed = 0u;
 #pragma unroll
             for (int kb = 0; kb < KP / 8; ++kb)
-                if (kb * 8 < k) scd_ls_block8<KP, true>(h, mu, kb, rel_tol, changed);
+                if (kb * 8 < k) scd_ls_block8<KP, true, PACKED>(h, mu, kb, rel_tol, changed);
         }
     } else {
         for (; t < max_iter && changed; ++t) {
             changed = 0u;
 #pragma unroll
             for (int kb = 0; kb < KP / 8; ++kb)
-                if (kb * 8 < k) scd_ls_block8<KP, false>(h, mu, kb, rel_tol, changed);
+                if (kb * 8 < k) scd_ls_block8<KP, false, PACKED>(h, mu, kb, rel_tol, changed);
         }
     }
     return t;
+}
+
+// Shared-memory variant with NC columns per thread: one broadcast LDS.128 fetch of a Gram row feeds NC
+// independent chains (the SM-wide shared-memory pipe, not the FMA pipe, limits the one-column form: ~19.5
+// SM-cycles per warp-step against ~14 with two columns; tools/micro/solver_bench2.cu).  Used inside the
+// tcgen05 pass kernel, where the compiler funnels constant-bank operands through a single uniform-register
+// quad and the constant-bank form loses its advantage.
+template <int KP, int NC, bool ANY_CHANGE>
+__device__ __forceinline__ void scd_ls_block8_smem(float (&h)[NC][KP], float2 (&mu)[NC][KP / 2], unsigned sg_addr, int kb,
+                                                   float rel_tol, unsigned (&changed)[NC])
+{
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int kk = kb * 8 + u;
+        // asm volatile: plain loads of the loop-invariant G' get hoisted out of the sweep loop and spilled
+        float4 g[KP / 4];
+#pragma unroll
+        for (int r = 0; r < KP / 4; ++r)
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(g[r].x), "=f"(g[r].y), "=f"(g[r].z), "=f"(g[r].w)
+                         : "r"(sg_addr + (unsigned)((kk * KP + 4 * r) * 4)));
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const float mk = (kk & 1) ? mu[c][kk / 2].y : mu[c][kk / 2].x;
+            const float tmp = fmaxf(h[c][kk] - mk, 0.f);
+            const float d = tmp - h[c][kk];
+            const float2 d2 = make_float2(d, d);
+#pragma unroll
+            for (int r = 0; r < KP / 4; ++r) {
+                mu[c][2 * r + 0] = __ffma2_rn(d2, make_float2(g[r].x, g[r].y), mu[c][2 * r + 0]);
+                mu[c][2 * r + 1] = __ffma2_rn(d2, make_float2(g[r].z, g[r].w), mu[c][2 * r + 1]);
+            }
+            if (ANY_CHANGE) changed[c] |= __float_as_uint(d);
+            else changed[c] |= (2.f * fabsf(d) > rel_tol * (tmp + h[c][kk] + TINY_NUM_F)) ? 1u : 0u;
+            h[c][kk] = tmp;
+        }
+    }
+}
+
+// sweeps[c] = the number of sweeps scd_ls_update would have run on column c (the sweep that finds no change
+// included); extra sweeps a converged column sits through while its neighbour finishes are exact no-ops.
+template <int KP, int NC>
+__device__ __forceinline__ void scd_ls_thread_smem(float (&h)[NC][KP], float2 (&mu)[NC][KP / 2], unsigned sg_addr, int k,
+                                                   int max_iter, float rel_tol, int (&sweeps)[NC])
+{
+    const bool any_change = rel_tol < 2.9e-8f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sweeps[c] = 1;
+    unsigned any = 1u;
+    for (int t = 0; t < max_iter && any; ++t) {
+        unsigned changed[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) changed[c] = 0u;
+        if (any_change) {
+#pragma unroll
+            for (int kb = 0; kb < KP / 8; ++kb)
+                if (kb * 8 < k) scd_ls_block8_smem<KP, NC, true>(h, mu, sg_addr, kb, rel_tol, changed);
+        } else {
+#pragma unroll
+            for (int kb = 0; kb < KP / 8; ++kb)
+                if (kb * 8 < k) scd_ls_block8_smem<KP, NC, false>(h, mu, sg_addr, kb, rel_tol, changed);
+        }
+        any = 0u;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (changed[c]) sweeps[c] = min(t + 2, max_iter);
+            any |= changed[c];
+        }
+    }
 }
 
 // mu' += sum_q h'_q G'[q,:]  with h'_q = X[q] * D[q]   (G' from the constant bank, q uniform)

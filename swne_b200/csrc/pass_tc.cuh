@@ -22,6 +22,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "kernels_simt.cuh"
 
@@ -39,7 +41,7 @@ constexpr int TC_H_SUB = TC_KP * 64 * 2;                // 4 KB: [32 factors][64
 constexpr int TC_H_TILE = 4 * TC_H_SUB;                 // hi (bf16) k-half 0/1, lo (fp16) k-half 0/1
 constexpr int TC_CBUF = 8;                              // C accumulators (32 TMEM columns each) in flight
 constexpr int TC_MT_PER_PASS = 8;                       // 128-gene accumulators per gene sub-pass (8 * 32 TMEM columns)
-constexpr int TC_SOLVER_WARPS = 12;
+constexpr int TC_SOLVER_WARPS = 8;
 constexpr int TC_THREADS = (4 + TC_SOLVER_WARPS) * 32;  // warps: 0 TMA, 1 MMA, 2 H-tile loader, 3 idle, 4.. solvers
 constexpr int TC_MAX_TILES = 256;                       // tiles per CTA (one mbarrier each)
 
@@ -49,7 +51,9 @@ struct TcSmem {
     static constexpr int a_lo = a_hi + TC_STAGES * TC_A_STAGE;
     static constexpr int w = a_lo + TC_STAGES * TC_A_STAGE;
     static constexpr int h = w + TC_STAGES * TC_W_STAGE;
-    static constexpr int dvec = h + 2 * TC_H_TILE;       // sqrt(diag), 1/sqrt(diag)
+    static constexpr int g = h + 2 * TC_H_TILE;          // unit-diagonal penalised Gram G'
+    static constexpr int g0 = g + TC_KP * TC_KP * 4;     // plain Gram (loss)
+    static constexpr int dvec = g0 + TC_KP * TC_KP * 4;  // sqrt(diag), 1/sqrt(diag)
     static constexpr int bars = dvec + 2 * TC_KP * 4;
     static constexpr int n_bars = 2 * TC_STAGES + 2 * TC_CBUF + 2 + 2 + 2 + TC_MAX_TILES;
     static constexpr int misc = bars + n_bars * 8;
@@ -66,6 +70,7 @@ struct TcPassParams {
     int max_iter;
     float rel_tol;
     float *H;                // [m][32] fp32 in/out
+    float *Cscr;             // [m][32] fp32 scratch: the contraction C = A W, kept for the loss after the solve
     float *B;                // [n][32] fp32, accumulated with red.add (zeroed by the caller)
     uint8_t *Himg;           // [grid][tiles_per_cta][TC_H_TILE] split 16-bit images of the H tiles
     int tiles_per_cta;
@@ -76,11 +81,19 @@ struct TcPassParams {
     int *overflow;           // device: set when a scaled H entry left the fp16 range
     int a_exp;               // A was scaled by 2^a_exp before the split
     int groups_total;        // ceil(m / 32)
+    unsigned long long *dbg; // optional timeline (SWNE_TC_TIMELINE): 64 globaltimer slots per CTA
 };
 
 // ------------------------------------------------------------------------------------------------
 // PTX helpers
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TC_MARK(slot) do { if (p.dbg) p.dbg[(size_t)blockIdx.x * 64 + (slot)] = gtimer(); } while (0)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -226,17 +239,224 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     float *sD = reinterpret_cast<float *>(smem + TcSmem::dvec), *sInvD = sD + TC_KP;
-    if (p.mode == 0 && threadIdx.x < 2 * TC_KP) sD[threadIdx.x] = p.pack[2 * TC_KP * TC_KP + threadIdx.x];
+    float *sGs = reinterpret_cast<float *>(smem + TcSmem::g);
+    if (p.mode == 0) {
+        for (int t = threadIdx.x; t < 2 * TC_KP * TC_KP; t += blockDim.x) sGs[t] = p.pack[t];   // G' then G0
+        if (threadIdx.x < 2 * TC_KP) sD[threadIdx.x] = p.pack[2 * TC_KP * TC_KP + threadIdx.x];
+    }
     // generic-proxy zero fill must be visible to the async proxy (TMA / UMMA)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (threadIdx.x == 0) TC_MARK(0);
     const uint32_t tmem_c = tmem;                       // columns [0,256): eight C accumulators
     const uint32_t tmem_d = tmem + TC_CBUF * 32;        // columns [256,512): eight 128 x 32 accumulators
 
-    if (warp == 0) {
+    if (warp >= 4) {
+        // =========================== solver warps ===========================
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+        const float descale = exp2f(-(float)(p.a_exp + *p.w_exp));
+        // fp16 scale of the H images: the previous max(H) maps to [8, 16), which leaves a factor 4096 of growth
+        // before fp16 overflows (flagged, never silent) while entries down to 1e-9 of the max keep their value
+        int h_exp = 0;
+        {
+            const float hm = __int_as_float(*p.hmax_prev);
+            if (hm > 0.f) {
+                int e;
+                frexpf(hm, &e);
+                h_exp = max(-100, min(100, 4 - e));
+            }
+        }
+        const float hscale = exp2f((float)h_exp);
+        float hmax = 0.f;
+        bool ovf = false;
+        double lp = 0.0;
+        unsigned long long its = 0;
+        const unsigned sg_addr = smem_u32(sGs);
+        const float *sG0 = sGs + TC_KP * TC_KP;
+        const float *sInvD = sD + TC_KP;
+        // a job = (pair of consecutive tiles, this warp's lane quarter): two cells per thread, one from each tile
+        for (;;) {
+            int u = 0;
+            if (lane == 0) u = atomicAdd(&s_next[quarter], 1);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            const int t0 = 2 * u;
+            if (t0 >= n_tiles) break;
+            const int nc = (t0 + 1 < n_tiles) ? 2 : 1;
+            if (lane == 0 && quarter == 0 && u < 4) TC_MARK(8 + u);   // job picked up
+            const int lc = quarter * 32 + lane;                      // cell within the tile
+            float h[2][32];
+            float2 mu[2][16];
+            bool valid[2];
+            float *hrow[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int t = t0 + c;
+                const int cell = cell_begin + t * TC_TILE + lc;
+                valid[c] = (c < nc) && (cell < cell_end);
+                hrow[c] = p.H + (size_t)(valid[c] ? cell : cell_begin) * TC_KP;
+                if (p.mode == 0 && c < nc) {
+                    const int b = t % TC_CBUF;
+                    mbar_wait(CFULL(b), (t / TC_CBUF) & 1);
+                    tc_fence_after();
+                    float cv[32];
+                    tc_ld32(tmem_c + b * 32 + ((uint32_t)(quarter * 32) << 16), cv);
+                    tc_fence_before();
+                    mbar_arrive(CEMPTY(b));
+                    if (valid[c]) {
+                        float *crow = p.Cscr + (size_t)cell * TC_KP;
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            const float4 v = reinterpret_cast<const float4 *>(hrow[c])[r];
+                            h[c][4 * r] = v.x * sD[4 * r]; h[c][4 * r + 1] = v.y * sD[4 * r + 1];
+                            h[c][4 * r + 2] = v.z * sD[4 * r + 2]; h[c][4 * r + 3] = v.w * sD[4 * r + 3];
+                            const float c0 = cv[4 * r] * descale, c1 = cv[4 * r + 1] * descale, c2 = cv[4 * r + 2] * descale,
+                                        c3 = cv[4 * r + 3] * descale;
+                            reinterpret_cast<float4 *>(crow)[r] = make_float4(c0, c1, c2, c3);
+                            mu[c][2 * r] = make_float2((p.l1 - c0) * sInvD[4 * r], (p.l1 - c1) * sInvD[4 * r + 1]);
+                            mu[c][2 * r + 1] = make_float2((p.l1 - c2) * sInvD[4 * r + 2], (p.l1 - c3) * sInvD[4 * r + 3]);
+                        }
+                        // mu' += G' h'
+#pragma unroll 1
+                        for (int q = 0; q < p.k; ++q) {
+                            const float hq = hrow[c][q] * sD[q];
+                            const float2 h2 = make_float2(hq, hq);
+                            const float4 *g4 = reinterpret_cast<const float4 *>(sGs + q * TC_KP);
+#pragma unroll
+                            for (int r = 0; r < 8; ++r) {
+                                const float4 g = g4[r];
+                                mu[c][2 * r] = __ffma2_rn(h2, make_float2(g.x, g.y), mu[c][2 * r]);
+                                mu[c][2 * r + 1] = __ffma2_rn(h2, make_float2(g.z, g.w), mu[c][2 * r + 1]);
+                            }
+                        }
+                    }
+                }
+                if (!(p.mode == 0 && valid[c])) {
+                    // idle column (tile past the end, cell past the end, or phase-3-only mode): an exact no-op
+#pragma unroll
+                    for (int f = 0; f < 32; ++f) h[c][f] = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) mu[c][r] = make_float2(0.f, 0.f);
+                }
+            }
+            if (p.mode == 0) {
+                int sw[2];
+                scd_ls_thread_smem<TC_KP, 2>(h, mu, sg_addr, p.k, p.max_iter, p.rel_tol, sw);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (valid[c]) {
+                        its += (unsigned long long)sw[c];
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            h[c][4 * r] *= sInvD[4 * r]; h[c][4 * r + 1] *= sInvD[4 * r + 1];
+                            h[c][4 * r + 2] *= sInvD[4 * r + 2]; h[c][4 * r + 3] *= sInvD[4 * r + 3];
+                            reinterpret_cast<float4 *>(hrow[c])[r] =
+                                make_float4(h[c][4 * r], h[c][4 * r + 1], h[c][4 * r + 2], h[c][4 * r + 3]);
+                        }
+                        // loss partial h' G0 h - 2 h' c  (mu reused for G0 h; c read back from the scratch row)
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) mu[c][r] = make_float2(0.f, 0.f);
+#pragma unroll 1
+                        for (int q = 0; q < p.k; ++q) {
+                            const float hq = hrow[c][q];
+                            const float2 h2 = make_float2(hq, hq);
+                            const float4 *g4 = reinterpret_cast<const float4 *>(sG0 + q * TC_KP);
+#pragma unroll
+                            for (int r = 0; r < 8; ++r) {
+                                const float4 g = g4[r];
+                                mu[c][2 * r] = __ffma2_rn(h2, make_float2(g.x, g.y), mu[c][2 * r]);
+                                mu[c][2 * r + 1] = __ffma2_rn(h2, make_float2(g.z, g.w), mu[c][2 * r + 1]);
+                            }
+                        }
+                        const float *crow = p.Cscr + (size_t)(cell_begin + (t0 + c) * TC_TILE + lc) * TC_KP;
+                        float s = 0.f;
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            const float4 cq = reinterpret_cast<const float4 *>(crow)[r];
+                            s = fmaf(h[c][4 * r + 0], mu[c][2 * r].x - 2.f * cq.x, s);
+                            s = fmaf(h[c][4 * r + 1], mu[c][2 * r].y - 2.f * cq.y, s);
+                            s = fmaf(h[c][4 * r + 2], mu[c][2 * r + 1].x - 2.f * cq.z, s);
+                            s = fmaf(h[c][4 * r + 3], mu[c][2 * r + 1].y - 2.f * cq.w, s);
+                        }
+                        lp += (double)s;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int cell = cell_begin + (t0 + c) * TC_TILE + lc;
+                    if (c < nc && cell < cell_end) {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            const float4 v = reinterpret_cast<const float4 *>(p.H + (size_t)cell * TC_KP)[r];
+                            h[c][4 * r] = v.x; h[c][4 * r + 1] = v.y; h[c][4 * r + 2] = v.z; h[c][4 * r + 3] = v.w;
+                        }
+                    }
+                }
+            }
+            // ---- split fp16 images of these cells' columns of their tiles: x = h * 2^h_exp, hi = fp16(x),
+            // lo = fp16(x - hi); K-major [factor][cell] sub-tiles of 64 cells, 128 B rows, swizzle-128B by hand
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (c < nc) {
+                    const int t = t0 + c;
+                    uint8_t *img = my_img + (size_t)t * TC_H_TILE + (lc >> 6) * TC_H_SUB;
+                    const int cc = lc & 63;
+#pragma unroll
+                    for (int f = 0; f < 32; ++f) {
+                        hmax = fmaxf(hmax, h[c][f]);
+                        float x = h[c][f] * hscale;
+                        if (x > 60000.f) { x = 60000.f; ovf = true; }
+                        const __half hi = __float2half_rn(x);
+                        const __half lo = __float2half_rn(x - __half2float(hi));
+                        const int off = f * 128 + ((((cc >> 3) ^ (f & 7)) << 4) | ((cc & 7) << 1));
+                        *reinterpret_cast<__half *>(img + off) = hi;
+                        *reinterpret_cast<__half *>(img + 2 * TC_H_SUB + off) = lo;
+                    }
+                    __threadfence();
+                    mbar_arrive(TDONE(t));
+                }
+            }
+            if (lane == 0 && quarter == 0 && u < 4) TC_MARK(16 + u);  // job done
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+        if (lane == 0) atomicMax(p.hmax_next, __float_as_int(hmax));
+        if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicOr(p.overflow, 1);
+        if (p.mode == 0) {
+            lp = warp_sum(lp);
+            const double itd = warp_sum((double)its);
+            if (lane == 0) {
+                atomicAdd(&p.scal->loss_part, lp);
+                atomicAdd(&p.scal->sweeps_h, (unsigned long long)(itd + 0.5));
+            }
+        }
+        // ---- drain each gene sub-pass: D (128 genes x 32) -> red.add into B
+        const float bdescale = exp2f(-(float)(p.a_exp + h_exp));
+        const int sgrp = (warp - 4) >> 2;        // 0..2: which M-tiles of the sub-pass this warp drains
+        for (int ps = 0; ps < n_pass; ++ps) {
+            const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
+            mbar_wait(DFULL, ps & 1);
+            tc_fence_after();
+            for (int mt = mt0 + sgrp; mt < mt1; mt += TC_SOLVER_WARPS / 4) {
+                float d[32];
+                tc_ld32(tmem_d + (mt - mt0) * 32 + ((uint32_t)(quarter * 32) << 16), d);
+                const int gene = mt * 128 + quarter * 32 + lane;
+                if (gene < p.n) {
+                    float *dst = p.B + (size_t)gene * TC_KP;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        red_add_v4(dst + 4 * r, d[4 * r] * bdescale, d[4 * r + 1] * bdescale, d[4 * r + 2] * bdescale,
+                                   d[4 * r + 3] * bdescale);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(DEMPTY);
+            if (warp == 4 && lane == 0) TC_MARK(32 + ps);
+        }
+    } else if (warp == 0) {
         // =========================== TMA producer ===========================
         if (lane == 0) {
             int stage = 0, phase = 0;
@@ -258,6 +478,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                     }
                 }
             }
+            TC_MARK(1);
             for (int ps = 0; ps < n_pass; ++ps) {
                 const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
                 for (int t = 0; t < n_tiles; ++t) {
@@ -309,6 +530,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                     tc_commit(CFULL(b));
                 }
             }
+            TC_MARK(2);
             int use = 0;  // H tile buffer uses
             for (int ps = 0; ps < n_pass; ++ps) {
                 const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
@@ -345,8 +567,10 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                         if (stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
                     tc_commit(HEMPTY(hb));
+                    if (ps == 0 && t < 8) TC_MARK(24 + t);
                 }
                 tc_commit(DFULL);
+                TC_MARK(3 + ps);
             }
         }
     } else if (warp == 2) {
@@ -365,135 +589,6 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(HFULL(hb));
             }
-        }
-    } else if (warp >= 4) {
-        // =========================== solver warps ===========================
-        const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-        const float descale = exp2f(-(float)(p.a_exp + *p.w_exp));
-        // fp16 scale of the H images: the previous max(H) maps to [8, 16), which leaves a factor 4096 of growth
-        // before fp16 overflows (flagged, never silent) while entries down to 1e-9 of the max keep their value
-        int h_exp = 0;
-        {
-            const float hm = __int_as_float(*p.hmax_prev);
-            if (hm > 0.f) {
-                int e;
-                frexpf(hm, &e);
-                h_exp = max(-100, min(100, 4 - e));
-            }
-        }
-        const float hscale = exp2f((float)h_exp);
-        float hmax = 0.f;
-        bool ovf = false;
-        double lp = 0.0;
-        unsigned long long its = 0;
-        for (;;) {
-            int t = 0;
-            if (lane == 0) t = atomicAdd(&s_next[quarter], 1);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            if (t >= n_tiles) break;
-            const int lc = quarter * 32 + lane;                      // cell within the tile
-            const int cell = cell_begin + t * TC_TILE + lc;
-            const bool valid = cell < cell_end;
-            float h[32];
-            float *hrow = p.H + (size_t)(valid ? cell : cell_begin) * TC_KP;
-            if (p.mode == 0) {
-                const int b = t % TC_CBUF;
-                mbar_wait(CFULL(b), (t / TC_CBUF) & 1);
-                tc_fence_after();
-                float c[32];
-                float2 mu[16];
-                tc_ld32(tmem_c + b * 32 + ((uint32_t)(quarter * 32) << 16), c);
-                tc_fence_before();
-                mbar_arrive(CEMPTY(b));
-                if (valid) {
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const float4 v = reinterpret_cast<const float4 *>(hrow)[r];
-                        h[4 * r] = v.x * sD[4 * r]; h[4 * r + 1] = v.y * sD[4 * r + 1];
-                        h[4 * r + 2] = v.z * sD[4 * r + 2]; h[4 * r + 3] = v.w * sD[4 * r + 3];
-                    }
-#pragma unroll
-                    for (int f = 0; f < 32; ++f) c[f] *= descale;
-#pragma unroll
-                    for (int r = 0; r < 16; ++r)
-                        mu[r] = make_float2((p.l1 - c[2 * r]) * sInvD[2 * r], (p.l1 - c[2 * r + 1]) * sInvD[2 * r + 1]);
-                    scd_mu_init<TC_KP>(mu, hrow, sD, p.k);
-                    its += scd_ls_thread<TC_KP>(h, mu, p.k, p.max_iter, p.rel_tol);
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        h[4 * r] *= sInvD[4 * r]; h[4 * r + 1] *= sInvD[4 * r + 1];
-                        h[4 * r + 2] *= sInvD[4 * r + 2]; h[4 * r + 3] *= sInvD[4 * r + 3];
-                        reinterpret_cast<float4 *>(hrow)[r] = make_float4(h[4 * r], h[4 * r + 1], h[4 * r + 2], h[4 * r + 3]);
-                    }
-                    // loss partial h' G0 h - 2 h' c  (mu reused for G0 h)
-                    scd_g0_times<TC_KP>(mu, hrow, p.k);
-                    float s = 0.f;
-#pragma unroll
-                    for (int f = 0; f < 32; ++f) s = fmaf(h[f], ((f & 1) ? mu[f / 2].y : mu[f / 2].x) - 2.f * c[f], s);
-                    lp += (double)s;
-                } else {
-#pragma unroll
-                    for (int f = 0; f < 32; ++f) h[f] = 0.f;
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid) v = reinterpret_cast<const float4 *>(hrow)[r];
-                    h[4 * r] = v.x; h[4 * r + 1] = v.y; h[4 * r + 2] = v.z; h[4 * r + 3] = v.w;
-                }
-            }
-            // ---- split fp16 image of this cell's column of the tile: x = h * 2^h_exp, hi = fp16(x), lo = fp16(x - hi);
-            // K-major [factor][cell] sub-tiles of 64 cells, 128 B rows, swizzle-128B by hand
-            uint8_t *img = my_img + (size_t)t * TC_H_TILE + (lc >> 6) * TC_H_SUB;
-            const int cc = lc & 63;
-#pragma unroll
-            for (int f = 0; f < 32; ++f) {
-                hmax = fmaxf(hmax, h[f]);
-                float x = h[f] * hscale;
-                if (x > 60000.f) { x = 60000.f; ovf = true; }
-                const __half hi = __float2half_rn(x);
-                const __half lo = __float2half_rn(x - __half2float(hi));
-                const int off = f * 128 + ((((cc >> 3) ^ (f & 7)) << 4) | ((cc & 7) << 1));
-                *reinterpret_cast<__half *>(img + off) = hi;
-                *reinterpret_cast<__half *>(img + 2 * TC_H_SUB + off) = lo;
-            }
-            __threadfence();
-            mbar_arrive(TDONE(t));
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
-        if (lane == 0) atomicMax(p.hmax_next, __float_as_int(hmax));
-        if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicOr(p.overflow, 1);
-        if (p.mode == 0) {
-            lp = warp_sum(lp);
-            const double itd = warp_sum((double)its);
-            if (lane == 0) {
-                atomicAdd(&p.scal->loss_part, lp);
-                atomicAdd(&p.scal->sweeps_h, (unsigned long long)(itd + 0.5));
-            }
-        }
-        // ---- drain each gene sub-pass: D (128 genes x 32) -> red.add into B
-        const float bdescale = exp2f(-(float)(p.a_exp + h_exp));
-        const int sgrp = (warp - 4) >> 2;        // 0..2: which M-tiles of the sub-pass this warp drains
-        for (int ps = 0; ps < n_pass; ++ps) {
-            const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
-            mbar_wait(DFULL, ps & 1);
-            tc_fence_after();
-            for (int mt = mt0 + sgrp; mt < mt1; mt += TC_SOLVER_WARPS / 4) {
-                float d[32];
-                tc_ld32(tmem_d + (mt - mt0) * 32 + ((uint32_t)(quarter * 32) << 16), d);
-                const int gene = mt * 128 + quarter * 32 + lane;
-                if (gene < p.n) {
-                    float *dst = p.B + (size_t)gene * TC_KP;
-#pragma unroll
-                    for (int r = 0; r < 8; ++r)
-                        red_add_v4(dst + 4 * r, d[4 * r] * bdescale, d[4 * r + 1] * bdescale, d[4 * r + 2] * bdescale,
-                                   d[4 * r + 3] * bdescale);
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(DEMPTY);
         }
     }
     // ---- teardown
@@ -559,6 +654,7 @@ struct TcMatrix {
     int n = 0, m = 0, n_pad = 0, a_exp = 0, sm_count = 148;
     __half *Ahi = nullptr, *Alo = nullptr, *Wst = nullptr;
     int *dev_ints = nullptr;   // [0] W max bits, [1] w_exp, [2] max(H) bits before the pass, [3] after, [4] overflow flag
+    unsigned long long *dbg = nullptr;   // timeline buffer when SWNE_TC_TIMELINE is set
     uint8_t *Himg = nullptr;   // split 16-bit H tile images, [grid][tiles_per_cta][TC_H_TILE]
     int grid = 0, tiles_per_cta = 0;
     CUtensorMap map_ahi, map_alo, map_w;
@@ -613,6 +709,7 @@ static inline void tc_release(TcMatrix &tc)
     if (tc.Wst) cudaFree(tc.Wst);
     if (tc.dev_ints) cudaFree(tc.dev_ints);
     if (tc.Himg) cudaFree(tc.Himg);
+    if (tc.dbg) cudaFree(tc.dbg);
     tc = TcMatrix();
 }
 
@@ -664,11 +761,10 @@ static inline void tc_update_w(TcMatrix &tc, const float *Wt, cudaStream_t st)
 
 // one pass.  mode 0: H update (phase 1 + solve) followed by B = A H' of the new H; mode 1: B = A H' only.
 // B must be zeroed by the caller.  launches: 1 (+3 for the W split in mode 0)
-static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, const float *pack, float l1, int k, int max_iter,
-                           float rel_tol, float *B, FitScalars *scal, cudaStream_t st)
+static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, float *Cscr, const float *pack, float l1, int k,
+                           int max_iter, float rel_tol, float *B, FitScalars *scal, cudaStream_t st)
 {
-    if (mode == 0)
-        CUDA_CHECK(cudaMemcpyToSymbolAsync(c_gram, pack, sizeof(float) * 2 * TC_KP * TC_KP, 0, cudaMemcpyDeviceToDevice, st));
+
     if (mode == 0) {
         tc_update_w(tc, Wt, st);
         // max(H) of the previous pass becomes the scale reference of this one
@@ -684,7 +780,7 @@ static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, co
     p.n_chunks = 2 * p.n_mtiles;
     p.mode = mode;
     p.pack = pack; p.l1 = l1; p.max_iter = max_iter; p.rel_tol = rel_tol;
-    p.H = H; p.B = B; p.scal = scal;
+    p.H = H; p.Cscr = Cscr; p.B = B; p.scal = scal;
     p.w_exp = tc.dev_ints + 1;
     p.hmax_prev = tc.dev_ints + 2;
     p.hmax_next = tc.dev_ints + 3;
@@ -693,6 +789,10 @@ static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, co
     p.groups_total = (tc.m + TC_GROUP - 1) / TC_GROUP;
     p.Himg = tc.Himg;
     p.tiles_per_cta = tc.tiles_per_cta;
+    const char *tl = getenv("SWNE_TC_TIMELINE");
+    if (tl && !tc.dbg) CUDA_CHECK(cudaMalloc(&tc.dbg, sizeof(unsigned long long) * 64 * 148));
+    p.dbg = tl ? tc.dbg : nullptr;
+    if (p.dbg) CUDA_CHECK(cudaMemsetAsync(tc.dbg, 0, sizeof(unsigned long long) * 64 * 148, st));
     const int grid = tc.grid;
     if (tc.tiles_per_cta > TC_MAX_TILES) {
         set_error("tcgen05 engine: too many cells per SM");
@@ -700,6 +800,23 @@ static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, co
     }
     tc_pass_kernel<<<grid, TC_THREADS, TcSmem::total + 1024, st>>>(tc.map_ahi, tc.map_alo, tc.map_w, p);
     CUDA_CHECK(cudaGetLastError());
+    if (p.dbg && mode == 0) {
+        // debug only: dump the per-CTA timeline of this launch (ns since the earliest CTA start)
+        std::vector<unsigned long long> hbuf(64 * 148);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(cudaMemcpy(hbuf.data(), tc.dbg, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull;
+        for (int c = 0; c < grid; ++c) if (hbuf[c * 64]) t0 = std::min(t0, hbuf[c * 64]);
+        FILE *f = fopen(tl, "w");
+        if (f) {
+            for (int c = 0; c < grid; ++c) {
+                fprintf(f, "cta %d", c);
+                for (int s = 0; s < 40; ++s) fprintf(f, " %lld", hbuf[c * 64 + s] ? (long long)(hbuf[c * 64 + s] - t0) : -1ll);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
 }
 static inline int tc_pass_launches(int mode) { return mode == 0 ? 4 : 1; }
 

@@ -510,7 +510,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         h->pinned_bytes = sizeof(HostTrace);
     }
     HostTrace *ht = (HostTrace *)h->pinned;
-    if (p.loss == SWNE_LOSS_MKL || p.full_traces) ensure_sparse(h);
+    if (p.loss == SWNE_LOSS_MKL || p.full_traces > 0) ensure_sparse(h);
     if (engine == SWNE_ENGINE_TC)
         tc_prepare(h->tc, h->dA, h->ldA, n, m, (double)__builtin_bit_cast(float, h->stats.max_bits), h->sm_count, st);
 
@@ -551,7 +551,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     if (engine == SWNE_ENGINE_TC) {
         prof.begin(0);
         CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
-        tc_pass(h->tc, 1, h->Wt.p, h->H.p, nullptr, 0.f, k, p.inner_max_iter, 0.f, h->B.p, h->dscal.p, st);
+        tc_pass(h->tc, 1, h->Wt.p, h->H.p, h->C.p, nullptr, 0.f, k, p.inner_max_iter, 0.f, h->B.p, h->dscal.p, st);
         prof.end(0, tc_pass_launches(1));
         if (h->nranks > 1) allreduce(h, h->B.p, (size_t)n * KPv, nullptr, 0);
         have_B = true;
@@ -563,7 +563,8 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
 
     auto error_block = [&](bool final_block) {
         // W'W is current (computed before the H update); H H' and the loss partials are current
-        if (!mse || !(p.full_traces || final_block)) {
+        const bool want_mkl = p.full_traces > 0 || (p.full_traces == 0 && final_block);
+        if (!mse || !want_mkl) {
             // nothing extra
         } else {
             ensure_sparse(h);
@@ -591,7 +592,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         const double nan_v = nan("");
         if (mse) {
             mse_v = (sumsqA + ht->sc.loss_part) / N;
-            mkl_v = (p.full_traces || final_block) ? (klcA - ht->sc.kl_part + sum_ahat) / N : nan_v;
+            mkl_v = want_mkl ? (klcA - ht->sc.kl_part + sum_ahat) / N : nan_v;
         } else {
             mse_v = (ht->sc.sq_part + wwhh) / N;
             mkl_v = (klcA - ht->sc.kl_part + sum_ahat) / N;
@@ -642,7 +643,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             if (engine == SWNE_ENGINE_TC) {
                 prof.begin(0);
                 CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
-                tc_pass(h->tc, 0, h->Wt.p, h->H.p, h->pack.p, (float)p.beta[2], k, p.inner_max_iter, inner_tol, h->B.p,
+                tc_pass(h->tc, 0, h->Wt.p, h->H.p, h->C.p, h->pack.p, (float)p.beta[2], k, p.inner_max_iter, inner_tol, h->B.p,
                         h->dscal.p, st);
                 prof.end(0, tc_pass_launches(0));
                 prof.begin(7);
@@ -698,7 +699,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         --i;  // error_block reports iteration i+1
         error_block(true);
         ++i;
-    } else if (mse && !p.full_traces && i_e > 0 && rc == SWNE_OK && mkl_tr) {
+    } else if (mse && p.full_traces == 0 && i_e > 0 && rc == SWNE_OK && mkl_tr) {
         // final state coincides with the last block: fill in its mkl
         ensure_sparse(h);
         CUDA_CHECK(cudaMemsetAsync(&h->dscal.p->kl_part, 0, sizeof(double), st));

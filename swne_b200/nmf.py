@@ -118,7 +118,7 @@ class NMFHandle:
         p.alpha[:] = list(C.pad3(alpha)); p.beta[:] = list(C.pad3(beta))
         p.loss = C.LOSS[loss]; p.max_iter = int(max_iter); p.rel_tol = float(rel_tol)
         p.inner_max_iter = int(inner_max_iter); p.inner_rel_tol = float(inner_rel_tol); p.trace = int(trace)
-        p.verbose = int(verbose); p.engine = C.ENGINE[engine]; p.full_traces = int(bool(full_traces))
+        p.verbose = int(verbose); p.engine = C.ENGINE[engine]; p.full_traces = int(full_traces)
         p.profile = int(bool(profile))
         imi = p.inner_max_iter if p.inner_max_iter > 0 else (50 if loss == "mse" else 1)
         tr = p.trace if p.trace > 0 else max(1, 100 // imi)

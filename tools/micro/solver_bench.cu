@@ -28,18 +28,31 @@ __global__ void __launch_bounds__(128) bench(const float *G, float *X, int sweep
                 for (int r = 0; r < KP / 4; ++r)
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g[r].x), "=f"(g[r].y), "=f"(g[r].z), "=f"(g[r].w)
                                  : "r"(sg_addr + (unsigned)((kk * KP + 4 * r) * 4)));
-            } else {
+            } else if (MODE == 1) {
 #pragma unroll
                 for (int r = 0; r < KP / 4; ++r) g[r] = make_float4(cG[kk * KP + 4 * r], cG[kk * KP + 4 * r + 1], cG[kk * KP + 4 * r + 2], cG[kk * KP + 4 * r + 3]);
+            } else if (MODE == 2) {
+#pragma unroll
+                for (int r = 0; r < KP / 4; ++r)
+                    asm volatile("ld.const.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g[r].x), "=f"(g[r].y), "=f"(g[r].z), "=f"(g[r].w)
+                                 : "l"(cG + kk * KP + 4 * r));
             }
             const float mk = (kk & 1) ? mu[kk / 2].y : mu[kk / 2].x;
             const float tmp = fmaxf(h[kk] - mk, 0.f);
             const float d = tmp - h[kk];
             const float2 d2 = make_float2(d, d);
+            if (MODE == 3) {
 #pragma unroll
-            for (int r = 0; r < KP / 4; ++r) {
-                mu[2 * r] = __ffma2_rn(d2, make_float2(g[r].x, g[r].y), mu[2 * r]);
-                mu[2 * r + 1] = __ffma2_rn(d2, make_float2(g[r].z, g[r].w), mu[2 * r + 1]);
+                for (int r = 0; r < KP / 2; ++r) {
+                    mu[r].x = fmaf(d, cG[kk * KP + 2 * r], mu[r].x);
+                    mu[r].y = fmaf(d, cG[kk * KP + 2 * r + 1], mu[r].y);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < KP / 4; ++r) {
+                    mu[2 * r] = __ffma2_rn(d2, make_float2(g[r].x, g[r].y), mu[2 * r]);
+                    mu[2 * r + 1] = __ffma2_rn(d2, make_float2(g[r].z, g[r].w), mu[2 * r + 1]);
+                }
             }
             ch |= __float_as_uint(d);
             h[kk] = tmp;
@@ -59,18 +72,21 @@ int main()
     cudaMemcpy(dG, G.data(), G.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpyToSymbol(cG, G.data(), G.size() * 4);
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    for (int grid : {148, 148 * 3, 148 * 6}) {
-        for (int mode = 0; mode < 2; ++mode) {
+    for (int grid : {148, 148 * 3}) {
+        for (int mode = 0; mode < 4; ++mode) {
             float best = 1e9;
             for (int rep = 0; rep < 3; ++rep) {
                 cudaMemcpy(dX, X.data(), X.size() * 4, cudaMemcpyHostToDevice);
                 cudaEventRecord(a);
-                if (mode == 0) bench<0><<<grid, 128>>>(dG, dX, sweeps); else bench<1><<<grid, 128>>>(dG, dX, sweeps);
+                if (mode == 0) bench<0><<<grid, 128>>>(dG, dX, sweeps);
+                else if (mode == 1) bench<1><<<grid, 128>>>(dG, dX, sweeps);
+                else if (mode == 2) bench<2><<<grid, 128>>>(dG, dX, sweeps);
+                else bench<3><<<grid, 128>>>(dG, dX, sweeps);
                 cudaEventRecord(b); cudaEventSynchronize(b);
                 float ms; cudaEventElapsedTime(&ms, a, b); best = ms < best ? ms : best;
             }
             const double steps = (double)grid * 4 * sweeps * KP;   // warp-steps
-            printf("grid %4d mode %s: %.3f ms  -> %.1f SM-cycles per warp-step at 1.9 GHz (%s)\n", grid, mode ? "const" : "smem ", best,
+            printf("grid %4d mode %s: %.3f ms  -> %.1f SM-cycles per warp-step at 1.9 GHz (%s)\n", grid, mode == 0 ? "smem LDS.128 " : mode == 1 ? "const LDCU+FFMA2" : mode == 2 ? "ld.const.v4 regs" : "FFMA c[] operand", best,
                    best * 1e-3 * 1.9e9 / (steps / 148), cudaGetErrorString(cudaGetLastError()));
         }
     }
