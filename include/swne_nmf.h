@@ -124,8 +124,7 @@ int swne_nmf_set_matrix_csc_f32(swne_nmf_handle_t h, const int *p, const int *i,
 /* A already in HBM (fp32, cell-major = R column-major, leading dimension n): no copy is made on the
  * host; used by bench.py for the HBM-resident measurement. */
 int swne_nmf_set_matrix_dense_f32_device(swne_nmf_handle_t h, const float *dA, int n, int m);
-/* replaces the resident matrix by a full random permutation of its entries (FindNumFactors'
- * A.rand <- matrix(sample(A), ...), R/nmf.R:165); perm is a host permutation of 0..n*m-1 */
+/* shape, nonzero count, sum and sum of squares of the resident matrix */
 int swne_nmf_matrix_info(swne_nmf_handle_t h, int *n, int *m, long long *nnz, double *sum, double *sumsq);
 
 /* ---- the fit.  W (n x k) and H (k x m_local) hold the init on entry (NNLM's init=list(W,H)) and the

@@ -1,0 +1,44 @@
+"""Multi-GPU parity check (run under torchrun on a box with >= 2 GPUs):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/test_multigpu.py
+Cells are sharded over the ranks; the result must match the single-GPU fit of the whole matrix (bars of the
+oracle parity tests: loss 1e-4 relative, W/H 1e-3 relative Frobenius) and W must be identical on all ranks."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch, torch.distributed as td
+from helpers import small_matrix, seeded_init, rel_fro, max_rel
+from swne_b200 import NMFHandle
+from swne_b200.dist import init_comm, shard_bounds, gather_H
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+td.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+for (n, m, kt, k, engine) in [(300, 1000, 5, 8, "simt"), (1000, 4000, 6, 16, "tc"), (3000, 20000, 9, 30, "tc")]:
+    A = small_matrix(n, m, kt, 3)
+    W0, H0 = seeded_init(A, k, 3)
+    b = shard_bounds(m, world)
+    h = NMFHandle(local)
+    init_comm(h)
+    h.set_matrix(np.asfortranarray(A[:, b[rank]:b[rank + 1]]))
+    r = h.fit(k, W0, H0[:, b[rank]:b[rank + 1]], max_iter=12, trace=1, rel_tol=-1.0, engine=engine, full_traces=1)
+    H = gather_H(r.H)
+    Ws = [None] * world
+    td.all_gather_object(Ws, r.W)
+    h.close()
+    if rank == 0:
+        h1 = NMFHandle(local)
+        h1.set_matrix(A)
+        r1 = h1.fit(k, W0, H0, max_iter=12, trace=1, rel_tol=-1.0, engine=engine, full_traces=1)
+        h1.close()
+        same_w = all(np.array_equal(Ws[0], w) for w in Ws)
+        e_loss, e_mkl = max_rel(r.target_loss, r1.target_loss), max_rel(r.mkl, r1.mkl)
+        e_w, e_h = rel_fro(r.W, r1.W), rel_fro(H, r1.H)
+        good = same_w and e_loss < 1e-4 and e_mkl < 1e-4 and e_w < 1e-3 and e_h < 1e-3
+        ok &= good
+        print("%s n=%d m=%d k=%d engine=%s ranks=%d: W identical on ranks %s, loss %.2e mkl %.2e W %.2e H %.2e" % (
+            "PASS" if good else "FAIL", n, m, k, r.options["engine"], world, same_w, e_loss, e_mkl, e_w, e_h), flush=True)
+td.barrier()
+td.destroy_process_group()
+sys.exit(0 if ok else 1)
