@@ -39,10 +39,11 @@ void kl_l(const int *ptr, const int *idx, const float *val, float *ajt, float *X
     scd_kl_kernel<KP><<<(cols + 3) / 4, 128, 0, st>>>(ptr, idx, val, ajt, X, Y, sumY, b0, b1, b2, k, cols, max_iter, rel_tol,
                                                       sweeps, kl_part, sq_part, err);
 }
-void kl_trace_l(const int *cptr, const int *cidx, const float *cval, const float *H, const float *Wt, int k, int m,
-                double *kl_part, cudaStream_t st)
+void kl_trace_l(const float *A, size_t ldA, int n, int m, const float *H, const float *Wt, int k, double *kl_part,
+                cudaStream_t st)
 {
-    kl_trace_kernel<KP><<<(m + 3) / 4, 128, 0, st>>>(cptr, cidx, cval, H, Wt, k, m, kl_part);
+    const int grid = (m + 7) / 8 < 148 * 8 ? (m + 7) / 8 : 148 * 8;
+    kl_trace_kernel<KP><<<grid, 256, 0, st>>>(A, ldA, n, m, H, Wt, k, kl_part);
 }
 void recon_error_l(const float *A, size_t ldA, int n, int m, const float *Wt, const float *H, int k, double *out2, int grid,
                    cudaStream_t st)

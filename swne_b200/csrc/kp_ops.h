@@ -20,8 +20,8 @@ struct KpOps {
     void (*kl)(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y, const float *sumY,
                float b0, float b1, float b2, int k, int cols, int max_iter, float rel_tol, unsigned long long *sweeps,
                double *kl_part, double *sq_part, int err, cudaStream_t st);
-    void (*kl_trace)(const int *cptr, const int *cidx, const float *cval, const float *H, const float *Wt, int k, int m,
-                     double *kl_part, cudaStream_t st);
+    void (*kl_trace)(const float *A, size_t ldA, int n, int m, const float *H, const float *Wt, int k, double *kl_part,
+                     cudaStream_t st);
     void (*recon_error)(const float *A, size_t ldA, int n, int m, const float *Wt, const float *H, int k, double *out2, int grid,
                         cudaStream_t st);
     void (*right_multiply)(float *X, size_t rows, const float *T, int l, cudaStream_t st);

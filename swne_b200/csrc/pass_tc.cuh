@@ -55,7 +55,7 @@ struct TcSmem {
     static constexpr int g0 = g + TC_KP * TC_KP * 4;     // plain Gram (loss)
     static constexpr int dvec = g0 + TC_KP * TC_KP * 4;  // sqrt(diag), 1/sqrt(diag)
     static constexpr int bars = dvec + 2 * TC_KP * 4;
-    static constexpr int n_bars = 2 * TC_STAGES + 2 * TC_CBUF + 2 + 2 + 2 + TC_MAX_TILES;
+    static constexpr int n_bars = 2 * TC_STAGES + 2 * TC_CBUF + 2 + 2 + 4 + TC_MAX_TILES;
     static constexpr int misc = bars + n_bars * 8;
     static constexpr int total = misc + 64;
 };
@@ -81,6 +81,7 @@ struct TcPassParams {
     int *overflow;           // device: set when a scaled H entry left the fp16 range
     int a_exp;               // A was scaled by 2^a_exp before the split
     int groups_total;        // ceil(m / 32)
+    int exp_flags;           // debug experiments (SWNE_TC_EXP)
     unsigned long long *dbg; // optional timeline (SWNE_TC_TIMELINE): 64 globaltimer slots per CTA
 };
 
@@ -217,8 +218,9 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     constexpr int B2 = 2 * TC_STAGES + 2 * TC_CBUF;
     auto HFULL = [&](int b) { return bar0 + 8u * (B2 + b); };
     auto HEMPTY = [&](int b) { return bar0 + 8u * (B2 + 2 + b); };
-    const uint32_t DFULL = bar0 + 8u * (B2 + 4), DEMPTY = bar0 + 8u * (B2 + 5);
-    auto TDONE = [&](int t) { return bar0 + 8u * (B2 + 6 + t); };
+    auto DFULL = [&](int r) { return bar0 + 8u * (B2 + 4 + r); };
+    auto DEMPTY = [&](int r) { return bar0 + 8u * (B2 + 6 + r); };
+    auto TDONE = [&](int t) { return bar0 + 8u * (B2 + 8 + t); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcSmem::misc);
     int *s_next = reinterpret_cast<int *>(smem + TcSmem::misc + 16);   // per-quarter job counters
 
@@ -229,7 +231,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
         for (int b = 0; b < TC_CBUF; ++b) { mbar_init(CFULL(b), 1); mbar_init(CEMPTY(b), 128); }
         for (int b = 0; b < 2; ++b) { mbar_init(HFULL(b), 1); mbar_init(HEMPTY(b), 1); }
-        mbar_init(DFULL, 1); mbar_init(DEMPTY, TC_SOLVER_WARPS * 32);
+        for (int r = 0; r < 2; ++r) { mbar_init(DFULL(r), 1); mbar_init(DEMPTY(r), TC_SOLVER_WARPS * 32); }
         for (int t = 0; t < n_tiles; ++t) mbar_init(TDONE(t), 128);
         for (int q = 0; q < 4; ++q) s_next[q] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -252,7 +254,10 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     const uint32_t tmem = *tmem_slot;
     if (threadIdx.x == 0) TC_MARK(0);
     const uint32_t tmem_c = tmem;                       // columns [0,256): eight C accumulators
-    const uint32_t tmem_d = tmem + TC_CBUF * 32;        // columns [256,512): eight 128 x 32 accumulators
+    // gene sub-pass ps accumulates into region ps & 1: columns [256,512) or, once every C tile has been consumed
+    // (all solves are done before sub-pass 0 can finish), the C region itself -> the drain of one sub-pass overlaps
+    // the MMAs of the next
+    auto tmem_d = [&](int ps) { return tmem + ((ps & 1) ? 0 : TC_CBUF * 32); };
 
     if (warp >= 4) {
         // =========================== solver warps ===========================
@@ -438,11 +443,11 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         const int sgrp = (warp - 4) >> 2;        // 0..2: which M-tiles of the sub-pass this warp drains
         for (int ps = 0; ps < n_pass; ++ps) {
             const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
-            mbar_wait(DFULL, ps & 1);
+            mbar_wait(DFULL(ps & 1), (ps >> 1) & 1);
             tc_fence_after();
             for (int mt = mt0 + sgrp; mt < mt1; mt += TC_SOLVER_WARPS / 4) {
                 float d[32];
-                tc_ld32(tmem_d + (mt - mt0) * 32 + ((uint32_t)(quarter * 32) << 16), d);
+                tc_ld32(tmem_d(ps) + (mt - mt0) * 32 + ((uint32_t)(quarter * 32) << 16), d);
                 const int gene = mt * 128 + quarter * 32 + lane;
                 if (gene < p.n) {
                     float *dst = p.B + (size_t)gene * TC_KP;
@@ -453,47 +458,63 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                 }
             }
             tc_fence_before();
-            mbar_arrive(DEMPTY);
+            mbar_arrive(DEMPTY(ps & 1));
             if (warp == 4 && lane == 0) TC_MARK(32 + ps);
         }
     } else if (warp == 0) {
         // =========================== TMA producer ===========================
-        if (lane == 0) {
+        // All lanes walk the same schedule; lane 0 waits for the slot and arms the barrier, then every box of the
+        // stage is issued by its own lane (one thread issuing 9..16 TMA ops back to back was the bottleneck of
+        // phase 3: ~80 cycles of issue per op).
+        {
             int stage = 0, phase = 0;
             if (p.mode == 0) {
                 for (int t = 0; t < n_tiles; ++t) {
                     const int cell0 = cell_begin + t * TC_TILE;
                     const int nbox = (min(TC_TILE, cell_end - cell0) + TC_GROUP - 1) / TC_GROUP;
                     for (int ch = 0; ch < p.n_chunks; ++ch) {
-                        mbar_wait(EMPTY(stage), phase ^ 1);
-                        mbar_expect_tx(FULL(stage), nbox * 2 * TC_BOX_BYTES + TC_W_STAGE);
-                        for (int b = 0; b < nbox; ++b) {
-                            tma_load_2d(sbase + TcSmem::a_hi + stage * TC_A_STAGE + b * TC_BOX_BYTES, &map_ahi, ch * TC_CHUNK,
-                                        cell0 + b * TC_GROUP, FULL(stage));
-                            tma_load_2d(sbase + TcSmem::a_lo + stage * TC_A_STAGE + b * TC_BOX_BYTES, &map_alo, ch * TC_CHUNK,
-                                        cell0 + b * TC_GROUP, FULL(stage));
+                        if (lane == 0) {
+                            mbar_wait(EMPTY(stage), phase ^ 1);
+                            mbar_expect_tx(FULL(stage), nbox * 2 * TC_BOX_BYTES + TC_W_STAGE);
                         }
-                        tma_load_2d(sbase + TcSmem::w + stage * TC_W_STAGE, &map_w, ch * TC_CHUNK, 0, FULL(stage));
+                        __syncwarp();
+                        if (lane < 2 * nbox) {
+                            const int b = lane >> 1;
+                            tma_load_2d(sbase + ((lane & 1) ? TcSmem::a_lo : TcSmem::a_hi) + stage * TC_A_STAGE + b * TC_BOX_BYTES,
+                                        (lane & 1) ? &map_alo : &map_ahi, ch * TC_CHUNK, cell0 + b * TC_GROUP, FULL(stage));
+                        } else if (lane == 2 * nbox) {
+                            tma_load_2d(sbase + TcSmem::w + stage * TC_W_STAGE, &map_w, ch * TC_CHUNK, 0, FULL(stage));
+                        }
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
-            TC_MARK(1);
+            if (lane == 0) TC_MARK(1);
+            // phase 3: a stage = 64 cells x 128 genes (two 64-gene boxes side by side: the MN-major M = 128 operand)
             for (int ps = 0; ps < n_pass; ++ps) {
                 const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
                 for (int t = 0; t < n_tiles; ++t) {
                     const int cell0 = cell_begin + t * TC_TILE;
                     const int nbox = (min(TC_TILE, cell_end - cell0) + TC_GROUP - 1) / TC_GROUP;
-                    for (int ch = 2 * mt0; ch < 2 * mt1; ++ch) {
-                        mbar_wait(EMPTY(stage), phase ^ 1);
-                        mbar_expect_tx(FULL(stage), nbox * 2 * TC_BOX_BYTES);
-                        for (int b = 0; b < nbox; ++b) {
-                            tma_load_2d(sbase + TcSmem::a_hi + stage * TC_A_STAGE + b * TC_BOX_BYTES, &map_ahi, ch * TC_CHUNK,
-                                        cell0 + b * TC_GROUP, FULL(stage));
-                            tma_load_2d(sbase + TcSmem::a_lo + stage * TC_A_STAGE + b * TC_BOX_BYTES, &map_alo, ch * TC_CHUNK,
-                                        cell0 + b * TC_GROUP, FULL(stage));
+                    for (int mt = mt0; mt < mt1; ++mt) {
+                        for (int hc = 0; hc < 2; ++hc) {
+                            const int nb = min(2, nbox - 2 * hc);
+                            if (nb <= 0) break;
+                            if (lane == 0) {
+                                mbar_wait(EMPTY(stage), phase ^ 1);
+                                mbar_expect_tx(FULL(stage), nb * 4 * TC_BOX_BYTES);
+                            }
+                            __syncwarp();
+                            {
+                                const int hl = lane & 1, gh = (lane >> 1) & 1, cg = lane >> 2;
+                                if (cg < nb) {
+                                    const int off = stage * TC_A_STAGE + gh * 2 * TC_BOX_BYTES + cg * TC_BOX_BYTES;
+                                    tma_load_2d(sbase + (hl ? TcSmem::a_lo : TcSmem::a_hi) + off, hl ? &map_alo : &map_ahi,
+                                                (2 * mt + gh) * TC_CHUNK, cell0 + (2 * hc + cg) * TC_GROUP, FULL(stage));
+                                }
+                            }
+                            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                         }
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -534,42 +555,46 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             int use = 0;  // H tile buffer uses
             for (int ps = 0; ps < n_pass; ++ps) {
                 const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
-                mbar_wait(DEMPTY, (ps & 1) ^ 1);
+                const int r = ps & 1;
+                mbar_wait(DEMPTY(r), ((ps >> 1) & 1) ^ 1);
                 tc_fence_after();
                 for (int t = 0; t < n_tiles; ++t, ++use) {
                     const int hb = use & 1;
+                    const int nbox = (min(TC_TILE, cell_end - (cell_begin + t * TC_TILE)) + TC_GROUP - 1) / TC_GROUP;
                     mbar_wait(HFULL(hb), (use >> 1) & 1);
                     tc_fence_after();
                     const uint32_t hs = sbase + TcSmem::h + hb * TC_H_TILE;
                     for (int mt = mt0; mt < mt1; ++mt) {
-                        mbar_wait(FULL(stage), phase);
-                        mbar_wait(FULL(stage + 1), phase);
-                        tc_fence_after();
-                        const uint32_t ahi = sbase + TcSmem::a_hi + stage * TC_A_STAGE;
-                        const uint32_t alo = sbase + TcSmem::a_lo + stage * TC_A_STAGE;
-                        const uint32_t dD = tmem_d + (mt - mt0) * 32;
+                        const uint32_t dD = tmem_d(ps) + (mt - mt0) * 32;
+                        for (int hc = 0; hc < 2; ++hc) {
+                            if (nbox - 2 * hc <= 0) break;
+                            mbar_wait(FULL(stage), phase);
+                            tc_fence_after();
+                            const uint32_t ahi = sbase + TcSmem::a_hi + stage * TC_A_STAGE;
+                            const uint32_t alo = sbase + TcSmem::a_lo + stage * TC_A_STAGE;
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {
-                            // A operand, MN-major: 64 genes contiguous (128 B), 8 cells per swizzle atom (SBO 1024),
-                            // second 64-gene atom in the next stage (LBO = stage stride)
-                            const uint64_t da_hi = desc_sw128(ahi + ks * 2048, TC_A_STAGE, 1024);
-                            const uint64_t da_lo = desc_sw128(alo + ks * 2048, TC_A_STAGE, 1024);
-                            const uint32_t hoff = (ks >> 2) * TC_H_SUB + (ks & 3) * 32;
-                            const uint64_t dh_hi = desc_sw128(hs + hoff, 16, 1024);
-                            const uint64_t dh_lo = desc_sw128(hs + 2 * TC_H_SUB + hoff, 16, 1024);
-                            tc_mma_f16(dD, da_hi, dh_hi, ID_P3, (t | ks) != 0);
-                            tc_mma_f16(dD, da_hi, dh_lo, ID_P3, 1);
-                            tc_mma_f16(dD, da_lo, dh_hi, ID_P3, 1);
+                            for (int ks = 0; ks < 4; ++ks) {
+                                // A operand, MN-major: 64 genes contiguous (128 B), 8 cells per swizzle atom (SBO 1024),
+                                // the second 64-gene atom 8 KB further (LBO)
+                                const uint64_t da_hi = desc_sw128(ahi + ks * 2048, 2 * TC_BOX_BYTES, 1024);
+                                const uint64_t da_lo = desc_sw128(alo + ks * 2048, 2 * TC_BOX_BYTES, 1024);
+                                const uint32_t hoff = hc * TC_H_SUB + ks * 32;
+                                const uint64_t dh_hi = desc_sw128(hs + hoff, 16, 1024);
+                                const uint64_t dh_lo = desc_sw128(hs + 2 * TC_H_SUB + hoff, 16, 1024);
+                                tc_mma_f16(dD, da_hi, dh_hi, ID_P3, (t | hc | ks) != 0);
+                                if (!(p.exp_flags & 1)) {
+                                    tc_mma_f16(dD, da_hi, dh_lo, ID_P3, 1);
+                                    tc_mma_f16(dD, da_lo, dh_hi, ID_P3, 1);
+                                }
+                            }
+                            tc_commit(EMPTY(stage));
+                            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                         }
-                        tc_commit(EMPTY(stage));
-                        tc_commit(EMPTY(stage + 1));
-                        stage += 2;
-                        if (stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
                     tc_commit(HEMPTY(hb));
                     if (ps == 0 && t < 8) TC_MARK(24 + t);
                 }
-                tc_commit(DFULL);
+                tc_commit(DFULL(r));
                 TC_MARK(3 + ps);
             }
         }
@@ -789,6 +814,7 @@ static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, fl
     p.groups_total = (tc.m + TC_GROUP - 1) / TC_GROUP;
     p.Himg = tc.Himg;
     p.tiles_per_cta = tc.tiles_per_cta;
+    p.exp_flags = getenv("SWNE_TC_EXP") ? atoi(getenv("SWNE_TC_EXP")) : 0;
     const char *tl = getenv("SWNE_TC_TIMELINE");
     if (tl && !tc.dbg) CUDA_CHECK(cudaMalloc(&tc.dbg, sizeof(unsigned long long) * 64 * 148));
     p.dbg = tl ? tc.dbg : nullptr;

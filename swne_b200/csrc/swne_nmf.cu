@@ -510,7 +510,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         h->pinned_bytes = sizeof(HostTrace);
     }
     HostTrace *ht = (HostTrace *)h->pinned;
-    if (p.loss == SWNE_LOSS_MKL || p.full_traces > 0) ensure_sparse(h);
+    if (p.loss == SWNE_LOSS_MKL) ensure_sparse(h);
     if (engine == SWNE_ENGINE_TC)
         tc_prepare(h->tc, h->dA, h->ldA, n, m, (double)__builtin_bit_cast(float, h->stats.max_bits), h->sm_count, st);
 
@@ -567,9 +567,8 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         if (!mse || !want_mkl) {
             // nothing extra
         } else {
-            ensure_sparse(h);
             prof.begin(4);
-            ops_of(KPv).kl_trace(h->sp.cptr.p, h->sp.cidx.p, h->sp.cval.p, h->H.p, h->Wt.p, k, m, &h->dscal.p->kl_part, st);
+            ops_of(KPv).kl_trace(h->dA, h->ldA, n, m, h->H.p, h->Wt.p, k, &h->dscal.p->kl_part, st);
             CUDA_CHECK(cudaGetLastError());
             prof.end(4, 1);
             if (h->nranks > 1) allreduce(h, nullptr, 0, &h->dscal.p->kl_part, 1);
@@ -701,9 +700,8 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         ++i;
     } else if (mse && p.full_traces == 0 && i_e > 0 && rc == SWNE_OK && mkl_tr) {
         // final state coincides with the last block: fill in its mkl
-        ensure_sparse(h);
         CUDA_CHECK(cudaMemsetAsync(&h->dscal.p->kl_part, 0, sizeof(double), st));
-        ops_of(KPv).kl_trace(h->sp.cptr.p, h->sp.cidx.p, h->sp.cval.p, h->H.p, h->Wt.p, k, m, &h->dscal.p->kl_part, st);
+        ops_of(KPv).kl_trace(h->dA, h->ldA, n, m, h->H.p, h->Wt.p, k, &h->dscal.p->kl_part, st);
         CUDA_CHECK(cudaGetLastError());
         if (h->nranks > 1) allreduce(h, nullptr, 0, &h->dscal.p->kl_part, 1);
         CUDA_CHECK(cudaMemcpyAsync(&ht->sc, h->dscal.p, sizeof(FitScalars), cudaMemcpyDeviceToHost, st));

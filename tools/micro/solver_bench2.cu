@@ -39,11 +39,21 @@ __global__ void __launch_bounds__(128) bench(const float *G, float *X, int sweep
                 const float tmp = fmaxf(h[c][kk] - mk, 0.f);
                 const float d = tmp - h[c][kk];
                 const float2 d2 = make_float2(d, d);
+#ifdef REORDER
+                // the pair holding mu[kk+1] first: the next coordinate's scalar chain can start right away
+#pragma unroll
+                for (int q = 0; q < KP / 2; ++q) {
+                    const int pr = (q + (kk + 1) / 2) % (KP / 2);
+                    const float4 gg = g[pr / 2];
+                    mu[c][pr] = __ffma2_rn(d2, (pr & 1) ? make_float2(gg.z, gg.w) : make_float2(gg.x, gg.y), mu[c][pr]);
+                }
+#else
 #pragma unroll
                 for (int r = 0; r < KP / 4; ++r) {
                     mu[c][2 * r] = __ffma2_rn(d2, make_float2(g[r].x, g[r].y), mu[c][2 * r]);
                     mu[c][2 * r + 1] = __ffma2_rn(d2, make_float2(g[r].z, g[r].w), mu[c][2 * r + 1]);
                 }
+#endif
                 ch |= __float_as_uint(d);
                 h[c][kk] = tmp;
             }
@@ -86,5 +96,8 @@ int main()
         run<1, 1>("const 1 col/thread", dG, dX, X, grid, sweeps);
         run<1, 2>("const 2 col/thread", dG, dX, X, grid, sweeps);
     }
+    run<0, 2>("smem  2 col/thread", dG, dX, X, 148, sweeps);
+    run<0, 1>("smem  1 col/thread", dG, dX, X, 148, sweeps);
+    run<1, 1>("const 1 col/thread", dG, dX, X, 148, sweeps);
     return 0;
 }
