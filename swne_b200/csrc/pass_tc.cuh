@@ -39,11 +39,31 @@ constexpr int TC_W_STAGE = 64 * TC_CHUNK * 2;           // 8 KB  (rows 0..31 W_h
 constexpr int TC_BOX_BYTES = TC_GROUP * TC_CHUNK * 2;   // 4 KB
 constexpr int TC_H_SUB = TC_KP * 64 * 2;                // 4 KB: [32 factors][64 cells] 16-bit, K-major
 constexpr int TC_H_TILE = 4 * TC_H_SUB;                 // hi (bf16) k-half 0/1, lo (fp16) k-half 0/1
-constexpr int TC_CBUF = 8;                              // C accumulators (32 TMEM columns each) in flight
-constexpr int TC_MT_PER_PASS = 8;                       // 128-gene accumulators per gene sub-pass (8 * 32 TMEM columns)
-constexpr int TC_SOLVER_WARPS = 8;
-constexpr int TC_THREADS = (4 + TC_SOLVER_WARPS) * 32;  // warps: 0 TMA, 1 MMA, 2 H-tile loader, 3 idle, 4.. solvers
-constexpr int TC_MAX_TILES = 256;                       // tiles per CTA (one mbarrier each)
+constexpr int TC_CBUF = 8;                              // C accumulators (32 TMEM columns each) in flight (SOLVER 0)
+// SOLVER 1 TMEM map: [0,192) six C / mu tiles, [192,320) the delta operands of the 4 groups (16 hi + 16 lo columns
+// each), [320,512) two phase-3 accumulator regions of 3 x 32 columns.  SOLVER 0: [0,256) eight C tiles, [256,448).
+__host__ __device__ constexpr int tc_cbuf(int solver) { return solver ? 6 : TC_CBUF; }
+constexpr int TC_DELTA_COL = 192;
+__host__ __device__ constexpr int tc_dcol(int solver) { return solver ? 320 : 256; }
+constexpr int TC_MT_PER_PASS = 3;                       // 128-gene accumulators per phase-3 unit (3 * 32 TMEM columns, two regions)
+// two solver variants (template parameter SOLVER of the kernel):
+//   0  CUDA-core sweeps, two cells per thread, 8 solver warps
+//   1  tensor-core block Gauss-Seidel: mu lives in TMEM, the rank-8 update of every 8-coordinate block is a
+//      3xTF32 MMA whose A operand (the deltas) also sits in TMEM, only the 8 x 8 triangular part of the block runs
+//      on CUDA cores; 4 groups of 4 warps
+constexpr int TC_TGROUPS = 4;
+__host__ __device__ constexpr int tc_solver_warps(int solver) { return solver ? 4 * TC_TGROUPS : 8; }
+// TC_DRAINERS = 1 adds four dedicated drain warps (4..7) to SOLVER 1 so that phase 3 can run in waves while tiles
+// are still being solved.  Measured on cfg3 (6 tiles per SM) it loses to 4 solver groups without waves (673 vs
+// 627 us per pass: the solve latency of the last tiles, not the stream, is the critical path), so it is off.
+#ifndef TC_DRAINERS
+#define TC_DRAINERS 1
+#endif
+__host__ __device__ constexpr int tc_solver_warp0(int solver) { return (solver && TC_DRAINERS) ? 8 : 4; }
+__host__ __device__ constexpr int tc_drain_threads(int solver) { return (solver && TC_DRAINERS) ? 128 : tc_solver_warps(solver) * 32; }
+__host__ __device__ constexpr int tc_threads(int solver) { return (tc_solver_warp0(solver) + tc_solver_warps(solver)) * 32; }
+constexpr int TC_MAX_TILES = 128;                       // tiles per CTA (one mbarrier each)
+constexpr int TC_GOP = 1024;                            // one [32 x 8] tf32 operand of G' (per block, hi / lo)
 
 struct TcSmem {
     // offsets from the 1024-aligned base
@@ -51,11 +71,13 @@ struct TcSmem {
     static constexpr int a_lo = a_hi + TC_STAGES * TC_A_STAGE;
     static constexpr int w = a_lo + TC_STAGES * TC_A_STAGE;
     static constexpr int h = w + TC_STAGES * TC_W_STAGE;
-    static constexpr int g = h + 2 * TC_H_TILE;          // unit-diagonal penalised Gram G'
-    static constexpr int g0 = g + TC_KP * TC_KP * 4;     // plain Gram (loss)
-    static constexpr int dvec = g0 + TC_KP * TC_KP * 4;  // sqrt(diag), 1/sqrt(diag)
+    // solver scratch: SOLVER 0: G' and G0 (fp32, 8 KB); SOLVER 1: 8 tf32 operands of G' (8 KB)
+    static constexpr int g = h + 2 * TC_H_TILE;
+    static constexpr int g0 = g + TC_KP * TC_KP * 4;
+    static constexpr int gops = g0 + TC_KP * TC_KP * 4;
+    static constexpr int dvec = gops + 8 * TC_GOP;       // sqrt(diag), 1/sqrt(diag)
     static constexpr int bars = dvec + 2 * TC_KP * 4;
-    static constexpr int n_bars = 2 * TC_STAGES + 2 * TC_CBUF + 2 + 2 + 4 + TC_MAX_TILES;
+    static constexpr int n_bars = 2 * TC_STAGES + 2 * TC_CBUF + 2 + 2 + 4 + TC_TGROUPS + TC_MAX_TILES;
     static constexpr int misc = bars + n_bars * 8;
     static constexpr int total = misc + 64;
 };
@@ -174,6 +196,108 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, i
            ((uint32_t)a_mn_major << 15) |
            ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// no-swizzle K-major descriptor: 8-row x 16 B core matrices, LBO = distance of the two K halves, SBO = 8-row groups
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N)
+{
+    return (1u << 4) /* C = F32 */ | (2u << 7) /* A = TF32 */ | (2u << 10) /* B = TF32 */ | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// A operand from TMEM (lane = row, one 32-bit column per K element)
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&a)[8], const float (&b)[8])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+        "r"(__float_as_uint(a[4])), "r"(__float_as_uint(a[5])), "r"(__float_as_uint(a[6])), "r"(__float_as_uint(a[7])),
+        "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])), "r"(__float_as_uint(b[2])), "r"(__float_as_uint(b[3])),
+        "r"(__float_as_uint(b[4])), "r"(__float_as_uint(b[5])), "r"(__float_as_uint(b[6])), "r"(__float_as_uint(b[7]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8])
+{
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ unsigned named_bar_or(int id, int nthreads, unsigned pred)
+{
+    unsigned out;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %1, 0;\n\t"
+        "bar.red.or.pred p, %2, %3, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(out)
+        : "r"(pred), "r"(id), "r"(nthreads)
+        : "memory");
+    return out;
+}
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
 {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -190,7 +314,8 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 //               write H, the loss partial and the tile image; afterwards drain D into B
 // Phase 3 of tile t only needs tile t's solve, so the second stream over A overlaps the remaining solves.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int SOLVER>
+__global__ void __launch_bounds__(tc_threads(SOLVER), 1)
 tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                const __grid_constant__ CUtensorMap map_w, const TcPassParams p)
 {
@@ -220,7 +345,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     auto HEMPTY = [&](int b) { return bar0 + 8u * (B2 + 2 + b); };
     auto DFULL = [&](int r) { return bar0 + 8u * (B2 + 4 + r); };
     auto DEMPTY = [&](int r) { return bar0 + 8u * (B2 + 6 + r); };
-    auto TDONE = [&](int t) { return bar0 + 8u * (B2 + 8 + t); };
+    auto MBG = [&](int g) { return bar0 + 8u * (B2 + 8 + g); };            // SOLVER 1: "block MMA of group g done"
+    auto TDONE = [&](int t) { return bar0 + 8u * (B2 + 8 + TC_TGROUPS + t); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcSmem::misc);
     int *s_next = reinterpret_cast<int *>(smem + TcSmem::misc + 16);   // per-quarter job counters
 
@@ -231,8 +357,9 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
         for (int b = 0; b < TC_CBUF; ++b) { mbar_init(CFULL(b), 1); mbar_init(CEMPTY(b), 128); }
         for (int b = 0; b < 2; ++b) { mbar_init(HFULL(b), 1); mbar_init(HEMPTY(b), 1); }
-        for (int r = 0; r < 2; ++r) { mbar_init(DFULL(r), 1); mbar_init(DEMPTY(r), TC_SOLVER_WARPS * 32); }
+        for (int r = 0; r < 2; ++r) { mbar_init(DFULL(r), 1); mbar_init(DEMPTY(r), tc_drain_threads(SOLVER)); }
         for (int t = 0; t < n_tiles; ++t) mbar_init(TDONE(t), 128);
+        for (int g = 0; g < TC_TGROUPS; ++g) mbar_init(MBG(g), 1);
         for (int q = 0; q < 4; ++q) s_next[q] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -243,7 +370,20 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     float *sD = reinterpret_cast<float *>(smem + TcSmem::dvec), *sInvD = sD + TC_KP;
     float *sGs = reinterpret_cast<float *>(smem + TcSmem::g);
     if (p.mode == 0) {
-        for (int t = threadIdx.x; t < 2 * TC_KP * TC_KP; t += blockDim.x) sGs[t] = p.pack[t];   // G' then G0
+        if (SOLVER == 0) {
+            for (int t = threadIdx.x; t < 2 * TC_KP * TC_KP; t += blockDim.x) sGs[t] = p.pack[t];   // G' then G0
+        } else {
+            // tf32 operands of G' for the block updates: op[blk][hi|lo][n][kq] = split(G'[8 blk + kq][n]), [32 x 8] K-major,
+            // no swizzle: 8-row x 16 B core matrices, the two K halves 128 B apart, 8-row groups 256 B apart
+            for (int t = threadIdx.x; t < 4 * 32 * 8; t += blockDim.x) {
+                const int blk = t >> 8, n = (t >> 3) & 31, kq = t & 7;
+                const float v = p.pack[(8 * blk + kq) * TC_KP + n];
+                const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+                const int off = (n >> 3) * 256 + (kq >> 2) * 128 + (n & 7) * 16 + (kq & 3) * 4;
+                *reinterpret_cast<float *>(smem + TcSmem::gops + (2 * blk) * TC_GOP + off) = hi;
+                *reinterpret_cast<float *>(smem + TcSmem::gops + (2 * blk + 1) * TC_GOP + off) = v - hi;
+            }
+        }
         if (threadIdx.x < 2 * TC_KP) sD[threadIdx.x] = p.pack[2 * TC_KP * TC_KP + threadIdx.x];
     }
     // generic-proxy zero fill must be visible to the async proxy (TMA / UMMA)
@@ -254,34 +394,69 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     const uint32_t tmem = *tmem_slot;
     if (threadIdx.x == 0) TC_MARK(0);
     const uint32_t tmem_c = tmem;                       // columns [0,256): eight C accumulators
-    // gene sub-pass ps accumulates into region ps & 1: columns [256,512) or, once every C tile has been consumed
-    // (all solves are done before sub-pass 0 can finish), the C region itself -> the drain of one sub-pass overlaps
-    // the MMAs of the next
-    auto tmem_d = [&](int ps) { return tmem + ((ps & 1) ? 0 : TC_CBUF * 32); };
+    // phase-3 unit u (= wave * n_pass + gene sub-pass) accumulates into region u & 1 (3 x 32 columns each): the drain
+    // of one unit overlaps the MMAs of the next
+    auto tmem_d = [&](int u) { return tmem + tc_dcol(SOLVER) + (u & 1) * (TC_MT_PER_PASS * 32); };
+    // phase 3 takes the tiles in waves (B += A'H is linear in the tiles and the drain is an atomic add), so the
+    // second stream over A starts on the tiles whose solves are done while the last tiles are still being solved
+    const int n_waves = (SOLVER == 0 || !TC_DRAINERS || p.mode != 0 || n_tiles <= 2) ? 1 : (n_tiles <= 6 ? (n_tiles + 1) / 2 : 3);
+    auto wave_lo = [&](int w) {
+        if (n_waves == 1) return w == 0 ? 0 : n_tiles;
+        if (n_tiles <= 6) return min(n_tiles, 2 * w);
+        return w == 0 ? 0 : min(n_tiles, n_tiles - 4 + 2 * (w - 1));
+    };
 
-    if (warp >= 4) {
+    // fp16 scale of the H images: the previous max(H) maps to [8, 16), which leaves a factor 4096 of growth before fp16
+    // overflows (flagged, never silent) while entries down to 1e-9 of the max keep their value
+    int h_exp = 0;
+    {
+        const float hm = __int_as_float(*p.hmax_prev);
+        if (hm > 0.f) {
+            int e;
+            frexpf(hm, &e);
+            h_exp = max(-100, min(100, 4 - e));
+        }
+    }
+    // drain of one phase-3 unit: D (128 genes x 32) -> red.add into B.  first / step select this warp's M-tiles
+    auto drain_units = [&](int first, int step) {
+        const int quarter = warp & 3;
+        const float bdescale = exp2f(-(float)(p.a_exp + h_exp));
+        for (int u = 0; u < n_waves * n_pass; ++u) {
+            const int ps = u % n_pass;
+            const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
+            mbar_wait(DFULL(u & 1), (u >> 1) & 1);
+            tc_fence_after();
+            for (int mt = mt0 + first; mt < mt1; mt += step) {
+                float d[32];
+                tc_ld32(tmem_d(u) + (mt - mt0) * 32 + ((uint32_t)(quarter * 32) << 16), d);
+                const int gene = mt * 128 + quarter * 32 + lane;
+                if (gene < p.n) {
+                    float *dst = p.B + (size_t)gene * TC_KP;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        red_add_v4(dst + 4 * r, d[4 * r] * bdescale, d[4 * r + 1] * bdescale, d[4 * r + 2] * bdescale,
+                                   d[4 * r + 3] * bdescale);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(DEMPTY(u & 1));
+            if ((warp & 3) == 0 && lane == 0 && u < 8) TC_MARK(32 + u);
+        }
+    };
+
+    if (warp >= tc_solver_warp0(SOLVER)) {
         // =========================== solver warps ===========================
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
         const float descale = exp2f(-(float)(p.a_exp + *p.w_exp));
-        // fp16 scale of the H images: the previous max(H) maps to [8, 16), which leaves a factor 4096 of growth
-        // before fp16 overflows (flagged, never silent) while entries down to 1e-9 of the max keep their value
-        int h_exp = 0;
-        {
-            const float hm = __int_as_float(*p.hmax_prev);
-            if (hm > 0.f) {
-                int e;
-                frexpf(hm, &e);
-                h_exp = max(-100, min(100, 4 - e));
-            }
-        }
         const float hscale = exp2f((float)h_exp);
         float hmax = 0.f;
         bool ovf = false;
         double lp = 0.0;
         unsigned long long its = 0;
+        const float *sInvD = sD + TC_KP;
+        if constexpr (SOLVER == 0) {
         const unsigned sg_addr = smem_u32(sGs);
         const float *sG0 = sGs + TC_KP * TC_KP;
-        const float *sInvD = sD + TC_KP;
         // a job = (pair of consecutive tiles, this warp's lane quarter): two cells per thread, one from each tile
         for (;;) {
             int u = 0;
@@ -421,10 +596,189 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                         *reinterpret_cast<__half *>(img + 2 * TC_H_SUB + off) = lo;
                     }
                     __threadfence();
+                    asm volatile("fence.proxy.async;" ::: "memory");
                     mbar_arrive(TDONE(t));
                 }
             }
             if (lane == 0 && quarter == 0 && u < 4) TC_MARK(16 + u);  // job done
+        }
+        } else {
+            // ---- tensor-core block Gauss-Seidel.  Group g (4 warps = the 4 lane quarters of a tile) solves tiles
+            // g, g+3, ...  mu' of the tile lives in its TMEM accumulator (the C tile is rewritten in place); for every
+            // block of 8 coordinates a thread reads its 8 mu' values, runs the 8 sequential coordinate steps with the
+            // triangular in-block corrections in registers, and hands the 8 deltas to one 3xTF32 MMA
+            //   Mu[128 x 32] += D[128 x 8] G'[8 x 32]
+            // (exactly the deferred rank-1 updates of scd_ls_update: entries outside the block are not read before the
+            // block ends).  Converged cells ride along with delta = 0.
+            const int grp = (warp - tc_solver_warp0(1)) >> 2;
+            const int lc = quarter * 32 + lane;
+            const uint32_t gop_u = sbase + TcSmem::gops;
+            constexpr uint32_t ID_TF32 = idesc_tf32(128, 32);
+            const uint32_t tdelta = tmem + TC_DELTA_COL + 32 * grp;          // 16 hi + 16 lo columns, 128 lanes
+            const bool any_change = p.rel_tol < 2.9e-8f;
+            uint32_t mb_parity = 0;
+            bool pending = false;
+            for (int t = grp; t < n_tiles; t += TC_TGROUPS) {
+                const int b = t % tc_cbuf(1);
+                const int cell = cell_begin + t * TC_TILE + lc;
+                const bool valid = cell < cell_end;
+                float *hrow = p.H + (size_t)(valid ? cell : cell_begin) * TC_KP;
+                const uint32_t trow = tmem_c + b * 32 + ((uint32_t)(quarter * 32) << 16);
+                if (lane == 0 && quarter == 0 && t < 8) TC_MARK(8 + t);
+                float h[32];
+                if (p.mode == 0) {
+                    mbar_wait(CFULL(b), (t / tc_cbuf(1)) & 1);
+                    tc_fence_after();
+                    {
+                        float cv[32];
+                        tc_ld32(trow, cv);
+                        float2 mu[16];
+                        if (valid) {
+                            float *crow = p.Cscr + (size_t)cell * TC_KP;
+#pragma unroll
+                            for (int r = 0; r < 8; ++r) {
+                                const float4 v = reinterpret_cast<const float4 *>(hrow)[r];
+                                h[4 * r] = v.x * sD[4 * r]; h[4 * r + 1] = v.y * sD[4 * r + 1];
+                                h[4 * r + 2] = v.z * sD[4 * r + 2]; h[4 * r + 3] = v.w * sD[4 * r + 3];
+                                const float c0 = cv[4 * r] * descale, c1 = cv[4 * r + 1] * descale, c2 = cv[4 * r + 2] * descale,
+                                            c3 = cv[4 * r + 3] * descale;
+                                reinterpret_cast<float4 *>(crow)[r] = make_float4(c0, c1, c2, c3);
+                                mu[2 * r] = make_float2((p.l1 - c0) * sInvD[4 * r], (p.l1 - c1) * sInvD[4 * r + 1]);
+                                mu[2 * r + 1] = make_float2((p.l1 - c2) * sInvD[4 * r + 2], (p.l1 - c3) * sInvD[4 * r + 3]);
+                            }
+                            scd_mu_init<TC_KP>(mu, hrow, sD, p.k);
+                        } else {
+#pragma unroll
+                            for (int f = 0; f < 32; ++f) h[f] = 0.f;
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) mu[r] = make_float2(0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) { cv[2 * r] = mu[r].x; cv[2 * r + 1] = mu[r].y; }
+                        tc_st32(trow, cv);
+                    }
+                    int my_sweeps = 1;
+                    unsigned any = 1u;
+                    long long tw = 0, tl = 0, tcmp = 0, tst = 0, tbar = 0, c0 = 0;
+                    const bool prof = p.dbg && t == 0 && quarter == 0 && lane == 0;
+                    int nrounds = 0;
+                    for (int sweep = 0; sweep < p.max_iter && any; ++sweep) {
+                        unsigned changed = 0u;
+#pragma unroll
+                        for (int blk = 0; blk < 2; ++blk) {
+                            if (blk * 16 < p.k) {
+                                if (prof) c0 = clock64();
+                                if (pending) { mbar_wait(MBG(grp), mb_parity); mb_parity ^= 1u; pending = false; }
+                                tc_fence_after();
+                                if (prof) { const long long c1 = clock64(); tw += c1 - c0; c0 = c1; }
+                                float m16[16], d[16];
+                                tc_ld16(trow + 16 * blk, m16);
+                                if (prof) { const long long c1 = clock64(); tl += c1 - c0; c0 = c1; ++nrounds; }
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    const int kk = 16 * blk + i;
+                                    const float tmp = fmaxf(h[kk] - m16[i], 0.f);
+                                    d[i] = tmp - h[kk];
+                                    if (any_change) changed |= __float_as_uint(d[i]);
+                                    else changed |= (2.f * fabsf(d[i]) > p.rel_tol * (tmp + h[kk] + TINY_NUM_F)) ? 1u : 0u;
+                                    h[kk] = tmp;
+#pragma unroll
+                                    for (int j = i + 1; j < 16; ++j) m16[j] = fmaf(d[i], c_gram[kk * TC_KP + 16 * blk + j], m16[j]);
+                                }
+                                if (prof) { const long long c1 = clock64(); tcmp += c1 - c0; c0 = c1; }
+                                {
+                                    // columns [0,16): hi (tf32-exact), [16,32): lo
+                                    float hl[32];
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) {
+                                        hl[i] = __uint_as_float(__float_as_uint(d[i]) & 0xffffe000u);
+                                        hl[16 + i] = d[i] - hl[i];
+                                    }
+                                    tc_st32(tdelta + ((uint32_t)(quarter * 32) << 16), hl);
+                                }
+                                tc_fence_before();
+                                if (prof) { const long long c1 = clock64(); tst += c1 - c0; c0 = c1; }
+                                named_bar_sync(1 + grp, 128);
+                                if (prof) { const long long c1 = clock64(); tbar += c1 - c0; c0 = c1; }
+                                if (quarter == 0 && lane == 0) {
+                                    tc_fence_after();
+                                    const uint32_t dmu = tmem_c + b * 32;
+#pragma unroll
+                                    for (int ks = 0; ks < 2; ++ks) {
+                                        const int b8 = 2 * blk + ks;     // 8-row block of G'
+                                        const uint64_t g_hi = desc_nosw(gop_u + (2 * b8) * TC_GOP, 128, 256);
+                                        const uint64_t g_lo = desc_nosw(gop_u + (2 * b8 + 1) * TC_GOP, 128, 256);
+                                        tc_mma_tf32_ts(dmu, tdelta + 8 * ks, g_hi, ID_TF32, 1);
+                                        tc_mma_tf32_ts(dmu, tdelta + 8 * ks, g_lo, ID_TF32, 1);
+                                        tc_mma_tf32_ts(dmu, tdelta + 16 + 8 * ks, g_hi, ID_TF32, 1);
+                                    }
+                                    tc_commit(MBG(grp));
+                                }
+                                pending = true;
+                            }
+                        }
+                        any = named_bar_or(1 + grp, 128, changed);
+                        if (changed) my_sweeps = min(sweep + 2, p.max_iter);
+                    }
+                    if (prof) {
+                        p.dbg[(size_t)blockIdx.x * 64 + 40] = tw; p.dbg[(size_t)blockIdx.x * 64 + 41] = tl;
+                        p.dbg[(size_t)blockIdx.x * 64 + 42] = tcmp; p.dbg[(size_t)blockIdx.x * 64 + 43] = tst;
+                        p.dbg[(size_t)blockIdx.x * 64 + 44] = tbar; p.dbg[(size_t)blockIdx.x * 64 + 45] = nrounds;
+                    }
+                    // the last block update must have landed before the accumulator goes back to the MMA warp
+                    if (pending) { mbar_wait(MBG(grp), mb_parity); mb_parity ^= 1u; pending = false; }
+                    tc_fence_after();
+                    tc_fence_before();
+                    mbar_arrive(CEMPTY(b));
+                    if (valid) {
+                        its += (unsigned long long)my_sweeps;
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            h[4 * r] *= sInvD[4 * r]; h[4 * r + 1] *= sInvD[4 * r + 1];
+                            h[4 * r + 2] *= sInvD[4 * r + 2]; h[4 * r + 3] *= sInvD[4 * r + 3];
+                            reinterpret_cast<float4 *>(hrow)[r] = make_float4(h[4 * r], h[4 * r + 1], h[4 * r + 2], h[4 * r + 3]);
+                        }
+                        float2 g0h[16];
+                        scd_g0_times<TC_KP>(g0h, hrow, p.k);
+                        const float *crow = p.Cscr + (size_t)cell * TC_KP;
+                        float s = 0.f;
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            const float4 cq = reinterpret_cast<const float4 *>(crow)[r];
+                            s = fmaf(h[4 * r + 0], g0h[2 * r].x - 2.f * cq.x, s);
+                            s = fmaf(h[4 * r + 1], g0h[2 * r].y - 2.f * cq.y, s);
+                            s = fmaf(h[4 * r + 2], g0h[2 * r + 1].x - 2.f * cq.z, s);
+                            s = fmaf(h[4 * r + 3], g0h[2 * r + 1].y - 2.f * cq.w, s);
+                        }
+                        lp += (double)s;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid) v = reinterpret_cast<const float4 *>(hrow)[r];
+                        h[4 * r] = v.x; h[4 * r + 1] = v.y; h[4 * r + 2] = v.z; h[4 * r + 3] = v.w;
+                    }
+                }
+                // split fp16 image of this cell's column of the tile (see SOLVER 0)
+                uint8_t *img = my_img + (size_t)t * TC_H_TILE + (lc >> 6) * TC_H_SUB;
+                const int cc = lc & 63;
+#pragma unroll
+                for (int f = 0; f < 32; ++f) {
+                    hmax = fmaxf(hmax, h[f]);
+                    float x = h[f] * hscale;
+                    if (x > 60000.f) { x = 60000.f; ovf = true; }
+                    const __half hi = __float2half_rn(x);
+                    const __half lo = __float2half_rn(x - __half2float(hi));
+                    const int off = f * 128 + ((((cc >> 3) ^ (f & 7)) << 4) | ((cc & 7) << 1));
+                    *reinterpret_cast<__half *>(img + off) = hi;
+                    *reinterpret_cast<__half *>(img + 2 * TC_H_SUB + off) = lo;
+                }
+                __threadfence();
+                asm volatile("fence.proxy.async;" ::: "memory");
+                mbar_arrive(TDONE(t));
+                if (lane == 0 && quarter == 0 && t < 8) TC_MARK(16 + t);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
@@ -438,29 +792,10 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                 atomicAdd(&p.scal->sweeps_h, (unsigned long long)(itd + 0.5));
             }
         }
-        // ---- drain each gene sub-pass: D (128 genes x 32) -> red.add into B
-        const float bdescale = exp2f(-(float)(p.a_exp + h_exp));
-        const int sgrp = (warp - 4) >> 2;        // 0..2: which M-tiles of the sub-pass this warp drains
-        for (int ps = 0; ps < n_pass; ++ps) {
-            const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
-            mbar_wait(DFULL(ps & 1), (ps >> 1) & 1);
-            tc_fence_after();
-            for (int mt = mt0 + sgrp; mt < mt1; mt += TC_SOLVER_WARPS / 4) {
-                float d[32];
-                tc_ld32(tmem_d(ps) + (mt - mt0) * 32 + ((uint32_t)(quarter * 32) << 16), d);
-                const int gene = mt * 128 + quarter * 32 + lane;
-                if (gene < p.n) {
-                    float *dst = p.B + (size_t)gene * TC_KP;
-#pragma unroll
-                    for (int r = 0; r < 8; ++r)
-                        red_add_v4(dst + 4 * r, d[4 * r] * bdescale, d[4 * r + 1] * bdescale, d[4 * r + 2] * bdescale,
-                                   d[4 * r + 3] * bdescale);
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(DEMPTY(ps & 1));
-            if (warp == 4 && lane == 0) TC_MARK(32 + ps);
-        }
+        if constexpr (SOLVER == 0 || !TC_DRAINERS) drain_units((warp - 4) >> 2, tc_solver_warps(SOLVER) / 4);
+    } else if (SOLVER == 1 && TC_DRAINERS && warp >= 4) {
+        // =========================== drain warps (SOLVER 1) ===========================
+        drain_units(0, 1);
     } else if (warp == 0) {
         // =========================== TMA producer ===========================
         // All lanes walk the same schedule; lane 0 waits for the slot and arms the barrier, then every box of the
@@ -491,9 +826,10 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             }
             if (lane == 0) TC_MARK(1);
             // phase 3: a stage = 64 cells x 128 genes (two 64-gene boxes side by side: the MN-major M = 128 operand)
-            for (int ps = 0; ps < n_pass; ++ps) {
+            for (int u = 0; u < n_waves * n_pass; ++u) {
+                const int ps = u % n_pass, wv = u / n_pass;
                 const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
-                for (int t = 0; t < n_tiles; ++t) {
+                for (int t = wave_lo(wv); t < wave_lo(wv + 1); ++t) {
                     const int cell0 = cell_begin + t * TC_TILE;
                     const int nbox = (min(TC_TILE, cell_end - cell0) + TC_GROUP - 1) / TC_GROUP;
                     for (int mt = mt0; mt < mt1; ++mt) {
@@ -527,8 +863,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             int stage = 0, phase = 0;
             if (p.mode == 0) {
                 for (int t = 0; t < n_tiles; ++t) {
-                    const int b = t % TC_CBUF;
-                    mbar_wait(CEMPTY(b), ((t / TC_CBUF) & 1) ^ 1);
+                    const int b = t % tc_cbuf(SOLVER);
+                    mbar_wait(CEMPTY(b), ((t / tc_cbuf(SOLVER)) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t dC = tmem_c + b * 32;
                     for (int ch = 0; ch < p.n_chunks; ++ch) {
@@ -553,19 +889,21 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             }
             TC_MARK(2);
             int use = 0;  // H tile buffer uses
-            for (int ps = 0; ps < n_pass; ++ps) {
+            for (int u = 0; u < n_waves * n_pass; ++u) {
+                const int ps = u % n_pass, wv = u / n_pass;
                 const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
-                const int r = ps & 1;
-                mbar_wait(DEMPTY(r), ((ps >> 1) & 1) ^ 1);
+                const int r = u & 1;
+                const int t_lo = wave_lo(wv);
+                mbar_wait(DEMPTY(r), ((u >> 1) & 1) ^ 1);
                 tc_fence_after();
-                for (int t = 0; t < n_tiles; ++t, ++use) {
+                for (int t = t_lo; t < wave_lo(wv + 1); ++t, ++use) {
                     const int hb = use & 1;
                     const int nbox = (min(TC_TILE, cell_end - (cell_begin + t * TC_TILE)) + TC_GROUP - 1) / TC_GROUP;
                     mbar_wait(HFULL(hb), (use >> 1) & 1);
                     tc_fence_after();
                     const uint32_t hs = sbase + TcSmem::h + hb * TC_H_TILE;
                     for (int mt = mt0; mt < mt1; ++mt) {
-                        const uint32_t dD = tmem_d(ps) + (mt - mt0) * 32;
+                        const uint32_t dD = tmem_d(u) + (mt - mt0) * 32;
                         for (int hc = 0; hc < 2; ++hc) {
                             if (nbox - 2 * hc <= 0) break;
                             mbar_wait(FULL(stage), phase);
@@ -581,7 +919,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                                 const uint32_t hoff = hc * TC_H_SUB + ks * 32;
                                 const uint64_t dh_hi = desc_sw128(hs + hoff, 16, 1024);
                                 const uint64_t dh_lo = desc_sw128(hs + 2 * TC_H_SUB + hoff, 16, 1024);
-                                tc_mma_f16(dD, da_hi, dh_hi, ID_P3, (t | hc | ks) != 0);
+                                tc_mma_f16(dD, da_hi, dh_hi, ID_P3, ((t - t_lo) | hc | ks) != 0);
                                 if (!(p.exp_flags & 1)) {
                                     tc_mma_f16(dD, da_hi, dh_lo, ID_P3, 1);
                                     tc_mma_f16(dD, da_lo, dh_hi, ID_P3, 1);
@@ -595,24 +933,29 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                     if (ps == 0 && t < 8) TC_MARK(24 + t);
                 }
                 tc_commit(DFULL(r));
-                TC_MARK(3 + ps);
+                if (u == n_waves * n_pass - 1) TC_MARK(3);
             }
         }
     } else if (warp == 2) {
         // =========================== H tile loader ===========================
         int use = 0;
-        for (int ps = 0; ps < n_pass; ++ps) {
-            for (int t = 0; t < n_tiles; ++t, ++use) {
+        for (int u = 0; u < n_waves * n_pass; ++u) {
+            const int wv = u / n_pass;
+            for (int t = wave_lo(wv); t < wave_lo(wv + 1); ++t, ++use) {
                 const int hb = use & 1;
                 mbar_wait(TDONE(t), 0);
                 mbar_wait(HEMPTY(hb), ((use >> 1) & 1) ^ 1);
-                const uint4 *src = reinterpret_cast<const uint4 *>(my_img + (size_t)t * TC_H_TILE);
-                uint4 *dst = reinterpret_cast<uint4 *>(smem + TcSmem::h + hb * TC_H_TILE);
-#pragma unroll 8
-                for (int i = lane; i < TC_H_TILE / 16; i += 32) dst[i] = __ldcg(src + i);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                // one 16 KB bulk copy (async proxy); the solver threads fenced their generic-proxy writes of the image
+                // with fence.proxy.async before arriving on TDONE
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    mbar_expect_tx(HFULL(hb), TC_H_TILE);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     sbase + TcSmem::h + hb * TC_H_TILE),
+                                 "l"(my_img + (size_t)t * TC_H_TILE), "r"(TC_H_TILE), "r"(HFULL(hb))
+                                 : "memory");
+                }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(HFULL(hb));
             }
         }
     }
@@ -770,7 +1113,8 @@ static inline void tc_prepare(TcMatrix &tc, const float *dA, size_t ldA, int n, 
     tc_make_map(&tc.map_ahi, tc.Ahi, (uint64_t)tc.n_pad, (uint64_t)m, pitch, TC_CHUNK, TC_GROUP);
     tc_make_map(&tc.map_alo, tc.Alo, (uint64_t)tc.n_pad, (uint64_t)m, pitch, TC_CHUNK, TC_GROUP);
     tc_make_map(&tc.map_w, tc.Wst, (uint64_t)tc.n_pad, 64, pitch, TC_CHUNK, 64);
-    CUDA_CHECK(cudaFuncSetAttribute(tc_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total + 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(tc_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total + 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(tc_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total + 1024));
     CUDA_CHECK(cudaStreamSynchronize(st));
     tc.ready = true;
 }
@@ -824,7 +1168,15 @@ static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, fl
         set_error("tcgen05 engine: too many cells per SM");
         throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};
     }
-    tc_pass_kernel<<<grid, TC_THREADS, TcSmem::total + 1024, st>>>(tc.map_ahi, tc.map_alo, tc.map_w, p);
+    // SWNE_TC_SOLVER=0 selects the CUDA-core sweeps (debug / comparison); default: tensor-core block Gauss-Seidel
+    static const int solver = getenv("SWNE_TC_SOLVER") ? atoi(getenv("SWNE_TC_SOLVER")) : 1;
+    if (solver == 0) {
+        tc_pass_kernel<0><<<grid, tc_threads(0), TcSmem::total + 1024, st>>>(tc.map_ahi, tc.map_alo, tc.map_w, p);
+    } else {
+        if (mode == 0)
+            CUDA_CHECK(cudaMemcpyToSymbolAsync(c_gram, pack, sizeof(float) * 2 * TC_KP * TC_KP, 0, cudaMemcpyDeviceToDevice, st));
+        tc_pass_kernel<1><<<grid, tc_threads(1), TcSmem::total + 1024, st>>>(tc.map_ahi, tc.map_alo, tc.map_w, p);
+    }
     CUDA_CHECK(cudaGetLastError());
     if (p.dbg && mode == 0) {
         // debug only: dump the per-CTA timeline of this launch (ns since the earliest CTA start)
@@ -838,6 +1190,7 @@ static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, fl
             for (int c = 0; c < grid; ++c) {
                 fprintf(f, "cta %d", c);
                 for (int s = 0; s < 40; ++s) fprintf(f, " %lld", hbuf[c * 64 + s] ? (long long)(hbuf[c * 64 + s] - t0) : -1ll);
+                for (int s = 40; s < 46; ++s) fprintf(f, " %lld", (long long)hbuf[c * 64 + s]);
                 fprintf(f, "\n");
             }
             fclose(f);

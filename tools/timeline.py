@@ -13,9 +13,14 @@ imi = int(sys.argv[1]) if len(sys.argv) > 1 else 50
 r = h.fit(c["k"], W0, H0, max_iter=8, rel_tol=-1.0, engine="tc", inner_max_iter=imi)
 rows = [list(map(int, l.split()[2:])) for l in open(os.environ["SWNE_TC_TIMELINE"])]
 a = np.array(rows, dtype=float) / 1000.0   # us
-names = {0: "start", 1: "prod_p1_end", 2: "mma_p1_end", 3: "mma_ps0_end", 4: "mma_ps1_end", 5: "mma_ps2_end", 32: "drain0", 33: "drain1", 34: "drain2"}
+names = {0: "start", 1: "prod_p1_end", 2: "mma_p1_end", 3: "mma_p3_end", 32: "drain0", 33: "drain1", 37: "drain5"}
 for s, nm in names.items():
     v = a[:, s]; v = v[v >= 0]
     print("%-12s min %.1f med %.1f max %.1f" % (nm, v.min(), np.median(v), v.max()))
+if a.shape[1] >= 46:
+    raw = np.array(rows, dtype=float)
+    for c_ in (0, 73):
+        n = max(raw[c_, 45], 1)
+        print("cta", c_, "tile-0 rounds", int(n), "cycles/round: wait_mma %.0f ld %.0f compute %.0f st %.0f barrier %.0f" % tuple(raw[c_, 40:45] / n))
 for c_ in (0, 73, 147):
     print("cta", c_, "job pick", a[c_, 8:16].round(0), "job done", a[c_, 16:24].round(0), "ps0 tile done", a[c_, 24:32].round(0))
