@@ -39,7 +39,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (one persistent nvidia-smi -lms process)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -47,37 +47,52 @@ class ClockSampler:
     def __init__(self, index=0):
         self.index = index
         self.samples = []
-        self._stop = threading.Event()
+        self._proc = None
         self._t = None
+        self.t_start = None
 
     def _loop(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        for line in self._proc.stdout:
+            parts = [x.strip() for x in line.strip().split(",")]
+            if len(parts) >= 7:
+                self.samples.append((time.perf_counter(), parts))
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._loop, daemon=True)
-        self._t.start()
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                           "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                          stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        except Exception:
+            self._proc = None
         return self
 
+    def mark(self):
+        """samples taken from now on count as 'under load'"""
+        self.t_start = time.perf_counter()
+
     def __exit__(self, *exc):
-        self._stop.set()
-        self._t.join(timeout=10)
+        if self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=5)
+            except Exception:
+                self._proc.kill()
+
+    def n_loaded(self):
+        return sum(1 for t, _ in self.samples if self.t_start is not None and t >= self.t_start)
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        rows = [r for t, r in self.samples if self.t_start is None or t >= self.t_start]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for i, nm in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(self.samples)}
+        reasons = [nm for i, nm in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(rows)}
 
 
 def cpu_oracle_leg(n, m_full, k, kt, scale, seed, cells, iters, threads=0):
@@ -103,7 +118,7 @@ def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cells = args.cells or 10000
+    cells = args.cells or 20000
     iters = max(1, args.steps)
     n, m, k = cfg["n"], cfg["m"], cfg["k"]
     t0 = time.perf_counter()
@@ -162,12 +177,16 @@ def run_ours(args, cfg):
     warm = h.fit(k, W0, H0, max_iter=max(args.warmup, 3), rel_tol=-1.0, engine=args.engine, full_traces=-1)
     barrier()
     with ClockSampler(local) as clk:
+        time.sleep(0.2)
+        clk.mark()
         t0 = time.perf_counter()
         r = h.fit(k, warm.W, warm.H, max_iter=args.steps, rel_tol=-1.0, engine=args.engine, full_traces=-1)
         barrier()
         wall = time.perf_counter() - t0
-        # keep the GPU under the same load while nvidia-smi catches a few more samples
-        if len(clk.samples) < 5:
+        # the timed region is a few tens of ms: keep the GPU under the same load (same step, untimed) until
+        # nvidia-smi has caught enough samples of the clocks under this load
+        t_load = time.perf_counter()
+        while clk.n_loaded() < 8 and time.perf_counter() - t_load < 3.0:
             h.fit(k, r.W, r.H, max_iter=max(args.steps, 20), rel_tol=-1.0, engine=args.engine, full_traces=-1)
     loop_ms = maxr(r.stats["loop_ms"])
     ms_per_step = loop_ms / args.steps
@@ -204,6 +223,8 @@ def run_ours(args, cfg):
         hostA = torch.empty((m_loc, n), dtype=torch.float32, pin_memory=True)
         hostA.copy_(dA)
         An = hostA.numpy().T          # (n, m) Fortran-ordered view of the pinned buffer: R's column-major layout
+        h.set_matrix(An)              # untimed warm-up of the host path (first-touch of staging buffers, allocator)
+        h.fit(k, warm.W, warm.H, max_iter=3, rel_tol=-1.0, engine=args.engine, full_traces=-1)
         barrier()
         t0 = time.perf_counter()
         h.set_matrix(An)
@@ -257,8 +278,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--cells", type=int, default=0, help="override the number of cells (debug / bounded CPU sample)")
-    ap.add_argument("--cpu-cells", type=int, default=10000)
-    ap.add_argument("--cpu-iters", type=int, default=4)
+    ap.add_argument("--cpu-cells", type=int, default=40000)
+    ap.add_argument("--cpu-iters", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-tol", action="store_true")

@@ -304,6 +304,175 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tensor-core block Gauss-Seidel sweeps for one tile of 128 columns (4 warps = the 4 TMEM lane quarters).
+//   mu' of the tile sits in TMEM ([128 lanes x 32 columns] at tmu, this thread's row at trow); h' in registers.
+//   Per block of 16 coordinates: read the 16 mu' values, run the 16 sequential coordinate steps with the triangular
+//   in-block corrections in registers, write the 16 deltas (tf32 hi | lo) to the TMEM operand columns and let one
+//   thread issue the 3xTF32 rank-16 update  Mu += D G'[block rows, :]  (A from TMEM, B = the G' operands in smem).
+//   Exactly the deferred rank-1 updates of scd_ls_update: entries outside the block are not read before the block
+//   ends.  Converged columns ride along with delta = 0.  Returns this column's sweep count (scd_ls_update's).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tc_block_gs(float (&h)[32], uint32_t trow, uint32_t tmu, uint32_t tdelta, uint32_t gop_u,
+                                           uint32_t mbar, uint32_t &mb_parity, bool &pending, int bar_id, int quarter, int lane,
+                                           int k, int max_iter, float rel_tol)
+{
+    constexpr uint32_t ID_TF32 = idesc_tf32(128, 32);
+    const bool any_change = rel_tol < 2.9e-8f;
+    int my_sweeps = 1;
+    unsigned any = 1u;
+    for (int sweep = 0; sweep < max_iter && any; ++sweep) {
+        unsigned changed = 0u;
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+            if (blk * 16 < k) {
+                if (pending) { mbar_wait(mbar, mb_parity); mb_parity ^= 1u; pending = false; }
+                tc_fence_after();
+                float m16[16], d[16];
+                tc_ld16(trow + 16 * blk, m16);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int kk = 16 * blk + i;
+                    const float tmp = fmaxf(h[kk] - m16[i], 0.f);
+                    d[i] = tmp - h[kk];
+                    if (any_change) changed |= __float_as_uint(d[i]);
+                    else changed |= (2.f * fabsf(d[i]) > rel_tol * (tmp + h[kk] + TINY_NUM_F)) ? 1u : 0u;
+                    h[kk] = tmp;
+#pragma unroll
+                    for (int j = i + 1; j < 16; ++j) m16[j] = fmaf(d[i], c_gram[kk * TC_KP + 16 * blk + j], m16[j]);
+                }
+                {
+                    // columns [0,16): hi (tf32-exact), [16,32): lo
+                    float hl[32];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        hl[i] = __uint_as_float(__float_as_uint(d[i]) & 0xffffe000u);
+                        hl[16 + i] = d[i] - hl[i];
+                    }
+                    tc_st32(tdelta + ((uint32_t)(quarter * 32) << 16), hl);
+                }
+                tc_fence_before();
+                named_bar_sync(bar_id, 128);
+                if (quarter == 0 && lane == 0) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const int b8 = 2 * blk + ks;     // 8-row block of G'
+                        const uint64_t g_hi = desc_nosw(gop_u + (2 * b8) * TC_GOP, 128, 256);
+                        const uint64_t g_lo = desc_nosw(gop_u + (2 * b8 + 1) * TC_GOP, 128, 256);
+                        tc_mma_tf32_ts(tmu, tdelta + 8 * ks, g_hi, ID_TF32, 1);
+                        tc_mma_tf32_ts(tmu, tdelta + 8 * ks, g_lo, ID_TF32, 1);
+                        tc_mma_tf32_ts(tmu, tdelta + 16 + 8 * ks, g_hi, ID_TF32, 1);
+                    }
+                    tc_commit(mbar);
+                }
+                pending = true;
+            }
+        }
+        any = named_bar_or(bar_id, 128, changed);
+        if (changed) my_sweeps = min(sweep + 2, max_iter);
+    }
+    return my_sweeps;
+}
+
+// tf32 operands of G' for the block updates: op[blk8][hi|lo][n][kq] = split(G'[8 blk8 + kq][n]), [32 x 8] K-major, no
+// swizzle: 8-row x 16 B core matrices, the two K halves 128 B apart, 8-row groups 256 B apart
+__device__ __forceinline__ void tc_fill_gops(uint8_t *gops, const float *__restrict__ pack, int tid, int nthreads)
+{
+    for (int t = tid; t < 4 * 32 * 8; t += nthreads) {
+        const int blk = t >> 8, n = (t >> 3) & 31, kq = t & 7;
+        const float v = pack[(8 * blk + kq) * TC_KP + n];
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const int off = (n >> 3) * 256 + (kq >> 2) * 128 + (n & 7) * 16 + (kq & 3) * 4;
+        *reinterpret_cast<float *>(gops + (2 * blk) * TC_GOP + off) = hi;
+        *reinterpret_cast<float *>(gops + (2 * blk + 1) * TC_GOP + off) = v - hi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// W-side solve with the same tensor-core sweeps: one CTA of 4 warps per 128 genes.
+//   X [cols][32] in/out, C [cols][32] = A H' (the contraction), pack = GramPack of H H' (c_gram holds its Grams).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+tc_wsolve_kernel(float *__restrict__ X, const float *__restrict__ C, const float *__restrict__ pack, float l1, int k, int cols,
+                 int max_iter, float rel_tol, unsigned long long *sweeps)
+{
+    __shared__ __align__(1024) uint8_t gops[8 * TC_GOP];
+    __shared__ float sD[2 * TC_KP];
+    __shared__ __align__(8) uint64_t mbar_store;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, quarter = warp;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(64));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    const uint32_t mbar = smem_u32(&mbar_store);
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fill_gops(gops, pack, threadIdx.x, blockDim.x);
+    if (threadIdx.x < 2 * TC_KP) sD[threadIdx.x] = pack[2 * TC_KP * TC_KP + threadIdx.x];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const float *sInvD = sD + TC_KP;
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    const bool valid = j < cols;
+    float *xrow = X + (size_t)(valid ? j : 0) * TC_KP;
+    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+    float h[32];
+    {
+        float mv[32];
+        float2 mu[16];
+        if (valid) {
+            const float4 *cp = reinterpret_cast<const float4 *>(C + (size_t)j * TC_KP);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float4 v = reinterpret_cast<const float4 *>(xrow)[r];
+                h[4 * r] = v.x * sD[4 * r]; h[4 * r + 1] = v.y * sD[4 * r + 1];
+                h[4 * r + 2] = v.z * sD[4 * r + 2]; h[4 * r + 3] = v.w * sD[4 * r + 3];
+                const float4 c = cp[r];
+                mu[2 * r] = make_float2((l1 - c.x) * sInvD[4 * r], (l1 - c.y) * sInvD[4 * r + 1]);
+                mu[2 * r + 1] = make_float2((l1 - c.z) * sInvD[4 * r + 2], (l1 - c.w) * sInvD[4 * r + 3]);
+            }
+            scd_mu_init<TC_KP>(mu, xrow, sD, k);
+        } else {
+#pragma unroll
+            for (int f = 0; f < 32; ++f) h[f] = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) mu[r] = make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { mv[2 * r] = mu[r].x; mv[2 * r + 1] = mu[r].y; }
+        tc_st32(trow, mv);
+    }
+    uint32_t mb_parity = 0;
+    bool pending = false;
+    const int my_sweeps = tc_block_gs(h, trow, tmem, tmem + 32, smem_u32(gops), mbar, mb_parity, pending, 1, quarter, lane, k,
+                                      max_iter, rel_tol);
+    if (pending) { mbar_wait(mbar, mb_parity); pending = false; }
+    tc_fence_after();
+    if (valid) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            reinterpret_cast<float4 *>(xrow)[r] = make_float4(h[4 * r] * sInvD[4 * r], h[4 * r + 1] * sInvD[4 * r + 1],
+                                                              h[4 * r + 2] * sInvD[4 * r + 2], h[4 * r + 3] * sInvD[4 * r + 3]);
+    }
+    int sw = valid ? my_sweeps : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sw += __shfl_xor_sync(0xffffffffu, sw, o);
+    if (lane == 0) atomicAdd(sweeps, (unsigned long long)sw);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // the pass kernel
 //
 //   warp 0      TMA producer: phase 1 streams (A_hi, A_lo, W) chunks of every tile, phase 3 streams (A_hi, A_lo)
@@ -373,16 +542,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         if (SOLVER == 0) {
             for (int t = threadIdx.x; t < 2 * TC_KP * TC_KP; t += blockDim.x) sGs[t] = p.pack[t];   // G' then G0
         } else {
-            // tf32 operands of G' for the block updates: op[blk][hi|lo][n][kq] = split(G'[8 blk + kq][n]), [32 x 8] K-major,
-            // no swizzle: 8-row x 16 B core matrices, the two K halves 128 B apart, 8-row groups 256 B apart
-            for (int t = threadIdx.x; t < 4 * 32 * 8; t += blockDim.x) {
-                const int blk = t >> 8, n = (t >> 3) & 31, kq = t & 7;
-                const float v = p.pack[(8 * blk + kq) * TC_KP + n];
-                const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-                const int off = (n >> 3) * 256 + (kq >> 2) * 128 + (n & 7) * 16 + (kq & 3) * 4;
-                *reinterpret_cast<float *>(smem + TcSmem::gops + (2 * blk) * TC_GOP + off) = hi;
-                *reinterpret_cast<float *>(smem + TcSmem::gops + (2 * blk + 1) * TC_GOP + off) = v - hi;
-            }
+            tc_fill_gops(smem + TcSmem::gops, p.pack, threadIdx.x, blockDim.x);
         }
         if (threadIdx.x < 2 * TC_KP) sD[threadIdx.x] = p.pack[2 * TC_KP * TC_KP + threadIdx.x];
     }
@@ -613,9 +773,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             const int grp = (warp - tc_solver_warp0(1)) >> 2;
             const int lc = quarter * 32 + lane;
             const uint32_t gop_u = sbase + TcSmem::gops;
-            constexpr uint32_t ID_TF32 = idesc_tf32(128, 32);
             const uint32_t tdelta = tmem + TC_DELTA_COL + 32 * grp;          // 16 hi + 16 lo columns, 128 lanes
-            const bool any_change = p.rel_tol < 2.9e-8f;
             uint32_t mb_parity = 0;
             bool pending = false;
             for (int t = grp; t < n_tiles; t += TC_TGROUPS) {
@@ -657,74 +815,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                         for (int r = 0; r < 16; ++r) { cv[2 * r] = mu[r].x; cv[2 * r + 1] = mu[r].y; }
                         tc_st32(trow, cv);
                     }
-                    int my_sweeps = 1;
-                    unsigned any = 1u;
-                    long long tw = 0, tl = 0, tcmp = 0, tst = 0, tbar = 0, c0 = 0;
-                    const bool prof = p.dbg && t == 0 && quarter == 0 && lane == 0;
-                    int nrounds = 0;
-                    for (int sweep = 0; sweep < p.max_iter && any; ++sweep) {
-                        unsigned changed = 0u;
-#pragma unroll
-                        for (int blk = 0; blk < 2; ++blk) {
-                            if (blk * 16 < p.k) {
-                                if (prof) c0 = clock64();
-                                if (pending) { mbar_wait(MBG(grp), mb_parity); mb_parity ^= 1u; pending = false; }
-                                tc_fence_after();
-                                if (prof) { const long long c1 = clock64(); tw += c1 - c0; c0 = c1; }
-                                float m16[16], d[16];
-                                tc_ld16(trow + 16 * blk, m16);
-                                if (prof) { const long long c1 = clock64(); tl += c1 - c0; c0 = c1; ++nrounds; }
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) {
-                                    const int kk = 16 * blk + i;
-                                    const float tmp = fmaxf(h[kk] - m16[i], 0.f);
-                                    d[i] = tmp - h[kk];
-                                    if (any_change) changed |= __float_as_uint(d[i]);
-                                    else changed |= (2.f * fabsf(d[i]) > p.rel_tol * (tmp + h[kk] + TINY_NUM_F)) ? 1u : 0u;
-                                    h[kk] = tmp;
-#pragma unroll
-                                    for (int j = i + 1; j < 16; ++j) m16[j] = fmaf(d[i], c_gram[kk * TC_KP + 16 * blk + j], m16[j]);
-                                }
-                                if (prof) { const long long c1 = clock64(); tcmp += c1 - c0; c0 = c1; }
-                                {
-                                    // columns [0,16): hi (tf32-exact), [16,32): lo
-                                    float hl[32];
-#pragma unroll
-                                    for (int i = 0; i < 16; ++i) {
-                                        hl[i] = __uint_as_float(__float_as_uint(d[i]) & 0xffffe000u);
-                                        hl[16 + i] = d[i] - hl[i];
-                                    }
-                                    tc_st32(tdelta + ((uint32_t)(quarter * 32) << 16), hl);
-                                }
-                                tc_fence_before();
-                                if (prof) { const long long c1 = clock64(); tst += c1 - c0; c0 = c1; }
-                                named_bar_sync(1 + grp, 128);
-                                if (prof) { const long long c1 = clock64(); tbar += c1 - c0; c0 = c1; }
-                                if (quarter == 0 && lane == 0) {
-                                    tc_fence_after();
-                                    const uint32_t dmu = tmem_c + b * 32;
-#pragma unroll
-                                    for (int ks = 0; ks < 2; ++ks) {
-                                        const int b8 = 2 * blk + ks;     // 8-row block of G'
-                                        const uint64_t g_hi = desc_nosw(gop_u + (2 * b8) * TC_GOP, 128, 256);
-                                        const uint64_t g_lo = desc_nosw(gop_u + (2 * b8 + 1) * TC_GOP, 128, 256);
-                                        tc_mma_tf32_ts(dmu, tdelta + 8 * ks, g_hi, ID_TF32, 1);
-                                        tc_mma_tf32_ts(dmu, tdelta + 8 * ks, g_lo, ID_TF32, 1);
-                                        tc_mma_tf32_ts(dmu, tdelta + 16 + 8 * ks, g_hi, ID_TF32, 1);
-                                    }
-                                    tc_commit(MBG(grp));
-                                }
-                                pending = true;
-                            }
-                        }
-                        any = named_bar_or(1 + grp, 128, changed);
-                        if (changed) my_sweeps = min(sweep + 2, p.max_iter);
-                    }
-                    if (prof) {
-                        p.dbg[(size_t)blockIdx.x * 64 + 40] = tw; p.dbg[(size_t)blockIdx.x * 64 + 41] = tl;
-                        p.dbg[(size_t)blockIdx.x * 64 + 42] = tcmp; p.dbg[(size_t)blockIdx.x * 64 + 43] = tst;
-                        p.dbg[(size_t)blockIdx.x * 64 + 44] = tbar; p.dbg[(size_t)blockIdx.x * 64 + 45] = nrounds;
-                    }
+                    const int my_sweeps = tc_block_gs(h, trow, tmem_c + b * 32, tdelta, gop_u, MBG(grp), mb_parity, pending, 1 + grp, quarter,
+                                                      lane, p.k, p.max_iter, p.rel_tol);
                     // the last block update must have landed before the accumulator goes back to the MMA warp
                     if (pending) { mbar_wait(MBG(grp), mb_parity); mb_parity ^= 1u; pending = false; }
                     tc_fence_after();
@@ -1196,6 +1288,14 @@ static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, fl
             fclose(f);
         }
     }
+}
+// W update through the tensor-core solver (k <= 32).  pack: GramPack of H H' with the alpha penalties
+static inline void tc_wsolve(float *Wt, const float *B, const float *pack, float l1, int k, int n, int max_iter, float rel_tol,
+                             unsigned long long *sweeps, cudaStream_t st)
+{
+    CUDA_CHECK(cudaMemcpyToSymbolAsync(c_gram, pack, sizeof(float) * 2 * TC_KP * TC_KP, 0, cudaMemcpyDeviceToDevice, st));
+    tc_wsolve_kernel<<<(n + 127) / 128, 128, 0, st>>>(Wt, B, pack, l1, k, n, max_iter, rel_tol, sweeps);
+    CUDA_CHECK(cudaGetLastError());
 }
 static inline int tc_pass_launches(int mode) { return mode == 0 ? 4 : 1; }
 

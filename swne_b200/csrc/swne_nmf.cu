@@ -631,8 +631,11 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             }
             prof.begin(3);
             launch_finalize_gram(h, k, KPv, h->G64h.p, h->pack.p, p.alpha[0], p.alpha[1]);
-            launch_solve(h, k, KPv, h->Wt.p, h->B.p, h->pack.p, (float)p.alpha[2], n, p.inner_max_iter, inner_tol,
-                         &h->dscal.p->sweeps_w, nullptr);
+            if (engine == SWNE_ENGINE_TC && !getenv("SWNE_TC_WSOLVE_SIMT"))
+                tc_wsolve(h->Wt.p, h->B.p, h->pack.p, (float)p.alpha[2], k, n, p.inner_max_iter, inner_tol, &h->dscal.p->sweeps_w, st);
+            else
+                launch_solve(h, k, KPv, h->Wt.p, h->B.p, h->pack.p, (float)p.alpha[2], n, p.inner_max_iter, inner_tol,
+                             &h->dscal.p->sweeps_w, nullptr);
             prof.end(3, 2);
             // ---------------- H update: A ~ Wt' H
             prof.begin(4);

@@ -17,10 +17,5 @@ names = {0: "start", 1: "prod_p1_end", 2: "mma_p1_end", 3: "mma_p3_end", 32: "dr
 for s, nm in names.items():
     v = a[:, s]; v = v[v >= 0]
     print("%-12s min %.1f med %.1f max %.1f" % (nm, v.min(), np.median(v), v.max()))
-if a.shape[1] >= 46:
-    raw = np.array(rows, dtype=float)
-    for c_ in (0, 73):
-        n = max(raw[c_, 45], 1)
-        print("cta", c_, "tile-0 rounds", int(n), "cycles/round: wait_mma %.0f ld %.0f compute %.0f st %.0f barrier %.0f" % tuple(raw[c_, 40:45] / n))
 for c_ in (0, 73, 147):
     print("cta", c_, "job pick", a[c_, 8:16].round(0), "job done", a[c_, 16:24].round(0), "ps0 tile done", a[c_, 24:32].round(0))
