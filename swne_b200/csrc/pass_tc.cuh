@@ -1,20 +1,21 @@
 // pass_tc.cuh -- tcgen05 engine (SWNE_ENGINE_TC) of the mse path: one persistent, warp-specialised kernel
 // per outer iteration that streams the cells x genes matrix through TMA-staged shared-memory tiles twice:
 //
-//   phase 1  C = A Wt          (cells x k)   M = 128 cells, K = genes; per tile the accumulator (TMEM) goes
-//            straight to the solver warps: thread-per-cell SCD NNLS (scd_ls_update), H written back;
+//   phase 1  C = A Wt          (cells x k)   M = 128 cells, K = genes; the accumulator of a tile (TMEM) is turned in
+//            place into the mu' of the per-cell SCD NNLS solve (scd_ls_update), which runs as a tensor-core block
+//            Gauss-Seidel on the TMEM-resident tile; H is written back;
 //   phase 3  B += A' H         (genes x k)   M = 128 genes (MN-major view of the SAME kind of tile), K = cells;
-//            accumulators for half of the genes live in TMEM (12 x 32 columns), so phase 3 runs once per gene
-//            half, each time reading only that half of every cell row; drained with vector red.add to global B.
+//            accumulators for 3 x 128 genes at a time live in TMEM (two regions), so phase 3 runs in 8 gene
+//            sub-passes, each reading only those genes of every cell row; drained with vector red.add to global B.
 //
 // Operands are "split fp16": x = hi + lo with hi = fp16(x), lo = fp16(x - hi), after a power-of-two scaling,
 // and every product is hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (the fp32-emulating scheme the
 // north star allows; error ~2^-21).  A is stored pre-split (2 + 2 bytes per entry = the 4 bytes of fp32), so
 // the algorithmic HBM traffic is unchanged and no SIMT split pass touches the streamed tile.
 //
-// Why two reads of A per iteration instead of one: the per-cell NNLS solve has a latency of 10^4..10^5
-// cycles; keeping a cell's 12 KB row on chip (smem or L2) for that long for enough cells in flight to keep the
-// CUDA cores busy needs > 200 MB chip-wide.  See DESIGN.md "pass structure".
+// Why two reads of A per iteration instead of one: the per-cell solve runs 35..50 sweeps in the iterations that
+// matter; keeping a cell's 12 KB row on chip (smem or L2) for that long for enough cells in flight needs > 200 MB
+// chip-wide.  See DESIGN.md section 5.
 //
 // Reference semantics restated: update() / scd_ls_update of NNLM, call sites
 // /root/reference/R/nmf.R:117,129.
