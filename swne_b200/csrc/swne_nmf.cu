@@ -458,6 +458,7 @@ static void validate_init(const double *x, size_t len, const char *name)
 // host mirror read back at every error block
 struct HostTrace {
     FitScalars sc;
+    int tc_overflow;   // the tcgen05 engine's "a scaled H entry left the fp16 range" flag
     double G64w[SWNE_MAX_K * SWNE_MAX_K + SWNE_MAX_K];  // W'W and column sums of W
     double G64h[SWNE_MAX_K * SWNE_MAX_K + SWNE_MAX_K];  // H H' and row sums of H (global)
 };
@@ -511,8 +512,11 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     }
     HostTrace *ht = (HostTrace *)h->pinned;
     if (p.loss == SWNE_LOSS_MKL) ensure_sparse(h);
-    if (engine == SWNE_ENGINE_TC)
+    if (engine == SWNE_ENGINE_TC) {
         tc_prepare(h->tc, h->dA, h->ldA, n, m, (double)__builtin_bit_cast(float, h->stats.max_bits), h->sm_count, st);
+        CUDA_CHECK(cudaMemsetAsync(h->tc.dev_ints + 4, 0, sizeof(int), st));
+    }
+    bool tc_overflow = false;
 
     // ---- global constants (all-reduced once)
     double gl[5] = {h->stats.sum, h->stats.sumsq, h->stats.klc, (double)h->stats.nnz, (double)m};
@@ -576,7 +580,11 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         CUDA_CHECK(cudaMemcpyAsync(&ht->sc, h->dscal.p, sizeof(FitScalars), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaMemcpyAsync(ht->G64w, h->G64w.p, sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaMemcpyAsync(ht->G64h, h->G64h.p, sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
+        ht->tc_overflow = 0;
+        if (engine == SWNE_ENGINE_TC)
+            CUDA_CHECK(cudaMemcpyAsync(&ht->tc_overflow, h->tc.dev_ints + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
+        if (ht->tc_overflow) tc_overflow = true;
         double w2 = 0, wg = 0, w1 = 0, h2 = 0, hg = 0, h1 = 0, wwhh = 0, sum_ahat = 0;
         for (int a = 0; a < k; ++a) {
             for (int b = 0; b < k; ++b) {
@@ -618,7 +626,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     };
 
     cudaEventRecord(e2, st);
-    for (; i < p.max_iter && fabs(rel_err) > p.rel_tol && rc == SWNE_OK; ++i) {
+    for (; i < p.max_iter && fabs(rel_err) > p.rel_tol && rc == SWNE_OK && !tc_overflow; ++i) {
         // loss partials restart every iteration (only the last one before a block is read)
         CUDA_CHECK(cudaMemsetAsync(h->dscal.p, 0, 3 * sizeof(double), st));
         if (mse) {
@@ -714,6 +722,18 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         mkl_tr[i_e - 1] = (klcA - ht->sc.kl_part + sum_ahat) / N;
     }
     cudaEventRecord(e3, st);
+    if (tc_overflow) {
+        // H grew by more than the 4096x headroom of its fp16 image between two iterations: the tcgen05 results of the
+        // last iterations are not trustworthy.  Nothing was written back yet (W/H still hold the caller's init): redo
+        // the fit on the fp32 engine.  Loud in verbose mode, never silent about which engine produced the result.
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+        swne_nmf_result_t dummy;
+        prof.finish(&dummy);
+        if (p.verbose) fprintf(stderr, "swne_nmf: fp16 range overflow in the tcgen05 engine, refitting with the fp32 engine\n");
+        swne_nmf_params_t p2 = *pp;
+        p2.engine = SWNE_ENGINE_SIMT;
+        return fit_impl(h, &p2, W, H, mse_tr, mkl_tr, terr_tr, epo_tr, trace_len, res);
+    }
 
     // ---- results
     download_factor_colmajor(h, h->Wt.p, W, k, KPv, n);

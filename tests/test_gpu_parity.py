@@ -315,3 +315,93 @@ def test_full_size_properties_cfg3(handle):
     assert (grad[Hs > 0].abs().max() / scale) < 5e-3
     assert (grad[Hs == 0].min() / scale) > -5e-3
     handle.set_matrix(np.zeros((4, 4)) + 1.0)    # drop the borrowed tensor
+
+
+def test_tcgen05_fp16_range_overflow_falls_back_to_fp32(handle):
+    """H images are fp16 with a scale from the previous iteration's max(H); a > 4096x jump in one iteration must be
+    detected and the fit redone on the fp32 engine (never a silent wrong answer)."""
+    from oracle import nnmf_ref
+    A = small_matrix(256, 384, 5, 21)
+    W0, H0 = seeded_init(A, 6, 21)
+    # a tiny H0 and a strong L2 penalty on W: the W update cannot absorb the scale, so the first H update grows H
+    # by many orders of magnitude within one iteration
+    H0 = H0 * 1e-6 + 1e-9
+    kw = dict(alpha=1e3, max_iter=6, trace=1, rel_tol=-1.0)
+    ref = nnmf_ref(A, 6, W0, H0, **kw)
+    assert ref["H"].max() / H0.max() > 1e5
+    handle.set_matrix(A)
+    r = handle.fit(6, W0, H0, engine="tc", **kw)
+    assert r.options["engine"] == "simt"
+    # this deliberately badly scaled start is beyond fp32-vs-fp64 parity; the fallback must equal a plain fp32-engine fit
+    rs = handle.fit(6, W0, H0, engine="simt", **kw)
+    assert np.array_equal(r["W"], rs["W"]) and np.array_equal(r["H"], rs["H"])
+    assert max_rel(r["target_loss"], rs["target_loss"]) < 1e-12 and np.all(np.isfinite(r["H"]))
+
+
+def test_one_shot_entry_points_and_progress_callback(handle):
+    """swne_nmf_fit_dense_f64 / swne_nmf_fit_csc_f64 (the NNLM_c_nnmf-shaped calls) and the interrupt callback."""
+    import ctypes
+    from swne_b200 import _capi as C
+    lib = C.load()
+    A = small_matrix(150, 260, 4, 22)
+    W0, H0 = seeded_init(A, 5, 22)
+    handle.set_matrix(A)
+    base = handle.fit(5, W0, H0, max_iter=8, trace=2, rel_tol=-1.0, engine="simt")
+    p = C.Params(); lib.swne_nmf_default_params(ctypes.byref(p), 5)
+    p.max_iter = 8; p.trace = 2; p.rel_tol = -1.0; p.engine = C.ENGINE["simt"]
+    L = 8 // 2 + 1
+    for kind in ("dense", "csc"):
+        W = np.asfortranarray(W0.copy()); H = np.asfortranarray(H0.copy())
+        mse = np.zeros(L); mkl = np.zeros(L); terr = np.zeros(L); epo = np.zeros(L)
+        res = C.Result()
+        if kind == "dense":
+            Af = np.asfortranarray(A, dtype=np.float64)
+            code = lib.swne_nmf_fit_dense_f64(handle._h, ctypes.byref(p), C.dptr(Af), 150, 260, C.dptr(W), C.dptr(H), C.dptr(mse),
+                                              C.dptr(mkl), C.dptr(terr), C.dptr(epo), L, ctypes.byref(res))
+        else:
+            S = scipy.sparse.csc_matrix(A)
+            ip = np.ascontiguousarray(S.indptr, dtype=np.int32); ii = np.ascontiguousarray(S.indices, dtype=np.int32)
+            xx = np.ascontiguousarray(S.data, dtype=np.float64)
+            code = lib.swne_nmf_fit_csc_f64(handle._h, ctypes.byref(p), C.iptr(ip), C.iptr(ii), C.dptr(xx), 150, 260, C.dptr(W),
+                                            C.dptr(H), C.dptr(mse), C.dptr(mkl), C.dptr(terr), C.dptr(epo), L, ctypes.byref(res))
+        assert code in (0, 1) and res.n_iteration == 8 and res.n_trace == len(base.mse)
+        assert np.array_equal(W, base.W) and np.array_equal(H, base.H)
+        assert max_rel(terr[:res.n_trace], base.target_loss) < 1e-12
+    # too-short trace arrays are rejected, not overrun
+    res = C.Result()
+    W = np.asfortranarray(W0.copy()); H = np.asfortranarray(H0.copy()); mse = np.zeros(2)
+    assert lib.swne_nmf_fit(handle._h, ctypes.byref(p), C.dptr(W), C.dptr(H), C.dptr(mse), None, None, None, 2, ctypes.byref(res)) == C.SWNE_ERR_BAD_ARG
+    # progress callback: called once per error block; a non-zero return interrupts (Rcpp::checkUserInterrupt hook)
+    calls = []
+    cb = C.PROGRESS_FN(lambda user, it, a, b, c, d: (calls.append(it), 1 if len(calls) == 2 else 0)[1])
+    lib.swne_nmf_set_progress(handle._h, cb, None)
+    try:
+        with pytest.raises(C.SwneError) as e:
+            handle.fit(5, W0, H0, max_iter=20, trace=2, rel_tol=-1.0)
+        assert e.value.code == C.SWNE_ERR_INTERRUPTED and calls == [1, 3]
+    finally:
+        lib.swne_nmf_set_progress(handle._h, C.PROGRESS_FN(0), None)
+
+
+def test_tcgen05_cuda_core_solver_variant(handle):
+    """SWNE_TC_SOLVER is read once per process, so the CUDA-core sweep variant of the pass kernel is exercised in a
+    child process: same parity bars."""
+    import subprocess, sys
+    code = r'''
+import sys, os
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+from helpers import small_matrix, seeded_init, rel_fro, max_rel
+from oracle import nnmf_ref
+from swne_b200 import NMFHandle
+A = small_matrix(600, 1500, 6, 5); W0, H0 = seeded_init(A, 12, 5)
+ref = nnmf_ref(A, 12, W0, H0, max_iter=10, trace=1, rel_tol=-1.0)
+h = NMFHandle(0); h.set_matrix(A)
+r = h.fit(12, W0, H0, max_iter=10, trace=1, rel_tol=-1.0, engine="tc")
+assert r.options["engine"] == "tc"
+assert max_rel(r.target_loss, ref["target_loss"]) < 1e-4 and rel_fro(r.W, ref["W"]) < 1e-3 and rel_fro(r.H, ref["H"]) < 1e-3
+print("ok")
+'''
+    env = dict(os.environ, SWNE_TC_SOLVER="0")
+    out = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
