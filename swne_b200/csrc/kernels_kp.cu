@@ -32,12 +32,43 @@ void solve_l(float *X, const float *C, const float *pack, float l1, int k, int c
     const int bs = cols <= 148 * 64 ? 32 : 128;
     scd_ls_solve_kernel<KP><<<(cols + bs - 1) / bs, bs, 0, st>>>(X, C, pack, l1, k, cols, max_iter, rel_tol, sweeps, loss_part);
 }
+template <int NT>
+static void kl_launch_nt(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y,
+                         const float *sumY, float b0, float b1, float b2, int k, int cols, int max_iter, float rel_tol,
+                         unsigned long long *sweeps, double *kl_part, double *sq_part, int err, int max_nnz, cudaStream_t st)
+{
+    // shared-memory staging of one column: (KP + 2) floats per nonzero; columns longer than cap run on global arrays
+    static bool attr_set = false;
+    const int smem_budget = 200 * 1024;
+    if (!attr_set) {
+        cudaFuncSetAttribute(scd_kl_kernel<KP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget);
+        attr_set = true;
+    }
+    const int cap_max = (smem_budget / (int)((KP + 2) * sizeof(float))) & ~3;
+    int cap = (max_nnz + 3) & ~3;
+    if (cap < 4) cap = 4;
+    if (cap > cap_max) cap = cap_max;
+    const size_t smem = (size_t)cap * (KP + 2) * sizeof(float);
+    int per_sm = (int)((220 * 1024) / (smem + 2048));
+    if (per_sm > 2048 / NT) per_sm = 2048 / NT;
+    if (per_sm < 1) per_sm = 1;
+    const int grid = cols < 148 * per_sm ? cols : 148 * per_sm;
+    scd_kl_kernel<KP, NT><<<grid, NT, smem, st>>>(ptr, idx, val, ajt, X, Y, sumY, b0, b1, b2, k, cols, max_iter, rel_tol,
+                                                  sweeps, kl_part, sq_part, err, cap);
+}
 void kl_l(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y, const float *sumY, float b0,
           float b1, float b2, int k, int cols, int max_iter, float rel_tol, unsigned long long *sweeps, double *kl_part,
-          double *sq_part, int err, cudaStream_t st)
+          double *sq_part, int err, int max_nnz, int avg_nnz, cudaStream_t st)
 {
-    scd_kl_kernel<KP><<<(cols + 3) / 4, 128, 0, st>>>(ptr, idx, val, ajt, X, Y, sumY, b0, b1, b2, k, cols, max_iter, rel_tol,
-                                                      sweeps, kl_part, sq_part, err);
+    if (avg_nnz > 320)
+        kl_launch_nt<512>(ptr, idx, val, ajt, X, Y, sumY, b0, b1, b2, k, cols, max_iter, rel_tol, sweeps, kl_part, sq_part, err,
+                          max_nnz, st);
+    else if (avg_nnz > 96)
+        kl_launch_nt<256>(ptr, idx, val, ajt, X, Y, sumY, b0, b1, b2, k, cols, max_iter, rel_tol, sweeps, kl_part, sq_part, err,
+                          max_nnz, st);
+    else
+        kl_launch_nt<64>(ptr, idx, val, ajt, X, Y, sumY, b0, b1, b2, k, cols, max_iter, rel_tol, sweeps, kl_part, sq_part, err,
+                         max_nnz, st);
 }
 void kl_trace_l(const float *A, size_t ldA, int n, int m, const float *H, const float *Wt, int k, double *kl_part,
                 cudaStream_t st)

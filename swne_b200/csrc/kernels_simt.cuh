@@ -436,87 +436,154 @@ __global__ void __launch_bounds__(128) scd_ls_solve_kernel(float *__restrict__ X
 }
 
 // ----------------------------------------------------------------------------------------------
-// SCD KL update, sparse aware, one warp per column.  (scd_kl_update)
+// SCD KL update, sparse aware, one NT-thread block per column (NT sized to the column length so that
+// every thread owns one or two nonzeros: the per-coordinate chain is latency bound, not work bound).  (scd_kl_update)
 //   ptr/idx/val : the sparse view whose "columns" are the columns being solved
 //   X  [cols][KP] in/out;  Y [rows][KP] the fixed factor (row r = factors of entity r);  sumY[KP]
-//   ajt : nnz scratch (A-hat on the support).  err != 0: add sum a log(ahat+tiny) and sum a^2-2 a ahat
+//   err != 0: add sum a log(ahat+tiny) and sum a^2-2 a ahat
+// A column with at most `cap` nonzeros is staged once in shared memory -- the gathered rows of Y
+// transposed to Yt[f][q] (lanes read consecutive words), A-hat on the support and the values -- so the
+// k coordinate passes of every sweep run out of shared memory instead of re-gathering Y through L2.
+// Longer columns take the same code on the global arrays (ajt_g is the nnz-sized A-hat scratch).
 // ----------------------------------------------------------------------------------------------
-template <int KP>
-__global__ void __launch_bounds__(128) scd_kl_kernel(const int *__restrict__ ptr, const int *__restrict__ idx,
-                                                     const float *__restrict__ val, float *__restrict__ ajt,
-                                                     float *__restrict__ X, const float *__restrict__ Y,
-                                                     const float *__restrict__ sumY, float b0, float b1, float b2, int k,
-                                                     int cols, int max_iter, float rel_tol, unsigned long long *sweeps,
-                                                     double *kl_part, double *sq_part, int err)
+template <int KP, int NT, bool SM>
+__device__ __forceinline__ int kl_column(const int *__restrict__ idx, const float *__restrict__ val,
+                                         float *__restrict__ ajt_g, const float *__restrict__ Y,
+                                         const float *__restrict__ sumY, float b0, float b1, float b2, int k, int nz,
+                                         int max_iter, float rel_tol, int cap, float *Yt, float *aj, float *av, float *h,
+                                         float (*part)[2][NT / 32], int err, double &klp, double &sqp)
 {
-    __shared__ float sh[4][KP];
-    __shared__ double scratch[32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int j = blockIdx.x * 4 + wid;
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // stage / initialise A-hat on the support
+    for (int q = tid; q < nz; q += NT) {
+        const float4 *y4 = reinterpret_cast<const float4 *>(Y + (size_t)idx[q] * KP);
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < KP / 4; ++r) {
+            const float4 y = __ldg(y4 + r);
+            const float4 hh = *reinterpret_cast<const float4 *>(h + 4 * r);
+            s = fmaf(y.x, hh.x, s); s = fmaf(y.y, hh.y, s); s = fmaf(y.z, hh.z, s); s = fmaf(y.w, hh.w, s);
+            if (SM) {
+                Yt[(4 * r + 0) * cap + q] = y.x; Yt[(4 * r + 1) * cap + q] = y.y;
+                Yt[(4 * r + 2) * cap + q] = y.z; Yt[(4 * r + 3) * cap + q] = y.w;
+            }
+        }
+        if (SM) { aj[q] = s; av[q] = val[q]; }
+        else ajt_g[q] = s;
+    }
+    float sumH = 0.f;
+    for (int f = 0; f < k; ++f) sumH += h[f];
     int it = 0;
-    double klp = 0.0, sqp = 0.0;
-    if (j < cols) {
-        float *h = sh[wid];
-        for (int f = lane; f < KP; f += 32) h[f] = X[(size_t)j * KP + f];
-        __syncwarp();
-        float sumH = 0.f;
-        for (int f = 0; f < k; ++f) sumH += h[f];
-        const int b = ptr[j], e = ptr[j + 1];
-        for (int q = b + lane; q < e; q += 32) {
-            const float *y = Y + (size_t)idx[q] * KP;
+    bool again = true;
+    // The A-hat update of coordinate kk (aj += d w_kk) is applied lazily inside the accumulation loop of
+    // the next coordinate: one pass over the column per coordinate instead of two, and the update of the
+    // last coordinate of the last sweep is never needed.
+    float d_prev = 0.f;
+    int k_prev = 0;
+    float *part_f = &part[0][0][0];
+    for (; it < max_iter && again; ++it) {
+        again = false;
+        for (int kk = 0; kk < k; ++kk) {
+            const float hk = h[kk];   // read before the barrier: thread 0 rewrites it after the barrier
+            float a2 = 0.f, bb = 0.f;
+#pragma unroll 2
+            for (int q = tid; q < nz; q += NT) {
+                float a = SM ? aj[q] : ajt_g[q];
+                if (d_prev != 0.f) {
+                    // exact arithmetic keeps A-hat >= 0 (d >= -h_kk); fp32 rounding may not: clamp
+                    const float wp = SM ? Yt[k_prev * cap + q] : Y[(size_t)idx[q] * KP + k_prev];
+                    a = fmaxf(fmaf(d_prev, wp, a), 0.f);
+                    if (SM) aj[q] = a; else ajt_g[q] = a;
+                }
+                const float w = SM ? Yt[kk * cap + q] : Y[(size_t)idx[q] * KP + kk];
+                const float v = SM ? av[q] : val[q];
+                // a + 1e-16 is a normal number far below 2^126: the 2-ulp fast division is safe here
+                const float mu = __fdividef(w, a + TINY_NUM_F);
+                a2 = fmaf(v * mu, mu, a2);
+                bb = fmaf(v, mu, bb);
+            }
+            // warp fold of the pair (a2, bb) in one butterfly: after the first exchange even lanes carry a2,
+            // odd lanes bb
+            float x = (lane & 1) ? bb : a2;
+            const float y = (lane & 1) ? a2 : bb;
+            x += __shfl_xor_sync(0xffffffffu, y, 1);
+#pragma unroll
+            for (int o = 2; o < 32; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            float *pk = part_f + (kk & 1) * 2 * NW;
+            if (lane < 2) pk[lane * NW + wid] = x;
+            __syncthreads();
+            // every warp folds the 2 NW partials with the same butterfly: identical totals in all threads
+            x = (lane < 2 * NW) ? pk[lane] : 0.f;
+#pragma unroll
+            for (int o = NW / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            a2 = __shfl_sync(0xffffffffu, x, 0);
+            bb = __shfl_sync(0xffffffffu, x, NW & 31);
+            bb -= sumY[kk];
+            a2 += b0;
+            bb += a2 * hk - b2 - b1 * (sumH - hk);
+            float tmp = bb / (a2 + TINY_NUM_F);
+            if (!(tmp > 0.f)) tmp = 0.f;
+            d_prev = tmp - hk;
+            k_prev = kk;
+            if (tmp != hk) {
+                again |= (2.f * fabsf(d_prev) > rel_tol * (tmp + hk + TINY_NUM_F));
+                sumH += d_prev;
+                if (tid == 0) h[kk] = tmp;
+            }
+        }
+        __syncthreads();   // h and the partial-sum slots are reused by the next sweep
+    }
+    if (err) {
+        // A-hat recomputed from the final h: the incrementally updated values keep fp32 residue where the
+        // exact value is 0, and log(ahat + 1e-16) is sensitive exactly there
+        for (int q = tid; q < nz; q += NT) {
             float s = 0.f;
-            for (int f = 0; f < k; ++f) s = fmaf(y[f], h[f], s);
-            ajt[q] = s;
-        }
-        __syncwarp();
-        bool again = true;
-        for (; it < max_iter && again; ++it) {
-            again = false;
-            for (int kk = 0; kk < k; ++kk) {
-                float a2 = 0.f, bb = 0.f;
-                for (int q = b + lane; q < e; q += 32) {
-                    const float w = Y[(size_t)idx[q] * KP + kk];
-                    const float mu = w / (ajt[q] + TINY_NUM_F);
-                    const float av = val[q];
-                    a2 = fmaf(av * mu, mu, a2);
-                    bb = fmaf(av, mu, bb);
-                }
-                a2 = warp_sum(a2); bb = warp_sum(bb);
-                const float hk = h[kk];
-                bb -= sumY[kk];
-                a2 += b0;
-                bb += a2 * hk - b2 - b1 * (sumH - hk);
-                float tmp = bb / (a2 + TINY_NUM_F);
-                if (!(tmp > 0.f)) tmp = 0.f;
-                if (tmp != hk) {
-                    const float d = tmp - hk;
-                    // exact arithmetic keeps ajt >= 0 (d >= -h_kk); fp32 rounding may not: clamp
-                    for (int q = b + lane; q < e; q += 32) ajt[q] = fmaxf(fmaf(d, Y[(size_t)idx[q] * KP + kk], ajt[q]), 0.f);
-                    again |= (2.f * fabsf(d) > rel_tol * (tmp + hk + TINY_NUM_F));
-                    sumH += d;
-                    __syncwarp();
-                    if (lane == 0) h[kk] = tmp;
-                    __syncwarp();
-                }
-            }
-        }
-        for (int f = lane; f < KP; f += 32) X[(size_t)j * KP + f] = h[f];
-        if (err) {
-            __syncwarp();
-            // A-hat recomputed from the final h: the incrementally updated ajt keeps fp32 residue where the
-            // exact value is 0, and log(ahat + 1e-16) is sensitive exactly there
-            for (int q = b + lane; q < e; q += 32) {
+            if (SM) {
+                for (int f = 0; f < k; ++f) s = fmaf(Yt[f * cap + q], h[f], s);
+            } else {
                 const float *y = Y + (size_t)idx[q] * KP;
-                float s = 0.f;
                 for (int f = 0; f < k; ++f) s = fmaf(y[f], h[f], s);
-                const double av = (double)val[q], ah = (double)s;
-                klp += av * log(ah + TINY_NUM_D);
-                sqp += av * av - 2.0 * av * ah;
             }
+            const double a = (double)(SM ? av[q] : val[q]), ah = (double)s;
+            klp += a * log(ah + TINY_NUM_D);
+            sqp += a * a - 2.0 * a * ah;
         }
     }
-    const double tot_it = block_sum((lane == 0) ? (double)it : 0.0, scratch);
-    if (threadIdx.x == 0) atomicAdd(sweeps, (unsigned long long)(tot_it + 0.5));
+    return it;
+}
+
+template <int KP, int NT>
+__global__ void __launch_bounds__(NT) scd_kl_kernel(const int *__restrict__ ptr, const int *__restrict__ idx,
+                                                    const float *__restrict__ val, float *__restrict__ ajt,
+                                                    float *__restrict__ X, const float *__restrict__ Y,
+                                                    const float *__restrict__ sumY, float b0, float b1, float b2, int k,
+                                                    int cols, int max_iter, float rel_tol, unsigned long long *sweeps,
+                                                    double *kl_part, double *sq_part, int err, int cap)
+{
+    extern __shared__ __align__(16) float kl_dyn[];   // Yt[KP][cap] | aj[cap] | av[cap]
+    __shared__ __align__(16) float h[KP];
+    __shared__ float part[2][2][NT / 32];
+    __shared__ double scratch[32];
+    float *Yt = kl_dyn, *aj = kl_dyn + (size_t)KP * cap, *av = aj + cap;
+    unsigned long long its = 0;
+    double klp = 0.0, sqp = 0.0;
+    for (int j = blockIdx.x; j < cols; j += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < KP) h[threadIdx.x] = X[(size_t)j * KP + threadIdx.x];
+        __syncthreads();
+        const int b = ptr[j], nz = ptr[j + 1] - b;
+        int it;
+        if (nz <= cap)
+            it = kl_column<KP, NT, true>(idx + b, val + b, ajt + b, Y, sumY, b0, b1, b2, k, nz, max_iter, rel_tol, cap, Yt, aj,
+                                         av, h, part, err, klp, sqp);
+        else
+            it = kl_column<KP, NT, false>(idx + b, val + b, ajt + b, Y, sumY, b0, b1, b2, k, nz, max_iter, rel_tol, cap, Yt, aj,
+                                          av, h, part, err, klp, sqp);
+        its += (unsigned long long)it;
+        if (threadIdx.x < KP) X[(size_t)j * KP + threadIdx.x] = h[threadIdx.x];
+    }
+    if (threadIdx.x == 0 && its) atomicAdd(sweeps, its);
     if (err) {
         const double t1 = block_sum(klp, scratch);
         if (threadIdx.x == 0) atomicAdd(kl_part, t1);

@@ -19,7 +19,7 @@ struct KpOps {
                   unsigned long long *sweeps, double *loss_part, cudaStream_t st);
     void (*kl)(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y, const float *sumY,
                float b0, float b1, float b2, int k, int cols, int max_iter, float rel_tol, unsigned long long *sweeps,
-               double *kl_part, double *sq_part, int err, cudaStream_t st);
+               double *kl_part, double *sq_part, int err, int max_nnz, int avg_nnz, cudaStream_t st);
     void (*kl_trace)(const float *A, size_t ldA, int n, int m, const float *H, const float *Wt, int k, double *kl_part,
                      cudaStream_t st);
     void (*recon_error)(const float *A, size_t ldA, int n, int m, const float *Wt, const float *H, int k, double *out2, int grid,

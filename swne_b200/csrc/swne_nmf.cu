@@ -108,6 +108,8 @@ struct SparseView {
     bool ready = false;
     DevBuf<int> cptr, cidx, gptr, gidx;
     DevBuf<float> cval, gval, ajt;
+    size_t nnz = 0;
+    int cmax = 0, gmax = 0;   // longest column of each view (sizes the shared-memory staging of the KL solver)
 };
 
 }  // namespace swne
@@ -281,6 +283,7 @@ static void ensure_sparse(swne_nmf_handle_s *h)
     int nnz = 0;
     CUDA_CHECK(cudaMemcpyAsync(&nnz, sp.cptr.p + m, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    sp.nnz = (size_t)nnz;
     sp.cidx.reserve((size_t)nnz); sp.cval.reserve((size_t)nnz);
     sp.gidx.reserve((size_t)nnz); sp.gval.reserve((size_t)nnz); sp.ajt.reserve((size_t)nnz);
     fill_by_cell_kernel<<<std::min((m + 7) / 8, h->sm_count * 16), 256, 0, st>>>(h->dA, h->ldA, n, m, sp.cptr.p, sp.cidx.p,
@@ -296,7 +299,14 @@ static void ensure_sparse(swne_nmf_handle_s *h)
     exclusive_scan_kernel<<<1, 1024, 0, st>>>(tot.p, sp.gptr.p, n);
     fill_by_gene_kernel<<<grid, 128, 0, st>>>(h->dA, h->ldA, n, m, chunk, cnt2.p, sp.gptr.p, sp.gidx.p, sp.gval.p);
     CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    {
+        std::vector<int> hc((size_t)m), hg((size_t)n);
+        CUDA_CHECK(cudaMemcpyAsync(hc.data(), cnt.p, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(hg.data(), tot.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        sp.cmax = m ? *std::max_element(hc.begin(), hc.end()) : 0;
+        sp.gmax = n ? *std::max_element(hg.begin(), hg.end()) : 0;
+    }
     cnt.release(); cnt2.release(); tot.release();
     sp.ready = true;
 }
@@ -400,8 +410,10 @@ static void launch_kl(swne_nmf_handle_s *h, int k, int KPv, const int *ptr, cons
                       const float *Y, const float *sumY, const double *pen, int cols, int max_iter, float rel_tol,
                       unsigned long long *sweeps, FitScalars *sc, int err)
 {
+    const int max_nnz = (ptr == h->sp.cptr.p) ? h->sp.cmax : h->sp.gmax;
+    const int avg_nnz = (int)(h->sp.nnz / (size_t)std::max(1, (ptr == h->sp.cptr.p) ? h->m : h->n));
     ops_of(KPv).kl(ptr, idx, val, h->sp.ajt.p, X, Y, sumY, (float)pen[0], (float)pen[1], (float)pen[2], k, cols, max_iter,
-                   rel_tol, sweeps, &sc->kl_part, &sc->sq_part, err, h->stream);
+                   rel_tol, sweeps, &sc->kl_part, &sc->sq_part, err, max_nnz, avg_nnz, h->stream);
     CUDA_CHECK(cudaGetLastError());
 }
 
