@@ -1,0 +1,498 @@
+// contract_tc.cuh -- tcgen05 contractions for 32 < k <= 64 (the "wide" variant of SWNE_ENGINE_TC).
+//
+// The fused pass of pass_tc.cuh keeps a tile's mu', the solver operands and the phase-3 accumulators in TMEM at once;
+// that budget (512 columns) only works for a 32-column factor block.  For wider factorizations (cfg5: k = 40,
+// FindNumFactors above k = 32) the two skinny contractions of update() still go to the tensor cores, un-fused:
+//
+//   tcx_cells_kernel   C = A Wt    (cells x 64)   M = 128 cells, N = 64, K = genes        -> global C (fp32)
+//   tcx_genes_kernel   B += A' H   (genes x 64)   M = 128 genes (MN-major view), N = 64, K = cells -> red.add into B
+//
+// and the per-column NNLS solves run on the CUDA-core kernels (scd_ls_solve_kernel<64>).  Operands are the same
+// split-fp16 pairs (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) on the same pre-split copy of A; W and H are
+// re-split every iteration with exact power-of-two scales taken from their maxima, so there is no range guess.
+// A is streamed twice per iteration (once by each kernel), like the fused pass.
+//
+// Reference semantics restated: the two products of update() in NNLM, call sites
+// /root/reference/R/nmf.R:117,129.
+#pragma once
+#include "pass_tc.cuh"
+
+namespace swne {
+
+constexpr int TCX_KP = 64;
+constexpr int TCX_W_STAGE = 2 * TCX_KP * TC_CHUNK * 2;   // 16 KB: rows 0..63 W_hi, 64..127 W_lo, 64 genes each
+constexpr int TCX_H_SUB = TCX_KP * 64 * 2;               // 8 KB: [64 factors][64 cells] fp16, K-major
+constexpr int TCX_H_TILE = 4 * TCX_H_SUB;                // hi cells 0..63, hi cells 64..127, lo, lo
+constexpr int TCX_THREADS_CELLS = 6 * 32;                // producer, MMA, 4 epilogue warps
+constexpr int TCX_THREADS_GENES = 8 * 32;                // producer, MMA, H loader, (idle), 4 drain warps
+
+struct TcxSmemCells {
+    static constexpr int a_hi = 0;
+    static constexpr int a_lo = a_hi + TC_STAGES * TC_A_STAGE;
+    static constexpr int w = a_lo + TC_STAGES * TC_A_STAGE;
+    static constexpr int bars = w + TC_STAGES * TCX_W_STAGE;
+    static constexpr int n_bars = 2 * TC_STAGES + 4;
+    static constexpr int misc = bars + n_bars * 8;
+    static constexpr int total = misc + 64;
+};
+struct TcxSmemGenes {
+    static constexpr int a_hi = 0;
+    static constexpr int a_lo = a_hi + TC_STAGES * TC_A_STAGE;
+    static constexpr int h = a_lo + TC_STAGES * TC_A_STAGE;
+    static constexpr int bars = h + 2 * TCX_H_TILE;
+    static constexpr int n_bars = 2 * TC_STAGES + 8;
+    static constexpr int misc = bars + n_bars * 8;
+    static constexpr int total = misc + 64;
+};
+
+struct TcxParams {
+    int n, m;
+    int ld;                // row stride (= padded factor count KP, a multiple of 8, <= 64) of C, B, Wt and H
+    int n_chunks;          // 64-gene chunks of the split copy (n_pad / 64)
+    int n_mtiles;          // ceil(n / 128)
+    int tiles_total;       // ceil(m / 128)
+    float *C;              // [m][ld] fp32 out (cells kernel)
+    float *B;              // [n][ld] fp32, accumulated with red.add (genes kernel; zeroed by the caller)
+    const uint8_t *Himg;   // [tiles_total][TCX_H_TILE] split images of H (genes kernel)
+    const int *x_exp;      // device: exponent the W (cells kernel) or H (genes kernel) operand was scaled by
+    int a_exp;
+};
+
+__device__ __forceinline__ void tcx_my_tiles(int tiles_total, int &t_begin, int &t_count)
+{
+    const int base = tiles_total / (int)gridDim.x, rem = tiles_total % (int)gridDim.x;
+    t_begin = (int)blockIdx.x * base + min((int)blockIdx.x, rem);
+    t_count = base + ((int)blockIdx.x < rem ? 1 : 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C = A Wt.  warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue (TMEM -> global), two accumulators
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TCX_THREADS_CELLS, 1)
+tcx_cells_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+                 const __grid_constant__ CUtensorMap map_w, const TcxParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t_begin, n_tiles;
+    tcx_my_tiles(p.tiles_total, t_begin, n_tiles);
+
+    const uint32_t bar0 = sbase + TcxSmemCells::bars;
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
+    auto CFULL = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + b); };
+    auto CEMPTY = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + 2 + b); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcxSmemCells::misc);
+
+    // rows of a partial tile that TMA never writes only feed C rows that are not stored, but keep them finite
+    for (int i = threadIdx.x; i < (2 * TC_STAGES * TC_A_STAGE) / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(smem + TcxSmemCells::a_hi)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(CFULL(b), 1); mbar_init(CEMPTY(b), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        int stage = 0, phase = 0;
+        for (int i = 0; i < n_tiles; ++i) {
+            const int cell0 = (t_begin + i) * TC_TILE;
+            const int nbox = (min(TC_TILE, p.m - cell0) + TC_GROUP - 1) / TC_GROUP;
+            for (int ch = 0; ch < p.n_chunks; ++ch) {
+                if (lane == 0) {
+                    mbar_wait(EMPTY(stage), phase ^ 1);
+                    mbar_expect_tx(FULL(stage), nbox * 2 * TC_BOX_BYTES + TCX_W_STAGE);
+                }
+                __syncwarp();
+                if (lane < 2 * nbox) {
+                    const int b = lane >> 1;
+                    tma_load_2d(sbase + ((lane & 1) ? TcxSmemCells::a_lo : TcxSmemCells::a_hi) + stage * TC_A_STAGE + b * TC_BOX_BYTES,
+                                (lane & 1) ? &map_alo : &map_ahi, ch * TC_CHUNK, cell0 + b * TC_GROUP, FULL(stage));
+                } else if (lane == 2 * nbox) {
+                    tma_load_2d(sbase + TcxSmemCells::w + stage * TCX_W_STAGE, &map_w, ch * TC_CHUNK, 0, FULL(stage));
+                }
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t ID = idesc_f16(128, TCX_KP, 0, 0, 0);
+            int stage = 0, phase = 0;
+            for (int i = 0; i < n_tiles; ++i) {
+                const int b = i & 1;
+                mbar_wait(CEMPTY(b), ((i >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t dC = tmem + b * TCX_KP;
+                for (int ch = 0; ch < p.n_chunks; ++ch) {
+                    mbar_wait(FULL(stage), phase);
+                    tc_fence_after();
+                    const uint32_t ahi = sbase + TcxSmemCells::a_hi + stage * TC_A_STAGE;
+                    const uint32_t alo = sbase + TcxSmemCells::a_lo + stage * TC_A_STAGE;
+                    const uint32_t ws = sbase + TcxSmemCells::w + stage * TCX_W_STAGE;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t da_hi = desc_sw128(ahi + ks * 32, 16, 1024);
+                        const uint64_t dw_hi = desc_sw128(ws + ks * 32, 16, 1024);
+                        tc_mma_f16(dC, da_hi, dw_hi, ID, (ch | ks) != 0);
+                        tc_mma_f16(dC, da_hi, desc_sw128(ws + TCX_KP * 128 + ks * 32, 16, 1024), ID, 1);
+                        tc_mma_f16(dC, desc_sw128(alo + ks * 32, 16, 1024), dw_hi, ID, 1);
+                    }
+                    tc_commit(EMPTY(stage));
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(CFULL(b));
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        const float descale = exp2f(-(float)(p.a_exp + *p.x_exp));
+        for (int i = 0; i < n_tiles; ++i) {
+            const int b = i & 1;
+            mbar_wait(CFULL(b), (i >> 1) & 1);
+            tc_fence_after();
+            float c0[32], c1[32];
+            const uint32_t trow = tmem + b * TCX_KP + ((uint32_t)(quarter * 32) << 16);
+            tc_ld32(trow, c0);
+            tc_ld32(trow + 32, c1);
+            tc_fence_before();
+            mbar_arrive(CEMPTY(b));
+            const int cell = (t_begin + i) * TC_TILE + quarter * 32 + lane;
+            if (cell < p.m) {
+                float4 *dst = reinterpret_cast<float4 *>(p.C + (size_t)cell * p.ld);
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (4 * r < p.ld)
+                        dst[r] = make_float4(c0[4 * r] * descale, c0[4 * r + 1] * descale, c0[4 * r + 2] * descale, c0[4 * r + 3] * descale);
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (32 + 4 * r < p.ld)
+                        dst[8 + r] = make_float4(c1[4 * r] * descale, c1[4 * r + 1] * descale, c1[4 * r + 2] * descale, c1[4 * r + 3] * descale);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// B += A' H.  warp 0 TMA producer (64 cells x 128 genes per stage), warp 1 MMA issuer, warp 2 H image loader,
+// warps 4..7 drain.  Genes are covered in sub-passes of 3 x 128 (two TMEM regions of 3 x 64 columns: the drain of
+// one sub-pass overlaps the MMAs of the next); each sub-pass streams those genes of all of this CTA's cells.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TCX_THREADS_GENES, 1)
+tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo, const TcxParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t_begin, n_tiles;
+    tcx_my_tiles(p.tiles_total, t_begin, n_tiles);
+    const int n_pass = (p.n_mtiles + TC_MT_PER_PASS - 1) / TC_MT_PER_PASS;
+
+    const uint32_t bar0 = sbase + TcxSmemGenes::bars;
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
+    constexpr int B2 = 2 * TC_STAGES;
+    auto HFULL = [&](int b) { return bar0 + 8u * (B2 + b); };
+    auto HEMPTY = [&](int b) { return bar0 + 8u * (B2 + 2 + b); };
+    auto DFULL = [&](int r) { return bar0 + 8u * (B2 + 4 + r); };
+    auto DEMPTY = [&](int r) { return bar0 + 8u * (B2 + 6 + r); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcxSmemGenes::misc);
+
+    // cells of a partial tile that TMA never writes meet zero rows of the H image: they must be finite
+    for (int i = threadIdx.x; i < (2 * TC_STAGES * TC_A_STAGE) / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(smem + TcxSmemGenes::a_hi)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(HFULL(b), 1); mbar_init(HEMPTY(b), 1); }
+        for (int r = 0; r < 2; ++r) { mbar_init(DFULL(r), 1); mbar_init(DEMPTY(r), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    auto tmem_d = [&](int u) { return tmem + (u & 1) * (TC_MT_PER_PASS * TCX_KP); };
+
+    if (warp == 0) {
+        int stage = 0, phase = 0;
+        for (int u = 0; u < n_pass; ++u) {
+            const int mt0 = u * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
+            for (int i = 0; i < n_tiles; ++i) {
+                const int cell0 = (t_begin + i) * TC_TILE;
+                const int nbox = (min(TC_TILE, p.m - cell0) + TC_GROUP - 1) / TC_GROUP;
+                for (int mt = mt0; mt < mt1; ++mt) {
+                    for (int hc = 0; hc < 2; ++hc) {
+                        const int nb = min(2, nbox - 2 * hc);
+                        if (nb <= 0) break;
+                        if (lane == 0) {
+                            mbar_wait(EMPTY(stage), phase ^ 1);
+                            mbar_expect_tx(FULL(stage), nb * 4 * TC_BOX_BYTES);
+                        }
+                        __syncwarp();
+                        {
+                            const int hl = lane & 1, gh = (lane >> 1) & 1, cg = lane >> 2;
+                            if (cg < nb) {
+                                const int off = stage * TC_A_STAGE + gh * 2 * TC_BOX_BYTES + cg * TC_BOX_BYTES;
+                                tma_load_2d(sbase + (hl ? TcxSmemGenes::a_lo : TcxSmemGenes::a_hi) + off, hl ? &map_alo : &map_ahi,
+                                            (2 * mt + gh) * TC_CHUNK, cell0 + (2 * hc + cg) * TC_GROUP, FULL(stage));
+                            }
+                        }
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t ID = idesc_f16(128, TCX_KP, 1, 0, 0);
+            int stage = 0, phase = 0, use = 0;
+            for (int u = 0; u < n_pass; ++u) {
+                const int mt0 = u * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
+                const int r = u & 1;
+                mbar_wait(DEMPTY(r), ((u >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int i = 0; i < n_tiles; ++i, ++use) {
+                    const int hb = use & 1;
+                    const int nbox = (min(TC_TILE, p.m - (t_begin + i) * TC_TILE) + TC_GROUP - 1) / TC_GROUP;
+                    mbar_wait(HFULL(hb), (use >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t hs = sbase + TcxSmemGenes::h + hb * TCX_H_TILE;
+                    for (int mt = mt0; mt < mt1; ++mt) {
+                        const uint32_t dD = tmem_d(u) + (mt - mt0) * TCX_KP;
+                        for (int hc = 0; hc < 2; ++hc) {
+                            if (nbox - 2 * hc <= 0) break;
+                            mbar_wait(FULL(stage), phase);
+                            tc_fence_after();
+                            const uint32_t ahi = sbase + TcxSmemGenes::a_hi + stage * TC_A_STAGE;
+                            const uint32_t alo = sbase + TcxSmemGenes::a_lo + stage * TC_A_STAGE;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                // A operand, MN-major: 64 genes contiguous (128 B), 8 cells per swizzle atom (SBO 1024),
+                                // the second 64-gene atom 8 KB further (LBO)
+                                const uint64_t da_hi = desc_sw128(ahi + ks * 2048, 2 * TC_BOX_BYTES, 1024);
+                                const uint64_t da_lo = desc_sw128(alo + ks * 2048, 2 * TC_BOX_BYTES, 1024);
+                                const uint32_t hoff = hc * TCX_H_SUB + ks * 32;
+                                const uint64_t dh_hi = desc_sw128(hs + hoff, 16, 1024);
+                                const uint64_t dh_lo = desc_sw128(hs + 2 * TCX_H_SUB + hoff, 16, 1024);
+                                tc_mma_f16(dD, da_hi, dh_hi, ID, (i | hc | ks) != 0);
+                                tc_mma_f16(dD, da_hi, dh_lo, ID, 1);
+                                tc_mma_f16(dD, da_lo, dh_hi, ID, 1);
+                            }
+                            tc_commit(EMPTY(stage));
+                            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    tc_commit(HEMPTY(hb));
+                }
+                tc_commit(DFULL(r));
+            }
+        }
+    } else if (warp == 2) {
+        int use = 0;
+        for (int u = 0; u < n_pass; ++u) {
+            for (int i = 0; i < n_tiles; ++i, ++use) {
+                const int hb = use & 1;
+                if (lane == 0) {
+                    mbar_wait(HEMPTY(hb), ((use >> 1) & 1) ^ 1);
+                    mbar_expect_tx(HFULL(hb), TCX_H_TILE);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     sbase + TcxSmemGenes::h + hb * TCX_H_TILE),
+                                 "l"(p.Himg + (size_t)(t_begin + i) * TCX_H_TILE), "r"(TCX_H_TILE), "r"(HFULL(hb))
+                                 : "memory");
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        const int quarter = warp & 3;
+        const float descale = exp2f(-(float)(p.a_exp + *p.x_exp));
+        for (int u = 0; u < n_pass; ++u) {
+            const int mt0 = u * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
+            mbar_wait(DFULL(u & 1), (u >> 1) & 1);
+            tc_fence_after();
+            for (int mt = mt0; mt < mt1; ++mt) {
+                const int gene = mt * 128 + quarter * 32 + lane;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float d[32];
+                    tc_ld32(tmem_d(u) + (mt - mt0) * TCX_KP + half * 32 + ((uint32_t)(quarter * 32) << 16), d);
+                    if (gene < p.n && n_tiles > 0) {
+                        float *dst = p.B + (size_t)gene * p.ld + half * 32;
+#pragma unroll
+                        for (int r = 0; r < 8; ++r)
+                            if (half * 32 + 4 * r < p.ld)
+                                red_add_v4(dst + 4 * r, d[4 * r] * descale, d[4 * r + 1] * descale, d[4 * r + 2] * descale,
+                                       d[4 * r + 3] * descale);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(DEMPTY(u & 1));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand preparation
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tcx_exp_of(int max_bits)
+{
+    const float mx = __int_as_float(max_bits);
+    int e = 0, x = 0;
+    if (mx > 0.f) {
+        frexpf(mx, &e);
+        x = 14 - e;
+    }
+    return max(-100, min(100, x));
+}
+// Wt fp32 [n][ld] -> Wst fp16 [128][n_pad] (rows 0..63 hi, 64..127 lo), scaled by 2^w_exp with max -> ~2^14
+__global__ void tcx_split_w_kernel(const float *__restrict__ Wt, int ld, int n, int n_pad, const int *__restrict__ max_bits,
+                                   int *__restrict__ w_exp_out, __half *__restrict__ Wst)
+{
+    const int w_exp = tcx_exp_of(*max_bits);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *w_exp_out = w_exp;
+    const float scale = exp2f((float)w_exp);
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_pad) return;
+#pragma unroll 4
+    for (int f = 0; f < TCX_KP; ++f) {
+        const float x = (g < n && f < ld) ? Wt[(size_t)g * ld + f] * scale : 0.f;
+        const __half h = __float2half_rn(x);
+        Wst[(size_t)f * n_pad + g] = h;
+        Wst[(size_t)(TCX_KP + f) * n_pad + g] = __float2half_rn(x - __half2float(h));
+    }
+}
+// H fp32 [m][ld] -> per 128-cell tile the smem-ready split image: four K-major [64 factors][64 cells] sub-tiles
+// (hi cells 0..63, hi cells 64..127, lo, lo) with 128 B rows in the 128B-swizzle pattern.  One block per tile.
+__global__ void __launch_bounds__(128) tcx_split_h_kernel(const float *__restrict__ H, int ld, int m, const int *__restrict__ max_bits,
+                                                          int *__restrict__ h_exp_out, uint8_t *__restrict__ Himg)
+{
+    const int h_exp = tcx_exp_of(*max_bits);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *h_exp_out = h_exp;
+    const float scale = exp2f((float)h_exp);
+    const int lc = threadIdx.x;
+    const int cell = blockIdx.x * TC_TILE + lc;
+    uint8_t *img = Himg + (size_t)blockIdx.x * TCX_H_TILE + (lc >> 6) * TCX_H_SUB;
+    const int cc = lc & 63;
+    const float4 *row = reinterpret_cast<const float4 *>(H + (size_t)min(cell, m - 1) * ld);
+#pragma unroll 4
+    for (int r = 0; r < TCX_KP / 4; ++r) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cell < m && 4 * r < ld) v = row[r];
+        const float xs[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int f = 4 * r + q;
+            const __half hi = __float2half_rn(xs[q]);
+            const __half lo = __float2half_rn(xs[q] - __half2float(hi));
+            const int off = f * 128 + ((((cc >> 3) ^ (f & 7)) << 4) | ((cc & 7) << 1));
+            *reinterpret_cast<__half *>(img + off) = hi;
+            *reinterpret_cast<__half *>(img + 2 * TCX_H_SUB + off) = lo;
+        }
+    }
+}
+
+struct TcxState {
+    int n_pad = 0, tiles_total = 0;
+    __half *Wst = nullptr;       // [128][n_pad]
+    uint8_t *Himg = nullptr;     // [tiles_total][TCX_H_TILE]
+    int *ints = nullptr;         // [0] W max bits, [1] w_exp, [2] H max bits, [3] h_exp
+    CUtensorMap map_w;
+    bool attr = false;
+};
+
+static inline void tcx_release(TcxState &x)
+{
+    if (x.Wst) cudaFree(x.Wst);
+    if (x.Himg) cudaFree(x.Himg);
+    if (x.ints) cudaFree(x.ints);
+    x = TcxState();
+}
+
+static inline bool tcx_supported(int n, int m, int k)
+{
+    return k > TC_KP && k <= TCX_KP && n >= 128 && m >= 128;
+}
+
+// tc must be prepared (split copy of A + its tensor maps)
+static inline void tcx_prepare(TcxState &x, const TcMatrix &tc)
+{
+    const int tiles_total = (tc.m + TC_TILE - 1) / TC_TILE;
+    if (x.Wst && x.n_pad == tc.n_pad && x.tiles_total == tiles_total) return;
+    tcx_release(x);
+    x.n_pad = tc.n_pad; x.tiles_total = tiles_total;
+    CUDA_CHECK(cudaMalloc(&x.Wst, (size_t)2 * TCX_KP * tc.n_pad * sizeof(__half)));
+    CUDA_CHECK(cudaMalloc(&x.Himg, (size_t)tiles_total * TCX_H_TILE));
+    CUDA_CHECK(cudaMalloc(&x.ints, 8 * sizeof(int)));
+    tc_make_map(&x.map_w, x.Wst, (uint64_t)tc.n_pad, 2 * TCX_KP, (uint64_t)tc.n_pad * sizeof(__half), TC_CHUNK, 2 * TCX_KP);
+    CUDA_CHECK(cudaFuncSetAttribute(tcx_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcxSmemCells::total + 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(tcx_genes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcxSmemGenes::total + 1024));
+}
+
+static inline TcxParams tcx_params(const TcxState &x, const TcMatrix &tc, int ld)
+{
+    TcxParams p;
+    p.n = tc.n; p.m = tc.m; p.ld = ld;
+    p.n_chunks = tc.n_pad / TC_CHUNK;
+    p.n_mtiles = (tc.n + 127) / 128;
+    p.tiles_total = x.tiles_total;
+    p.C = nullptr; p.B = nullptr; p.Himg = x.Himg; p.x_exp = nullptr;
+    p.a_exp = tc.a_exp;
+    return p;
+}
+
+// C[m][ld] = A Wt.  launches: 3
+static inline void tcx_contract_cells(TcxState &x, const TcMatrix &tc, int ld, const float *Wt, float *C, cudaStream_t st)
+{
+    CUDA_CHECK(cudaMemsetAsync(x.ints, 0, sizeof(int), st));
+    tc_absmax_kernel<<<32, 256, 0, st>>>(Wt, (size_t)tc.n * ld, x.ints);
+    tcx_split_w_kernel<<<(tc.n_pad + 127) / 128, 128, 0, st>>>(Wt, ld, tc.n, tc.n_pad, x.ints, x.ints + 1, x.Wst);
+    TcxParams p = tcx_params(x, tc, ld);
+    p.C = C; p.x_exp = x.ints + 1;
+    const int grid = std::min(tc.sm_count, x.tiles_total);
+    tcx_cells_kernel<<<grid, TCX_THREADS_CELLS, TcxSmemCells::total + 1024, st>>>(tc.map_ahi, tc.map_alo, x.map_w, p);
+    CUDA_CHECK(cudaGetLastError());
+}
+// B[n][ld] += A' H (B zeroed here).  launches: 3
+static inline void tcx_contract_genes(TcxState &x, const TcMatrix &tc, int ld, const float *H, float *B, cudaStream_t st)
+{
+    CUDA_CHECK(cudaMemsetAsync(B, 0, sizeof(float) * (size_t)tc.n * ld, st));
+    CUDA_CHECK(cudaMemsetAsync(x.ints + 2, 0, sizeof(int), st));
+    tc_absmax_kernel<<<148, 256, 0, st>>>(H, (size_t)tc.m * ld, x.ints + 2);
+    tcx_split_h_kernel<<<x.tiles_total, 128, 0, st>>>(H, ld, tc.m, x.ints + 2, x.ints + 3, x.Himg);
+    TcxParams p = tcx_params(x, tc, ld);
+    p.B = B; p.x_exp = x.ints + 3;
+    const int grid = std::min(tc.sm_count, x.tiles_total);
+    tcx_genes_kernel<<<grid, TCX_THREADS_GENES, TcxSmemGenes::total + 1024, st>>>(tc.map_ahi, tc.map_alo, p);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace swne

@@ -1178,21 +1178,25 @@ static inline void tc_release(TcMatrix &tc)
 static inline void tc_prepare(TcMatrix &tc, const float *dA, size_t ldA, int n, int m, double a_max, int sm_count, cudaStream_t st)
 {
     if (tc.ready && tc.src == dA && tc.n == n && tc.m == m) return;
-    tc_release(tc);
-    tc.n = n; tc.m = m; tc.sm_count = sm_count; tc.src = dA;
-    tc.n_pad = round_up(n, 64);
-    const size_t cnt = (size_t)m * tc.n_pad;
-    CUDA_CHECK(cudaMalloc(&tc.Ahi, cnt * sizeof(__half)));
-    CUDA_CHECK(cudaMalloc(&tc.Alo, cnt * sizeof(__half)));
-    CUDA_CHECK(cudaMalloc(&tc.Wst, (size_t)64 * tc.n_pad * sizeof(__half)));
-    CUDA_CHECK(cudaMalloc(&tc.dev_ints, 8 * sizeof(int)));
-    {
+    // a new matrix of the same shape (repeated RunNMF calls, FindNumFactors on resampled data) reuses the
+    // buffers: cudaFree/cudaMalloc of the 4-byte-per-entry split copy cost more than the split itself
+    const bool reuse = tc.Ahi && tc.n == n && tc.m == m && tc.sm_count == sm_count;
+    if (!reuse) {
+        tc_release(tc);
+        tc.n = n; tc.m = m; tc.sm_count = sm_count;
+        tc.n_pad = round_up(n, 64);
+        const size_t cnt = (size_t)m * tc.n_pad;
+        CUDA_CHECK(cudaMalloc(&tc.Ahi, cnt * sizeof(__half)));
+        CUDA_CHECK(cudaMalloc(&tc.Alo, cnt * sizeof(__half)));
+        CUDA_CHECK(cudaMalloc(&tc.Wst, (size_t)64 * tc.n_pad * sizeof(__half)));
+        CUDA_CHECK(cudaMalloc(&tc.dev_ints, 8 * sizeof(int)));
         const int groups = (m + TC_GROUP - 1) / TC_GROUP;
         tc.grid = std::min(sm_count, groups);
         const int max_groups = (groups + tc.grid - 1) / tc.grid;
         tc.tiles_per_cta = (max_groups * TC_GROUP + TC_TILE - 1) / TC_TILE;
         CUDA_CHECK(cudaMalloc(&tc.Himg, (size_t)tc.grid * tc.tiles_per_cta * TC_H_TILE));
     }
+    tc.src = dA;
     CUDA_CHECK(cudaMemsetAsync(tc.dev_ints, 0, 8 * sizeof(int), st));
     tc.a_exp = 0;
     if (a_max > 0) {

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <chrono>
 #include <vector>
 
@@ -18,6 +19,7 @@
 #include "kp_ops.h"
 #include "linalg_small.h"
 #include "pass_tc.cuh"
+#include "contract_tc.cuh"
 
 namespace swne {
 
@@ -127,6 +129,7 @@ struct swne_nmf_handle_s {
     swne::MatStats stats{};          // local
     swne::SparseView sp;
     swne::TcMatrix tc;               // split-fp16 copy + TMA descriptors for the tcgen05 engine
+    swne::TcxState tcx;              // operands of the un-fused tcgen05 contractions (32 < k <= 64)
     // communicator
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
@@ -213,6 +216,16 @@ static void set_dense(swne_nmf_handle_s *h, const T *A, int n, int m)
 {
     if (!A) FAIL(SWNE_ERR_BAD_ARG, "A is NULL");
     begin_matrix(h, n, m, true);
+    if (std::is_same<T, float>::value && h->ldA == (size_t)n) {
+        // fp32 with no row padding: the host buffer is already the device layout -- one copy straight into place,
+        // then a read-only pass for the statistics and the validation
+        CUDA_CHECK(cudaMemcpyAsync(h->dA, A, (size_t)m * n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        const int grid = (int)std::min<size_t>((size_t)m, (size_t)h->sm_count * 8);
+        ingest_dense_kernel<float><<<grid, 256, 0, h->stream>>>(h->dA, (size_t)n, nullptr, h->ldA, n, m, h->dstats.p);
+        CUDA_CHECK(cudaGetLastError());
+        check_stats(h);
+        return;
+    }
     const size_t rows_per_chunk = std::max<size_t>(1, ((size_t)256 << 20) / ((size_t)n * sizeof(T)));
     DevBuf<T> stagebuf;
     stagebuf.reserve(std::min<size_t>(rows_per_chunk, m) * (size_t)n);
@@ -505,11 +518,15 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
 
     int engine = p.engine;
     if (p.loss == SWNE_LOSS_MKL) engine = SWNE_ENGINE_SIMT;
-    if (engine == SWNE_ENGINE_AUTO) engine = tc_supported(h->n, h->m, k) ? SWNE_ENGINE_TC : SWNE_ENGINE_SIMT;
-    if (engine == SWNE_ENGINE_TC && !tc_supported(h->n, h->m, k))
+    // k <= 32: the fused pass (pass_tc.cuh); 32 < k <= 64: tcgen05 contractions + CUDA-core solves (contract_tc.cuh)
+    const bool tc_ok = (k > TC_KP) ? tcx_supported(h->n, h->m, k) : tc_supported(h->n, h->m, k);
+    if (engine == SWNE_ENGINE_AUTO) engine = tc_ok ? SWNE_ENGINE_TC : SWNE_ENGINE_SIMT;
+    if (engine == SWNE_ENGINE_TC && !tc_ok)
         FAIL(SWNE_ERR_UNSUPPORTED, "tcgen05 engine does not support this shape (n=%d, k=%d)", n, k);
     res->engine_used = engine;
-    const int KPv = (engine == SWNE_ENGINE_TC) ? TC_KP : kp_of(k);
+    const bool tcx = engine == SWNE_ENGINE_TC && k > TC_KP;   // wide variant: the loop below runs its fp32-engine branch
+    const bool fused = engine == SWNE_ENGINE_TC && !tcx;
+    const int KPv = fused ? TC_KP : kp_of(k);
     const int GS = KPv * KPv + KPv;  // Gram + column sums
 
     // ---- workspaces
@@ -527,6 +544,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     if (engine == SWNE_ENGINE_TC) {
         tc_prepare(h->tc, h->dA, h->ldA, n, m, (double)__builtin_bit_cast(float, h->stats.max_bits), h->sm_count, st);
         CUDA_CHECK(cudaMemsetAsync(h->tc.dev_ints + 4, 0, sizeof(int), st));
+        if (tcx) tcx_prepare(h->tcx, h->tc);
     }
     bool tc_overflow = false;
 
@@ -564,7 +582,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     prof.end(4, 1);
     if (h->nranks > 1) allreduce(h, nullptr, 0, h->G64h.p, GS);
     bool have_B = false;  // the tcgen05 pass leaves A H' of the *new* H behind for the next W update
-    if (engine == SWNE_ENGINE_TC) {
+    if (fused) {
         prof.begin(0);
         CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
         tc_pass(h->tc, 1, h->Wt.p, h->H.p, h->C.p, nullptr, 0.f, k, p.inner_max_iter, 0.f, h->B.p, h->dscal.p, st);
@@ -593,7 +611,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         CUDA_CHECK(cudaMemcpyAsync(ht->G64w, h->G64w.p, sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaMemcpyAsync(ht->G64h, h->G64h.p, sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
         ht->tc_overflow = 0;
-        if (engine == SWNE_ENGINE_TC)
+        if (fused)
             CUDA_CHECK(cudaMemcpyAsync(&ht->tc_overflow, h->tc.dev_ints + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         if (ht->tc_overflow) tc_overflow = true;
@@ -645,13 +663,14 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             // ---------------- W update: A' ~ H' Wt
             if (!have_B) {
                 prof.begin(2);
-                launch_contract_genes(h, KPv, h->H.p, h->B.p);
-                prof.end(2, 1);
+                if (tcx) tcx_contract_genes(h->tcx, h->tc, KPv, h->H.p, h->B.p, st);
+                else launch_contract_genes(h, KPv, h->H.p, h->B.p);
+                prof.end(2, tcx ? 3 : 1);
                 if (h->nranks > 1) { prof.begin(6); allreduce(h, h->B.p, (size_t)n * KPv, nullptr, 0); prof.end(6, 1); }
             }
             prof.begin(3);
             launch_finalize_gram(h, k, KPv, h->G64h.p, h->pack.p, p.alpha[0], p.alpha[1]);
-            if (engine == SWNE_ENGINE_TC && !getenv("SWNE_TC_WSOLVE_SIMT"))
+            if (fused && !getenv("SWNE_TC_WSOLVE_SIMT"))
                 tc_wsolve(h->Wt.p, h->B.p, h->pack.p, (float)p.alpha[2], k, n, p.inner_max_iter, inner_tol, &h->dscal.p->sweeps_w, st);
             else
                 launch_solve(h, k, KPv, h->Wt.p, h->B.p, h->pack.p, (float)p.alpha[2], n, p.inner_max_iter, inner_tol,
@@ -662,7 +681,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             launch_gram(h, KPv, h->Wt.p, n, h->G64w.p);
             launch_finalize_gram(h, k, KPv, h->G64w.p, h->pack.p, p.beta[0], p.beta[1]);
             prof.end(4, 2);
-            if (engine == SWNE_ENGINE_TC) {
+            if (fused) {
                 prof.begin(0);
                 CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
                 tc_pass(h->tc, 0, h->Wt.p, h->H.p, h->C.p, h->pack.p, (float)p.beta[2], k, p.inner_max_iter, inner_tol, h->B.p,
@@ -679,8 +698,9 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
                 }
             } else {
                 prof.begin(0);
-                launch_contract_cells(h, KPv, h->Wt.p, h->C.p);
-                prof.end(0, 1);
+                if (tcx) tcx_contract_cells(h->tcx, h->tc, KPv, h->Wt.p, h->C.p, st);
+                else launch_contract_cells(h, KPv, h->Wt.p, h->C.p);
+                prof.end(0, tcx ? 3 : 1);
                 prof.begin(1);
                 launch_solve(h, k, KPv, h->H.p, h->C.p, h->pack.p, (float)p.beta[2], m, p.inner_max_iter, inner_tol,
                              &h->dscal.p->sweeps_h, &h->dscal.p->loss_part);
@@ -1151,6 +1171,7 @@ int swne_nmf_destroy(swne_nmf_handle_t h)
     h->sp.cptr.release(); h->sp.cidx.release(); h->sp.gptr.release(); h->sp.gidx.release();
     h->sp.cval.release(); h->sp.gval.release(); h->sp.ajt.release();
     tc_release(h->tc);
+    tcx_release(h->tcx);
     h->Wt.release(); h->H.release(); h->C.release(); h->B.release(); h->G.release(); h->pack.release();
     h->G64w.release(); h->G64h.release(); h->stage.release(); h->dstats.release(); h->dscal.release(); h->red.release();
     if (h->pinned) cudaFreeHost(h->pinned);

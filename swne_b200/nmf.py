@@ -109,8 +109,9 @@ class NMFHandle:
         if self.n == 0:
             raise C.SwneError(C.SWNE_ERR_NO_MATRIX, "set_matrix first")
         n, m = self.n, self.m
-        W = np.asfortranarray(np.array(W0, dtype=np.float64, copy=True))
-        H = np.asfortranarray(np.array(H0, dtype=np.float64, copy=True))
+        # one copy each, straight into R's column-major layout (the library overwrites them with the result)
+        W = np.array(W0, dtype=np.float64, order="F", copy=True)
+        H = np.array(H0, dtype=np.float64, order="F", copy=True)
         if W.shape != (n, k) or H.shape != (k, m):
             raise ValueError("init shapes must be W %s and H %s" % ((n, k), (k, m)))
         p = C.Params()
@@ -133,7 +134,7 @@ class NMFHandle:
             import warnings
             warnings.warn("Target tolerance not reached. Try a larger max.iter.")
         t = res.n_trace
-        out = NNMF(W=np.array(W), H=np.array(H), mse=mse[:t].copy(), mkl=mkl[:t].copy(), target_loss=terr[:t].copy(),
+        out = NNMF(W=W, H=H, mse=mse[:t].copy(), mkl=mkl[:t].copy(), target_loss=terr[:t].copy(),
                    average_epochs=epo[:t].copy(), n_iteration=res.n_iteration, run_time=wall,
                    options=dict(method="scd", loss=loss, alpha=C.pad3(alpha), beta=C.pad3(beta), max_iter=max_iter,
                                 rel_tol=rel_tol, inner_max_iter=imi, inner_rel_tol=inner_rel_tol, trace=tr,

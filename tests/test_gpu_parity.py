@@ -79,6 +79,29 @@ def test_tcgen05_engine_vs_oracle(handle, n, m, kt, k, seed):
     _check_against(handle.fit(k, W0, H0, engine="tc", **kw), nnmf_ref(A, k, W0, H0, **kw))
 
 
+@pytest.mark.parametrize("n,m,kt,k,seed", [(300, 700, 12, 40, 31), (520, 1000, 20, 64, 32), (257, 385, 10, 33, 33)])
+def test_tcgen05_wide_contractions_vs_oracle(handle, n, m, kt, k, seed):
+    """32 < k <= 64: un-fused tcgen05 contractions (contract_tc.cuh) + CUDA-core solves against the fp64 oracle,
+    including partial tiles in both directions and padded factor columns"""
+    from oracle import nnmf_ref
+    A = small_matrix(n, m, kt, seed)
+    W0, H0 = seeded_init(A, k, seed)
+    iters = 10
+    ref = nnmf_ref(A, k, W0, H0, max_iter=iters, trace=1, rel_tol=-1.0)
+    handle.set_matrix(A)
+    r = handle.fit(k, W0, H0, max_iter=iters, trace=1, rel_tol=-1.0, engine="tc")
+    assert r.options["engine"] == "tc"
+    _check_against(r, ref)
+    assert r["H"].min() >= 0 and r["W"].min() >= 0
+    # the automatic choice takes the same engine, and the fp32 engine agrees to fp32 accuracy
+    ra = handle.fit(k, W0, H0, max_iter=iters, trace=1, rel_tol=-1.0)
+    assert ra.options["engine"] == "tc"
+    rs = handle.fit(k, W0, H0, max_iter=iters, trace=1, rel_tol=-1.0, engine="simt")
+    assert max_rel(r["target_loss"], rs["target_loss"]) < 1e-5
+    kw = dict(alpha=[0.05, 0.02, 0.01], beta=[0.03, 0.01, 0.02], max_iter=6, trace=1, rel_tol=-1.0)
+    _check_against(handle.fit(k, W0, H0, engine="tc", **kw), nnmf_ref(A, k, W0, H0, **kw))
+
+
 def test_mse_default_stopping_rule_matches(handle):
     from oracle import nnmf_ref
     A = small_matrix(300, 500, 6, 4)
