@@ -420,11 +420,219 @@ __global__ void __launch_bounds__(128) tcx_split_h_kernel(const float *__restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core block Gauss-Seidel solve for up to 64 coordinates (the k <= 32 form is tc_block_gs in pass_tc.cuh).
+// One CTA of 4 warps per 128 columns; mu' of the tile lives in TMEM columns [0,64), the delta operand in [64,96).
+// c_gram must hold G' and G0 at row stride 64 (tcx_repack_gram_kernel); gsrc is the same data in global memory.
+//   X [cols][ld] in/out, C [cols][ld] the contraction, dvec = D[ld] | invD[ld] of the GramPack.
+// NB = number of 16-coordinate blocks in use (ceil(k / 16)): blocks past k are never touched.
+// ------------------------------------------------------------------------------------------------
+constexpr int TCX_GOP = 2048;   // one [64 x 8] tf32 operand of G' (per 8-row block, hi / lo)
+
+__global__ void tcx_repack_gram_kernel(const float *__restrict__ pack, int ld, float *__restrict__ out)
+{
+    // out[0][64][64] = G' (unit diagonal scaled), out[1][64][64] = G0; zero outside ld x ld
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 2 * 64 * 64; t += gridDim.x * blockDim.x) {
+        const int which = t >> 12, r = (t >> 6) & 63, c = t & 63;
+        out[t] = (r < ld && c < ld) ? pack[which * ld * ld + r * ld + c] : 0.f;
+    }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(128)
+tcx_solve_kernel(float *__restrict__ X, const float *__restrict__ C, const float *__restrict__ gsrc,
+                 const float *__restrict__ dvec, int ld, float l1, int k, int cols, int max_iter, float rel_tol,
+                 unsigned long long *sweeps, double *loss_part)
+{
+    constexpr int KW = 16 * NB;
+    __shared__ __align__(1024) uint8_t gops[4 * NB * TCX_GOP];
+    __shared__ float sD[64], sInvD[64];
+    __shared__ __align__(8) uint64_t mbar_store;
+    __shared__ uint32_t tmem_slot;
+    __shared__ double scratch[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, quarter = warp;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    const uint32_t mbar = smem_u32(&mbar_store);
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // tf32 operands of G': op[b8][hi|lo][n][kq] = split(G'[8 b8 + kq][n]), [64 x 8] K-major, no swizzle
+    for (int t = threadIdx.x; t < 2 * NB * 64 * 8; t += blockDim.x) {
+        const int b8 = t >> 9, n = (t >> 3) & 63, kq = t & 7;
+        const float v = gsrc[(8 * b8 + kq) * 64 + n];
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const int off = (n >> 3) * 256 + (kq >> 2) * 128 + (n & 7) * 16 + (kq & 3) * 4;
+        *reinterpret_cast<float *>(gops + (2 * b8) * TCX_GOP + off) = hi;
+        *reinterpret_cast<float *>(gops + (2 * b8 + 1) * TCX_GOP + off) = v - hi;
+    }
+    if (threadIdx.x < 64) {
+        sD[threadIdx.x] = threadIdx.x < ld ? dvec[threadIdx.x] : 1.f;
+        sInvD[threadIdx.x] = threadIdx.x < ld ? dvec[ld + threadIdx.x] : 1.f;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t tmu = tmem, tdelta = tmem + 64;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t trow = tmu + lane_off;
+    const uint32_t gop_u = smem_u32(gops);
+    constexpr uint32_t ID_TF32 = idesc_tf32(128, 64);
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    const bool valid = j < cols;
+    float *xrow = X + (size_t)(valid ? j : 0) * ld;
+    const float *crow = C + (size_t)(valid ? j : 0) * ld;
+
+    uint32_t mb_parity = 0;
+    bool pending = false;
+    // rank-16 update Mu += D G'[16 blk .. 16 blk + 15, :] of the deltas sitting in the operand columns
+    auto issue_update = [&](int blk) {
+        tc_fence_before();
+        named_bar_sync(1, 128);
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const int b8 = 2 * blk + ks;
+                const uint64_t g_hi = desc_nosw(gop_u + (2 * b8) * TCX_GOP, 128, 256);
+                const uint64_t g_lo = desc_nosw(gop_u + (2 * b8 + 1) * TCX_GOP, 128, 256);
+                tc_mma_tf32_ts(tmu, tdelta + 8 * ks, g_hi, ID_TF32, 1);
+                tc_mma_tf32_ts(tmu, tdelta + 8 * ks, g_lo, ID_TF32, 1);
+                tc_mma_tf32_ts(tmu, tdelta + 16 + 8 * ks, g_hi, ID_TF32, 1);
+            }
+            tc_commit(mbar);
+        }
+        pending = true;
+    };
+    auto wait_update = [&]() {
+        if (pending) { mbar_wait(mbar, mb_parity); mb_parity ^= 1u; pending = false; }
+        tc_fence_after();
+    };
+    auto put_deltas = [&](const float (&d)[16]) {
+        float hl[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            hl[i] = __uint_as_float(__float_as_uint(d[i]) & 0xffffe000u);
+            hl[16 + i] = d[i] - hl[i];
+        }
+        tc_st32(tdelta + lane_off, hl);
+    };
+
+    // ---- h' = D o x; mu' = (l1 - c) / D + G' h'  (the G' h' term through the same rank-16 updates, from h' = 0)
+    float h[KW];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        float mv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int f = 16 * b + i;
+            const bool in = valid && f < ld;
+            h[f] = in ? xrow[f] * sD[f] : 0.f;
+            mv[i] = in ? (l1 - crow[f]) * sInvD[f] : 0.f;
+        }
+        {
+            uint32_t r[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(mv[i]);
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+                    trow + 16 * b),
+                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                : "memory");
+        }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        if (b * 16 < k) {
+            wait_update();
+            float d[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) d[i] = h[16 * b + i];
+            put_deltas(d);
+            issue_update(b);
+        }
+    }
+
+    // ---- sweeps
+    const bool any_change = rel_tol < 2.9e-8f;
+    int my_sweeps = 1;
+    unsigned any = 1u;
+    for (int sweep = 0; sweep < max_iter && any; ++sweep) {
+        unsigned changed = 0u;
+#pragma unroll
+        for (int blk = 0; blk < NB; ++blk) {
+            if (blk * 16 < k) {
+                wait_update();
+                float m16[16], d[16];
+                tc_ld16(trow + 16 * blk, m16);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int kk = 16 * blk + i;
+                    const float tmp = fmaxf(h[kk] - m16[i], 0.f);
+                    d[i] = tmp - h[kk];
+                    if (any_change) changed |= __float_as_uint(d[i]);
+                    else changed |= (2.f * fabsf(d[i]) > rel_tol * (tmp + h[kk] + TINY_NUM_F)) ? 1u : 0u;
+                    h[kk] = tmp;
+#pragma unroll
+                    for (int jj = i + 1; jj < 16; ++jj) m16[jj] = fmaf(d[i], c_gram[kk * 64 + 16 * blk + jj], m16[jj]);
+                }
+                put_deltas(d);
+                issue_update(blk);
+            }
+        }
+        any = named_bar_or(1, 128, changed);
+        if (changed) my_sweeps = min(sweep + 2, max_iter);
+    }
+    wait_update();
+
+    double lp = 0.0;
+    if (valid) {
+#pragma unroll
+        for (int f = 0; f < KW; ++f) {
+            h[f] *= sInvD[f];
+            if (f < ld) xrow[f] = h[f];
+        }
+        if (loss_part) {
+            // h' G0 h - 2 h' c
+            float s = 0.f;
+#pragma unroll 1
+            for (int q = 0; q < k; ++q) {
+                float t = 0.f;
+                const float *g0 = c_gram + 64 * 64 + q * 64;
+#pragma unroll
+                for (int f = 0; f < KW; ++f) t = fmaf(g0[f], h[f], t);
+                s = fmaf(xrow[q], t - 2.f * crow[q], s);
+            }
+            lp = (double)s;
+        }
+    }
+    const double tot_it = block_sum(valid ? (double)my_sweeps : 0.0, scratch);
+    if (threadIdx.x == 0) atomicAdd(sweeps, (unsigned long long)(tot_it + 0.5));
+    if (loss_part) {
+        const double tot = block_sum(lp, scratch);
+        if (threadIdx.x == 0) atomicAdd(loss_part, tot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+    }
+}
+
 struct TcxState {
     int n_pad = 0, tiles_total = 0;
     __half *Wst = nullptr;       // [128][n_pad]
     uint8_t *Himg = nullptr;     // [tiles_total][TCX_H_TILE]
     int *ints = nullptr;         // [0] W max bits, [1] w_exp, [2] H max bits, [3] h_exp
+    float *gram64 = nullptr;     // G' and G0 repacked to row stride 64 (source of c_gram and of the tf32 operands)
     CUtensorMap map_w;
     bool attr = false;
 };
@@ -434,6 +642,7 @@ static inline void tcx_release(TcxState &x)
     if (x.Wst) cudaFree(x.Wst);
     if (x.Himg) cudaFree(x.Himg);
     if (x.ints) cudaFree(x.ints);
+    if (x.gram64) cudaFree(x.gram64);
     x = TcxState();
 }
 
@@ -452,6 +661,7 @@ static inline void tcx_prepare(TcxState &x, const TcMatrix &tc)
     CUDA_CHECK(cudaMalloc(&x.Wst, (size_t)2 * TCX_KP * tc.n_pad * sizeof(__half)));
     CUDA_CHECK(cudaMalloc(&x.Himg, (size_t)tiles_total * TCX_H_TILE));
     CUDA_CHECK(cudaMalloc(&x.ints, 8 * sizeof(int)));
+    CUDA_CHECK(cudaMalloc(&x.gram64, 2 * 64 * 64 * sizeof(float)));
     tc_make_map(&x.map_w, x.Wst, (uint64_t)tc.n_pad, 2 * TCX_KP, (uint64_t)tc.n_pad * sizeof(__half), TC_CHUNK, 2 * TCX_KP);
     CUDA_CHECK(cudaFuncSetAttribute(tcx_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcxSmemCells::total + 1024));
     CUDA_CHECK(cudaFuncSetAttribute(tcx_genes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcxSmemGenes::total + 1024));
@@ -492,6 +702,22 @@ static inline void tcx_contract_genes(TcxState &x, const TcMatrix &tc, int ld, c
     p.B = B; p.x_exp = x.ints + 3;
     const int grid = std::min(tc.sm_count, x.tiles_total);
     tcx_genes_kernel<<<grid, TCX_THREADS_GENES, TcxSmemGenes::total + 1024, st>>>(tc.map_ahi, tc.map_alo, p);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// per-column NNLS solves (H side: cols = cells, loss partial wanted; W side: cols = genes).  pack: GramPack at row
+// stride ld.  launches: 2
+static inline void tcx_solve(TcxState &x, float *X, const float *C, const float *pack, int ld, float l1, int k, int cols,
+                             int max_iter, float rel_tol, unsigned long long *sweeps, double *loss_part, cudaStream_t st)
+{
+    tcx_repack_gram_kernel<<<8, 1024, 0, st>>>(pack, ld, x.gram64);
+    CUDA_CHECK(cudaMemcpyToSymbolAsync(c_gram, x.gram64, sizeof(float) * 2 * 64 * 64, 0, cudaMemcpyDeviceToDevice, st));
+    const float *dvec = pack + 2 * ld * ld;
+    const int grid = (cols + 127) / 128;
+    if (k <= 48)
+        tcx_solve_kernel<3><<<grid, 128, 0, st>>>(X, C, x.gram64, dvec, ld, l1, k, cols, max_iter, rel_tol, sweeps, loss_part);
+    else
+        tcx_solve_kernel<4><<<grid, 128, 0, st>>>(X, C, x.gram64, dvec, ld, l1, k, cols, max_iter, rel_tol, sweeps, loss_part);
     CUDA_CHECK(cudaGetLastError());
 }
 

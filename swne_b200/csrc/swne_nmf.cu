@@ -672,6 +672,9 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             launch_finalize_gram(h, k, KPv, h->G64h.p, h->pack.p, p.alpha[0], p.alpha[1]);
             if (fused && !getenv("SWNE_TC_WSOLVE_SIMT"))
                 tc_wsolve(h->Wt.p, h->B.p, h->pack.p, (float)p.alpha[2], k, n, p.inner_max_iter, inner_tol, &h->dscal.p->sweeps_w, st);
+            else if (tcx && !getenv("SWNE_TCX_SOLVE_SIMT"))
+                tcx_solve(h->tcx, h->Wt.p, h->B.p, h->pack.p, KPv, (float)p.alpha[2], k, n, p.inner_max_iter, inner_tol,
+                          &h->dscal.p->sweeps_w, nullptr, st);
             else
                 launch_solve(h, k, KPv, h->Wt.p, h->B.p, h->pack.p, (float)p.alpha[2], n, p.inner_max_iter, inner_tol,
                              &h->dscal.p->sweeps_w, nullptr);
@@ -702,8 +705,12 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
                 else launch_contract_cells(h, KPv, h->Wt.p, h->C.p);
                 prof.end(0, tcx ? 3 : 1);
                 prof.begin(1);
-                launch_solve(h, k, KPv, h->H.p, h->C.p, h->pack.p, (float)p.beta[2], m, p.inner_max_iter, inner_tol,
-                             &h->dscal.p->sweeps_h, &h->dscal.p->loss_part);
+                if (tcx && !getenv("SWNE_TCX_SOLVE_SIMT"))
+                    tcx_solve(h->tcx, h->H.p, h->C.p, h->pack.p, KPv, (float)p.beta[2], k, m, p.inner_max_iter, inner_tol,
+                              &h->dscal.p->sweeps_h, &h->dscal.p->loss_part, st);
+                else
+                    launch_solve(h, k, KPv, h->H.p, h->C.p, h->pack.p, (float)p.beta[2], m, p.inner_max_iter, inner_tol,
+                                 &h->dscal.p->sweeps_h, &h->dscal.p->loss_part);
                 prof.end(1, 1);
                 prof.begin(4);
                 launch_gram(h, KPv, h->H.p, m, h->G64h.p);
