@@ -185,8 +185,16 @@ def run_ours(args, cfg):
         wall = time.perf_counter() - t0
         # the timed region is a few tens of ms: keep the GPU under the same load (same step, untimed) until
         # nvidia-smi has caught enough samples of the clocks under this load
+        # (every fit is a collective over the ranks: the decision to run one more is all-reduced, never local)
         t_load = time.perf_counter()
-        while clk.n_loaded() < 8 and time.perf_counter() - t_load < 3.0:
+        while True:
+            more = clk.n_loaded() < 8 and time.perf_counter() - t_load < 3.0
+            if world > 1:
+                flag = torch.tensor([1 if more else 0], dtype=torch.int32, device="cuda")
+                td.all_reduce(flag, op=td.ReduceOp.MAX)
+                more = bool(flag.item())
+            if not more:
+                break
             h.fit(k, r.W, r.H, max_iter=max(args.steps, 20), rel_tol=-1.0, engine=args.engine, full_traces=-1)
     loop_ms = maxr(r.stats["loop_ms"])
     ms_per_step = loop_ms / args.steps

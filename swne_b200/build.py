@@ -31,9 +31,11 @@ def _sources():
 
 
 def _digest():
+    # file names relative to the package: the tree is copied to another absolute path on the GPU box and the
+    # shipped .so must still count as current there
     h = hashlib.sha256()
     for p in _sources():
-        h.update(p.encode())
+        h.update(os.path.relpath(p, HERE).replace(os.sep, "/").encode())
         with open(p, "rb") as f:
             h.update(f.read())
     h.update(" ".join(FLAGS).encode())
@@ -47,12 +49,29 @@ def _run(cmd):
     return r.stdout
 
 
+def _current(stamp, dig):
+    return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig
+
+
 def build(force=False, verbose=False):
     stamp = os.path.join(OBJ, "digest.txt")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+    if not force and _current(stamp, dig):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
+    # several ranks of one job may get here at once: one builds, the others wait and then find the stamp current
+    import fcntl
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _current(stamp, dig):
+                return LIB
+            return _build_locked(stamp, dig, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(stamp, dig, verbose):
     jobs = []
     objs = []
     main_o = os.path.join(OBJ, "swne_nmf.o")

@@ -611,6 +611,9 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         CUDA_CHECK(cudaMemcpyAsync(ht->G64w, h->G64w.p, sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaMemcpyAsync(ht->G64h, h->G64h.p, sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
         ht->tc_overflow = 0;
+        // every rank must take the same decision (the refit is a collective): the flag is max-reduced first
+        if (fused && h->nranks > 1)
+            NCCL_CHECK(g_nccl.AllReduce(h->tc.dev_ints + 4, h->tc.dev_ints + 4, 1, ncclInt32, ncclMax, h->comm, h->stream));
         if (fused)
             CUDA_CHECK(cudaMemcpyAsync(&ht->tc_overflow, h->tc.dev_ints + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));

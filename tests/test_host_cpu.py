@@ -119,3 +119,19 @@ def test_sharded_algorithm_equals_unsharded_gloo(tmp_path):
     assert rel_fro(r0["W"], ref["W"]) < 1e-9
     assert rel_fro(np.concatenate([r0["H"], r1["H"]], axis=1), ref["H"]) < 1e-9
     assert np.max(np.abs(r0["terr"] - ref["target_loss"]) / ref["target_loss"]) < 1e-10
+
+
+def test_build_digest_is_location_independent(tmp_path):
+    """the tree is copied to another absolute path on the GPU box: the shipped .so must still count as current there
+    (a rebuild on the box costs GPU minutes, and eight ranks rebuilding at once used to race)"""
+    import importlib.util, shutil
+    src = os.path.join(ROOT, "swne_b200")
+    dst = tmp_path / "elsewhere" / "swne_b200"
+    shutil.copytree(src, dst, ignore=shutil.ignore_patterns("*.so", "*.o", "build", "__pycache__"))
+    os.makedirs(tmp_path / "elsewhere" / "include")
+    shutil.copy(os.path.join(ROOT, "include", "swne_nmf.h"), tmp_path / "elsewhere" / "include" / "swne_nmf.h")
+    spec = importlib.util.spec_from_file_location("build_elsewhere", str(dst / "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from swne_b200 import build as here
+    assert mod._digest() == here._digest()
