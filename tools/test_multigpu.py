@@ -15,7 +15,8 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 td.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for (n, m, kt, k, engine) in [(300, 1000, 5, 8, "simt"), (1000, 4000, 6, 16, "tc"), (3000, 20000, 9, 30, "tc")]:
+for (n, m, kt, k, engine) in [(300, 1000, 5, 8, "simt"), (1000, 4000, 6, 16, "tc"), (3000, 20000, 9, 30, "tc"),
+                              (1500, 6000, 12, 40, "tc")]:
     A = small_matrix(n, m, kt, 3)
     W0, H0 = seeded_init(A, k, 3)
     b = shard_bounds(m, world)
