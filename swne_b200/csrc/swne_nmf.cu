@@ -925,18 +925,33 @@ static int nnsvd_impl(swne_nmf_handle_s *h, int k, int oversample, int power_ite
     h->Wt.reserve((size_t)n * KPv); h->H.reserve((size_t)m * KPv);
     h->G.reserve((size_t)KPv * KPv); h->G64w.reserve(GS);
     float *Y = h->Wt.p, *Z = h->H.p;  // Y [n][KP] gene side, Z [m][KP] cell side
+    // the 2 + 2 q sketch products are the same skinny contractions as the fit's: through the tcgen05 kernels of
+    // contract_tc.cuh (split-fp16 operands, fp32-level accuracy) when the shape allows, else the fp32 kernels
+    const bool use_tc = n >= 128 && m >= 128 && l <= TCX_KP && !getenv("SWNE_NNSVD_SIMT");
+    if (use_tc) {
+        tc_prepare(h->tc, h->dA, h->ldA, n, m, (double)__builtin_bit_cast(float, h->stats.max_bits), h->sm_count, st);
+        tcx_prepare(h->tcx, h->tc);
+    }
+    auto a_times = [&](const float *Zin, float *Yout) {       // Yout (n x l) = A Zin
+        if (use_tc) tcx_contract_genes(h->tcx, h->tc, KPv, Zin, Yout, st);
+        else launch_contract_genes(h, KPv, Zin, Yout);
+    };
+    auto at_times = [&](const float *Yin, float *Zout) {      // Zout (m x l) = A' Yin
+        if (use_tc) tcx_contract_cells(h->tcx, h->tc, KPv, Yin, Zout, st);
+        else launch_contract_cells(h, KPv, Yin, Zout);
+    };
     const size_t totz = (size_t)m * KPv;
     fill_gaussian_kernel<<<(unsigned)((totz + 255) / 256), 256, 0, st>>>(Z, (size_t)m, l, KPv, seed);
     CUDA_CHECK(cudaGetLastError());
-    launch_contract_genes(h, KPv, Z, Y);                    // Y = A Omega
+    a_times(Z, Y);                                          // Y = A Omega
     cholesky_qr2(h, KPv, l, Y, n, h->G64w.p, h->G.p);
     for (int q = 0; q < power_iters; ++q) {
-        launch_contract_cells(h, KPv, Y, Z);                // Z = A' Q
+        at_times(Y, Z);                                     // Z = A' Q
         cholesky_qr2(h, KPv, l, Z, m, h->G64w.p, h->G.p);
-        launch_contract_genes(h, KPv, Z, Y);                // Y = A Z
+        a_times(Z, Y);                                      // Y = A Z
         cholesky_qr2(h, KPv, l, Y, n, h->G64w.p, h->G.p);
     }
-    launch_contract_cells(h, KPv, Y, Z);                    // Z = A' Q  (m x l) = B'
+    at_times(Y, Z);                                         // Z = A' Q  (m x l) = B'
     launch_gram(h, KPv, Z, m, h->G64w.p);                   // B B' = Z'Z
     std::vector<double> G(GS);
     CUDA_CHECK(cudaMemcpyAsync(G.data(), h->G64w.p, sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
@@ -960,37 +975,54 @@ static int nnsvd_impl(swne_nmf_handle_s *h, int k, int oversample, int power_ite
     CUDA_CHECK(cudaMemcpyAsync(h->G.p, T.data(), sizeof(float) * T.size(), cudaMemcpyHostToDevice, st));
     ops_of(KPv).right_multiply(Z, (size_t)m, h->G.p, l, st);
     CUDA_CHECK(cudaGetLastError());
-    // NNDSVD split on the host in double (O((n+m) k))
-    std::vector<double> U((size_t)n * l), V((size_t)m * l);
-    download_factor_colmajor(h, Y, U.data(), l, KPv, n);          // U[i + n f]
-    {
-        std::vector<double> Vt((size_t)m * l);
-        download_factor_cellmajor(h, Z, Vt.data(), l, KPv, (size_t)m);  // [cell][f]
-        for (size_t j = 0; j < (size_t)m; ++j)
-            for (int f = 0; f < l; ++f) V[j + (size_t)m * f] = Vt[j * l + f];
+    // NNDSVD split on the host in double (O((n+m) k)).  V stays cell-major ([cell][l], as downloaded) and H is
+    // cell-major too (k x m column-major), so both passes over the cells are contiguous.
+    std::vector<double> U((size_t)n * l), Vt((size_t)m * l);
+    download_factor_colmajor(h, Y, U.data(), l, KPv, n);              // U[i + n f]
+    download_factor_cellmajor(h, Z, Vt.data(), l, KPv, (size_t)m);    // Vt[j l + f]
+    std::vector<double> nvp(k, 0.0), nvn(k, 0.0);
+    for (size_t j = 0; j < (size_t)m; ++j) {
+        const double *v = &Vt[j * l];
+        for (int f = 1; f < k; ++f) {
+            const double x = v[f];
+            if (x >= 0) nvp[f] += x * x; else nvn[f] += x * x;
+        }
     }
+    // per factor: which sign part is kept, and the scale of the u and v sides
+    std::vector<double> cv(k, 0.0);
+    std::vector<char> keep_pos(k, 1);
     for (int f = 0; f < k; ++f) {
         const double s = sqrt(std::max(eval[f], 0.0));
         if (sv) sv[f] = s;
-        const double *u = &U[(size_t)n * f], *v = &V[(size_t)m * f];
+        const double *u = &U[(size_t)n * f];
         if (f == 0) {
             for (int i = 0; i < n; ++i) W[i] = sqrt(s) * fabs(u[i]);
-            for (int j = 0; j < m; ++j) H[(size_t)j * k] = sqrt(s) * fabs(v[j]);
+            cv[0] = sqrt(s);
             continue;
         }
-        double nup = 0, nun = 0, nvp = 0, nvn = 0;
+        double nup = 0, nun = 0;
         for (int i = 0; i < n; ++i) { if (u[i] >= 0) nup += u[i] * u[i]; else nun += u[i] * u[i]; }
-        for (int j = 0; j < m; ++j) { if (v[j] >= 0) nvp += v[j] * v[j]; else nvn += v[j] * v[j]; }
-        nup = sqrt(nup); nun = sqrt(nun); nvp = sqrt(nvp); nvn = sqrt(nvn);
-        const double termp = nup * nvp, termn = nun * nvn;
+        nup = sqrt(nup); nun = sqrt(nun);
+        const double vp = sqrt(nvp[f]), vn = sqrt(nvn[f]);
+        const double termp = nup * vp, termn = nun * vn;
         if (termp >= termn) {
             const double c = sqrt(s * termp);
             for (int i = 0; i < n; ++i) W[i + (size_t)n * f] = (u[i] >= 0) ? c * u[i] / nup : 0.0;
-            for (int j = 0; j < m; ++j) H[f + (size_t)j * k] = (v[j] >= 0) ? c * v[j] / nvp : 0.0;
+            cv[f] = vp > 0 ? c / vp : 0.0;
         } else {
             const double c = sqrt(s * termn);
             for (int i = 0; i < n; ++i) W[i + (size_t)n * f] = (u[i] < 0) ? -c * u[i] / nun : 0.0;
-            for (int j = 0; j < m; ++j) H[f + (size_t)j * k] = (v[j] < 0) ? -c * v[j] / nvn : 0.0;
+            cv[f] = vn > 0 ? -c / vn : 0.0;
+            keep_pos[f] = 0;
+        }
+    }
+    for (size_t j = 0; j < (size_t)m; ++j) {
+        const double *v = &Vt[j * l];
+        double *hj = H + j * (size_t)k;
+        hj[0] = cv[0] * fabs(v[0]);
+        for (int f = 1; f < k; ++f) {
+            const double x = v[f];
+            hj[f] = keep_pos[f] ? ((x >= 0) ? cv[f] * x : 0.0) : ((x < 0) ? cv[f] * x : 0.0);
         }
     }
     return SWNE_OK;
