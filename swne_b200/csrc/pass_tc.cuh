@@ -43,8 +43,13 @@ constexpr int TC_H_TILE = 4 * TC_H_SUB;                 // hi (bf16) k-half 0/1,
 constexpr int TC_CBUF = 8;                              // C accumulators (32 TMEM columns each) in flight (SOLVER 0)
 // SOLVER 1 TMEM map: [0,192) six C / mu tiles, [192,320) the delta operands of the 4 groups (16 hi + 16 lo columns
 // each), [320,512) two phase-3 accumulator regions of 3 x 32 columns.  SOLVER 0: [0,256) eight C tiles, [256,448).
-__host__ __device__ constexpr int tc_cbuf(int solver) { return solver ? 6 : TC_CBUF; }
-constexpr int TC_DELTA_COL = 192;
+// solver groups of the fused pass.  5 groups (896 threads, 72 registers -> 0.9 KB of spills, 5 C tiles) measured
+// 0.565 ms per pass against 0.548 ms with 4 on cfg3, so 4 it is.
+#ifndef TC_NGROUPS
+#define TC_NGROUPS 4
+#endif
+__host__ __device__ constexpr int tc_cbuf(int solver) { return solver ? (TC_NGROUPS == 5 ? 5 : 6) : TC_CBUF; }
+constexpr int TC_DELTA_COL = (TC_NGROUPS == 5) ? 160 : 192;
 __host__ __device__ constexpr int tc_dcol(int solver) { return solver ? 320 : 256; }
 constexpr int TC_MT_PER_PASS = 3;                       // 128-gene accumulators per phase-3 unit (3 * 32 TMEM columns, two regions)
 // two solver variants (template parameter SOLVER of the kernel):
@@ -52,7 +57,7 @@ constexpr int TC_MT_PER_PASS = 3;                       // 128-gene accumulators
 //   1  tensor-core block Gauss-Seidel: mu lives in TMEM, the rank-8 update of every 8-coordinate block is a
 //      3xTF32 MMA whose A operand (the deltas) also sits in TMEM, only the 8 x 8 triangular part of the block runs
 //      on CUDA cores; 4 groups of 4 warps
-constexpr int TC_TGROUPS = 4;
+constexpr int TC_TGROUPS = TC_NGROUPS;
 __host__ __device__ constexpr int tc_solver_warps(int solver) { return solver ? 4 * TC_TGROUPS : 8; }
 // TC_DRAINERS = 1 adds four dedicated drain warps (4..7) to SOLVER 1 so that phase 3 can run in waves while tiles
 // are still being solved.  Measured on cfg3 (6 tiles per SM) it loses to 4 solver groups without waves (673 vs
