@@ -71,22 +71,49 @@ def build(force=False, verbose=False):
             fcntl.flock(lock, fcntl.LOCK_UN)
 
 
+KP_DEPS = ("kernels_kp.cu", "kernels_simt.cuh", "common.cuh", "kp_ops.h")
+
+
+def _files_digest(paths, extra=""):
+    h = hashlib.sha256()
+    for p in paths:
+        h.update(os.path.relpath(p, HERE).replace(os.sep, "/").encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update((" ".join(FLAGS) + extra).encode())
+    return h.hexdigest()
+
+
 def _build_locked(stamp, dig, verbose):
-    jobs = []
-    objs = []
+    # per-object stamps: the eight per-KP translation units only depend on KP_DEPS, so an edit of the tcgen05
+    # engine or the host loop recompiles one file
+    jobs, objs, stamps = [], [], []
+
+    def add(obj, cmd, deps, extra=""):
+        objs.append(obj)
+        d = _files_digest(deps, extra)
+        st = obj + ".digest"
+        if os.path.exists(obj) and os.path.exists(st) and open(st).read() == d:
+            return
+        jobs.append(cmd)
+        stamps.append((st, d))
+
     main_o = os.path.join(OBJ, "swne_nmf.o")
-    jobs.append([NVCC] + FLAGS + ["-c", os.path.join(CSRC, "swne_nmf.cu"), "-o", main_o])
-    objs.append(main_o)
+    add(main_o, [NVCC] + FLAGS + ["-c", os.path.join(CSRC, "swne_nmf.cu"), "-o", main_o], _sources())
+    kp_deps = [os.path.join(CSRC, f) for f in KP_DEPS] + [os.path.join(HERE, "..", "include", "swne_nmf.h")]
     for kp in KPS:
         o = os.path.join(OBJ, "kernels_kp%d.o" % kp)
-        jobs.append([NVCC] + FLAGS + ["-DKP_VALUE=%d" % kp, "-c", os.path.join(CSRC, "kernels_kp.cu"), "-o", o])
-        objs.append(o)
-    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
-        outs = list(ex.map(_run, jobs))
-    if verbose:
-        for o in outs:
-            if o.strip():
-                print(o)
+        add(o, [NVCC] + FLAGS + ["-DKP_VALUE=%d" % kp, "-c", os.path.join(CSRC, "kernels_kp.cu"), "-o", o], kp_deps, " kp%d" % kp)
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            outs = list(ex.map(_run, jobs))
+        if verbose:
+            for o in outs:
+                if o.strip():
+                    print(o)
+        for st, d in stamps:
+            with open(st, "w") as f:
+                f.write(d)
     _run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"])
     with open(stamp, "w") as f:
         f.write(dig)
