@@ -73,7 +73,7 @@ void kl_l(const int *ptr, const int *idx, const float *val, float *ajt, float *X
 void kl_trace_l(const float *A, size_t ldA, int n, int m, const float *H, const float *Wt, int k, double *kl_part,
                 cudaStream_t st)
 {
-    const int grid = (m + 7) / 8 < 148 * 8 ? (m + 7) / 8 : 148 * 8;
+    dim3 grid((n + 255) / 256, (m + KL_CELLS - 1) / KL_CELLS);
     kl_trace_kernel<KP><<<grid, 256, 0, st>>>(A, ldA, n, m, H, Wt, k, kl_part);
 }
 void recon_error_l(const float *A, size_t ldA, int n, int m, const float *Wt, const float *H, int k, double *out2, int grid,

@@ -593,44 +593,46 @@ __global__ void __launch_bounds__(NT) scd_kl_kernel(const int *__restrict__ ptr,
 }
 
 // A-hat on the support only: kl_part += sum_nz a log(ahat + tiny)   (the mkl trace of an mse fit).
-// Works on the dense rows directly (no sparse view to build): one warp per cell, lanes stride over the
-// genes, a lane that meets a nonzero gathers its gene's row of Wt (L1/L2 resident) and dots it with the
-// cell's h held in shared memory.
+// Works on the dense rows directly (no sparse view to build).  A thread owns one gene and keeps that gene's row of
+// Wt in registers; a block walks KL_CELLS cells whose h vectors sit in shared memory (broadcast reads), so the
+// only streamed operand is A itself (coalesced 128 B per warp and cell) -- no per-nonzero gather of W rows.
+constexpr int KL_CELLS = 128;
 template <int KP>
 __global__ void __launch_bounds__(256) kl_trace_kernel(const float *__restrict__ A, size_t ldA, int n, int m,
                                                        const float *__restrict__ H, const float *__restrict__ Wt, int k,
                                                        double *kl_part)
 {
-    __shared__ __align__(16) float sh[8][KP];
+    __shared__ __align__(16) float sh[KL_CELLS][KP];
     __shared__ double scratch[32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * 256 + threadIdx.x;
+    const int c0 = blockIdx.y * KL_CELLS;
+    const int nc = min(KL_CELLS, m - c0);
+    for (int t = threadIdx.x; t < nc * KP; t += 256) sh[t / KP][t % KP] = H[(size_t)c0 * KP + t];
+    float w[KP];
+#pragma unroll
+    for (int r = 0; r < KP / 4; ++r) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < n) v = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)g * KP) + r);
+        w[4 * r] = v.x; w[4 * r + 1] = v.y; w[4 * r + 2] = v.z; w[4 * r + 3] = v.w;
+    }
+    __syncthreads();
     double klp = 0.0;
-    for (int j = blockIdx.x * 8 + wid; j < m; j += gridDim.x * 8) {
-        __syncwarp();
-        for (int f = lane; f < KP; f += 32) sh[wid][f] = H[(size_t)j * KP + f];
-        __syncwarp();
-        const float *arow = A + (size_t)j * ldA;
-        for (int g0 = 0; g0 < n; g0 += 128) {
-            // four genes per lane in flight: the row read stays coalesced and the gathers overlap
-            float av[4];
+    if (g < n) {
+        const float *ap = A + (size_t)c0 * ldA + g;
+#pragma unroll 4
+        for (int c = 0; c < nc; ++c) {
+            const float av = __ldg(ap + (size_t)c * ldA);
+            if (av != 0.f) {
+                float s = 0.f;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int g = g0 + u * 32 + lane;
-                av[u] = (g < n) ? __ldg(arow + g) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (av[u] != 0.f) {
-                    const float4 *w4 = reinterpret_cast<const float4 *>(Wt + (size_t)(g0 + u * 32 + lane) * KP);
-                    float s = 0.f;
-#pragma unroll
-                    for (int r = 0; r < KP / 4; ++r) {
-                        const float4 w = __ldg(w4 + r);
-                        const float4 hh = *reinterpret_cast<const float4 *>(&sh[wid][4 * r]);
-                        s = fmaf(w.x, hh.x, s); s = fmaf(w.y, hh.y, s); s = fmaf(w.z, hh.z, s); s = fmaf(w.w, hh.w, s);
-                    }
-                    klp += (double)av[u] * log((double)s + TINY_NUM_D);
+                for (int r = 0; r < KP / 4; ++r) {
+                    const float4 hh = *reinterpret_cast<const float4 *>(&sh[c][4 * r]);
+                    s = fmaf(w[4 * r], hh.x, s); s = fmaf(w[4 * r + 1], hh.y, s);
+                    s = fmaf(w[4 * r + 2], hh.z, s); s = fmaf(w[4 * r + 3], hh.w, s);
                 }
+                // fp32 log (1 ulp): a warp almost always holds a nonzero lane, so a double-precision log here is paid
+                // for every entry of A and was 80 % of this kernel; the sum itself stays in double
+                klp += (double)av * (double)logf(s + TINY_NUM_F);
             }
         }
     }
