@@ -39,7 +39,7 @@ constexpr int TC_A_STAGE = TC_TILE * TC_CHUNK * 2;      // 16 KB
 constexpr int TC_W_STAGE = 64 * TC_CHUNK * 2;           // 8 KB  (rows 0..31 W_hi, 32..63 W_lo)
 constexpr int TC_BOX_BYTES = TC_GROUP * TC_CHUNK * 2;   // 4 KB
 constexpr int TC_H_SUB = TC_KP * 64 * 2;                // 4 KB: [32 factors][64 cells] 16-bit, K-major
-constexpr int TC_H_TILE = 4 * TC_H_SUB;                 // hi (bf16) k-half 0/1, lo (fp16) k-half 0/1
+constexpr int TC_H_TILE = 4 * TC_H_SUB;                 // hi cells 0..63, hi cells 64..127, lo, lo (all fp16)
 constexpr int TC_CBUF = 8;                              // C accumulators (32 TMEM columns each) in flight (SOLVER 0)
 // SOLVER 1 TMEM map: [0,192) six C / mu tiles, [192,320) the delta operands of the 4 groups (16 hi + 16 lo columns
 // each), [320,512) two phase-3 accumulator regions of 3 x 32 columns.  SOLVER 0: [0,256) eight C tiles, [256,448).
@@ -54,14 +54,14 @@ __host__ __device__ constexpr int tc_dcol(int solver) { return solver ? 320 : 25
 constexpr int TC_MT_PER_PASS = 3;                       // 128-gene accumulators per phase-3 unit (3 * 32 TMEM columns, two regions)
 // two solver variants (template parameter SOLVER of the kernel):
 //   0  CUDA-core sweeps, two cells per thread, 8 solver warps
-//   1  tensor-core block Gauss-Seidel: mu lives in TMEM, the rank-8 update of every 8-coordinate block is a
-//      3xTF32 MMA whose A operand (the deltas) also sits in TMEM, only the 8 x 8 triangular part of the block runs
-//      on CUDA cores; 4 groups of 4 warps
+//   1  tensor-core block Gauss-Seidel: mu lives in TMEM, the rank-16 update of every 16-coordinate block is a
+//      3xTF32 MMA whose A operand (the deltas) also sits in TMEM, only the 16 x 16 triangular part of the block
+//      runs on CUDA cores; 4 groups of 4 warps
 constexpr int TC_TGROUPS = TC_NGROUPS;
 __host__ __device__ constexpr int tc_solver_warps(int solver) { return solver ? 4 * TC_TGROUPS : 8; }
-// TC_DRAINERS = 1 adds four dedicated drain warps (4..7) to SOLVER 1 so that phase 3 can run in waves while tiles
-// are still being solved.  Measured on cfg3 (6 tiles per SM) it loses to 4 solver groups without waves (673 vs
-// 627 us per pass: the solve latency of the last tiles, not the stream, is the critical path), so it is off.
+// TC_DRAINERS = 1 gives SOLVER 1 four dedicated drain warps (4..7) so that phase 3 runs in waves while the last
+// tiles are still being solved (with the solver warps doing the drains, waves lost: a busy group delays the drain
+// and with it the whole second stream).  Measured on cfg3: 0.63 -> 0.55 ms per pass.
 #ifndef TC_DRAINERS
 #define TC_DRAINERS 1
 #endif
@@ -109,7 +109,6 @@ struct TcPassParams {
     int *overflow;           // device: set when a scaled H entry left the fp16 range
     int a_exp;               // A was scaled by 2^a_exp before the split
     int groups_total;        // ceil(m / 32)
-    int exp_flags;           // debug experiments (SWNE_TC_EXP)
     unsigned long long *dbg; // optional timeline (SWNE_TC_TIMELINE): 64 globaltimer slots per CTA
 };
 
@@ -1018,10 +1017,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                                 const uint64_t dh_hi = desc_sw128(hs + hoff, 16, 1024);
                                 const uint64_t dh_lo = desc_sw128(hs + 2 * TC_H_SUB + hoff, 16, 1024);
                                 tc_mma_f16(dD, da_hi, dh_hi, ID_P3, ((t - t_lo) | hc | ks) != 0);
-                                if (!(p.exp_flags & 1)) {
-                                    tc_mma_f16(dD, da_hi, dh_lo, ID_P3, 1);
-                                    tc_mma_f16(dD, da_lo, dh_hi, ID_P3, 1);
-                                }
+                                tc_mma_f16(dD, da_hi, dh_lo, ID_P3, 1);
+                                tc_mma_f16(dD, da_lo, dh_hi, ID_P3, 1);
                             }
                             tc_commit(EMPTY(stage));
                             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -1260,7 +1257,6 @@ static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, fl
     p.groups_total = (tc.m + TC_GROUP - 1) / TC_GROUP;
     p.Himg = tc.Himg;
     p.tiles_per_cta = tc.tiles_per_cta;
-    p.exp_flags = getenv("SWNE_TC_EXP") ? atoi(getenv("SWNE_TC_EXP")) : 0;
     const char *tl = getenv("SWNE_TC_TIMELINE");
     if (tl && !tc.dbg) CUDA_CHECK(cudaMalloc(&tc.dbg, sizeof(unsigned long long) * 64 * 148));
     p.dbg = tl ? tc.dbg : nullptr;

@@ -465,12 +465,14 @@ static void download_factor_colmajor(swne_nmf_handle_s *h, const float *src, dou
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
 }
 
-static void allreduce(swne_nmf_handle_s *h, float *f, size_t nf, double *d, size_t nd)
+// one NCCL group (one launch) for up to three buffers of the per-iteration exchange
+static void allreduce(swne_nmf_handle_s *h, float *f, size_t nf, double *d, size_t nd, double *d2 = nullptr, size_t nd2 = 0)
 {
     if (h->nranks <= 1) return;
     NCCL_CHECK(g_nccl.GroupStart());
     if (nf) NCCL_CHECK(g_nccl.AllReduce(f, f, nf, ncclFloat32, ncclSum, h->comm, h->stream));
     if (nd) NCCL_CHECK(g_nccl.AllReduce(d, d, nd, ncclFloat64, ncclSum, h->comm, h->stream));
+    if (nd2) NCCL_CHECK(g_nccl.AllReduce(d2, d2, nd2, ncclFloat64, ncclSum, h->comm, h->stream));
     NCCL_CHECK(g_nccl.GroupEnd());
 }
 
@@ -698,9 +700,8 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
                 prof.end(7, 1);
                 if (h->nranks > 1) {
                     prof.begin(6);
-                    allreduce(h, h->B.p, (size_t)n * KPv, h->G64h.p, GS);
-                    allreduce(h, nullptr, 0, &h->dscal.p->loss_part, 1);
-                    prof.end(6, 2);
+                    allreduce(h, h->B.p, (size_t)n * KPv, h->G64h.p, GS, &h->dscal.p->loss_part, 1);
+                    prof.end(6, 1);
                 }
             } else {
                 prof.begin(0);
@@ -720,9 +721,8 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
                 prof.end(4, 1);
                 if (h->nranks > 1) {
                     prof.begin(6);
-                    allreduce(h, nullptr, 0, h->G64h.p, GS);
-                    allreduce(h, nullptr, 0, &h->dscal.p->loss_part, 1);
-                    prof.end(6, 2);
+                    allreduce(h, nullptr, 0, h->G64h.p, GS, &h->dscal.p->loss_part, 1);
+                    prof.end(6, 1);
                 }
             }
         } else {
