@@ -38,12 +38,9 @@ static void kl_launch_nt(const int *ptr, const int *idx, const float *val, float
                          unsigned long long *sweeps, double *kl_part, double *sq_part, int err, int max_nnz, cudaStream_t st)
 {
     // shared-memory staging of one column: (KP + 2) floats per nonzero; columns longer than cap run on global arrays
-    static bool attr_set = false;
+    // set on every launch: the attribute is per device, and one process may drive several GPUs (one handle each)
     const int smem_budget = 200 * 1024;
-    if (!attr_set) {
-        cudaFuncSetAttribute(scd_kl_kernel<KP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget);
-        attr_set = true;
-    }
+    cudaFuncSetAttribute(scd_kl_kernel<KP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget);
     const int cap_max = (smem_budget / (int)((KP + 2) * sizeof(float))) & ~3;
     int cap = (max_nnz + 3) & ~3;
     if (cap < 4) cap = 4;
