@@ -93,12 +93,16 @@ __global__ void ingest_csc_kernel(const int *__restrict__ p, const int *__restri
 }
 
 // host layouts <-> device layouts for the factors.  src double [cols][k] (R's k x cols column-major)
-__global__ void factor_in_cellmajor_kernel(const double *__restrict__ src, float *__restrict__ dst, int k, int KP, size_t cols)
+// bad != nullptr: validate on the way in (negative / NaN / Inf entries set `bit`), so the host does not walk k x m doubles
+__global__ void factor_in_cellmajor_kernel(const double *__restrict__ src, float *__restrict__ dst, int k, int KP, size_t cols,
+                                           unsigned *bad = nullptr, unsigned bit = 0)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= cols * (size_t)KP) return;
     const size_t j = t / KP; const int f = (int)(t % KP);
-    dst[t] = (f < k) ? (float)src[j * k + f] : 0.f;
+    const double v = (f < k) ? src[j * k + f] : 0.0;
+    if (bad && (!(v >= 0.0) || isinf(v))) atomicOr(bad, bit);
+    dst[t] = (float)v;
 }
 __global__ void factor_out_cellmajor_kernel(const float *__restrict__ src, double *__restrict__ dst, int k, int KP, size_t cols)
 {
@@ -108,12 +112,15 @@ __global__ void factor_out_cellmajor_kernel(const float *__restrict__ src, doubl
     dst[t] = (double)src[j * KP + f];
 }
 // W: host n x k column-major  W[i + n f]  <->  device [n][KP]
-__global__ void factor_in_colmajor_kernel(const double *__restrict__ src, float *__restrict__ dst, int k, int KP, int n)
+__global__ void factor_in_colmajor_kernel(const double *__restrict__ src, float *__restrict__ dst, int k, int KP, int n,
+                                          unsigned *bad = nullptr, unsigned bit = 0)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)n * KP) return;
     const int i = (int)(t / KP), f = (int)(t % KP);
-    dst[t] = (f < k) ? (float)src[(size_t)f * n + i] : 0.f;
+    const double v = (f < k) ? src[(size_t)f * n + i] : 0.0;
+    if (bad && (!(v >= 0.0) || isinf(v))) atomicOr(bad, bit);
+    dst[t] = (float)v;
 }
 __global__ void factor_out_colmajor_kernel(const float *__restrict__ src, double *__restrict__ dst, int k, int KP, int n)
 {

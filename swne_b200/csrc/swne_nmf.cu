@@ -139,6 +139,7 @@ struct swne_nmf_handle_s {
     swne::DevBuf<swne::MatStats> dstats;
     swne::DevBuf<swne::FitScalars> dscal;
     swne::DevBuf<double> red;        // packed all-reduce buffer of doubles
+    swne::DevBuf<unsigned> flags;    // device-side validation flags of the init
     void *pinned = nullptr;          // host mirror of scalars + Grams
     size_t pinned_bytes = 0;
     swne_nmf_progress_fn progress = nullptr;
@@ -430,12 +431,13 @@ static void launch_kl(swne_nmf_handle_s *h, int k, int KPv, const int *ptr, cons
     CUDA_CHECK(cudaGetLastError());
 }
 
-static void upload_factor_cellmajor(swne_nmf_handle_s *h, const double *src, float *dst, int k, int KPv, size_t cols)
+static void upload_factor_cellmajor(swne_nmf_handle_s *h, const double *src, float *dst, int k, int KPv, size_t cols,
+                                    unsigned *bad = nullptr, unsigned bit = 0)
 {
     h->stage.reserve(cols * (size_t)k);
     CUDA_CHECK(cudaMemcpyAsync(h->stage.p, src, cols * k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     const size_t tot = cols * (size_t)KPv;
-    factor_in_cellmajor_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->stage.p, dst, k, KPv, cols);
+    factor_in_cellmajor_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->stage.p, dst, k, KPv, cols, bad, bit);
     CUDA_CHECK(cudaGetLastError());
 }
 static void download_factor_cellmajor(swne_nmf_handle_s *h, const float *src, double *dst, int k, int KPv, size_t cols)
@@ -447,12 +449,13 @@ static void download_factor_cellmajor(swne_nmf_handle_s *h, const float *src, do
     CUDA_CHECK(cudaMemcpyAsync(dst, h->stage.p, tot * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
 }
-static void upload_factor_colmajor(swne_nmf_handle_s *h, const double *src, float *dst, int k, int KPv, int n)
+static void upload_factor_colmajor(swne_nmf_handle_s *h, const double *src, float *dst, int k, int KPv, int n,
+                                   unsigned *bad = nullptr, unsigned bit = 0)
 {
     h->stage.reserve((size_t)n * k);
     CUDA_CHECK(cudaMemcpyAsync(h->stage.p, src, (size_t)n * k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     const size_t tot = (size_t)n * KPv;
-    factor_in_colmajor_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->stage.p, dst, k, KPv, n);
+    factor_in_colmajor_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->stage.p, dst, k, KPv, n, bad, bit);
     CUDA_CHECK(cudaGetLastError());
 }
 static void download_factor_colmajor(swne_nmf_handle_s *h, const float *src, double *dst, int k, int KPv, int n)
@@ -512,8 +515,6 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     if ((mse_tr || mkl_tr || terr_tr || epo_tr) && trace_len < need_len)
         FAIL(SWNE_ERR_BAD_ARG, "trace arrays need ceil(max_iter/trace)+1 = %d entries", need_len);
     if (p.loss == SWNE_LOSS_MKL && h->nranks > 1) FAIL(SWNE_ERR_UNSUPPORTED, "mkl loss is single-GPU only");
-    validate_init(W, (size_t)n * k, "W");
-    validate_init(H, (size_t)k * m, "H");
 
     cudaStream_t st = h->stream;
     memset(res, 0, sizeof(*res));
@@ -565,11 +566,23 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     cudaEvent_t e0, e1, e2, e3;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
     cudaEventRecord(e0, st);
-    upload_factor_colmajor(h, W, h->Wt.p, k, KPv, n);
+    // the init is validated on the device while it is converted (NNLM: negative or non-finite init is an error)
+    h->flags.reserve(1);
+    CUDA_CHECK(cudaMemsetAsync(h->flags.p, 0, sizeof(unsigned), st));
+    upload_factor_colmajor(h, W, h->Wt.p, k, KPv, n, h->flags.p, 1u);
     CUDA_CHECK(cudaStreamSynchronize(st));  // stage buffer is reused
-    upload_factor_cellmajor(h, H, h->H.p, k, KPv, (size_t)m);
+    upload_factor_cellmajor(h, H, h->H.p, k, KPv, (size_t)m, h->flags.p, 2u);
     CUDA_CHECK(cudaMemsetAsync(h->dscal.p, 0, sizeof(FitScalars), st));
     cudaEventRecord(e1, st);
+    {
+        unsigned bad = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&bad, h->flags.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (bad) {
+            cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+            FAIL(SWNE_ERR_BAD_ARG, "init %s has negative or non-finite entries", (bad & 1u) ? "W" : "H");
+        }
+    }
 
     Prof prof;
     prof.on = p.profile != 0;
@@ -1215,7 +1228,7 @@ int swne_nmf_destroy(swne_nmf_handle_t h)
     tc_release(h->tc);
     tcx_release(h->tcx);
     h->Wt.release(); h->H.release(); h->C.release(); h->B.release(); h->G.release(); h->pack.release();
-    h->G64w.release(); h->G64h.release(); h->stage.release(); h->dstats.release(); h->dscal.release(); h->red.release();
+    h->G64w.release(); h->G64h.release(); h->stage.release(); h->dstats.release(); h->dscal.release(); h->red.release(); h->flags.release();
     if (h->pinned) cudaFreeHost(h->pinned);
     cudaStreamDestroy(h->stream);
     delete h;

@@ -303,8 +303,13 @@ def test_run_nmf_front_end(handle):
     with pytest.raises(SwneError):
         handle.set_matrix(B)
     handle.set_matrix(A)
-    with pytest.raises(SwneError):
+    with pytest.raises(SwneError, match="init W"):
         handle.fit(4, -np.ones((100, 4)), np.ones((4, 150)))
+    Hbad = np.ones((4, 150)); Hbad[2, 7] = np.nan          # validated on the device while the init is converted
+    with pytest.raises(SwneError, match="init H"):
+        handle.fit(4, np.ones((100, 4)), Hbad)
+    ok = handle.fit(4, np.ones((100, 4)), np.ones((4, 150)), max_iter=2)     # the handle stays usable after the error
+    assert np.all(np.isfinite(ok["W"]))
     with pytest.raises(SwneError):
         handle.fit(70, np.ones((100, 70)), np.ones((70, 150)))     # k > SWNE_MAX_K
     rk = RunNMF(A, 4, init="nnsvd", loss="mkl", max_iter=20, seed=1, handle=handle)
