@@ -372,6 +372,10 @@ struct Prof {
         for (auto e : pool) cudaEventDestroy(e);
         pool.clear(); pool_next = 0;
     }
+    ~Prof()
+    {
+        for (auto e : pool) cudaEventDestroy(e);   // exit through an exception: finish() never ran
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -485,6 +489,15 @@ static void validate_init(const double *x, size_t len, const char *name)
         if (!(x[i] >= 0.0) || isinf(x[i])) FAIL(SWNE_ERR_BAD_ARG, "init %s has negative or non-finite entries", name);
 }
 
+// the five timing events of one fit; destroyed on every exit path, including exceptions from CUDA_CHECK / FAIL
+struct FitEvents {
+    cudaEvent_t e[5];
+    FitEvents() { for (auto &x : e) cudaEventCreate(&x); }
+    ~FitEvents() { for (auto &x : e) cudaEventDestroy(x); }
+    FitEvents(const FitEvents &) = delete;
+    FitEvents &operator=(const FitEvents &) = delete;
+};
+
 // host mirror read back at every error block
 struct HostTrace {
     FitScalars sc;
@@ -563,8 +576,8 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     const double N = (double)n * m_glob;
 
     // ---- upload the init
-    cudaEvent_t e0, e1, e2, e3;
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    FitEvents ev;
+    cudaEvent_t e0 = ev.e[0], e1 = ev.e[1], e2 = ev.e[2], e3 = ev.e[3], e4 = ev.e[4];
     cudaEventRecord(e0, st);
     // the init is validated on the device while it is converted (NNLM: negative or non-finite init is an error)
     h->flags.reserve(1);
@@ -579,7 +592,6 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         CUDA_CHECK(cudaMemcpyAsync(&bad, h->flags.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         if (bad) {
-            cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
             FAIL(SWNE_ERR_BAD_ARG, "init %s has negative or non-finite entries", (bad & 1u) ? "W" : "H");
         }
     }
@@ -781,7 +793,6 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         // H grew by more than the 4096x headroom of its fp16 image between two iterations: the tcgen05 results of the
         // last iterations are not trustworthy.  Nothing was written back yet (W/H still hold the caller's init): redo
         // the fit on the fp32 engine.  Loud in verbose mode, never silent about which engine produced the result.
-        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
         swne_nmf_result_t dummy;
         prof.finish(&dummy);
         if (p.verbose) fprintf(stderr, "swne_nmf: fp16 range overflow in the tcgen05 engine, refitting with the fp32 engine\n");
@@ -793,15 +804,12 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     // ---- results
     download_factor_colmajor(h, h->Wt.p, W, k, KPv, n);
     download_factor_cellmajor(h, h->H.p, H, k, KPv, (size_t)m);
-    cudaEvent_t e4;
-    cudaEventCreate(&e4);
     cudaEventRecord(e4, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1); res->upload_ms = ms;
     cudaEventElapsedTime(&ms, e2, e3); res->loop_ms = ms;
     cudaEventElapsedTime(&ms, e3, e4); res->download_ms = ms;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3); cudaEventDestroy(e4);
     prof.finish(res);
     res->n_iteration = i;
     res->n_trace = i_e;
@@ -988,14 +996,14 @@ static int nnsvd_impl(swne_nmf_handle_s *h, int k, int oversample, int power_ite
     CUDA_CHECK(cudaMemcpyAsync(h->G.p, T.data(), sizeof(float) * T.size(), cudaMemcpyHostToDevice, st));
     ops_of(KPv).right_multiply(Z, (size_t)m, h->G.p, l, st);
     CUDA_CHECK(cudaGetLastError());
-    // NNDSVD split on the host in double (O((n+m) k)).  V stays cell-major ([cell][l], as downloaded) and H is
-    // cell-major too (k x m column-major), so both passes over the cells are contiguous.
-    std::vector<double> U((size_t)n * l), Vt((size_t)m * l);
-    download_factor_colmajor(h, Y, U.data(), l, KPv, n);              // U[i + n f]
-    download_factor_cellmajor(h, Z, Vt.data(), l, KPv, (size_t)m);    // Vt[j l + f]
+    // NNDSVD split on the host in double (O((n+m) k)), in place in the caller's buffers: the first k columns of U
+    // land in W (n x k column-major) and of V in H (k x m column-major == cell-major), so every pass is contiguous
+    // and no (k + oversample) x m temporary is touched.
+    download_factor_colmajor(h, Y, W, k, KPv, n);                  // W[i + n f] = U[i][f]
+    download_factor_cellmajor(h, Z, H, k, KPv, (size_t)m);         // H[f + k j] = V[j][f]
     std::vector<double> nvp(k, 0.0), nvn(k, 0.0);
     for (size_t j = 0; j < (size_t)m; ++j) {
-        const double *v = &Vt[j * l];
+        const double *v = H + j * (size_t)k;
         for (int f = 1; f < k; ++f) {
             const double x = v[f];
             if (x >= 0) nvp[f] += x * x; else nvn[f] += x * x;
@@ -1007,9 +1015,9 @@ static int nnsvd_impl(swne_nmf_handle_s *h, int k, int oversample, int power_ite
     for (int f = 0; f < k; ++f) {
         const double s = sqrt(std::max(eval[f], 0.0));
         if (sv) sv[f] = s;
-        const double *u = &U[(size_t)n * f];
+        double *u = W + (size_t)n * f;
         if (f == 0) {
-            for (int i = 0; i < n; ++i) W[i] = sqrt(s) * fabs(u[i]);
+            for (int i = 0; i < n; ++i) u[i] = sqrt(s) * fabs(u[i]);
             cv[0] = sqrt(s);
             continue;
         }
@@ -1019,22 +1027,21 @@ static int nnsvd_impl(swne_nmf_handle_s *h, int k, int oversample, int power_ite
         const double vp = sqrt(nvp[f]), vn = sqrt(nvn[f]);
         const double termp = nup * vp, termn = nun * vn;
         if (termp >= termn) {
-            const double c = sqrt(s * termp);
-            for (int i = 0; i < n; ++i) W[i + (size_t)n * f] = (u[i] >= 0) ? c * u[i] / nup : 0.0;
+            const double c = sqrt(s * termp), cu = nup > 0 ? c / nup : 0.0;
+            for (int i = 0; i < n; ++i) u[i] = (u[i] >= 0) ? cu * u[i] : 0.0;
             cv[f] = vp > 0 ? c / vp : 0.0;
         } else {
-            const double c = sqrt(s * termn);
-            for (int i = 0; i < n; ++i) W[i + (size_t)n * f] = (u[i] < 0) ? -c * u[i] / nun : 0.0;
+            const double c = sqrt(s * termn), cu = nun > 0 ? -c / nun : 0.0;
+            for (int i = 0; i < n; ++i) u[i] = (u[i] < 0) ? cu * u[i] : 0.0;
             cv[f] = vn > 0 ? -c / vn : 0.0;
             keep_pos[f] = 0;
         }
     }
     for (size_t j = 0; j < (size_t)m; ++j) {
-        const double *v = &Vt[j * l];
         double *hj = H + j * (size_t)k;
-        hj[0] = cv[0] * fabs(v[0]);
+        hj[0] = cv[0] * fabs(hj[0]);
         for (int f = 1; f < k; ++f) {
-            const double x = v[f];
+            const double x = hj[f];
             hj[f] = keep_pos[f] ? ((x >= 0) ? cv[f] * x : 0.0) : ((x < 0) ? cv[f] * x : 0.0);
         }
     }
