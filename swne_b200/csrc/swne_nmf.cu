@@ -1421,15 +1421,24 @@ int swne_zero_replace(double *x, size_t len, double eps, const double *fill, siz
 {
     API_BEGIN
     if (!x && len) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    // branch-free passes: about half of an NNDSVD seed is zero, in no predictable pattern
     size_t z = 0;
     for (size_t i = 0; i < len; ++i) {
-        if (x[i] < eps) x[i] = 0.0;
-        if (x[i] == 0.0) {
-            if (fill) {
-                if (z >= n_fill) FAIL(SWNE_ERR_BAD_ARG, "fill vector shorter than the number of zeros");
-                x[i] = fill[z];
+        const double v = (x[i] < eps) ? 0.0 : x[i];
+        x[i] = v;
+        z += (v == 0.0) ? 1u : 0u;
+    }
+    if (fill) {
+        if (z > n_fill) FAIL(SWNE_ERR_BAD_ARG, "fill vector shorter than the number of zeros");
+        if (z) {
+            size_t q = 0;
+            const size_t last = z - 1;
+            for (size_t i = 0; i < len; ++i) {
+                const double v = x[i];
+                const bool isz = (v == 0.0);
+                x[i] = isz ? fill[q < last ? q : last] : v;
+                q += isz ? 1u : 0u;
             }
-            ++z;
         }
     }
     if (n_zero) *n_zero = z;
