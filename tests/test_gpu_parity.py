@@ -433,3 +433,29 @@ print("ok")
     out = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), env=env,
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_debug_variants_of_the_wide_engine_and_the_seed(handle):
+    """SWNE_TCX_SOLVE_SIMT (wide contractions + CUDA-core solves) and SWNE_NNSVD_SIMT (fp32 sketch products) are read
+    with getenv at call time, so they can be flipped in-process: both variants must meet the same bars."""
+    from oracle import nnmf_ref
+    A = small_matrix(400, 900, 12, 41)
+    W0, H0 = seeded_init(A, 36, 41)
+    ref = nnmf_ref(A, 36, W0, H0, max_iter=8, trace=1, rel_tol=-1.0)
+    handle.set_matrix(A)
+    os.environ["SWNE_TCX_SOLVE_SIMT"] = "1"
+    try:
+        r = handle.fit(36, W0, H0, max_iter=8, trace=1, rel_tol=-1.0, engine="tc")
+    finally:
+        del os.environ["SWNE_TCX_SOLVE_SIMT"]
+    assert r.options["engine"] == "tc"
+    _check_against(r, ref)
+    # the seed: tensor-core sketch products against the fp32 kernels (same random test matrix -> same subspace)
+    W1, H1, s1 = handle.nnsvd_init(4, seed=3)
+    os.environ["SWNE_NNSVD_SIMT"] = "1"
+    try:
+        W2, H2, s2 = handle.nnsvd_init(4, seed=3)
+    finally:
+        del os.environ["SWNE_NNSVD_SIMT"]
+    assert np.max(np.abs(s1 - s2) / s2) < 1e-4
+    assert rel_fro(W1, W2) < 1e-2 and rel_fro(H1, H2) < 1e-2
