@@ -646,9 +646,10 @@ static inline void tcx_release(TcxState &x)
     x = TcxState();
 }
 
+// shapes the un-fused kernels handle: any k up to 64 (the row stride of C, B, W, H is k rounded up to 8)
 static inline bool tcx_supported(int n, int m, int k)
 {
-    return k > TC_KP && k <= TCX_KP && n >= 128 && m >= 128;
+    return k >= 1 && k <= TCX_KP && n >= 128 && m >= 128;
 }
 
 // tc must be prepared (split copy of A + its tensor maps)

@@ -535,12 +535,15 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     int engine = p.engine;
     if (p.loss == SWNE_LOSS_MKL) engine = SWNE_ENGINE_SIMT;
     // k <= 32: the fused pass (pass_tc.cuh); 32 < k <= 64: tcgen05 contractions + CUDA-core solves (contract_tc.cuh)
-    const bool tc_ok = (k > TC_KP) ? tcx_supported(h->n, h->m, k) : tc_supported(h->n, h->m, k);
+    // (the un-fused kernels also take k <= 32 when the fused pass cannot: more than ~1.2 M cells on one GPU;
+    // SWNE_TC_FORCE_WIDE selects them for any k, for tests and comparisons)
+    const bool fused_ok = k <= TC_KP && tc_supported(h->n, h->m, k) && !getenv("SWNE_TC_FORCE_WIDE");
+    const bool tc_ok = fused_ok || tcx_supported(h->n, h->m, k);
     if (engine == SWNE_ENGINE_AUTO) engine = tc_ok ? SWNE_ENGINE_TC : SWNE_ENGINE_SIMT;
     if (engine == SWNE_ENGINE_TC && !tc_ok)
         FAIL(SWNE_ERR_UNSUPPORTED, "tcgen05 engine does not support this shape (n=%d, k=%d)", n, k);
     res->engine_used = engine;
-    const bool tcx = engine == SWNE_ENGINE_TC && k > TC_KP;   // wide variant: the loop below runs its fp32-engine branch
+    const bool tcx = engine == SWNE_ENGINE_TC && !fused_ok;   // wide variant: the loop below runs its fp32-engine branch
     const bool fused = engine == SWNE_ENGINE_TC && !tcx;
     const int KPv = fused ? TC_KP : kp_of(k);
     const int GS = KPv * KPv + KPv;  // Gram + column sums

@@ -450,6 +450,16 @@ def test_debug_variants_of_the_wide_engine_and_the_seed(handle):
         del os.environ["SWNE_TCX_SOLVE_SIMT"]
     assert r.options["engine"] == "tc"
     _check_against(r, ref)
+    # the un-fused kernels also serve k <= 32 (their job when a shard is too long for the fused pass)
+    W0s, H0s = seeded_init(A, 16, 42)
+    refs = nnmf_ref(A, 16, W0s, H0s, max_iter=8, trace=1, rel_tol=-1.0)
+    os.environ["SWNE_TC_FORCE_WIDE"] = "1"
+    try:
+        rw = handle.fit(16, W0s, H0s, max_iter=8, trace=1, rel_tol=-1.0, engine="tc")
+    finally:
+        del os.environ["SWNE_TC_FORCE_WIDE"]
+    assert rw.options["engine"] == "tc"
+    _check_against(rw, refs)
     # the seed: tensor-core sketch products against the fp32 kernels (same random test matrix -> same subspace)
     W1, H1, s1 = handle.nnsvd_init(4, seed=3)
     os.environ["SWNE_NNSVD_SIMT"] = "1"
