@@ -135,3 +135,14 @@ def test_build_digest_is_location_independent(tmp_path):
     spec.loader.exec_module(mod)
     from swne_b200 import build as here
     assert mod._digest() == here._digest()
+
+
+def test_permuted_entries_is_a_permutation():
+    """A_rand of FindNumFactors (R/nmf.R:163) -- the host fallback taken where there is no CUDA device: same shape,
+    same multiset of entries, different arrangement"""
+    from swne_b200.nmf import _permuted_entries
+    rng = np.random.default_rng(3)
+    A = rng.gamma(0.3, 1.0, size=(40, 70))
+    P = np.asarray(_permuted_entries(A, np.random.default_rng(5)))
+    assert P.shape == A.shape
+    assert np.array_equal(np.sort(P.ravel()), np.sort(A.ravel())) and not np.array_equal(P, A)
