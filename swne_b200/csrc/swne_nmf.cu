@@ -537,8 +537,27 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     // k <= 32: the fused pass (pass_tc.cuh); 32 < k <= 64: tcgen05 contractions + CUDA-core solves (contract_tc.cuh)
     // (the un-fused kernels also take k <= 32 when the fused pass cannot: more than ~1.2 M cells on one GPU;
     // SWNE_TC_FORCE_WIDE selects them for any k, for tests and comparisons)
-    const bool fused_ok = k <= TC_KP && tc_supported(h->n, h->m, k) && !getenv("SWNE_TC_FORCE_WIDE");
-    const bool tc_ok = fused_ok || tcx_supported(h->n, h->m, k);
+    bool fused_ok = k <= TC_KP && tc_supported(h->n, h->m, k) && !getenv("SWNE_TC_FORCE_WIDE");
+    bool wide_ok = tcx_supported(h->n, h->m, k);
+
+    // ---- global constants (all-reduced once).  The engine is part of the exchange: the engines differ in their
+    // per-iteration collectives, so every rank must take the same one even when a shard boundary leaves one rank
+    // with a shape another engine would refuse.
+    double gl[7] = {h->stats.sum, h->stats.sumsq, h->stats.klc, (double)h->stats.nnz, (double)m,
+                    fused_ok ? 0.0 : 1.0, wide_ok ? 0.0 : 1.0};
+    if (h->nranks > 1) {
+        h->red.reserve(8);
+        CUDA_CHECK(cudaMemcpyAsync(h->red.p, gl, sizeof(gl), cudaMemcpyHostToDevice, st));
+        allreduce(h, nullptr, 0, h->red.p, 7);
+        CUDA_CHECK(cudaMemcpyAsync(gl, h->red.p, sizeof(gl), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        fused_ok = gl[5] == 0.0;
+        wide_ok = gl[6] == 0.0;
+    }
+    const double sumsqA = gl[1], klcA = gl[2], m_glob = gl[4];
+    const double N = (double)n * m_glob;
+
+    const bool tc_ok = fused_ok || wide_ok;
     if (engine == SWNE_ENGINE_AUTO) engine = tc_ok ? SWNE_ENGINE_TC : SWNE_ENGINE_SIMT;
     if (engine == SWNE_ENGINE_TC && !tc_ok)
         FAIL(SWNE_ERR_UNSUPPORTED, "tcgen05 engine does not support this shape (n=%d, k=%d)", n, k);
@@ -567,16 +586,6 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     }
     bool tc_overflow = false;
 
-    // ---- global constants (all-reduced once)
-    double gl[5] = {h->stats.sum, h->stats.sumsq, h->stats.klc, (double)h->stats.nnz, (double)m};
-    if (h->nranks > 1) {
-        CUDA_CHECK(cudaMemcpyAsync(h->red.p, gl, sizeof(gl), cudaMemcpyHostToDevice, st));
-        allreduce(h, nullptr, 0, h->red.p, 5);
-        CUDA_CHECK(cudaMemcpyAsync(gl, h->red.p, sizeof(gl), cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
-    }
-    const double sumsqA = gl[1], klcA = gl[2], m_glob = gl[4];
-    const double N = (double)n * m_glob;
 
     // ---- upload the init
     FitEvents ev;
