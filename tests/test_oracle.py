@@ -2,6 +2,7 @@
 pinned by independent cross-checks -- scipy NNLS (KKT of every half step), monotone target loss, direct
 vs Gram-identity mse, NNDSVD invariants -- and by the committed golden fixtures (regression pin)."""
 import glob
+import math
 import os
 
 import numpy as np
@@ -203,3 +204,156 @@ def test_oracle_self_noise_floor_mse():
     p = np.random.default_rng(0).permutation(60)
     b = nnmf_ref(A[p], 5, W0[p], H0, max_iter=30, rel_tol=-1, n_threads=3)
     assert rel_fro(b["W"], a["W"][p]) < 1e-9 and rel_fro(b["H"], a["H"]) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------
+# A second, independently written restatement (plain Python loops, tiny sizes only) of SURVEY Appendix A.
+# It shares no code with oracle/nnmf_ref.c: agreement pins the C oracle against transcription slips in the
+# coordinate order, the penalty placement (A2 AFTER adding beta0 in the KL step), the skip-if-unchanged rule,
+# the sweep counts and the error block.
+# ------------------------------------------------------------------------------------------------
+TINY = 1e-16
+
+
+def _py_scd_ls(h, G, mu, max_iter, rel_tol):
+    K = len(h)
+    rel_err, t = 1.0 + rel_tol, 0
+    while t < max_iter and rel_err > rel_tol:
+        rel_err = 0.0
+        for kk in range(K):
+            tmp = h[kk] - mu[kk] / G[kk][kk]
+            if tmp < 0:
+                tmp = 0.0
+            if tmp != h[kk]:
+                d = tmp - h[kk]
+                for q in range(K):
+                    mu[q] += d * G[q][kk]
+                rel_err = max(rel_err, 2.0 * abs(h[kk] - tmp) / (tmp + h[kk] + TINY))
+                h[kk] = tmp
+        t += 1
+    return t
+
+
+def _py_scd_kl(h, Wt, a, sumW, pen, max_iter, rel_tol):
+    K, R = len(h), len(a)
+    sumH = sum(h)
+    Ajt = [sum(Wt[kk][r] * h[kk] for kk in range(K)) for r in range(R)]
+    rel_err, t = 1.0 + rel_tol, 0
+    while t < max_iter and rel_err > rel_tol:
+        rel_err = 0.0
+        for kk in range(K):
+            A2 = B = 0.0
+            for r in range(R):
+                mu = Wt[kk][r] / (Ajt[r] + TINY)
+                A2 += a[r] * mu * mu
+                B += a[r] * mu
+            B -= sumW[kk]
+            A2 += pen[0]
+            B += A2 * h[kk] - pen[2] - pen[1] * (sumH - h[kk])
+            tmp = B / (A2 + TINY)
+            if tmp < 0:
+                tmp = 0.0
+            if tmp != h[kk]:
+                d = tmp - h[kk]
+                for r in range(R):
+                    Ajt[r] += d * Wt[kk][r]
+                rel_err = max(rel_err, 2.0 * abs(h[kk] - tmp) / (tmp + h[kk] + TINY))
+                sumH += d
+                h[kk] = tmp
+        t += 1
+    return t
+
+
+def _py_update(X, Yt, A_cols, pen, max_iter, rel_tol, method):
+    """solves A ~= Yt' X column by column.  X: K x C (list of columns), Yt: K x R, A_cols: C columns of length R"""
+    K, R = len(Yt), len(Yt[0])
+    total = 0
+    if method == 1:
+        G = [[sum(Yt[a][r] * Yt[b][r] for r in range(R)) for b in range(K)] for a in range(K)]
+        for a in range(K):
+            if pen[0] != pen[1]:
+                G[a][a] += pen[0] - pen[1]
+        if pen[1] != 0:
+            for a in range(K):
+                for b in range(K):
+                    G[a][b] += pen[1]
+        for a in range(K):
+            G[a][a] += TINY
+        for j, h in enumerate(X):
+            mu = [sum(G[q][b] * h[b] for b in range(K)) - sum(Yt[q][r] * A_cols[j][r] for r in range(R)) for q in range(K)]
+            if pen[2] != 0:
+                mu = [v + pen[2] for v in mu]
+            total += _py_scd_ls(h, G, mu, max_iter, rel_tol)
+    else:
+        sumW = [sum(Yt[kk]) for kk in range(K)]
+        for j, h in enumerate(X):
+            total += _py_scd_kl(h, Yt, A_cols[j], sumW, pen, max_iter, rel_tol)
+    return total
+
+
+def _py_nnmf(A, k, W0, H0, alpha, beta, loss, max_iter, inner_max_iter, trace):
+    n, m = A.shape
+    method = 1 if loss == "mse" else 3
+    Wt = [[float(W0[i, f]) for f in range(k)] for i in range(n)]      # columns of the k x n matrix W'
+    H = [[float(H0[f, j]) for f in range(k)] for j in range(m)]       # columns of H
+    A_rows = [[float(A[i, j]) for j in range(m)] for i in range(n)]   # columns of A'
+    A_cols = [[float(A[i, j]) for i in range(n)] for j in range(m)]
+    N = float(n * m)
+    const_kl = sum((A[i, j] + TINY) * math.log(A[i, j] + TINY) - A[i, j] for i in range(n) for j in range(m)) / N
+    out = dict(mse=[], mkl=[], target=[], epochs=[])
+    raw = 0
+
+    def block():
+        nonlocal raw
+        Ahat = [[sum(Wt[i][f] * H[j][f] for f in range(k)) for j in range(m)] for i in range(n)]
+        mse = sum((A[i, j] - Ahat[i][j]) ** 2 for i in range(n) for j in range(m)) / N
+        mkl = const_kl + sum(-(A[i, j] + TINY) * math.log(Ahat[i][j] + TINY) + Ahat[i][j] for i in range(n) for j in range(m)) / N
+        terr = 0.5 * mse if method < 3 else mkl
+        for pen, X in ((alpha, Wt), (beta, H)):
+            K = k
+            if pen[0] != pen[1]:
+                terr += 0.5 * (pen[0] - pen[1]) * sum(v * v for col in X for v in col) / N
+            if pen[1] != 0:
+                rows = [sum(col[f] for col in X) for f in range(K)]          # row sums of the k x c matrix
+                gram_sum = sum(sum(col[a] * col[b] for col in X) for a in range(K) for b in range(K))
+                assert abs(gram_sum - sum(sum(col) ** 2 for col in X)) <= 1e-9 * max(1.0, abs(gram_sum)) and rows is not None
+                terr += 0.5 * pen[1] * gram_sum / N
+            if pen[2] != 0:
+                terr += pen[2] * sum(v for col in X for v in col) / N
+        out["mse"].append(mse); out["mkl"].append(mkl); out["target"].append(terr); out["epochs"].append(raw / float(n + m))
+        raw = 0
+
+    i = 0
+    while i < max_iter:
+        Hk = [[H[j][f] for j in range(m)] for f in range(k)]         # H as k x m rows = the fixed factor of the W update
+        raw += _py_update(Wt, Hk, A_rows, alpha, inner_max_iter, 1e-9, method)
+        Wk = [[Wt[i2][f] for i2 in range(n)] for f in range(k)]
+        raw += _py_update(H, Wk, A_cols, beta, inner_max_iter, 1e-9, method)
+        if i % trace == 0:
+            block()
+        i += 1
+    if (i - 1) % trace != 0:
+        block()
+    W = np.array([[Wt[i2][f] for f in range(k)] for i2 in range(n)])
+    Hm = np.array([[H[j][f] for j in range(m)] for f in range(k)])
+    return dict(W=W, H=Hm, **{kk: np.array(v) for kk, v in out.items()})
+
+
+@pytest.mark.parametrize("loss,alpha,beta,inner", [("mse", [0, 0, 0], [0, 0, 0], 50), ("mse", [0.05, 0.02, 0.01], [0.03, 0.01, 0.02], 50),
+                                                   ("mkl", [0, 0, 0], [0, 0, 0], 1), ("mkl", [0.04, 0.02, 0.01], [0.02, 0.01, 0.03], 2)])
+def test_c_oracle_matches_independent_python_restatement(loss, alpha, beta, inner):
+    rng = np.random.default_rng(11)
+    n, m, k = 9, 13, 3
+    A = rng.gamma(0.6, 1.0, size=(n, m)) * (rng.uniform(size=(n, m)) < 0.6)
+    W0 = rng.uniform(size=(n, k)) * 0.5 + 0.01
+    H0 = rng.uniform(size=(k, m)) * 0.5 + 0.01
+    iters, trace = 5, 2
+    ref = nnmf_ref(A, k, W0, H0, alpha=alpha, beta=beta, loss=loss, max_iter=iters, rel_tol=-1.0, inner_max_iter=inner, trace=trace)
+    py = _py_nnmf(A, k, W0, H0, alpha, beta, loss, iters, inner, trace)
+    assert len(ref["target_loss"]) == len(py["target"]) == 3          # blocks after iterations 1, 3, 5; (5-1) % 2 == 0: no extra one
+    np.testing.assert_allclose(ref["W"], py["W"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(ref["H"], py["H"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(ref["mse"], py["mse"], rtol=1e-10)
+    np.testing.assert_allclose(ref["mkl"], py["mkl"], rtol=1e-10)
+    np.testing.assert_allclose(ref["target_loss"], py["target"], rtol=1e-10)
+    np.testing.assert_allclose(ref["average_epochs"], py["epochs"], rtol=0, atol=1e-12)
