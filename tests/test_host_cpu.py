@@ -146,3 +146,83 @@ def test_permuted_entries_is_a_permutation():
     P = np.asarray(_permuted_entries(A, np.random.default_rng(5)))
     assert P.shape == A.shape
     assert np.array_equal(np.sort(P.ravel()), np.sort(A.ravel())) and not np.array_equal(P, A)
+
+
+def test_block_deferred_gauss_seidel_equals_sequential_sweeps():
+    """The tensor-core solver (pass_tc.cuh tc_block_gs / contract_tc.cuh tcx_solve_kernel) defers, inside a block of
+    16 coordinates, the rank-1 updates of all mu entries outside the block to one rank-16 update at the block's end,
+    and works in the unit-diagonal scaled variables h' = d o h, mu' = mu / d, G' = G / (d d').  Both rewrites leave
+    the iterates of scd_ls_update unchanged: numpy model of exactly that schedule against the plain loop."""
+    rng = np.random.default_rng(7)
+    K, sweeps = 40, 6
+    X = rng.gamma(0.5, 1.0, size=(K, 90))
+    G = X @ X.T + 0.05 * np.eye(K) + 1e-16 * np.eye(K)
+    a = rng.gamma(0.5, 1.0, size=90)
+    h0 = rng.uniform(size=K)
+
+    def plain(h):
+        h = h.copy(); mu = G @ h - X @ a
+        for _ in range(sweeps):
+            for kk in range(K):
+                tmp = max(h[kk] - mu[kk] / G[kk, kk], 0.0)
+                if tmp != h[kk]:
+                    mu += (tmp - h[kk]) * G[:, kk]
+                    h[kk] = tmp
+        return h
+
+    def blocked(h):
+        d = np.sqrt(np.diag(G)); Gs = G / np.outer(d, d)
+        hs = h * d; mus = (G @ h - X @ a) / d
+        for _ in range(sweeps):
+            for b0 in range(0, K, 16):
+                b1 = min(K, b0 + 16)
+                m16 = mus[b0:b1].copy(); delta = np.zeros(b1 - b0)
+                for i in range(b1 - b0):
+                    kk = b0 + i
+                    tmp = max(hs[kk] - m16[i], 0.0)
+                    delta[i] = tmp - hs[kk]
+                    hs[kk] = tmp
+                    m16[i + 1:] += delta[i] * Gs[kk, b0 + i + 1:b1]          # triangular in-block part, in registers
+                mus += delta @ Gs[b0:b1, :]                                  # the deferred rank-16 update (one MMA)
+        return hs / d
+
+    hp, hb = plain(h0), blocked(h0)
+    assert np.max(np.abs(hp - hb)) <= 1e-12 * max(1.0, np.max(np.abs(hp)))
+    assert np.array_equal(hp == 0, hb == 0)                                   # the same active set
+
+
+def test_lazy_ahat_update_of_the_kl_sweep_equals_the_eager_one():
+    """scd_kl_kernel applies A-hat += delta * w_kk inside the accumulation loop of the NEXT coordinate (one pass over
+    the column per coordinate instead of two) and never applies the last one: same iterates as scd_kl_update."""
+    rng = np.random.default_rng(8)
+    K, R = 6, 50
+    Wt = rng.gamma(0.5, 1.0, size=(K, R)); a = rng.gamma(0.5, 1.0, size=R) * (rng.uniform(size=R) < 0.5)
+    sumW = Wt.sum(1); pen = (0.03, 0.01, 0.02); T = 1e-16
+
+    def step(h, kk, Ajt, sumH):
+        mu = Wt[kk] / (Ajt + T)
+        A2 = a @ (mu * mu) + pen[0]
+        B = a @ mu - sumW[kk] + A2 * h[kk] - pen[2] - pen[1] * (sumH - h[kk])
+        return max(B / (A2 + T), 0.0)
+
+    def eager(h):
+        h = h.copy(); Ajt = Wt.T @ h; sumH = h.sum()
+        for _ in range(3):
+            for kk in range(K):
+                tmp = step(h, kk, Ajt, sumH)
+                Ajt = Ajt + (tmp - h[kk]) * Wt[kk]; sumH += tmp - h[kk]; h[kk] = tmp
+        return h
+
+    def lazy(h):
+        h = h.copy(); Ajt = Wt.T @ h; sumH = h.sum(); d_prev, k_prev = 0.0, 0
+        for _ in range(3):
+            for kk in range(K):
+                if d_prev != 0.0:
+                    Ajt = np.maximum(Ajt + d_prev * Wt[k_prev], 0.0)          # applied on the way into the next coordinate
+                tmp = step(h, kk, Ajt, sumH)
+                d_prev, k_prev = tmp - h[kk], kk
+                sumH += d_prev; h[kk] = tmp
+        return h
+
+    h0 = rng.uniform(size=K) + 0.1
+    assert np.allclose(eager(h0), lazy(h0), rtol=1e-12, atol=1e-14)
