@@ -226,3 +226,31 @@ def test_lazy_ahat_update_of_the_kl_sweep_equals_the_eager_one():
 
     h0 = rng.uniform(size=K) + 0.1
     assert np.allclose(eager(h0), lazy(h0), rtol=1e-12, atol=1e-14)
+
+
+def test_split_fp16_three_product_scheme_is_fp32_grade():
+    """numpy model of the tensor-core operands (pass_tc.cuh / contract_tc.cuh): x * 2^e = hi + lo in fp16 with the
+    maximum scaled to ~2^14, product = hi*hi + hi*lo + lo*hi accumulated in fp32.  Its error must sit at fp32
+    level (the parity bar is 1e-4 on the loss, 1e-3 on W/H), where a single fp16 or TF32 pass does not."""
+    rng = np.random.default_rng(9)
+    A = (rng.gamma(0.6, 1.0, size=(256, 600)) * (rng.uniform(size=(256, 600)) < 0.25)).astype(np.float32)   # cells x genes
+    W = rng.gamma(0.5, 0.3, size=(600, 30)).astype(np.float32)
+
+    def split(x):
+        e = 14 - int(np.frexp(float(np.abs(x).max()))[1])
+        xs = x.astype(np.float64) * 2.0 ** e
+        hi = xs.astype(np.float16)
+        lo = (xs - hi.astype(np.float64)).astype(np.float16)
+        return hi.astype(np.float32), lo.astype(np.float32), e
+
+    ah, al, ea = split(A); wh, wl, ew = split(W)
+    assert np.isfinite(ah).all() and np.isfinite(wh).all() and float(ah.max()) < 65504
+    emu = (ah @ wh + ah @ wl + al @ wh).astype(np.float64) * 2.0 ** (-(ea + ew))
+    exact = A.astype(np.float64) @ W.astype(np.float64)
+    scale = np.abs(exact).max()
+    err3 = np.abs(emu - exact).max() / scale
+    err1 = np.abs((ah @ wh).astype(np.float64) * 2.0 ** (-(ea + ew)) - exact).max() / scale
+    tf32 = lambda x: (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    errt = np.abs((tf32(A.copy()) @ tf32(W.copy())).astype(np.float64) - exact).max() / scale
+    assert err3 < 2e-6, err3                      # fp32-grade (2^-21 operand error, fp32 accumulation)
+    assert err1 > 20 * err3 and errt > 20 * err3  # one fp16 pass / one TF32 pass are 2-3 orders worse
