@@ -450,7 +450,7 @@ tcx_solve_kernel(float *__restrict__ X, const float *__restrict__ C, const float
     __shared__ __align__(8) uint64_t mbar_store;
     __shared__ uint32_t tmem_slot;
     __shared__ double scratch[32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, quarter = warp;
+    const int warp = threadIdx.x >> 5, quarter = warp;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");

@@ -541,7 +541,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    float *sD = reinterpret_cast<float *>(smem + TcSmem::dvec), *sInvD = sD + TC_KP;
+    float *sD = reinterpret_cast<float *>(smem + TcSmem::dvec);   // D[32] | invD[32]
     float *sGs = reinterpret_cast<float *>(smem + TcSmem::g);
     if (p.mode == 0) {
         if (SOLVER == 0) {
