@@ -254,3 +254,27 @@ def test_split_fp16_three_product_scheme_is_fp32_grade():
     errt = np.abs((tf32(A.copy()) @ tf32(W.copy())).astype(np.float64) - exact).max() / scale
     assert err3 < 2e-6, err3                      # fp32-grade (2^-21 operand error, fp32 accumulation)
     assert err1 > 20 * err3 and errt > 20 * err3  # one fp16 pass / one TF32 pass are 2-3 orders worse
+
+
+def test_bench_clock_sampler_summary_and_peaks(tmp_path, monkeypatch):
+    """bench.py's clock line: median SM clock under load, throttle reasons by name, only samples after mark();
+    the roofline denominator comes from MEASURED_PEAKS.json when present, else the profiling guide's fallback"""
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    cs = bench.ClockSampler(0)
+    cs.samples = [(1.0, ["210", "1965", "80.1", "Not Active", "Not Active", "Not Active", "Not Active"])]
+    cs.t_start = 2.0
+    cs.samples += [(2.1, ["1965", "1965", "410.5", "Not Active", "Not Active", "Not Active", "Active"]),
+                   (2.2, ["1950", "1965", "455.0", "Not Active", "Not Active", "Not Active", "Not Active"]),
+                   (2.3, ["1965", "1965", "430.0", "Not Active", "Not Active", "Not Active", "Not Active"])]
+    assert cs.n_loaded() == 3
+    out = cs.summary()
+    assert out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    assert out["power_w_max"] == 455.0 and out["samples"] == 3
+    empty = bench.ClockSampler(0).summary()
+    assert empty["samples"] == 0 and empty["sm_mhz"] is None
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.peaks() == (6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)")
+    (tmp_path / "MEASURED_PEAKS.json").write_text('{"hbm_gbs": 6549.1, "bf16_tflops": 1645}')
+    assert bench.peaks()[0] == 6549.1
