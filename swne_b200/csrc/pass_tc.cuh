@@ -40,34 +40,13 @@ constexpr int TC_W_STAGE = 64 * TC_CHUNK * 2;           // 8 KB  (rows 0..31 W_h
 constexpr int TC_BOX_BYTES = TC_GROUP * TC_CHUNK * 2;   // 4 KB
 constexpr int TC_H_SUB = TC_KP * 64 * 2;                // 4 KB: [32 factors][64 cells] 16-bit, K-major
 constexpr int TC_H_TILE = 4 * TC_H_SUB;                 // hi cells 0..63, hi cells 64..127, lo, lo (all fp16)
-constexpr int TC_CBUF = 8;                              // C accumulators (32 TMEM columns each) in flight (SOLVER 0)
-// SOLVER 1 TMEM map: [0,192) six C / mu tiles, [192,320) the delta operands of the 4 groups (16 hi + 16 lo columns
-// each), [320,512) two phase-3 accumulator regions of 3 x 32 columns.  SOLVER 0: [0,256) eight C tiles, [256,448).
-// solver groups of the fused pass.  5 groups (896 threads, 72 registers -> 0.9 KB of spills, 5 C tiles) measured
-// 0.565 ms per pass against 0.548 ms with 4 on cfg3, so 4 it is.
-#ifndef TC_NGROUPS
-#define TC_NGROUPS 4
-#endif
-__host__ __device__ constexpr int tc_cbuf(int solver) { return solver ? (TC_NGROUPS == 5 ? 5 : 6) : TC_CBUF; }
-constexpr int TC_DELTA_COL = (TC_NGROUPS == 5) ? 160 : 192;
-__host__ __device__ constexpr int tc_dcol(int solver) { return solver ? 320 : 256; }
+constexpr int TC_CBUF = 6;                              // C / mu' accumulators (32 TMEM columns each) in flight
+// TMEM map (512 columns): [0,192) six C / mu' tiles, [192,320) the delta operands of the 4 solver groups (16 hi + 16 lo
+// columns each), [320,512) two phase-3 accumulator regions of 3 x 32 columns.
+constexpr int TC_TGROUPS = 4;                           // solver groups (4 warps each) of the fused pass
+constexpr int TC_DELTA_COL = 192;
+constexpr int TC_D_COL = 320;
 constexpr int TC_MT_PER_PASS = 3;                       // 128-gene accumulators per phase-3 unit (3 * 32 TMEM columns, two regions)
-// two solver variants (template parameter SOLVER of the kernel):
-//   0  CUDA-core sweeps, two cells per thread, 8 solver warps
-//   1  tensor-core block Gauss-Seidel: mu lives in TMEM, the rank-16 update of every 16-coordinate block is a
-//      3xTF32 MMA whose A operand (the deltas) also sits in TMEM, only the 16 x 16 triangular part of the block
-//      runs on CUDA cores; 4 groups of 4 warps
-constexpr int TC_TGROUPS = TC_NGROUPS;
-__host__ __device__ constexpr int tc_solver_warps(int solver) { return solver ? 4 * TC_TGROUPS : 8; }
-// TC_DRAINERS = 1 gives SOLVER 1 four dedicated drain warps (4..7) so that phase 3 runs in waves while the last
-// tiles are still being solved (with the solver warps doing the drains, waves lost: a busy group delays the drain
-// and with it the whole second stream).  Measured on cfg3: 0.63 -> 0.55 ms per pass.
-#ifndef TC_DRAINERS
-#define TC_DRAINERS 1
-#endif
-__host__ __device__ constexpr int tc_solver_warp0(int solver) { return (solver && TC_DRAINERS) ? 8 : 4; }
-__host__ __device__ constexpr int tc_drain_threads(int solver) { return (solver && TC_DRAINERS) ? 128 : tc_solver_warps(solver) * 32; }
-__host__ __device__ constexpr int tc_threads(int solver) { return (tc_solver_warp0(solver) + tc_solver_warps(solver)) * 32; }
 constexpr int TC_MAX_TILES = 128;                       // tiles per CTA (one mbarrier each)
 constexpr int TC_GOP = 1024;                            // one [32 x 8] tf32 operand of G' (per block, hi / lo)
 
@@ -77,10 +56,7 @@ struct TcSmem {
     static constexpr int a_lo = a_hi + TC_STAGES * TC_A_STAGE;
     static constexpr int w = a_lo + TC_STAGES * TC_A_STAGE;
     static constexpr int h = w + TC_STAGES * TC_W_STAGE;
-    // solver scratch: SOLVER 0: G' and G0 (fp32, 8 KB); SOLVER 1: 8 tf32 operands of G' (8 KB)
-    static constexpr int g = h + 2 * TC_H_TILE;
-    static constexpr int g0 = g + TC_KP * TC_KP * 4;
-    static constexpr int gops = g0 + TC_KP * TC_KP * 4;
+    static constexpr int gops = h + 2 * TC_H_TILE;       // 8 tf32 operands of G' (8 KB)
     static constexpr int dvec = gops + 8 * TC_GOP;       // sqrt(diag), 1/sqrt(diag)
     static constexpr int bars = dvec + 2 * TC_KP * 4;
     static constexpr int n_bars = 2 * TC_STAGES + 2 * TC_CBUF + 2 + 2 + 4 + TC_TGROUPS + TC_MAX_TILES;
@@ -95,6 +71,7 @@ struct TcPassParams {
     int mode;                // 0: phase 1 + solve + phase 3; 1: phase 3 only (A H' of the given H)
     const float *pack;       // GramPack of W'W (D / invD read here; the Grams themselves sit in c_gram)
     float l1;
+    float pen_diag, pen_all; // G = G0 + pen_diag I + pen_all 11' (+ tiny I): the L2 / angle penalties folded into the Gram
     int max_iter;
     float rel_tol;
     float *H;                // [m][32] fp32 in/out
@@ -110,7 +87,9 @@ struct TcPassParams {
     int a_exp;               // A was scaled by 2^a_exp before the split
     int groups_total;        // ceil(m / 32)
     unsigned long long *dbg; // optional timeline (SWNE_TC_TIMELINE): 64 globaltimer slots per CTA
+    long long *clk;          // optional solver clock ring (SWNE_TC_CLOCKS): [cta][group][TC_CLK_RECS][8] clock64 stamps
 };
+constexpr int TC_CLK_RECS = 1024;   // records per (CTA, solver group): one per block update / per tile
 
 // ------------------------------------------------------------------------------------------------
 // PTX helpers
@@ -309,71 +288,141 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tensor-core block Gauss-Seidel sweeps for one tile of 128 columns (4 warps = the 4 TMEM lane quarters).
-//   mu' of the tile sits in TMEM ([128 lanes x 32 columns] at tmu, this thread's row at trow); h' in registers.
+// Tensor-core block Gauss-Seidel for one tile of 128 columns (4 warps = the 4 TMEM lane quarters).
+//   mu' of the tile sits in TMEM ([128 lanes x 32 columns] at L.tmu, this thread's row at trow); h' in registers.
 //   Per block of 16 coordinates: read the 16 mu' values, run the 16 sequential coordinate steps with the triangular
 //   in-block corrections in registers, write the 16 deltas (tf32 hi | lo) to the TMEM operand columns and let one
-//   thread issue the 3xTF32 rank-16 update  Mu += D G'[block rows, :]  (A from TMEM, B = the G' operands in smem).
-//   Exactly the deferred rank-1 updates of scd_ls_update: entries outside the block are not read before the block
-//   ends.  Converged columns ride along with delta = 0.  Returns this column's sweep count (scd_ls_update's).
+//   elected thread issue the 3xTF32 rank-16 update  Mu += D G'[block rows, :]  (A from TMEM, B = the G' operands in
+//   smem).  Exactly the deferred rank-1 updates of scd_ls_update: entries outside the block are not read before the
+//   block ends.  Converged columns ride along with delta = 0.
+//   The same "push" (gs_push) also builds mu' = G' h' + ... at the start of a solve and G' h' for the loss at its end,
+//   so the O(k^2) matrix-vector products of a column never run on the CUDA cores.
+// Round-2 measurements behind this form (tools/micro/gs_bench.cu, profiles/r2_gs_bench_*.txt): a tcgen05.mma issued under
+// `if (lane == 0)` compiles to an ELECT/BRA.U.ANY loop per instruction (~80 cycles each); under elect.sync in warp-uniform
+// control flow the six UTCHMMA issue back to back.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int tc_block_gs(float (&h)[32], uint32_t trow, uint32_t tmu, uint32_t tdelta, uint32_t gop_u,
-                                           uint32_t mbar, uint32_t &mb_parity, bool &pending, int bar_id, int quarter, int lane,
-                                           int k, int max_iter, float rel_tol)
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+struct GsLink {
+    uint32_t tmu;       // TMEM address of the tile's mu' accumulator (column base, lane 0)
+    uint32_t tdelta;    // TMEM operand columns of this group: 16 hi + 16 lo
+    uint32_t gop_u;     // shared-memory address of the tf32 operands of G'
+    uint32_t mbar;      // "block MMA done" barrier of this group
+    uint32_t parity;
+    bool pending;
+    int bar_id;         // named barrier of the group's 128 threads
+    int quarter;        // TMEM lane quarter of this warp
+};
+
+__device__ __forceinline__ void gs_wait(GsLink &L)
+{
+    if (L.pending) { mbar_wait(L.mbar, L.parity); L.parity ^= 1u; L.pending = false; }
+    tc_fence_after();
+}
+
+// Mu (+)= V G'[16 BLK .. 16 BLK + 15, :] for the 16 values v of every column of the tile.  OVERWRITE: the tile is
+// replaced instead of accumulated (only with BLK == 0).  The previous push must have been waited for (gs_wait).
+template <int BLK, bool OVERWRITE>
+__device__ __forceinline__ void gs_push(GsLink &L, const float (&h)[32], const float (&d)[16], bool from_h)
 {
     constexpr uint32_t ID_TF32 = idesc_tf32(128, 32);
+    {
+        // columns [0,16): hi (tf32-exact), [16,32): lo
+        float hl[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float v = from_h ? h[16 * BLK + i] : d[i];
+            hl[i] = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            hl[16 + i] = v - hl[i];
+        }
+        tc_st32(L.tdelta + ((uint32_t)(L.quarter * 32) << 16), hl);
+    }
+    tc_fence_before();
+    named_bar_sync(L.bar_id, 128);
+    if (L.quarter == 0) {
+        if (elect_one_sync()) {
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const int b8 = 2 * BLK + ks;     // 8-row block of G'
+                const uint64_t g_hi = desc_nosw(L.gop_u + (2 * b8) * TC_GOP, 128, 256);
+                const uint64_t g_lo = desc_nosw(L.gop_u + (2 * b8 + 1) * TC_GOP, 128, 256);
+                tc_mma_tf32_ts(L.tmu, L.tdelta + 8 * ks, g_hi, ID_TF32, (OVERWRITE && ks == 0) ? 0 : 1);
+                tc_mma_tf32_ts(L.tmu, L.tdelta + 8 * ks, g_lo, ID_TF32, 1);
+                tc_mma_tf32_ts(L.tmu, L.tdelta + 16 + 8 * ks, g_hi, ID_TF32, 1);
+            }
+            tc_commit(L.mbar);
+        }
+        __syncwarp();
+    }
+    L.pending = true;
+}
+
+// mu' += G' h'  (start of a solve; mu' holds (l1 - c) / d) or  mu' = G' h'  (OVERWRITE: for the loss)
+template <bool OVERWRITE>
+__device__ __forceinline__ void gs_push_h(GsLink &L, const float (&h)[32], int k)
+{
+    const float none[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    gs_wait(L);
+    gs_push<0, OVERWRITE>(L, h, none, true);
+    if (16 < k) {
+        gs_wait(L);
+        gs_push<1, false>(L, h, none, true);
+    }
+}
+
+template <int BLK>
+__device__ __forceinline__ void gs_block(float (&h)[32], uint32_t trow, GsLink &L, bool any_change, float rel_tol, unsigned &changed,
+                                         long long *clk, int *clk_n)
+{
+    long long *rec = nullptr;
+#ifdef TC_SOLVER_CLOCKS
+    if (clk && *clk_n < TC_CLK_RECS) { rec = clk + 8 * (*clk_n)++; rec[0] = clock64(); rec[7] = 1; }
+#endif
+    gs_wait(L);
+    if (rec) rec[1] = clock64();
+    float m16[16], d[16];
+    tc_ld16(trow + 16 * BLK, m16);
+    if (rec) rec[2] = clock64();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int kk = 16 * BLK + i;
+        const float tmp = fmaxf(h[kk] - m16[i], 0.f);
+        d[i] = tmp - h[kk];
+        if (any_change) changed |= __float_as_uint(d[i]);
+        else changed |= (2.f * fabsf(d[i]) > rel_tol * (tmp + h[kk] + TINY_NUM_F)) ? 1u : 0u;
+        h[kk] = tmp;
+#pragma unroll
+        for (int j = i + 1; j < 16; ++j) m16[j] = fmaf(d[i], c_gram[kk * TC_KP + 16 * BLK + j], m16[j]);
+    }
+    if (rec) rec[3] = clock64();
+    gs_push<BLK, false>(L, h, d, false);
+    if (rec) { rec[4] = rec[5] = rec[6] = clock64(); }
+}
+
+// the sweeps of scd_ls_update on the tile; returns this column's sweep count
+__device__ __forceinline__ int tc_block_gs(float (&h)[32], uint32_t trow, GsLink &L, int k, int max_iter, float rel_tol,
+                                           long long *clk = nullptr, int *clk_n = nullptr)
+{
     const bool any_change = rel_tol < 2.9e-8f;
     int my_sweeps = 1;
     unsigned any = 1u;
     for (int sweep = 0; sweep < max_iter && any; ++sweep) {
         unsigned changed = 0u;
-#pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
-            if (blk * 16 < k) {
-                if (pending) { mbar_wait(mbar, mb_parity); mb_parity ^= 1u; pending = false; }
-                tc_fence_after();
-                float m16[16], d[16];
-                tc_ld16(trow + 16 * blk, m16);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int kk = 16 * blk + i;
-                    const float tmp = fmaxf(h[kk] - m16[i], 0.f);
-                    d[i] = tmp - h[kk];
-                    if (any_change) changed |= __float_as_uint(d[i]);
-                    else changed |= (2.f * fabsf(d[i]) > rel_tol * (tmp + h[kk] + TINY_NUM_F)) ? 1u : 0u;
-                    h[kk] = tmp;
-#pragma unroll
-                    for (int j = i + 1; j < 16; ++j) m16[j] = fmaf(d[i], c_gram[kk * TC_KP + 16 * blk + j], m16[j]);
-                }
-                {
-                    // columns [0,16): hi (tf32-exact), [16,32): lo
-                    float hl[32];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        hl[i] = __uint_as_float(__float_as_uint(d[i]) & 0xffffe000u);
-                        hl[16 + i] = d[i] - hl[i];
-                    }
-                    tc_st32(tdelta + ((uint32_t)(quarter * 32) << 16), hl);
-                }
-                tc_fence_before();
-                named_bar_sync(bar_id, 128);
-                if (quarter == 0 && lane == 0) {
-                    tc_fence_after();
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const int b8 = 2 * blk + ks;     // 8-row block of G'
-                        const uint64_t g_hi = desc_nosw(gop_u + (2 * b8) * TC_GOP, 128, 256);
-                        const uint64_t g_lo = desc_nosw(gop_u + (2 * b8 + 1) * TC_GOP, 128, 256);
-                        tc_mma_tf32_ts(tmu, tdelta + 8 * ks, g_hi, ID_TF32, 1);
-                        tc_mma_tf32_ts(tmu, tdelta + 8 * ks, g_lo, ID_TF32, 1);
-                        tc_mma_tf32_ts(tmu, tdelta + 16 + 8 * ks, g_hi, ID_TF32, 1);
-                    }
-                    tc_commit(mbar);
-                }
-                pending = true;
-            }
-        }
-        any = named_bar_or(bar_id, 128, changed);
+        gs_block<0>(h, trow, L, any_change, rel_tol, changed, clk, clk_n);
+        if (16 < k) gs_block<1>(h, trow, L, any_change, rel_tol, changed, clk, clk_n);
+        any = named_bar_or(L.bar_id, 128, changed);
         if (changed) my_sweeps = min(sweep + 2, max_iter);
     }
     return my_sweeps;
@@ -427,10 +476,11 @@ tc_wsolve_kernel(float *__restrict__ X, const float *__restrict__ C, const float
     const bool valid = j < cols;
     float *xrow = X + (size_t)(valid ? j : 0) * TC_KP;
     const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+    GsLink L{tmem, tmem + 32, smem_u32(gops), mbar, 0u, false, 1, quarter};
     float h[32];
     {
+        // mu'_0 = (l1 - c) / d; the G' h' part is added by the tensor core
         float mv[32];
-        float2 mu[16];
         if (valid) {
             const float4 *cp = reinterpret_cast<const float4 *>(C + (size_t)j * TC_KP);
 #pragma unroll
@@ -439,26 +489,18 @@ tc_wsolve_kernel(float *__restrict__ X, const float *__restrict__ C, const float
                 h[4 * r] = v.x * sD[4 * r]; h[4 * r + 1] = v.y * sD[4 * r + 1];
                 h[4 * r + 2] = v.z * sD[4 * r + 2]; h[4 * r + 3] = v.w * sD[4 * r + 3];
                 const float4 c = cp[r];
-                mu[2 * r] = make_float2((l1 - c.x) * sInvD[4 * r], (l1 - c.y) * sInvD[4 * r + 1]);
-                mu[2 * r + 1] = make_float2((l1 - c.z) * sInvD[4 * r + 2], (l1 - c.w) * sInvD[4 * r + 3]);
+                mv[4 * r] = (l1 - c.x) * sInvD[4 * r]; mv[4 * r + 1] = (l1 - c.y) * sInvD[4 * r + 1];
+                mv[4 * r + 2] = (l1 - c.z) * sInvD[4 * r + 2]; mv[4 * r + 3] = (l1 - c.w) * sInvD[4 * r + 3];
             }
-            scd_mu_init<TC_KP>(mu, xrow, sD, k);
         } else {
 #pragma unroll
-            for (int f = 0; f < 32; ++f) h[f] = 0.f;
-#pragma unroll
-            for (int r = 0; r < 16; ++r) mu[r] = make_float2(0.f, 0.f);
+            for (int f = 0; f < 32; ++f) { h[f] = 0.f; mv[f] = 0.f; }
         }
-#pragma unroll
-        for (int r = 0; r < 16; ++r) { mv[2 * r] = mu[r].x; mv[2 * r + 1] = mu[r].y; }
         tc_st32(trow, mv);
     }
-    uint32_t mb_parity = 0;
-    bool pending = false;
-    const int my_sweeps = tc_block_gs(h, trow, tmem, tmem + 32, smem_u32(gops), mbar, mb_parity, pending, 1, quarter, lane, k,
-                                      max_iter, rel_tol);
-    if (pending) { mbar_wait(mbar, mb_parity); pending = false; }
-    tc_fence_after();
+    gs_push_h<false>(L, h, k);
+    const int my_sweeps = tc_block_gs(h, trow, L, k, max_iter, rel_tol);
+    gs_wait(L);
     if (valid) {
 #pragma unroll
         for (int r = 0; r < 8; ++r)
@@ -478,18 +520,22 @@ tc_wsolve_kernel(float *__restrict__ X, const float *__restrict__ C, const float
 }
 
 // ------------------------------------------------------------------------------------------------
-// the pass kernel
+// the pass kernel (768 threads, one CTA per SM)
 //
-//   warp 0      TMA producer: phase 1 streams (A_hi, A_lo, W) chunks of every tile, phase 3 streams (A_hi, A_lo)
-//               for one third of the genes at a time
-//   warp 1      MMA issuer (one lane): phase 1 C[t] = A W' into one of 8 TMEM accumulators; phase 3 D += A' H
-//   warp 2      H-tile loader: copies the split 16-bit image of a solved tile from global scratch to smem
-//   warps 4-15  solvers: take (tile, lane-quarter) jobs from four queues, read C from TMEM, run the SCD solve,
-//               write H, the loss partial and the tile image; afterwards drain D into B
+//   warp 0       TMA producer (one elected lane): phase 1 streams (A_hi, A_lo, W) chunks of every tile, phase 3 streams
+//                (A_hi, A_lo) for one third-of-an-eighth of the genes at a time
+//   warp 1       MMA issuer (one elected lane): phase 1 C[t] = A W' into one of 6 TMEM accumulators; phase 3 D += A' H
+//   warp 2       H-tile loader: copies the split 16-bit image of a solved tile from global scratch to smem
+//   warps 4-7    drain: phase-3 accumulators -> red.add into B
+//   warps 8-23   4 solver groups x 4 warps: tensor-core block Gauss-Seidel on tiles g, g+4, ...
+// Registers are redistributed with setmaxnreg (launch: 80 per thread): service warps 40, drain 56, solvers 96 --
+// with 80 the solver spilled 24 of its 32 h' values to local memory inside the sweep (round 1).
 // Phase 3 of tile t only needs tile t's solve, so the second stream over A overlaps the remaining solves.
 // ------------------------------------------------------------------------------------------------
-template <int SOLVER>
-__global__ void __launch_bounds__(tc_threads(SOLVER), 1)
+constexpr int TC_REGS_SERVICE = 40, TC_REGS_DRAIN = 56, TC_REGS_SOLVER = 96;
+static_assert(128 * TC_REGS_SERVICE + 128 * TC_REGS_DRAIN + 512 * TC_REGS_SOLVER <= 768 * 80, "register pool of the pass kernel");
+
+__global__ void __launch_bounds__(768, 1)
 tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                const __grid_constant__ CUtensorMap map_w, const TcPassParams p)
 {
@@ -519,10 +565,9 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     auto HEMPTY = [&](int b) { return bar0 + 8u * (B2 + 2 + b); };
     auto DFULL = [&](int r) { return bar0 + 8u * (B2 + 4 + r); };
     auto DEMPTY = [&](int r) { return bar0 + 8u * (B2 + 6 + r); };
-    auto MBG = [&](int g) { return bar0 + 8u * (B2 + 8 + g); };            // SOLVER 1: "block MMA of group g done"
+    auto MBG = [&](int g) { return bar0 + 8u * (B2 + 8 + g); };            // "block MMA of group g done"
     auto TDONE = [&](int t) { return bar0 + 8u * (B2 + 8 + TC_TGROUPS + t); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcSmem::misc);
-    int *s_next = reinterpret_cast<int *>(smem + TcSmem::misc + 16);   // per-quarter job counters
 
     // zero the A stages once: rows of a partial tile that TMA never writes must hold finite values
     for (int i = threadIdx.x; i < (2 * TC_STAGES * TC_A_STAGE) / 16; i += blockDim.x)
@@ -531,10 +576,9 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
         for (int b = 0; b < TC_CBUF; ++b) { mbar_init(CFULL(b), 1); mbar_init(CEMPTY(b), 128); }
         for (int b = 0; b < 2; ++b) { mbar_init(HFULL(b), 1); mbar_init(HEMPTY(b), 1); }
-        for (int r = 0; r < 2; ++r) { mbar_init(DFULL(r), 1); mbar_init(DEMPTY(r), tc_drain_threads(SOLVER)); }
+        for (int r = 0; r < 2; ++r) { mbar_init(DFULL(r), 1); mbar_init(DEMPTY(r), 128); }
         for (int t = 0; t < n_tiles; ++t) mbar_init(TDONE(t), 128);
         for (int g = 0; g < TC_TGROUPS; ++g) mbar_init(MBG(g), 1);
-        for (int q = 0; q < 4; ++q) s_next[q] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -542,13 +586,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     float *sD = reinterpret_cast<float *>(smem + TcSmem::dvec);   // D[32] | invD[32]
-    float *sGs = reinterpret_cast<float *>(smem + TcSmem::g);
     if (p.mode == 0) {
-        if (SOLVER == 0) {
-            for (int t = threadIdx.x; t < 2 * TC_KP * TC_KP; t += blockDim.x) sGs[t] = p.pack[t];   // G' then G0
-        } else {
-            tc_fill_gops(smem + TcSmem::gops, p.pack, threadIdx.x, blockDim.x);
-        }
+        tc_fill_gops(smem + TcSmem::gops, p.pack, threadIdx.x, blockDim.x);
         if (threadIdx.x < 2 * TC_KP) sD[threadIdx.x] = p.pack[2 * TC_KP * TC_KP + threadIdx.x];
     }
     // generic-proxy zero fill must be visible to the async proxy (TMA / UMMA)
@@ -558,17 +597,23 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     if (threadIdx.x == 0) TC_MARK(0);
-    const uint32_t tmem_c = tmem;                       // columns [0,256): eight C accumulators
+    const uint32_t tmem_c = tmem;                       // columns [0,192): six C / mu' accumulators
     // phase-3 unit u (= wave * n_pass + gene sub-pass) accumulates into region u & 1 (3 x 32 columns each): the drain
     // of one unit overlaps the MMAs of the next
-    auto tmem_d = [&](int u) { return tmem + tc_dcol(SOLVER) + (u & 1) * (TC_MT_PER_PASS * 32); };
+    auto tmem_d = [&](int u) { return tmem + TC_D_COL + (u & 1) * (TC_MT_PER_PASS * 32); };
     // phase 3 takes the tiles in waves (B += A'H is linear in the tiles and the drain is an atomic add), so the
     // second stream over A starts on the tiles whose solves are done while the last tiles are still being solved
-    const int n_waves = (SOLVER == 0 || !TC_DRAINERS || p.mode != 0 || n_tiles <= 2) ? 1 : (n_tiles <= 6 ? (n_tiles + 1) / 2 : 3);
+    // Waves: pairs of tiles, the last one or two tiles as waves of their own -- a wave can only start when its tiles
+    // are solved, and what is streamed after the last solve is the exposed tail of the kernel.  Long CTAs (> 8 tiles)
+    // take everything but their last 6 tiles as one leading wave (every wave costs 8 accumulator drains).
+    const int w_base = (n_tiles > 8) ? n_tiles - 6 : 0;                   // tiles [0, w_base): the leading wave
+    const int w_rest = n_tiles - w_base;
+    const int n_pairs = (w_rest > 2) ? (w_rest - 1) / 2 : 0;               // then pairs, then single tiles
+    const int n_waves = (p.mode != 0 || n_tiles <= 1) ? 1 : (w_base > 0 ? 1 : 0) + n_pairs + (w_rest - 2 * n_pairs);
     auto wave_lo = [&](int w) {
         if (n_waves == 1) return w == 0 ? 0 : n_tiles;
-        if (n_tiles <= 6) return min(n_tiles, 2 * w);
-        return w == 0 ? 0 : min(n_tiles, n_tiles - 4 + 2 * (w - 1));
+        if (w_base > 0) { if (w == 0) return 0; --w; }
+        return w_base + (w <= n_pairs ? 2 * w : min(w_rest, 2 * n_pairs + (w - n_pairs)));
     };
 
     // fp16 scale of the H images: the previous max(H) maps to [8, 16), which leaves a factor 4096 of growth before fp16
@@ -582,35 +627,10 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             h_exp = max(-100, min(100, 4 - e));
         }
     }
-    // drain of one phase-3 unit: D (128 genes x 32) -> red.add into B.  first / step select this warp's M-tiles
-    auto drain_units = [&](int first, int step) {
-        const int quarter = warp & 3;
-        const float bdescale = exp2f(-(float)(p.a_exp + h_exp));
-        for (int u = 0; u < n_waves * n_pass; ++u) {
-            const int ps = u % n_pass;
-            const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
-            mbar_wait(DFULL(u & 1), (u >> 1) & 1);
-            tc_fence_after();
-            for (int mt = mt0 + first; mt < mt1; mt += step) {
-                float d[32];
-                tc_ld32(tmem_d(u) + (mt - mt0) * 32 + ((uint32_t)(quarter * 32) << 16), d);
-                const int gene = mt * 128 + quarter * 32 + lane;
-                if (gene < p.n) {
-                    float *dst = p.B + (size_t)gene * TC_KP;
-#pragma unroll
-                    for (int r = 0; r < 8; ++r)
-                        red_add_v4(dst + 4 * r, d[4 * r] * bdescale, d[4 * r + 1] * bdescale, d[4 * r + 2] * bdescale,
-                                   d[4 * r + 3] * bdescale);
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(DEMPTY(u & 1));
-            if ((warp & 3) == 0 && lane == 0 && u < 8) TC_MARK(32 + u);
-        }
-    };
 
-    if (warp >= tc_solver_warp0(SOLVER)) {
+    if (warp >= 8) {
         // =========================== solver warps ===========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_SOLVER));
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
         const float descale = exp2f(-(float)(p.a_exp + *p.w_exp));
         const float hscale = exp2f((float)h_exp);
@@ -619,263 +639,122 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         double lp = 0.0;
         unsigned long long its = 0;
         const float *sInvD = sD + TC_KP;
-        if constexpr (SOLVER == 0) {
-        const unsigned sg_addr = smem_u32(sGs);
-        const float *sG0 = sGs + TC_KP * TC_KP;
-        // a job = (pair of consecutive tiles, this warp's lane quarter): two cells per thread, one from each tile
-        for (;;) {
-            int u = 0;
-            if (lane == 0) u = atomicAdd(&s_next[quarter], 1);
-            u = __shfl_sync(0xffffffffu, u, 0);
-            const int t0 = 2 * u;
-            if (t0 >= n_tiles) break;
-            const int nc = (t0 + 1 < n_tiles) ? 2 : 1;
-            if (lane == 0 && quarter == 0 && u < 4) TC_MARK(8 + u);   // job picked up
-            const int lc = quarter * 32 + lane;                      // cell within the tile
-            float h[2][32];
-            float2 mu[2][16];
-            bool valid[2];
-            float *hrow[2];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int t = t0 + c;
-                const int cell = cell_begin + t * TC_TILE + lc;
-                valid[c] = (c < nc) && (cell < cell_end);
-                hrow[c] = p.H + (size_t)(valid[c] ? cell : cell_begin) * TC_KP;
-                if (p.mode == 0 && c < nc) {
-                    const int b = t % TC_CBUF;
-                    mbar_wait(CFULL(b), (t / TC_CBUF) & 1);
-                    tc_fence_after();
+        // Group g (4 warps = the 4 lane quarters of a tile) solves tiles g, g+4, ...  mu' of the tile lives in its
+        // TMEM accumulator (the C tile is rewritten in place).
+        const int grp = (warp - 8) >> 2;
+        const int lc = quarter * 32 + lane;
+        GsLink L{tmem_c, tmem + TC_DELTA_COL + 32 * grp, sbase + TcSmem::gops, MBG(grp), 0u, false, 1 + grp, quarter};
+        // optional clock ring of this group (thread 0 of the group writes it)
+#ifdef TC_SOLVER_CLOCKS
+        long long *clk = (p.clk && quarter == 0 && lane == 0) ? p.clk + ((size_t)blockIdx.x * TC_TGROUPS + grp) * TC_CLK_RECS * 8 : nullptr;
+#else
+        long long *clk = nullptr;   // build with -DTC_SOLVER_CLOCKS for the SWNE_TC_CLOCKS ring (tools/solver_clocks.py)
+#endif
+        int clk_n = 0;
+        for (int t = grp; t < n_tiles; t += TC_TGROUPS) {
+            const int b = t % TC_CBUF;
+            const int cell = cell_begin + t * TC_TILE + lc;
+            const bool valid = cell < cell_end;
+            float *hrow = p.H + (size_t)(valid ? cell : cell_begin) * TC_KP;
+            L.tmu = tmem_c + b * 32;
+            const uint32_t trow = L.tmu + ((uint32_t)(quarter * 32) << 16);
+            long long *trec = nullptr;
+#ifdef TC_SOLVER_CLOCKS
+            if (clk && clk_n < TC_CLK_RECS) { trec = clk + 8 * clk_n++; trec[0] = clock64(); trec[7] = 2; trec[6] = t; }
+#endif
+            if (lane == 0 && quarter == 0 && t < 8) TC_MARK(8 + t);
+            float h[32];
+            if (p.mode == 0) {
+                mbar_wait(CFULL(b), (t / TC_CBUF) & 1);
+                tc_fence_after();
+                if (trec) trec[1] = clock64();
+                {
+                    // mu'_0 = (l1 - c) / d   (c = the contraction, kept in the scratch row for the loss); h' = d o h
                     float cv[32];
-                    tc_ld32(tmem_c + b * 32 + ((uint32_t)(quarter * 32) << 16), cv);
-                    tc_fence_before();
-                    mbar_arrive(CEMPTY(b));
-                    if (valid[c]) {
+                    tc_ld32(trow, cv);
+                    if (valid) {
                         float *crow = p.Cscr + (size_t)cell * TC_KP;
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
-                            const float4 v = reinterpret_cast<const float4 *>(hrow[c])[r];
-                            h[c][4 * r] = v.x * sD[4 * r]; h[c][4 * r + 1] = v.y * sD[4 * r + 1];
-                            h[c][4 * r + 2] = v.z * sD[4 * r + 2]; h[c][4 * r + 3] = v.w * sD[4 * r + 3];
+                            const float4 v = reinterpret_cast<const float4 *>(hrow)[r];
+                            h[4 * r] = v.x * sD[4 * r]; h[4 * r + 1] = v.y * sD[4 * r + 1];
+                            h[4 * r + 2] = v.z * sD[4 * r + 2]; h[4 * r + 3] = v.w * sD[4 * r + 3];
                             const float c0 = cv[4 * r] * descale, c1 = cv[4 * r + 1] * descale, c2 = cv[4 * r + 2] * descale,
                                         c3 = cv[4 * r + 3] * descale;
                             reinterpret_cast<float4 *>(crow)[r] = make_float4(c0, c1, c2, c3);
-                            mu[c][2 * r] = make_float2((p.l1 - c0) * sInvD[4 * r], (p.l1 - c1) * sInvD[4 * r + 1]);
-                            mu[c][2 * r + 1] = make_float2((p.l1 - c2) * sInvD[4 * r + 2], (p.l1 - c3) * sInvD[4 * r + 3]);
+                            cv[4 * r] = (p.l1 - c0) * sInvD[4 * r]; cv[4 * r + 1] = (p.l1 - c1) * sInvD[4 * r + 1];
+                            cv[4 * r + 2] = (p.l1 - c2) * sInvD[4 * r + 2]; cv[4 * r + 3] = (p.l1 - c3) * sInvD[4 * r + 3];
                         }
-                        // mu' += G' h'
-#pragma unroll 1
-                        for (int q = 0; q < p.k; ++q) {
-                            const float hq = hrow[c][q] * sD[q];
-                            const float2 h2 = make_float2(hq, hq);
-                            const float4 *g4 = reinterpret_cast<const float4 *>(sGs + q * TC_KP);
+                    } else {
 #pragma unroll
-                            for (int r = 0; r < 8; ++r) {
-                                const float4 g = g4[r];
-                                mu[c][2 * r] = __ffma2_rn(h2, make_float2(g.x, g.y), mu[c][2 * r]);
-                                mu[c][2 * r + 1] = __ffma2_rn(h2, make_float2(g.z, g.w), mu[c][2 * r + 1]);
-                            }
-                        }
+                        for (int f = 0; f < 32; ++f) { h[f] = 0.f; cv[f] = 0.f; }
                     }
+                    tc_st32(trow, cv);
                 }
-                if (!(p.mode == 0 && valid[c])) {
-                    // idle column (tile past the end, cell past the end, or phase-3-only mode): an exact no-op
+                // mu' += G' h' on the tensor core
+                gs_push_h<false>(L, h, p.k);
+                if (trec) trec[2] = clock64();
+                const int my_sweeps = tc_block_gs(h, trow, L, p.k, p.max_iter, p.rel_tol, clk, &clk_n);
+                if (trec) { trec[3] = clock64(); trec[5] = my_sweeps; }
+                // loss partial h' G0 h - 2 h' c:  T = G' h' freshly on the tensor core (the accumulator is free now),
+                // G0 h = d o T - (p0 - p1) h - p1 sum(h)   (G = G0 + (p0 - p1) I + p1 11' is what G' was scaled from)
+                gs_push_h<true>(L, h, p.k);
+                gs_wait(L);
+                {
+                    float T[32];
+                    tc_ld32(trow, T);
+                    tc_fence_before();
+                    mbar_arrive(CEMPTY(b));          // the accumulator goes back to the MMA warp
+                    if (valid) {
+                        its += (unsigned long long)my_sweeps;
+                        float hs = 0.f;
 #pragma unroll
-                    for (int f = 0; f < 32; ++f) h[c][f] = 0.f;
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) mu[c][r] = make_float2(0.f, 0.f);
-                }
-            }
-            if (p.mode == 0) {
-                int sw[2];
-                scd_ls_thread_smem<TC_KP, 2>(h, mu, sg_addr, p.k, p.max_iter, p.rel_tol, sw);
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (valid[c]) {
-                        its += (unsigned long long)sw[c];
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            h[c][4 * r] *= sInvD[4 * r]; h[c][4 * r + 1] *= sInvD[4 * r + 1];
-                            h[c][4 * r + 2] *= sInvD[4 * r + 2]; h[c][4 * r + 3] *= sInvD[4 * r + 3];
-                            reinterpret_cast<float4 *>(hrow[c])[r] =
-                                make_float4(h[c][4 * r], h[c][4 * r + 1], h[c][4 * r + 2], h[c][4 * r + 3]);
-                        }
-                        // loss partial h' G0 h - 2 h' c  (mu reused for G0 h; c read back from the scratch row)
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) mu[c][r] = make_float2(0.f, 0.f);
-#pragma unroll 1
-                        for (int q = 0; q < p.k; ++q) {
-                            const float hq = hrow[c][q];
-                            const float2 h2 = make_float2(hq, hq);
-                            const float4 *g4 = reinterpret_cast<const float4 *>(sG0 + q * TC_KP);
-#pragma unroll
-                            for (int r = 0; r < 8; ++r) {
-                                const float4 g = g4[r];
-                                mu[c][2 * r] = __ffma2_rn(h2, make_float2(g.x, g.y), mu[c][2 * r]);
-                                mu[c][2 * r + 1] = __ffma2_rn(h2, make_float2(g.z, g.w), mu[c][2 * r + 1]);
-                            }
-                        }
-                        const float *crow = p.Cscr + (size_t)(cell_begin + (t0 + c) * TC_TILE + lc) * TC_KP;
+                        for (int f = 0; f < 32; ++f) { h[f] *= sInvD[f]; hs += h[f]; }
+                        const float *crow = p.Cscr + (size_t)cell * TC_KP;
                         float s = 0.f;
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
+                            reinterpret_cast<float4 *>(hrow)[r] = make_float4(h[4 * r], h[4 * r + 1], h[4 * r + 2], h[4 * r + 3]);
                             const float4 cq = reinterpret_cast<const float4 *>(crow)[r];
-                            s = fmaf(h[c][4 * r + 0], mu[c][2 * r].x - 2.f * cq.x, s);
-                            s = fmaf(h[c][4 * r + 1], mu[c][2 * r].y - 2.f * cq.y, s);
-                            s = fmaf(h[c][4 * r + 2], mu[c][2 * r + 1].x - 2.f * cq.z, s);
-                            s = fmaf(h[c][4 * r + 3], mu[c][2 * r + 1].y - 2.f * cq.w, s);
+                            const float cc[4] = {cq.x, cq.y, cq.z, cq.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int f = 4 * r + e;
+                                const float g0h = fmaf(sD[f], T[f], -fmaf(p.pen_diag, h[f], p.pen_all * hs));
+                                s = fmaf(h[f], g0h - 2.f * cc[e], s);
+                            }
                         }
                         lp += (double)s;
                     }
                 }
             } else {
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int cell = cell_begin + (t0 + c) * TC_TILE + lc;
-                    if (c < nc && cell < cell_end) {
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            const float4 v = reinterpret_cast<const float4 *>(p.H + (size_t)cell * TC_KP)[r];
-                            h[c][4 * r] = v.x; h[c][4 * r + 1] = v.y; h[c][4 * r + 2] = v.z; h[c][4 * r + 3] = v.w;
-                        }
-                    }
+                for (int r = 0; r < 8; ++r) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) v = reinterpret_cast<const float4 *>(hrow)[r];
+                    h[4 * r] = v.x; h[4 * r + 1] = v.y; h[4 * r + 2] = v.z; h[4 * r + 3] = v.w;
                 }
             }
-            // ---- split fp16 images of these cells' columns of their tiles: x = h * 2^h_exp, hi = fp16(x),
-            // lo = fp16(x - hi); K-major [factor][cell] sub-tiles of 64 cells, 128 B rows, swizzle-128B by hand
+            // ---- split fp16 image of this cell's column of the tile: x = h * 2^h_exp, hi = fp16(x), lo = fp16(x - hi);
+            // K-major [factor][cell] sub-tiles of 64 cells, 128 B rows, swizzle-128B by hand
+            uint8_t *img = my_img + (size_t)t * TC_H_TILE + (lc >> 6) * TC_H_SUB;
+            const int cc = lc & 63;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (c < nc) {
-                    const int t = t0 + c;
-                    uint8_t *img = my_img + (size_t)t * TC_H_TILE + (lc >> 6) * TC_H_SUB;
-                    const int cc = lc & 63;
-#pragma unroll
-                    for (int f = 0; f < 32; ++f) {
-                        hmax = fmaxf(hmax, h[c][f]);
-                        float x = h[c][f] * hscale;
-                        if (x > 60000.f) { x = 60000.f; ovf = true; }
-                        const __half hi = __float2half_rn(x);
-                        const __half lo = __float2half_rn(x - __half2float(hi));
-                        const int off = f * 128 + ((((cc >> 3) ^ (f & 7)) << 4) | ((cc & 7) << 1));
-                        *reinterpret_cast<__half *>(img + off) = hi;
-                        *reinterpret_cast<__half *>(img + 2 * TC_H_SUB + off) = lo;
-                    }
-                    __threadfence();
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    mbar_arrive(TDONE(t));
-                }
+            for (int f = 0; f < 32; ++f) {
+                hmax = fmaxf(hmax, h[f]);
+                float x = h[f] * hscale;
+                if (x > 60000.f) { x = 60000.f; ovf = true; }
+                const __half hi = __float2half_rn(x);
+                const __half lo = __float2half_rn(x - __half2float(hi));
+                const int off = f * 128 + ((((cc >> 3) ^ (f & 7)) << 4) | ((cc & 7) << 1));
+                *reinterpret_cast<__half *>(img + off) = hi;
+                *reinterpret_cast<__half *>(img + 2 * TC_H_SUB + off) = lo;
             }
-            if (lane == 0 && quarter == 0 && u < 4) TC_MARK(16 + u);  // job done
-        }
-        } else {
-            // ---- tensor-core block Gauss-Seidel.  Group g (4 warps = the 4 lane quarters of a tile) solves tiles
-            // g, g+3, ...  mu' of the tile lives in its TMEM accumulator (the C tile is rewritten in place); for every
-            // block of 8 coordinates a thread reads its 8 mu' values, runs the 8 sequential coordinate steps with the
-            // triangular in-block corrections in registers, and hands the 8 deltas to one 3xTF32 MMA
-            //   Mu[128 x 32] += D[128 x 8] G'[8 x 32]
-            // (exactly the deferred rank-1 updates of scd_ls_update: entries outside the block are not read before the
-            // block ends).  Converged cells ride along with delta = 0.
-            const int grp = (warp - tc_solver_warp0(1)) >> 2;
-            const int lc = quarter * 32 + lane;
-            const uint32_t gop_u = sbase + TcSmem::gops;
-            const uint32_t tdelta = tmem + TC_DELTA_COL + 32 * grp;          // 16 hi + 16 lo columns, 128 lanes
-            uint32_t mb_parity = 0;
-            bool pending = false;
-            for (int t = grp; t < n_tiles; t += TC_TGROUPS) {
-                const int b = t % tc_cbuf(1);
-                const int cell = cell_begin + t * TC_TILE + lc;
-                const bool valid = cell < cell_end;
-                float *hrow = p.H + (size_t)(valid ? cell : cell_begin) * TC_KP;
-                const uint32_t trow = tmem_c + b * 32 + ((uint32_t)(quarter * 32) << 16);
-                if (lane == 0 && quarter == 0 && t < 8) TC_MARK(8 + t);
-                float h[32];
-                if (p.mode == 0) {
-                    mbar_wait(CFULL(b), (t / tc_cbuf(1)) & 1);
-                    tc_fence_after();
-                    {
-                        float cv[32];
-                        tc_ld32(trow, cv);
-                        float2 mu[16];
-                        if (valid) {
-                            float *crow = p.Cscr + (size_t)cell * TC_KP;
-#pragma unroll
-                            for (int r = 0; r < 8; ++r) {
-                                const float4 v = reinterpret_cast<const float4 *>(hrow)[r];
-                                h[4 * r] = v.x * sD[4 * r]; h[4 * r + 1] = v.y * sD[4 * r + 1];
-                                h[4 * r + 2] = v.z * sD[4 * r + 2]; h[4 * r + 3] = v.w * sD[4 * r + 3];
-                                const float c0 = cv[4 * r] * descale, c1 = cv[4 * r + 1] * descale, c2 = cv[4 * r + 2] * descale,
-                                            c3 = cv[4 * r + 3] * descale;
-                                reinterpret_cast<float4 *>(crow)[r] = make_float4(c0, c1, c2, c3);
-                                mu[2 * r] = make_float2((p.l1 - c0) * sInvD[4 * r], (p.l1 - c1) * sInvD[4 * r + 1]);
-                                mu[2 * r + 1] = make_float2((p.l1 - c2) * sInvD[4 * r + 2], (p.l1 - c3) * sInvD[4 * r + 3]);
-                            }
-                            scd_mu_init<TC_KP>(mu, hrow, sD, p.k);
-                        } else {
-#pragma unroll
-                            for (int f = 0; f < 32; ++f) h[f] = 0.f;
-#pragma unroll
-                            for (int r = 0; r < 16; ++r) mu[r] = make_float2(0.f, 0.f);
-                        }
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) { cv[2 * r] = mu[r].x; cv[2 * r + 1] = mu[r].y; }
-                        tc_st32(trow, cv);
-                    }
-                    const int my_sweeps = tc_block_gs(h, trow, tmem_c + b * 32, tdelta, gop_u, MBG(grp), mb_parity, pending, 1 + grp, quarter,
-                                                      lane, p.k, p.max_iter, p.rel_tol);
-                    // the last block update must have landed before the accumulator goes back to the MMA warp
-                    if (pending) { mbar_wait(MBG(grp), mb_parity); mb_parity ^= 1u; pending = false; }
-                    tc_fence_after();
-                    tc_fence_before();
-                    mbar_arrive(CEMPTY(b));
-                    if (valid) {
-                        its += (unsigned long long)my_sweeps;
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            h[4 * r] *= sInvD[4 * r]; h[4 * r + 1] *= sInvD[4 * r + 1];
-                            h[4 * r + 2] *= sInvD[4 * r + 2]; h[4 * r + 3] *= sInvD[4 * r + 3];
-                            reinterpret_cast<float4 *>(hrow)[r] = make_float4(h[4 * r], h[4 * r + 1], h[4 * r + 2], h[4 * r + 3]);
-                        }
-                        float2 g0h[16];
-                        scd_g0_times<TC_KP>(g0h, hrow, p.k);
-                        const float *crow = p.Cscr + (size_t)cell * TC_KP;
-                        float s = 0.f;
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            const float4 cq = reinterpret_cast<const float4 *>(crow)[r];
-                            s = fmaf(h[4 * r + 0], g0h[2 * r].x - 2.f * cq.x, s);
-                            s = fmaf(h[4 * r + 1], g0h[2 * r].y - 2.f * cq.y, s);
-                            s = fmaf(h[4 * r + 2], g0h[2 * r + 1].x - 2.f * cq.z, s);
-                            s = fmaf(h[4 * r + 3], g0h[2 * r + 1].y - 2.f * cq.w, s);
-                        }
-                        lp += (double)s;
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid) v = reinterpret_cast<const float4 *>(hrow)[r];
-                        h[4 * r] = v.x; h[4 * r + 1] = v.y; h[4 * r + 2] = v.z; h[4 * r + 3] = v.w;
-                    }
-                }
-                // split fp16 image of this cell's column of the tile (see SOLVER 0)
-                uint8_t *img = my_img + (size_t)t * TC_H_TILE + (lc >> 6) * TC_H_SUB;
-                const int cc = lc & 63;
-#pragma unroll
-                for (int f = 0; f < 32; ++f) {
-                    hmax = fmaxf(hmax, h[f]);
-                    float x = h[f] * hscale;
-                    if (x > 60000.f) { x = 60000.f; ovf = true; }
-                    const __half hi = __float2half_rn(x);
-                    const __half lo = __float2half_rn(x - __half2float(hi));
-                    const int off = f * 128 + ((((cc >> 3) ^ (f & 7)) << 4) | ((cc & 7) << 1));
-                    *reinterpret_cast<__half *>(img + off) = hi;
-                    *reinterpret_cast<__half *>(img + 2 * TC_H_SUB + off) = lo;
-                }
-                __threadfence();
-                asm volatile("fence.proxy.async;" ::: "memory");
-                mbar_arrive(TDONE(t));
-                if (lane == 0 && quarter == 0 && t < 8) TC_MARK(16 + t);
-            }
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            mbar_arrive(TDONE(t));
+            if (trec) trec[4] = clock64();
+            if (lane == 0 && quarter == 0 && t < 8) TC_MARK(16 + t);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
@@ -889,34 +768,57 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                 atomicAdd(&p.scal->sweeps_h, (unsigned long long)(itd + 0.5));
             }
         }
-        if constexpr (SOLVER == 0 || !TC_DRAINERS) drain_units((warp - 4) >> 2, tc_solver_warps(SOLVER) / 4);
-    } else if (SOLVER == 1 && TC_DRAINERS && warp >= 4) {
-        // =========================== drain warps (SOLVER 1) ===========================
-        drain_units(0, 1);
-    } else if (warp == 0) {
-        // =========================== TMA producer ===========================
-        // All lanes walk the same schedule; lane 0 waits for the slot and arms the barrier, then every box of the
-        // stage is issued by its own lane (one thread issuing 9..16 TMA ops back to back was the bottleneck of
-        // phase 3: ~80 cycles of issue per op).
-        {
+    } else if (warp >= 4) {
+        // =========================== drain warps ===========================
+        // D (128 genes x 32 factors per M-tile) -> descale -> red.add into B
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_DRAIN));
+        const int quarter = warp & 3;
+        const float bdescale = exp2f(-(float)(p.a_exp + h_exp));
+        for (int u = 0; u < n_waves * n_pass; ++u) {
+            const int ps = u % n_pass;
+            const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
+            mbar_wait(DFULL(u & 1), (u >> 1) & 1);
+            tc_fence_after();
+            for (int mt = mt0; mt < mt1; ++mt) {
+                float d[32];
+                tc_ld32(tmem_d(u) + (mt - mt0) * 32 + ((uint32_t)(quarter * 32) << 16), d);
+                const int gene = mt * 128 + quarter * 32 + lane;
+                if (gene < p.n) {
+                    float *dst = p.B + (size_t)gene * TC_KP;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        red_add_v4(dst + 4 * r, d[4 * r] * bdescale, d[4 * r + 1] * bdescale, d[4 * r + 2] * bdescale,
+                                   d[4 * r + 3] * bdescale);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(DEMPTY(u & 1));
+            if (quarter == 0 && lane == 0 && u < 8) TC_MARK(32 + u);
+        }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SERVICE));
+        if (warp == 0) {
+            // =========================== TMA producer ===========================
+            // All lanes walk the schedule and wait for the slot; one elected lane arms the barrier and issues the boxes
+            // of the stage back to back (under elect.sync the UTMALDG are straight-line code)
             int stage = 0, phase = 0;
             if (p.mode == 0) {
                 for (int t = 0; t < n_tiles; ++t) {
                     const int cell0 = cell_begin + t * TC_TILE;
                     const int nbox = (min(TC_TILE, cell_end - cell0) + TC_GROUP - 1) / TC_GROUP;
                     for (int ch = 0; ch < p.n_chunks; ++ch) {
-                        if (lane == 0) {
-                            mbar_wait(EMPTY(stage), phase ^ 1);
+                        mbar_wait(EMPTY(stage), phase ^ 1);
+                        if (elect_one_sync()) {
                             mbar_expect_tx(FULL(stage), nbox * 2 * TC_BOX_BYTES + TC_W_STAGE);
-                        }
-                        __syncwarp();
-                        if (lane < 2 * nbox) {
-                            const int b = lane >> 1;
-                            tma_load_2d(sbase + ((lane & 1) ? TcSmem::a_lo : TcSmem::a_hi) + stage * TC_A_STAGE + b * TC_BOX_BYTES,
-                                        (lane & 1) ? &map_alo : &map_ahi, ch * TC_CHUNK, cell0 + b * TC_GROUP, FULL(stage));
-                        } else if (lane == 2 * nbox) {
+                            for (int b = 0; b < nbox; ++b) {
+                                tma_load_2d(sbase + TcSmem::a_hi + stage * TC_A_STAGE + b * TC_BOX_BYTES, &map_ahi, ch * TC_CHUNK,
+                                            cell0 + b * TC_GROUP, FULL(stage));
+                                tma_load_2d(sbase + TcSmem::a_lo + stage * TC_A_STAGE + b * TC_BOX_BYTES, &map_alo, ch * TC_CHUNK,
+                                            cell0 + b * TC_GROUP, FULL(stage));
+                            }
                             tma_load_2d(sbase + TcSmem::w + stage * TC_W_STAGE, &map_w, ch * TC_CHUNK, 0, FULL(stage));
                         }
+                        __syncwarp();
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -933,67 +835,70 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                         for (int hc = 0; hc < 2; ++hc) {
                             const int nb = min(2, nbox - 2 * hc);
                             if (nb <= 0) break;
-                            if (lane == 0) {
-                                mbar_wait(EMPTY(stage), phase ^ 1);
+                            mbar_wait(EMPTY(stage), phase ^ 1);
+                            if (elect_one_sync()) {
                                 mbar_expect_tx(FULL(stage), nb * 4 * TC_BOX_BYTES);
+                                for (int cg = 0; cg < nb; ++cg)
+#pragma unroll
+                                    for (int gh = 0; gh < 2; ++gh) {
+                                        const int off = stage * TC_A_STAGE + gh * 2 * TC_BOX_BYTES + cg * TC_BOX_BYTES;
+                                        tma_load_2d(sbase + TcSmem::a_hi + off, &map_ahi, (2 * mt + gh) * TC_CHUNK,
+                                                    cell0 + (2 * hc + cg) * TC_GROUP, FULL(stage));
+                                        tma_load_2d(sbase + TcSmem::a_lo + off, &map_alo, (2 * mt + gh) * TC_CHUNK,
+                                                    cell0 + (2 * hc + cg) * TC_GROUP, FULL(stage));
+                                    }
                             }
                             __syncwarp();
-                            {
-                                const int hl = lane & 1, gh = (lane >> 1) & 1, cg = lane >> 2;
-                                if (cg < nb) {
-                                    const int off = stage * TC_A_STAGE + gh * 2 * TC_BOX_BYTES + cg * TC_BOX_BYTES;
-                                    tma_load_2d(sbase + (hl ? TcSmem::a_lo : TcSmem::a_hi) + off, hl ? &map_alo : &map_ahi,
-                                                (2 * mt + gh) * TC_CHUNK, cell0 + (2 * hc + cg) * TC_GROUP, FULL(stage));
-                                }
-                            }
                             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
                 }
             }
-        }
-    } else if (warp == 1) {
-        // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        } else if (warp == 1) {
+            // =========================== MMA issuer ===========================
+            // all lanes follow the barriers; one elected lane issues the MMAs and the commits
             constexpr uint32_t ID_P1 = idesc_f16(128, 32, 0, 0, 0);
             constexpr uint32_t ID_P3 = idesc_f16(128, 32, 1, 0, 0);
             int stage = 0, phase = 0;
             if (p.mode == 0) {
                 for (int t = 0; t < n_tiles; ++t) {
-                    const int b = t % tc_cbuf(SOLVER);
-                    mbar_wait(CEMPTY(b), ((t / tc_cbuf(SOLVER)) & 1) ^ 1);
+                    const int b = t % TC_CBUF;
+                    mbar_wait(CEMPTY(b), ((t / TC_CBUF) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t dC = tmem_c + b * 32;
                     for (int ch = 0; ch < p.n_chunks; ++ch) {
                         mbar_wait(FULL(stage), phase);
                         tc_fence_after();
-                        const uint32_t ahi = sbase + TcSmem::a_hi + stage * TC_A_STAGE;
-                        const uint32_t alo = sbase + TcSmem::a_lo + stage * TC_A_STAGE;
-                        const uint32_t ws = sbase + TcSmem::w + stage * TC_W_STAGE;
+                        if (elect_one_sync()) {
+                            const uint32_t ahi = sbase + TcSmem::a_hi + stage * TC_A_STAGE;
+                            const uint32_t alo = sbase + TcSmem::a_lo + stage * TC_A_STAGE;
+                            const uint32_t ws = sbase + TcSmem::w + stage * TC_W_STAGE;
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t da_hi = desc_sw128(ahi + ks * 32, 16, 1024);
-                            const uint64_t dw_hi = desc_sw128(ws + ks * 32, 16, 1024);
-                            tc_mma_f16(dC, da_hi, dw_hi, ID_P1, (ch | ks) != 0);
-                            tc_mma_f16(dC, da_hi, desc_sw128(ws + 32 * 128 + ks * 32, 16, 1024), ID_P1, 1);
-                            tc_mma_f16(dC, desc_sw128(alo + ks * 32, 16, 1024), dw_hi, ID_P1, 1);
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t da_hi = desc_sw128(ahi + ks * 32, 16, 1024);
+                                const uint64_t dw_hi = desc_sw128(ws + ks * 32, 16, 1024);
+                                tc_mma_f16(dC, da_hi, dw_hi, ID_P1, (ch | ks) != 0);
+                                tc_mma_f16(dC, da_hi, desc_sw128(ws + 32 * 128 + ks * 32, 16, 1024), ID_P1, 1);
+                                tc_mma_f16(dC, desc_sw128(alo + ks * 32, 16, 1024), dw_hi, ID_P1, 1);
+                            }
+                            tc_commit(EMPTY(stage));
+                            if (ch == p.n_chunks - 1) tc_commit(CFULL(b));
                         }
-                        tc_commit(EMPTY(stage));
+                        __syncwarp();
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(CFULL(b));
                 }
             }
-            TC_MARK(2);
+            if (lane == 0) TC_MARK(2);
             int use = 0;  // H tile buffer uses
             for (int u = 0; u < n_waves * n_pass; ++u) {
                 const int ps = u % n_pass, wv = u / n_pass;
                 const int mt0 = ps * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
                 const int r = u & 1;
-                const int t_lo = wave_lo(wv);
+                const int t_lo = wave_lo(wv), t_hi = wave_lo(wv + 1);
                 mbar_wait(DEMPTY(r), ((u >> 1) & 1) ^ 1);
                 tc_fence_after();
-                for (int t = t_lo; t < wave_lo(wv + 1); ++t, ++use) {
+                for (int t = t_lo; t < t_hi; ++t, ++use) {
                     const int hb = use & 1;
                     const int nbox = (min(TC_TILE, cell_end - (cell_begin + t * TC_TILE)) + TC_GROUP - 1) / TC_GROUP;
                     mbar_wait(HFULL(hb), (use >> 1) & 1);
@@ -1005,52 +910,58 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                             if (nbox - 2 * hc <= 0) break;
                             mbar_wait(FULL(stage), phase);
                             tc_fence_after();
-                            const uint32_t ahi = sbase + TcSmem::a_hi + stage * TC_A_STAGE;
-                            const uint32_t alo = sbase + TcSmem::a_lo + stage * TC_A_STAGE;
+                            if (elect_one_sync()) {
+                                const uint32_t ahi = sbase + TcSmem::a_hi + stage * TC_A_STAGE;
+                                const uint32_t alo = sbase + TcSmem::a_lo + stage * TC_A_STAGE;
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                // A operand, MN-major: 64 genes contiguous (128 B), 8 cells per swizzle atom (SBO 1024),
-                                // the second 64-gene atom 8 KB further (LBO)
-                                const uint64_t da_hi = desc_sw128(ahi + ks * 2048, 2 * TC_BOX_BYTES, 1024);
-                                const uint64_t da_lo = desc_sw128(alo + ks * 2048, 2 * TC_BOX_BYTES, 1024);
-                                const uint32_t hoff = hc * TC_H_SUB + ks * 32;
-                                const uint64_t dh_hi = desc_sw128(hs + hoff, 16, 1024);
-                                const uint64_t dh_lo = desc_sw128(hs + 2 * TC_H_SUB + hoff, 16, 1024);
-                                tc_mma_f16(dD, da_hi, dh_hi, ID_P3, ((t - t_lo) | hc | ks) != 0);
-                                tc_mma_f16(dD, da_hi, dh_lo, ID_P3, 1);
-                                tc_mma_f16(dD, da_lo, dh_hi, ID_P3, 1);
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    // A operand, MN-major: 64 genes contiguous (128 B), 8 cells per swizzle atom (SBO 1024),
+                                    // the second 64-gene atom 8 KB further (LBO)
+                                    const uint64_t da_hi = desc_sw128(ahi + ks * 2048, 2 * TC_BOX_BYTES, 1024);
+                                    const uint64_t da_lo = desc_sw128(alo + ks * 2048, 2 * TC_BOX_BYTES, 1024);
+                                    const uint32_t hoff = hc * TC_H_SUB + ks * 32;
+                                    const uint64_t dh_hi = desc_sw128(hs + hoff, 16, 1024);
+                                    const uint64_t dh_lo = desc_sw128(hs + 2 * TC_H_SUB + hoff, 16, 1024);
+                                    tc_mma_f16(dD, da_hi, dh_hi, ID_P3, ((t - t_lo) | hc | ks) != 0);
+                                    tc_mma_f16(dD, da_hi, dh_lo, ID_P3, 1);
+                                    tc_mma_f16(dD, da_lo, dh_hi, ID_P3, 1);
+                                }
+                                tc_commit(EMPTY(stage));
                             }
-                            tc_commit(EMPTY(stage));
+                            __syncwarp();
                             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
-                    tc_commit(HEMPTY(hb));
-                    if (ps == 0 && t < 8) TC_MARK(24 + t);
+                    if (elect_one_sync()) {
+                        tc_commit(HEMPTY(hb));
+                        if (t == t_hi - 1) tc_commit(DFULL(r));
+                    }
+                    __syncwarp();
+                    if (lane == 0 && ps == 0 && t < 8) TC_MARK(24 + t);
                 }
-                tc_commit(DFULL(r));
-                if (u == n_waves * n_pass - 1) TC_MARK(3);
+                if (lane == 0 && u == n_waves * n_pass - 1) TC_MARK(3);
             }
-        }
-    } else if (warp == 2) {
-        // =========================== H tile loader ===========================
-        int use = 0;
-        for (int u = 0; u < n_waves * n_pass; ++u) {
-            const int wv = u / n_pass;
-            for (int t = wave_lo(wv); t < wave_lo(wv + 1); ++t, ++use) {
-                const int hb = use & 1;
-                mbar_wait(TDONE(t), 0);
-                mbar_wait(HEMPTY(hb), ((use >> 1) & 1) ^ 1);
-                // one 16 KB bulk copy (async proxy); the solver threads fenced their generic-proxy writes of the image
-                // with fence.proxy.async before arriving on TDONE
-                if (lane == 0) {
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    mbar_expect_tx(HFULL(hb), TC_H_TILE);
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                     sbase + TcSmem::h + hb * TC_H_TILE),
-                                 "l"(my_img + (size_t)t * TC_H_TILE), "r"(TC_H_TILE), "r"(HFULL(hb))
-                                 : "memory");
+        } else if (warp == 2) {
+            // =========================== H tile loader ===========================
+            int use = 0;
+            for (int u = 0; u < n_waves * n_pass; ++u) {
+                const int wv = u / n_pass;
+                for (int t = wave_lo(wv); t < wave_lo(wv + 1); ++t, ++use) {
+                    const int hb = use & 1;
+                    mbar_wait(TDONE(t), 0);
+                    mbar_wait(HEMPTY(hb), ((use >> 1) & 1) ^ 1);
+                    // one 16 KB bulk copy (async proxy); the solver threads fenced their generic-proxy writes of the image
+                    // with fence.proxy.async before arriving on TDONE
+                    if (elect_one_sync()) {
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        mbar_expect_tx(HFULL(hb), TC_H_TILE);
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                         sbase + TcSmem::h + hb * TC_H_TILE),
+                                     "l"(my_img + (size_t)t * TC_H_TILE), "r"(TC_H_TILE), "r"(HFULL(hb))
+                                     : "memory");
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     }
@@ -1118,6 +1029,7 @@ struct TcMatrix {
     __half *Ahi = nullptr, *Alo = nullptr, *Wst = nullptr;
     int *dev_ints = nullptr;   // [0] W max bits, [1] w_exp, [2] max(H) bits before the pass, [3] after, [4] overflow flag
     unsigned long long *dbg = nullptr;   // timeline buffer when SWNE_TC_TIMELINE is set
+    long long *clk = nullptr;            // solver clock ring when SWNE_TC_CLOCKS is set
     uint8_t *Himg = nullptr;   // split 16-bit H tile images, [grid][tiles_per_cta][TC_H_TILE]
     int grid = 0, tiles_per_cta = 0;
     CUtensorMap map_ahi, map_alo, map_w;
@@ -1173,6 +1085,7 @@ static inline void tc_release(TcMatrix &tc)
     if (tc.dev_ints) cudaFree(tc.dev_ints);
     if (tc.Himg) cudaFree(tc.Himg);
     if (tc.dbg) cudaFree(tc.dbg);
+    if (tc.clk) cudaFree(tc.clk);
     tc = TcMatrix();
 }
 
@@ -1212,8 +1125,7 @@ static inline void tc_prepare(TcMatrix &tc, const float *dA, size_t ldA, int n, 
     tc_make_map(&tc.map_ahi, tc.Ahi, (uint64_t)tc.n_pad, (uint64_t)m, pitch, TC_CHUNK, TC_GROUP);
     tc_make_map(&tc.map_alo, tc.Alo, (uint64_t)tc.n_pad, (uint64_t)m, pitch, TC_CHUNK, TC_GROUP);
     tc_make_map(&tc.map_w, tc.Wst, (uint64_t)tc.n_pad, 64, pitch, TC_CHUNK, 64);
-    CUDA_CHECK(cudaFuncSetAttribute(tc_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total + 1024));
-    CUDA_CHECK(cudaFuncSetAttribute(tc_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total + 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(tc_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total + 1024));
     CUDA_CHECK(cudaStreamSynchronize(st));
     tc.ready = true;
 }
@@ -1229,8 +1141,8 @@ static inline void tc_update_w(TcMatrix &tc, const float *Wt, cudaStream_t st)
 
 // one pass.  mode 0: H update (phase 1 + solve) followed by B = A H' of the new H; mode 1: B = A H' only.
 // B must be zeroed by the caller.  launches: 1 (+3 for the W split in mode 0)
-static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, float *Cscr, const float *pack, float l1, int k,
-                           int max_iter, float rel_tol, float *B, FitScalars *scal, cudaStream_t st)
+static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, float *Cscr, const float *pack, float l1, float pen_diag,
+                           float pen_all, int k, int max_iter, float rel_tol, float *B, FitScalars *scal, cudaStream_t st)
 {
 
     if (mode == 0) {
@@ -1247,7 +1159,7 @@ static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, fl
     p.n_mtiles = (tc.n + 127) / 128;
     p.n_chunks = 2 * p.n_mtiles;
     p.mode = mode;
-    p.pack = pack; p.l1 = l1; p.max_iter = max_iter; p.rel_tol = rel_tol;
+    p.pack = pack; p.l1 = l1; p.pen_diag = pen_diag; p.pen_all = pen_all; p.max_iter = max_iter; p.rel_tol = rel_tol;
     p.H = H; p.Cscr = Cscr; p.B = B; p.scal = scal;
     p.w_exp = tc.dev_ints + 1;
     p.hmax_prev = tc.dev_ints + 2;
@@ -1261,21 +1173,33 @@ static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, fl
     if (tl && !tc.dbg) CUDA_CHECK(cudaMalloc(&tc.dbg, sizeof(unsigned long long) * 64 * 148));
     p.dbg = tl ? tc.dbg : nullptr;
     if (p.dbg) CUDA_CHECK(cudaMemsetAsync(tc.dbg, 0, sizeof(unsigned long long) * 64 * 148, st));
+    // SWNE_TC_CLOCKS=<file>: clock64 stamps of every block update of every solver group (tools/solver_clocks.py reads it)
+    const char *ck = getenv("SWNE_TC_CLOCKS");
+    const size_t clk_count = (size_t)tc.grid * TC_TGROUPS * TC_CLK_RECS * 8;
+    if (ck && !tc.clk) CUDA_CHECK(cudaMalloc(&tc.clk, clk_count * sizeof(long long)));
+    p.clk = (ck && mode == 0) ? tc.clk : nullptr;
+    if (p.clk) CUDA_CHECK(cudaMemsetAsync(tc.clk, 0, clk_count * sizeof(long long), st));
     const int grid = tc.grid;
     if (tc.tiles_per_cta > TC_MAX_TILES) {
         set_error("tcgen05 engine: too many cells per SM");
         throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};
     }
-    // SWNE_TC_SOLVER=0 selects the CUDA-core sweeps (debug / comparison); default: tensor-core block Gauss-Seidel
-    static const int solver = getenv("SWNE_TC_SOLVER") ? atoi(getenv("SWNE_TC_SOLVER")) : 1;
-    if (solver == 0) {
-        tc_pass_kernel<0><<<grid, tc_threads(0), TcSmem::total + 1024, st>>>(tc.map_ahi, tc.map_alo, tc.map_w, p);
-    } else {
-        if (mode == 0)
-            CUDA_CHECK(cudaMemcpyToSymbolAsync(c_gram, pack, sizeof(float) * 2 * TC_KP * TC_KP, 0, cudaMemcpyDeviceToDevice, st));
-        tc_pass_kernel<1><<<grid, tc_threads(1), TcSmem::total + 1024, st>>>(tc.map_ahi, tc.map_alo, tc.map_w, p);
-    }
+    if (mode == 0)
+        CUDA_CHECK(cudaMemcpyToSymbolAsync(c_gram, pack, sizeof(float) * 2 * TC_KP * TC_KP, 0, cudaMemcpyDeviceToDevice, st));
+    tc_pass_kernel<<<grid, 768, TcSmem::total + 1024, st>>>(tc.map_ahi, tc.map_alo, tc.map_w, p);
     CUDA_CHECK(cudaGetLastError());
+    if (p.clk) {
+        std::vector<long long> hbuf(clk_count);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(cudaMemcpy(hbuf.data(), tc.clk, clk_count * sizeof(long long), cudaMemcpyDeviceToHost));
+        FILE *f = fopen(ck, "wb");
+        if (f) {
+            const int hdr[4] = {tc.grid, TC_TGROUPS, TC_CLK_RECS, 8};
+            fwrite(hdr, sizeof(int), 4, f);
+            fwrite(hbuf.data(), sizeof(long long), clk_count, f);
+            fclose(f);
+        }
+    }
     if (p.dbg && mode == 0) {
         // debug only: dump the per-CTA timeline of this launch (ns since the earliest CTA start)
         std::vector<unsigned long long> hbuf(64 * 148);

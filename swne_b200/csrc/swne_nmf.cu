@@ -624,7 +624,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     if (fused) {
         prof.begin(0);
         CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
-        tc_pass(h->tc, 1, h->Wt.p, h->H.p, h->C.p, nullptr, 0.f, k, p.inner_max_iter, 0.f, h->B.p, h->dscal.p, st);
+        tc_pass(h->tc, 1, h->Wt.p, h->H.p, h->C.p, nullptr, 0.f, 0.f, 0.f, k, p.inner_max_iter, 0.f, h->B.p, h->dscal.p, st);
         prof.end(0, tc_pass_launches(1));
         if (h->nranks > 1) allreduce(h, h->B.p, (size_t)n * KPv, nullptr, 0);
         have_B = true;
@@ -729,8 +729,8 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             if (fused) {
                 prof.begin(0);
                 CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
-                tc_pass(h->tc, 0, h->Wt.p, h->H.p, h->C.p, h->pack.p, (float)p.beta[2], k, p.inner_max_iter, inner_tol, h->B.p,
-                        h->dscal.p, st);
+                tc_pass(h->tc, 0, h->Wt.p, h->H.p, h->C.p, h->pack.p, (float)p.beta[2], (float)(p.beta[0] - p.beta[1]), (float)p.beta[1], k,
+                        p.inner_max_iter, inner_tol, h->B.p, h->dscal.p, st);
                 prof.end(0, tc_pass_launches(0));
                 prof.begin(7);
                 launch_gram(h, KPv, h->H.p, m, h->G64h.p);

@@ -411,30 +411,6 @@ def test_one_shot_entry_points_and_progress_callback(handle):
         lib.swne_nmf_set_progress(handle._h, C.PROGRESS_FN(0), None)
 
 
-def test_tcgen05_cuda_core_solver_variant(handle):
-    """SWNE_TC_SOLVER is read once per process, so the CUDA-core sweep variant of the pass kernel is exercised in a
-    child process: same parity bars."""
-    import subprocess, sys
-    code = r'''
-import sys, os
-sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
-from helpers import small_matrix, seeded_init, rel_fro, max_rel
-from oracle import nnmf_ref
-from swne_b200 import NMFHandle
-A = small_matrix(600, 1500, 6, 5); W0, H0 = seeded_init(A, 12, 5)
-ref = nnmf_ref(A, 12, W0, H0, max_iter=10, trace=1, rel_tol=-1.0)
-h = NMFHandle(0); h.set_matrix(A)
-r = h.fit(12, W0, H0, max_iter=10, trace=1, rel_tol=-1.0, engine="tc")
-assert r.options["engine"] == "tc"
-assert max_rel(r.target_loss, ref["target_loss"]) < 1e-4 and rel_fro(r.W, ref["W"]) < 1e-3 and rel_fro(r.H, ref["H"]) < 1e-3
-print("ok")
-'''
-    env = dict(os.environ, SWNE_TC_SOLVER="0")
-    out = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), env=env,
-                         capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
-
-
 def test_debug_variants_of_the_wide_engine_and_the_seed(handle):
     """SWNE_TCX_SOLVE_SIMT (wide contractions + CUDA-core solves) and SWNE_NNSVD_SIMT (fp32 sketch products) are read
     with getenv at call time, so they can be flipped in-process: both variants must meet the same bars."""
