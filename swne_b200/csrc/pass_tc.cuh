@@ -33,7 +33,7 @@ namespace swne {
 constexpr int TC_KP = 32;             // padded factor count handled by this engine (k <= 32)
 constexpr int TC_TILE = 128;          // cells per tile (MMA M in phase 1, K in phase 3)
 constexpr int TC_CHUNK = 64;          // genes per stage (128 B of fp16: one swizzle-128B row)
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 3;                  // 3 x 40 KB: the CTA stays under 164 KB of shared memory, which leaves ~90 KB of L1 (local-memory traffic of the solver then hits L1)
 constexpr int TC_GROUP = 32;          // cells per TMA box / work granule
 constexpr int TC_A_STAGE = TC_TILE * TC_CHUNK * 2;      // 16 KB
 constexpr int TC_W_STAGE = 64 * TC_CHUNK * 2;           // 8 KB  (rows 0..31 W_hi, 32..63 W_lo)
@@ -542,7 +542,10 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // broadcast from lane 0: the compiler then knows the warp index (and everything derived from it: the role, the
+    // solver group, the TMEM lane quarter, barrier addresses) is warp-uniform and keeps it in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
 
     // ---- my cells: a contiguous range of 32-cell groups
     const int gpc = p.groups_total / gridDim.x, grem = p.groups_total % gridDim.x;
@@ -603,17 +606,15 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     auto tmem_d = [&](int u) { return tmem + TC_D_COL + (u & 1) * (TC_MT_PER_PASS * 32); };
     // phase 3 takes the tiles in waves (B += A'H is linear in the tiles and the drain is an atomic add), so the
     // second stream over A starts on the tiles whose solves are done while the last tiles are still being solved
-    // Waves: pairs of tiles, the last one or two tiles as waves of their own -- a wave can only start when its tiles
-    // are solved, and what is streamed after the last solve is the exposed tail of the kernel.  Long CTAs (> 8 tiles)
-    // take everything but their last 6 tiles as one leading wave (every wave costs 8 accumulator drains).
-    const int w_base = (n_tiles > 8) ? n_tiles - 6 : 0;                   // tiles [0, w_base): the leading wave
-    const int w_rest = n_tiles - w_base;
-    const int n_pairs = (w_rest > 2) ? (w_rest - 1) / 2 : 0;               // then pairs, then single tiles
-    const int n_waves = (p.mode != 0 || n_tiles <= 1) ? 1 : (w_base > 0 ? 1 : 0) + n_pairs + (w_rest - 2 * n_pairs);
+    // Waves: pairs of tiles (a wave can only start when its tiles are solved; every wave drains all accumulators once
+    // more, i.e. adds one more round of red.add traffic to L2).  Long CTAs (> 8 tiles) take everything but their last
+    // 4 tiles as one leading wave.
+    const int w_base = (n_tiles > 8) ? n_tiles - 4 : 0;                   // tiles [0, w_base): the leading wave
+    const int n_waves = (p.mode != 0 || n_tiles <= 2) ? 1 : (w_base > 0 ? 1 : 0) + (n_tiles - w_base + 1) / 2;
     auto wave_lo = [&](int w) {
         if (n_waves == 1) return w == 0 ? 0 : n_tiles;
         if (w_base > 0) { if (w == 0) return 0; --w; }
-        return w_base + (w <= n_pairs ? 2 * w : min(w_rest, 2 * n_pairs + (w - n_pairs)));
+        return min(n_tiles, w_base + 2 * w);
     };
 
     // fp16 scale of the H images: the previous max(H) maps to [8, 16), which leaves a factor 4096 of growth before fp16
@@ -634,10 +635,6 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
         const float descale = exp2f(-(float)(p.a_exp + *p.w_exp));
         const float hscale = exp2f((float)h_exp);
-        float hmax = 0.f;
-        bool ovf = false;
-        double lp = 0.0;
-        unsigned long long its = 0;
         const float *sInvD = sD + TC_KP;
         // Group g (4 warps = the 4 lane quarters of a tile) solves tiles g, g+4, ...  mu' of the tile lives in its
         // TMEM accumulator (the C tile is rewritten in place).
@@ -705,8 +702,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                     tc_ld32(trow, T);
                     tc_fence_before();
                     mbar_arrive(CEMPTY(b));          // the accumulator goes back to the MMA warp
+                    float s_tile = 0.f;
                     if (valid) {
-                        its += (unsigned long long)my_sweeps;
                         float hs = 0.f;
 #pragma unroll
                         for (int f = 0; f < 32; ++f) { h[f] *= sInvD[f]; hs += h[f]; }
@@ -724,7 +721,16 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                                 s = fmaf(h[f], g0h - 2.f * cc[e], s);
                             }
                         }
-                        lp += (double)s;
+                        s_tile = s;
+                    }
+                    // per tile: one loss / sweep-count atomic per warp (nothing is carried across tiles in registers)
+                    const float sw = warp_sum(s_tile);
+                    int sc = valid ? my_sweeps : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+                    if (lane == 0) {
+                        atomicAdd(&p.scal->loss_part, (double)sw);
+                        atomicAdd(&p.scal->sweeps_h, (unsigned long long)sc);
                     }
                 }
             } else {
@@ -739,6 +745,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             // K-major [factor][cell] sub-tiles of 64 cells, 128 B rows, swizzle-128B by hand
             uint8_t *img = my_img + (size_t)t * TC_H_TILE + (lc >> 6) * TC_H_SUB;
             const int cc = lc & 63;
+            float hmax = 0.f;
+            bool ovf = false;
 #pragma unroll
             for (int f = 0; f < 32; ++f) {
                 hmax = fmaxf(hmax, h[f]);
@@ -753,20 +761,12 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             __threadfence();
             asm volatile("fence.proxy.async;" ::: "memory");
             mbar_arrive(TDONE(t));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+            if (lane == 0) atomicMax(p.hmax_next, __float_as_int(hmax));
+            if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicOr(p.overflow, 1);
             if (trec) trec[4] = clock64();
             if (lane == 0 && quarter == 0 && t < 8) TC_MARK(16 + t);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
-        if (lane == 0) atomicMax(p.hmax_next, __float_as_int(hmax));
-        if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicOr(p.overflow, 1);
-        if (p.mode == 0) {
-            lp = warp_sum(lp);
-            const double itd = warp_sum((double)its);
-            if (lane == 0) {
-                atomicAdd(&p.scal->loss_part, lp);
-                atomicAdd(&p.scal->sweeps_h, (unsigned long long)(itd + 0.5));
-            }
         }
     } else if (warp >= 4) {
         // =========================== drain warps ===========================

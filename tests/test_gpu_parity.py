@@ -345,6 +345,76 @@ def test_full_size_properties_cfg3(handle):
     handle.set_matrix(np.zeros((4, 4)) + 1.0)    # drop the borrowed tensor
 
 
+def _cfg3_slice(cells, seed_shift=0):
+    """the first `cells` cells of a cfg3-shaped matrix (same generator as bench.py), on the device and as host fp64"""
+    from swne_b200 import synth
+    c = synth.CONFIGS["cfg3"]
+    dA = synth.make_matrix_torch(c["n"], cells, c["kt"], c["scale"], c["seed"] + seed_shift)
+    A64 = np.asfortranarray(dA.cpu().numpy().T.astype(np.float64))
+    return c, dA, A64
+
+
+@pytest.mark.parametrize("cells,iters", [(20000, 10), (100000, 6)])
+def test_cfg3_slice_vs_oracle(handle, cells, iters):
+    """The headline configuration against the oracle itself: 3000 genes, k = 30, fused tcgen05 engine, NNLM's random
+    start, every iteration traced.  20 000 cells = 157 tiles (one or two per CTA: the multi-tile queues, the waves of the
+    second stream, partial last tiles); 100 000 cells = the full BASELINE config 3 (5-6 tiles per CTA)."""
+    from oracle import nnmf_ref
+    from swne_b200 import synth
+    c, dA, A64 = _cfg3_slice(cells)
+    W0, H0 = synth.random_init(c["n"], cells, c["k"], 0)
+    ref = nnmf_ref(A64, c["k"], W0, H0, max_iter=iters, trace=1, rel_tol=-1.0)
+    handle.set_matrix(dA)
+    r = handle.fit(c["k"], W0, H0, max_iter=iters, trace=1, rel_tol=-1.0, engine="tc")
+    assert r.options["engine"] == "tc"
+    _check_against(r, ref)
+    assert max_rel(r["mse"], ref["mse"]) < LOSS_TOL
+    # sweep counts: fp32 stops a column a sweep or two earlier than fp64 once its updates fall below fp32 resolution
+    assert max_rel(r["average_epochs"], ref["average_epochs"]) < 0.15
+    handle.set_matrix(np.zeros((4, 4)) + 1.0)    # drop the borrowed tensor
+
+
+def test_cfg2_mkl_at_size_vs_oracle(handle):
+    """BASELINE config 2 at size: 2000 x 3000, k = 16, loss = mkl with an L1 penalty on H (beta = (0, 0, 0.1)), and the
+    scalar-alpha variant RunNMF can express (L2 on W)."""
+    from oracle import nnmf_ref
+    from swne_b200 import synth
+    c = synth.CONFIGS["cfg1"]
+    A = synth.make_matrix_np(c["n"], c["m"], c["kt"], c["scale"], c["seed"], dtype=np.float64)
+    W0, H0 = seeded_init(A, c["k"], 1)
+    handle.set_matrix(A)
+    for kw in (dict(beta=[0, 0, 0.1]), dict(alpha=0.05)):
+        kw.update(loss="mkl", max_iter=40, trace=1, rel_tol=-1.0)
+        ref = nnmf_ref(A, c["k"], W0, H0, **kw)
+        r = handle.fit(c["k"], W0, H0, **kw)
+        assert max_rel(r["target_loss"], ref["target_loss"]) < LOSS_TOL
+        assert max_rel(r["mkl"], ref["mkl"]) < LOSS_TOL
+        assert max_rel(r["mse"], ref["mse"]) < 1e-3
+        # SURVEY H3: the KL coordinate step amplifies rounding where a factor row collapses; W/H are held to the looser bar
+        assert rel_fro(r["W"], ref["W"]) < 2e-2 and rel_fro(r["H"], ref["H"]) < 2e-2
+
+
+def test_csc_ingest_at_size_equals_dense(handle):
+    """dgCMatrix slots (int32 p / i, double x; src/swne_cpp_funcs.cpp:27-31) for a 3000 x 50000 cfg3-shaped matrix:
+    same statistics, and the same fit as the dense upload of the same values."""
+    from swne_b200 import synth
+    c, dA, A64 = _cfg3_slice(50000, seed_shift=7)
+    S = scipy.sparse.csc_matrix(A64)
+    W0, H0 = synth.random_init(c["n"], 50000, c["k"], 3)
+    handle.set_matrix(dA)
+    info_d = handle.matrix_info()
+    rd = handle.fit(c["k"], W0, H0, max_iter=6, trace=1, rel_tol=-1.0, engine="tc")
+    handle.set_matrix(S)
+    info_s = handle.matrix_info()
+    rs = handle.fit(c["k"], W0, H0, max_iter=6, trace=1, rel_tol=-1.0, engine="tc")
+    assert info_d["nnz"] == info_s["nnz"] == S.nnz
+    assert abs(info_d["sumsq"] - info_s["sumsq"]) < 1e-9 * info_d["sumsq"]
+    # same fp32 values on the device; the second stream accumulates with atomics, so agreement is to rounding
+    assert max_rel(rs["target_loss"], rd["target_loss"]) < 1e-6
+    assert rel_fro(rs["W"], rd["W"]) < 1e-4 and rel_fro(rs["H"], rd["H"]) < 1e-4
+    handle.set_matrix(np.zeros((4, 4)) + 1.0)
+
+
 def test_tcgen05_fp16_range_overflow_falls_back_to_fp32(handle):
     """H images are fp16 with a scale from the previous iteration's max(H); a > 4096x jump in one iteration must be
     detected and the fit redone on the fp32 engine (never a silent wrong answer)."""
