@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SWNE_NMF_ABI_VERSION 1
+#define SWNE_NMF_ABI_VERSION 2
 
 /* status codes */
 #define SWNE_OK 0
@@ -75,8 +75,14 @@ typedef struct swne_nmf_params {
     int full_traces;       /* the loss that is not being optimised (mkl in an mse fit) is evaluated
                               1: at every trace point, as NNLM does; 0: only in the final error block;
                               -1: never (NaN in the mkl trace) */
-    int profile;           /* 1: bracket every kernel family with CUDA events (disables graph replay) */
+    int profile;           /* 1: bracket every kernel family with CUDA events (per-family times in the result) */
+    int nnlm_variant;      /* SWNE_VARIANT_* bits: readings of NNLM details that no golden vector pins yet (0 = as
+                              recalled in SURVEY.md Appendix A) */
 } swne_nmf_params_t;
+
+/* scd_kl_update with an L2 penalty: Appendix A recalls "a += beta0; b += a*h - ..." (the default); this bit selects
+   "b += a*h - ...; a += beta0" (the exact Newton step).  Only matters for loss = mkl with alpha[0] / beta[0] != 0. */
+#define SWNE_VARIANT_KL_L2_LATE 1
 
 #define SWNE_PROF_SLOTS 8
 typedef struct swne_nmf_result {
@@ -140,6 +146,23 @@ int swne_nmf_fit_csc_f64(swne_nmf_handle_t h, const swne_nmf_params_t *p, const 
                          const double *cx, int n, int m, double *W, double *H, double *mse, double *mkl,
                          double *target_loss, double *average_epochs, int trace_len, swne_nmf_result_t *res);
 
+/* ---- RunNMF in one call on the resident matrix (R/nmf.R:96-134): seed -> zero replacement (R/nmf.R:121-127) -> nnmf.
+ * The seed is computed on the device and handed to the fit without a host round trip; W (n x k) and H (k x m) are
+ * outputs, except for SWNE_INIT_GIVEN where they hold the init (then this is swne_nmf_fit).  Random draws come from a
+ * counter-based generator keyed by `seed` (R's RNG streams cannot be reproduced by any other program).
+ *   RANDOM    NNLM's own start, U(0,1) * 0.01            (RunNMF(init = "random"), FindNumFactors)
+ *   NNSVD     nnsvd_init (R/nmf.R:12-47) from a randomized truncated SVD
+ *   ICA       ica_init(ica.fast = F) (R/nmf.R:63-64): FastICA on the top-k principal subspace of the centred data
+ *   ICA_FAST  ica_init(ica.fast = T) (R/nmf.R:58-61): 50 principal components, W = (A - rowMeans) S */
+#define SWNE_INIT_GIVEN 0
+#define SWNE_INIT_RANDOM 1
+#define SWNE_INIT_NNSVD 2
+#define SWNE_INIT_ICA 3
+#define SWNE_INIT_ICA_FAST 4
+int swne_run_nmf(swne_nmf_handle_t h, const swne_nmf_params_t *p, int init, uint64_t seed, double *W, double *H,
+                 double *mse, double *mkl, double *target_loss, double *average_epochs, int trace_len,
+                 swne_nmf_result_t *res);
+
 /* ---- NNLM::nnlm on the resident matrix: side 0 solves H (k x m) given W (ProjectSamples),
  * side 1 solves W (n x k) given H (ProjectFeatures on the fitted genes).  coef holds the init. */
 int swne_nnlm(swne_nmf_handle_t h, int side, int k, const double *X, double *coef, const double *alpha3,
@@ -149,6 +172,8 @@ int swne_nnlm(swne_nmf_handle_t h, int side, int k, const double *X, double *coe
 /* NNDSVD of the resident matrix from a randomized truncated SVD (oversample p, q power iterations). */
 int swne_nnsvd_init(swne_nmf_handle_t h, int k, int oversample, int power_iters, uint64_t seed,
                     double *W, double *H, double *singular_values);
+/* ica_init (R/nmf.R:56-66) of the resident matrix: signed W (n x k) and H (k x m), components up to sign and order */
+int swne_ica_init(swne_nmf_handle_t h, int k, int ica_fast, uint64_t seed, double *W, double *H);
 /* x < eps -> 0 in place; returns the number of zeros so the caller can draw its runif()s */
 int swne_zero_replace(double *x, size_t len, double eps, const double *fill, size_t n_fill, size_t *n_zero);
 

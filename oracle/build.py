@@ -36,5 +36,7 @@ def load_oracle():
     lib.nnlm_ref.argtypes = [d, d, d, ctypes.c_int, ctypes.c_int, ctypes.c_int, d, ctypes.c_int,
                              ctypes.c_double, ctypes.c_int, ctypes.c_int]
     lib.oracle_num_threads.restype = ctypes.c_int
+    lib.oracle_set_variant.argtypes = [ctypes.c_int]
+    lib.oracle_set_variant.restype = None
     _lib = lib
     return lib

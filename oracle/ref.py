@@ -23,7 +23,7 @@ def _pad3(v):
 
 
 def nnmf_ref(A, k, W0, H0, alpha=0.0, beta=0.0, loss="mse", max_iter=500, rel_tol=1e-4,
-             inner_max_iter=None, inner_rel_tol=1e-9, trace=None, n_threads=0):
+             inner_max_iter=None, inner_rel_tol=1e-9, trace=None, n_threads=0, kl_l2_late=False):
     """NNLM::nnmf(A, k, init=list(W=W0,H=H0), method='scd', loss=...) restated (SURVEY Appendix A;
     call sites /root/reference/R/nmf.R:117,129,167,168).  W0/H0 must be given: NNLM's random init uses
     R's RNG, which cannot be reproduced here."""
@@ -46,9 +46,11 @@ def nnmf_ref(A, k, W0, H0, alpha=0.0, beta=0.0, loss="mse", max_iter=500, rel_to
     mse = np.zeros(L); mkl = np.zeros(L); terr = np.zeros(L); epo = np.zeros(L)
     nit = ctypes.c_int(0); ntr = ctypes.c_int(0)
     lib = load_oracle()
+    lib.oracle_set_variant(1 if kl_l2_late else 0)      # the second reading of scd_kl_update's L2 step (nnmf_ref.c header)
     warn = lib.nnmf_ref(_dp(A), n, m, k, _dp(W), _dp(H), _dp(al), _dp(be), int(max_iter), float(rel_tol),
                         int(inner_max_iter), float(inner_rel_tol), method, int(trace), int(n_threads),
                         _dp(mse), _dp(mkl), _dp(terr), _dp(epo), ctypes.byref(nit), ctypes.byref(ntr))
+    lib.oracle_set_variant(0)
     t = ntr.value
     return dict(W=np.array(W), H=np.array(H), mse=mse[:t].copy(), mkl=mkl[:t].copy(),
                 target_loss=terr[:t].copy(), average_epochs=epo[:t].copy(), n_iteration=nit.value,

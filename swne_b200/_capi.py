@@ -22,6 +22,8 @@ SWNE_ERR_INTERRUPTED = -6
 LOSS = {"mse": 0, "mkl": 1}
 ENGINE = {"auto": 0, "simt": 1, "tc": 2}
 ENGINE_NAME = {0: "auto", 1: "simt", 2: "tc"}
+VARIANT_KL_L2_LATE = 1      # include/swne_nmf.h SWNE_VARIANT_KL_L2_LATE
+INIT = {"given": 0, "random": 1, "nnsvd": 2, "ica": 3, "ica_fast": 4}
 MAX_K = 64
 PROF_SLOTS = 8
 PROF_NAMES = ("contract_H_or_pass", "solve_H", "contract_W", "solve_W", "gram_loss", "mkl_update", "allreduce", "other")
@@ -32,7 +34,7 @@ SYMBOLS = (
     "swne_nmf_create", "swne_nmf_destroy", "swne_nmf_set_progress", "swne_nmf_comm_unique_id", "swne_nmf_comm_init",
     "swne_nmf_set_matrix_dense_f64", "swne_nmf_set_matrix_dense_f32", "swne_nmf_set_matrix_csc_f64",
     "swne_nmf_set_matrix_csc_f32", "swne_nmf_set_matrix_dense_f32_device", "swne_nmf_matrix_info", "swne_nmf_fit",
-    "swne_nmf_fit_dense_f64", "swne_nmf_fit_csc_f64", "swne_nnlm", "swne_nnsvd_init", "swne_zero_replace",
+    "swne_nmf_fit_dense_f64", "swne_nmf_fit_csc_f64", "swne_run_nmf", "swne_nnlm", "swne_nnsvd_init", "swne_ica_init", "swne_zero_replace",
     "swne_sample_coords", "swne_factor_distance", "swne_recon_error",
 )
 
@@ -48,7 +50,7 @@ class Params(ctypes.Structure):
                 ("loss", ctypes.c_int), ("max_iter", ctypes.c_int), ("rel_tol", ctypes.c_double),
                 ("inner_max_iter", ctypes.c_int), ("inner_rel_tol", ctypes.c_double), ("trace", ctypes.c_int),
                 ("verbose", ctypes.c_int), ("engine", ctypes.c_int), ("full_traces", ctypes.c_int),
-                ("profile", ctypes.c_int)]
+                ("profile", ctypes.c_int), ("nnlm_variant", ctypes.c_int)]
 
 
 class Result(ctypes.Structure):
@@ -98,8 +100,10 @@ def load(build_if_missing=True):
                                            ctypes.POINTER(Result)]
     lib.swne_nmf_fit_csc_f64.argtypes = [vp, ctypes.POINTER(Params), ip, ip, dp, c_int, c_int, dp, dp, dp, dp, dp, dp,
                                          c_int, ctypes.POINTER(Result)]
+    lib.swne_run_nmf.argtypes = [vp, ctypes.POINTER(Params), c_int, ctypes.c_uint64, dp, dp, dp, dp, dp, dp, c_int, ctypes.POINTER(Result)]
     lib.swne_nnlm.argtypes = [vp, c_int, c_int, dp, dp, dp, c_int, c_int, c_dbl, ctypes.POINTER(ctypes.c_longlong)]
     lib.swne_nnsvd_init.argtypes = [vp, c_int, c_int, c_int, ctypes.c_uint64, dp, dp, dp]
+    lib.swne_ica_init.argtypes = [vp, c_int, c_int, ctypes.c_uint64, dp, dp]
     lib.swne_zero_replace.argtypes = [dp, ctypes.c_size_t, c_dbl, dp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     lib.swne_sample_coords.argtypes = [vp, dp, c_int, c_int, dp, c_dbl, c_int, dp]
     lib.swne_factor_distance.argtypes = [vp, dp, c_int, c_int, c_int, dp]

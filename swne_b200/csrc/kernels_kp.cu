@@ -70,8 +70,13 @@ void kl_l(const int *ptr, const int *idx, const float *val, float *ajt, float *X
 void kl_trace_l(const float *A, size_t ldA, int n, int m, const float *H, const float *Wt, int k, double *kl_part,
                 cudaStream_t st)
 {
-    dim3 grid((n + 255) / 256, (m + KL_CELLS - 1) / KL_CELLS);
-    kl_trace_kernel<KP><<<grid, 256, 0, st>>>(A, ldA, n, m, H, Wt, k, kl_part);
+    // grid.y is capped at 65535 blocks of KL_CELLS cells: longer matrices go in slabs
+    const int slab = 65535 * KL_CELLS;
+    for (int c0 = 0; c0 < m; c0 += slab) {
+        const int mc = (m - c0 < slab) ? m - c0 : slab;
+        dim3 grid((n + 255) / 256, (mc + KL_CELLS - 1) / KL_CELLS);
+        kl_trace_kernel<KP><<<grid, 256, 0, st>>>(A + (size_t)c0 * ldA, ldA, n, mc, H + (size_t)c0 * KP, Wt, k, kl_part);
+    }
 }
 void recon_error_l(const float *A, size_t ldA, int n, int m, const float *Wt, const float *H, int k, double *out2, int grid,
                    cudaStream_t st)
@@ -82,10 +87,14 @@ void right_multiply_l(float *X, size_t rows, const float *T, int l, cudaStream_t
 {
     right_multiply_kernel<KP><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(X, rows, T, l);
 }
+void ica_step_l(const float *Y, int rows, int nc, const float *R, double *out, int grid, cudaStream_t st)
+{
+    ica_step_kernel<KP><<<grid, 256, 0, st>>>(Y, rows, nc, R, out);
+}
 }  // namespace
 
 #define KP_OPS_NAME2(v) kp_ops_table_##v
 #define KP_OPS_NAME(v) KP_OPS_NAME2(v)
 extern const KpOps KP_OPS_NAME(KP_VALUE) = {gram_l, contract_cells_l, contract_genes_l, solve_l, kl_l, kl_trace_l,
-                                            recon_error_l, right_multiply_l};
+                                            recon_error_l, right_multiply_l, ica_step_l};
 }  // namespace swne

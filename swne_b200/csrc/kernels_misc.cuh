@@ -73,8 +73,10 @@ __global__ void ingest_csc_kernel(const int *__restrict__ p, const int *__restri
             const double v = (double)x[q];
             if (g < 0 || g >= n) { bad |= 4u; continue; }
             if (!(v >= 0.0)) bad |= (v < 0.0) ? 1u : 2u;
-            if (isinf(v)) bad |= 2u;
-            dst[(size_t)j * dst_ld + g] = (float)v;
+            if (isinf(v) || isinf((float)v)) bad |= 2u;      // also a finite double beyond the fp32 range
+            // duplicate (i, j) entries add up, as in a dgCMatrix built by Matrix::sparseMatrix (the statistics below count
+            // them separately either way, which only matters for nnz)
+            atomicAdd(&dst[(size_t)j * dst_ld + g], (float)v);
             mx = fmaxf(mx, (float)v);
             s += v; s2 += v * v;
             if (v != 0.0) { ++nz; kc += (v + TINY_NUM_D) * log(v + TINY_NUM_D) - v; }

@@ -70,6 +70,70 @@ __global__ void __launch_bounds__(256) gram_kernel(const float *__restrict__ X, 
 }
 
 // ----------------------------------------------------------------------------------------------
+// One FastICA iteration (ica::icafast, alg = "par", fun = "logcosh", alpha = 1; call sites R/nmf.R:59,63) on the whitened
+// data Y [rows][KP] (nc sources):   S = Y R,  g = tanh(S),  out[a KP + b] += sum_r y_a g_b,  out[KP^2 + b] += sum_r (1 - g_b^2)
+// (the host forms R+ = Y'g / nobs - R diag(mean(1 - g^2)) and orthogonalises it: nc x nc work).  One pass over Y.
+// ----------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(256) ica_step_kernel(const float *__restrict__ Y, int rows, int nc, const float *__restrict__ Rm,
+                                                       double *__restrict__ out)
+{
+    constexpr int ROWS = 32;
+    constexpr int PAIRS = (KP * KP + 255) / 256;
+    __shared__ float ys[ROWS][KP + 1];
+    __shared__ float gs[ROWS][KP + 1];
+    __shared__ float sR[KP][KP + 1];
+    __shared__ float sg2[KP];
+    for (int t = threadIdx.x; t < KP * KP; t += 256) sR[t / KP][t % KP] = Rm[t];
+    if (threadIdx.x < KP) sg2[threadIdx.x] = 0.f;
+    float acc[PAIRS];
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q) acc[q] = 0.f;
+    const int per = ((rows + gridDim.x - 1) / gridDim.x + ROWS - 1) / ROWS * ROWS;
+    const int row_begin = blockIdx.x * per;
+    const int row_end = min(rows, row_begin + per);
+    for (int r0 = row_begin; r0 < row_end; r0 += ROWS) {
+        const int nr = min(ROWS, row_end - r0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < ROWS * KP; t += 256) {
+            const int r = t / KP, f = t % KP;
+            ys[r][f] = (r < nr) ? Y[(size_t)(r0 + r) * KP + f] : 0.f;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < ROWS * KP; t += 256) {
+            const int r = t / KP, b = t % KP;
+            float g = 0.f;
+            if (b < nc && r < nr) {
+                float sv = 0.f;
+                for (int a = 0; a < nc; ++a) sv = fmaf(ys[r][a], sR[a][b], sv);
+                g = tanhf(sv);
+                atomicAdd(&sg2[b], 1.f - g * g);
+            }
+            gs[r][b] = g;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PAIRS; ++q) {
+            const int pr = threadIdx.x + q * 256;
+            if (pr < KP * KP) {
+                const int a = pr / KP, b = pr % KP;
+                float sv = 0.f;
+#pragma unroll 8
+                for (int r = 0; r < ROWS; ++r) sv = fmaf(ys[r][a], gs[r][b], sv);
+                acc[q] += sv;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q) {
+        const int pr = threadIdx.x + q * 256;
+        if (pr < KP * KP && pr / KP < nc && pr % KP < nc) atomicAdd(&out[pr], (double)acc[q]);
+    }
+    if (threadIdx.x < nc) atomicAdd(&out[KP * KP + threadIdx.x], (double)sg2[threadIdx.x]);
+}
+
+// ----------------------------------------------------------------------------------------------
 // C[m][KP] = A[m][n] * Wt[n][KP]        (H side: c_j = Wt a_j for a tile of 64 cells)
 // 128 threads; thread (ty = t/8, tx = t%8) owns cells ty*4..+4 and factors tx*FPT..+FPT
 // ----------------------------------------------------------------------------------------------
@@ -440,12 +504,14 @@ __global__ void __launch_bounds__(128) scd_ls_solve_kernel(float *__restrict__ X
 // every thread owns one or two nonzeros: the per-coordinate chain is latency bound, not work bound).  (scd_kl_update)
 //   ptr/idx/val : the sparse view whose "columns" are the columns being solved
 //   X  [cols][KP] in/out;  Y [rows][KP] the fixed factor (row r = factors of entity r);  sumY[KP]
-//   err != 0: add sum a log(ahat+tiny) and sum a^2-2 a ahat
+//   err: bit 0 (KL_ERR) add sum a log(ahat+tiny) and sum a^2-2 a ahat;  bit 1 (KL_L2_LATE) the other reading of NNLM's
+//        Newton step with an L2 penalty (see kl_column)
 // A column with at most `cap` nonzeros is staged once in shared memory -- the gathered rows of Y
 // transposed to Yt[f][q] (lanes read consecutive words), A-hat on the support and the values -- so the
 // k coordinate passes of every sweep run out of shared memory instead of re-gathering Y through L2.
 // Longer columns take the same code on the global arrays (ajt_g is the nnz-sized A-hat scratch).
 // ----------------------------------------------------------------------------------------------
+constexpr int KL_ERR = 1, KL_L2_LATE = 2;
 template <int KP, int NT, bool SM>
 __device__ __forceinline__ int kl_column(const int *__restrict__ idx, const float *__restrict__ val,
                                          float *__restrict__ ajt_g, const float *__restrict__ Y,
@@ -520,8 +586,14 @@ __device__ __forceinline__ int kl_column(const int *__restrict__ idx, const floa
             a2 = __shfl_sync(0xffffffffu, x, 0);
             bb = __shfl_sync(0xffffffffu, x, NW & 31);
             bb -= sumY[kk];
-            a2 += b0;
-            bb += a2 * hk - b2 - b1 * (sumH - hk);
+            // NNLM's scd_kl_update as recalled: "a += beta0; b += a*h - ..." -- the L2 penalty is part of
+            // the `a` that multiplies h.  The other reading (the exact Newton step: b += a*h BEFORE a += beta0) is kept
+            // behind KL_L2_LATE so that a golden vector from real NNLM can decide without a code change; the two differ
+            // only when the L2 penalty (alpha[0] / beta[0]) is non-zero.
+            float a2h;
+            if (err & KL_L2_LATE) { a2h = a2 * hk; a2 += b0; }
+            else { a2 += b0; a2h = a2 * hk; }
+            bb += a2h - b2 - b1 * (sumH - hk);
             float tmp = bb / (a2 + TINY_NUM_F);
             if (!(tmp > 0.f)) tmp = 0.f;
             d_prev = tmp - hk;
@@ -534,7 +606,7 @@ __device__ __forceinline__ int kl_column(const int *__restrict__ idx, const floa
         }
         __syncthreads();   // h and the partial-sum slots are reused by the next sweep
     }
-    if (err) {
+    if (err & KL_ERR) {
         // A-hat recomputed from the final h: the incrementally updated values keep fp32 residue where the
         // exact value is 0, and log(ahat + 1e-16) is sensitive exactly there
         for (int q = tid; q < nz; q += NT) {
@@ -584,7 +656,7 @@ __global__ void __launch_bounds__(NT) scd_kl_kernel(const int *__restrict__ ptr,
         if (threadIdx.x < KP) X[(size_t)j * KP + threadIdx.x] = h[threadIdx.x];
     }
     if (threadIdx.x == 0 && its) atomicAdd(sweeps, its);
-    if (err) {
+    if (err & KL_ERR) {
         const double t1 = block_sum(klp, scratch);
         if (threadIdx.x == 0) atomicAdd(kl_part, t1);
         const double t2 = block_sum(sqp, scratch);

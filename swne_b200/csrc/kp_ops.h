@@ -25,6 +25,8 @@ struct KpOps {
     void (*recon_error)(const float *A, size_t ldA, int n, int m, const float *Wt, const float *H, int k, double *out2, int grid,
                         cudaStream_t st);
     void (*right_multiply)(float *X, size_t rows, const float *T, int l, cudaStream_t st);
+    // one FastICA pass over the whitened data (ica_step_kernel): out[KP*KP + KP] doubles, zeroed by the caller
+    void (*ica_step)(const float *Y, int rows, int nc, const float *R, double *out, int grid, cudaStream_t st);
 };
 
 const KpOps *kp_ops(int KP);  // nullptr when KP is not one of 8,16,...,64

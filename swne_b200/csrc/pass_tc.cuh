@@ -40,13 +40,19 @@ constexpr int TC_W_STAGE = 64 * TC_CHUNK * 2;           // 8 KB  (rows 0..31 W_h
 constexpr int TC_BOX_BYTES = TC_GROUP * TC_CHUNK * 2;   // 4 KB
 constexpr int TC_H_SUB = TC_KP * 64 * 2;                // 4 KB: [32 factors][64 cells] 16-bit, K-major
 constexpr int TC_H_TILE = 4 * TC_H_SUB;                 // hi cells 0..63, hi cells 64..127, lo, lo (all fp16)
-constexpr int TC_CBUF = 6;                              // C / mu' accumulators (32 TMEM columns each) in flight
-// TMEM map (512 columns): [0,192) six C / mu' tiles, [192,320) the delta operands of the 4 solver groups (16 hi + 16 lo
-// columns each), [320,512) two phase-3 accumulator regions of 3 x 32 columns.
+constexpr int TC_CBUF = 5;                              // C / mu' accumulators (32 TMEM columns each) in flight
+// TMEM map (512 columns): [0,160) five C / mu' tiles, [160,192) the H H' accumulator of the CTA, [192,320) the delta
+// operands of the 4 solver groups (16 hi + 16 lo columns each), [320,512) two phase-3 accumulator regions of 3 x 32.
 constexpr int TC_TGROUPS = 4;                           // solver groups (4 warps each) of the fused pass
+constexpr int TC_GRAM_COL = 160;
 constexpr int TC_DELTA_COL = 192;
 constexpr int TC_D_COL = 320;
 constexpr int TC_MT_PER_PASS = 3;                       // 128-gene accumulators per phase-3 unit (3 * 32 TMEM columns, two regions)
+// device-side state of a fit (ints): scales and counters that used to be separate memset / absmax / copy launches
+//   [0,1] max(W) float bits of the even / odd iteration   [2,3] max(H) likewise   [4] fp16 overflow flag
+//   [5] ticket counter of the W-side kernel   [6] ticket counter of the pass kernel
+constexpr int TC_ST_WMAX = 0, TC_ST_HMAX = 2, TC_ST_OVF = 4, TC_ST_CNT_W = 5, TC_ST_CNT_P = 6, TC_ST_INTS = 8;
+constexpr int TC_GS = TC_KP * TC_KP + TC_KP;            // doubles of one Gram + sums buffer
 constexpr int TC_MAX_TILES = 128;                       // tiles per CTA (one mbarrier each)
 constexpr int TC_GOP = 1024;                            // one [32 x 8] tf32 operand of G' (per block, hi / lo)
 
@@ -60,8 +66,8 @@ struct TcSmem {
     static constexpr int dvec = gops + 8 * TC_GOP;       // sqrt(diag), 1/sqrt(diag)
     static constexpr int bars = dvec + 2 * TC_KP * 4;
     static constexpr int n_bars = 2 * TC_STAGES + 2 * TC_CBUF + 2 + 2 + 4 + TC_TGROUPS + TC_MAX_TILES;
-    static constexpr int misc = bars + n_bars * 8;
-    static constexpr int total = misc + 64;
+    static constexpr int misc = bars + n_bars * 8;       // [0] TMEM base, [4] last-CTA flag, [64,192) row sums of H (fp32)
+    static constexpr int total = misc + 256;
 };
 
 struct TcPassParams {
@@ -69,21 +75,23 @@ struct TcPassParams {
     int n_chunks;            // gene chunks per tile in phase 1 (even, >= ceil(n/64))
     int n_mtiles;            // ceil(n/128)
     int mode;                // 0: phase 1 + solve + phase 3; 1: phase 3 only (A H' of the given H)
-    const float *pack;       // GramPack of W'W (D / invD read here; the Grams themselves sit in c_gram)
+    int par;                 // iteration parity: which half of the double-buffered state this launch writes
+    int finalize;            // 1: the last CTA turns H H' into the GramPack of the next W update (single GPU)
+    const float *pack;       // GramPack of W'W (D / invD / G' operands read here; the triangular part sits in c_gram)
+    float *pack_next;        // GramPack of H H' + alpha penalties, written by the last CTA (finalize)
+    double pen_next0, pen_next1;   // alpha[0], alpha[1] of that GramPack
     float l1;
     float pen_diag, pen_all; // G = G0 + pen_diag I + pen_all 11' (+ tiny I): the L2 / angle penalties folded into the Gram
     int max_iter;
     float rel_tol;
     float *H;                // [m][32] fp32 in/out
     float *Cscr;             // [m][32] fp32 scratch: the contraction C = A W, kept for the loss after the solve
-    float *B;                // [n][32] fp32, accumulated with red.add (zeroed by the caller)
+    float *B;                // [n][32] fp32, accumulated with red.add (zeroed by the W-side kernel / the caller)
     uint8_t *Himg;           // [grid][tiles_per_cta][TC_H_TILE] split 16-bit images of the H tiles
     int tiles_per_cta;
     FitScalars *scal;
-    const int *w_exp;        // device: W was scaled by 2^w_exp before the split
-    const int *hmax_prev;    // device: float bits of max(H) before this pass (sets the fp16 scale of the H images)
-    int *hmax_next;          // device: atomicMax of the float bits of the new H
-    int *overflow;           // device: set when a scaled H entry left the fp16 range
+    int *state;              // TC_ST_* ints
+    double *G64h;            // [2][TC_GS]: H H' and row sums of H, accumulated into half `par`; half par^1 is zeroed
     int a_exp;               // A was scaled by 2^a_exp before the split
     int groups_total;        // ceil(m / 32)
     unsigned long long *dbg; // optional timeline (SWNE_TC_TIMELINE): 64 globaltimer slots per CTA
@@ -442,19 +450,102 @@ __device__ __forceinline__ void tc_fill_gops(uint8_t *gops, const float *__restr
     }
 }
 
+// fp16 scale exponent of a factor whose largest entry was `max_bits` (float bits) one iteration ago: that maximum maps
+// to [8, 16), which leaves a factor 4096 of growth before fp16 overflows (flagged, never silent) while entries down to
+// 1e-9 of the maximum keep their value in the hi + lo pair
+__device__ __forceinline__ int tc_exp_of(int max_bits)
+{
+    const float mx = __int_as_float(max_bits);
+    if (!(mx > 0.f)) return 0;
+    int e;
+    frexpf(mx, &e);
+    return max(-100, min(100, 4 - e));
+}
+
+// GramPack from the fp64 sums, by one whole CTA (finalize_gram_kernel of kernels_misc.cuh restated as a device function;
+// update() of NNLM: G = G0 + (p0 - p1) I + p1 11' + tiny I).  G64 is read through L2 (other CTAs' atomics).
+__device__ __forceinline__ void tc_finalize_gram(const double *G64, float *pack, int k, double p0, double p1, float *sInv)
+{
+    constexpr int KP = TC_KP;
+    for (int t = threadIdx.x; t < KP; t += blockDim.x) {
+        double g = 1.0;
+        if (t < k) {
+            g = __ldcg(G64 + t * KP + t);
+            if (p0 != p1) g += p0 - p1;
+            if (p1 != 0.0) g += p1;
+            g += TINY_NUM_D;
+        }
+        const float d = sqrtf((float)g);
+        pack[2 * KP * KP + t] = d;
+        pack[2 * KP * KP + KP + t] = 1.f / d;
+        sInv[t] = 1.f / d;
+        pack[2 * KP * KP + 2 * KP + t] = (t < k) ? (float)__ldcg(G64 + KP * KP + t) : 0.f;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < KP * KP; t += blockDim.x) {
+        const int a = t / KP, b = t % KP;
+        float gs = 0.f, g0 = 0.f;
+        if (a < k && b < k) {
+            double g = __ldcg(G64 + t);
+            g0 = (float)g;
+            if (p1 != 0.0) g += p1;
+            gs = (a == b) ? 1.f : (float)g * sInv[a] * sInv[b];
+        }
+        pack[t] = gs;
+        pack[KP * KP + t] = g0;
+    }
+}
+
+// "last CTA done": every CTA calls this once after its global writes; true in exactly one CTA, after all the others'
+// writes are visible.  The counter is reset for the next launch.
+__device__ __forceinline__ bool tc_last_cta(int *counter, int *s_flag)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int ticket = atomicAdd(counter, 1);
+        const int last = (ticket == (int)gridDim.x - 1) ? 1 : 0;
+        if (last) { *counter = 0; __threadfence(); }
+        *s_flag = last;
+    }
+    __syncthreads();
+    return *s_flag != 0;
+}
+
 // ------------------------------------------------------------------------------------------------
-// W-side solve with the same tensor-core sweeps: one CTA of 4 warps per 128 genes.
-//   X [cols][32] in/out, C [cols][32] = A H' (the contraction), pack = GramPack of H H' (c_gram holds its Grams).
+// The W side of one outer iteration in ONE kernel (one CTA of 4 warps per 128 genes):
+//   solve the 128 columns with the tensor-core sweeps (X [cols][32] in/out, C = A H' the contraction, pack = GramPack of
+//   H H', c_gram its triangular coefficients), write W and its split-fp16 image for the pass (scale from the previous
+//   iteration's max(W)), add this tile's W'W and column sums into the fp64 sums, zero the consumed rows of C (the pass
+//   accumulates the next A H' into them), and let the last CTA build the GramPack of the H update.
+// Replaces, per iteration: finalize_gram, tc_wsolve, zero_fill, gram(W), finalize_gram, absmax, split_w and three
+// memsets (round 1: 0.15 ms of serial launches).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1)
-tc_wsolve_kernel(float *__restrict__ X, const float *__restrict__ C, const float *__restrict__ pack, float l1, int k, int cols,
-                 int max_iter, float rel_tol, unsigned long long *sweeps)
+struct TcWsideParams {
+    float *X;                 // Wt [n][32]
+    float *C;                 // B [n][32] = A H' (all-reduced); rows zeroed after they are read
+    const float *pack;        // GramPack of H H' (alpha penalties)
+    float *pack_next;         // GramPack of W'W (beta penalties), written by the last CTA
+    double pen_next0, pen_next1;
+    float l1;
+    int k, cols, n_pad, max_iter;
+    float rel_tol;
+    __half *Wst;              // [64][n_pad] split image
+    int *state;
+    int par;
+    double *G64w;             // [2][TC_GS]
+    FitScalars *scal;
+};
+
+__global__ void __launch_bounds__(128, 1) tc_wside_kernel(const TcWsideParams p)
 {
     __shared__ __align__(1024) uint8_t gops[8 * TC_GOP];
     __shared__ float sD[2 * TC_KP];
+    __shared__ float ws[128][TC_KP + 1];
     __shared__ __align__(8) uint64_t mbar_store;
     __shared__ uint32_t tmem_slot;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, quarter = warp;
+    __shared__ int s_flag;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31, quarter = warp;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(64));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -464,8 +555,9 @@ tc_wsolve_kernel(float *__restrict__ X, const float *__restrict__ C, const float
         mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    tc_fill_gops(gops, pack, threadIdx.x, blockDim.x);
-    if (threadIdx.x < 2 * TC_KP) sD[threadIdx.x] = pack[2 * TC_KP * TC_KP + threadIdx.x];
+    tc_fill_gops(gops, p.pack, threadIdx.x, blockDim.x);
+    if (threadIdx.x < 2 * TC_KP) sD[threadIdx.x] = p.pack[2 * TC_KP * TC_KP + threadIdx.x];
+    const int w_exp = tc_exp_of(p.state[TC_ST_WMAX + (p.par ^ 1)]);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
@@ -473,8 +565,8 @@ tc_wsolve_kernel(float *__restrict__ X, const float *__restrict__ C, const float
     const uint32_t tmem = tmem_slot;
     const float *sInvD = sD + TC_KP;
     const int j = blockIdx.x * 128 + threadIdx.x;
-    const bool valid = j < cols;
-    float *xrow = X + (size_t)(valid ? j : 0) * TC_KP;
+    const bool valid = j < p.cols;
+    float *xrow = p.X + (size_t)(valid ? j : 0) * TC_KP;
     const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
     GsLink L{tmem, tmem + 32, smem_u32(gops), mbar, 0u, false, 1, quarter};
     float h[32];
@@ -482,15 +574,16 @@ tc_wsolve_kernel(float *__restrict__ X, const float *__restrict__ C, const float
         // mu'_0 = (l1 - c) / d; the G' h' part is added by the tensor core
         float mv[32];
         if (valid) {
-            const float4 *cp = reinterpret_cast<const float4 *>(C + (size_t)j * TC_KP);
+            float4 *cp = reinterpret_cast<float4 *>(p.C + (size_t)j * TC_KP);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const float4 v = reinterpret_cast<const float4 *>(xrow)[r];
                 h[4 * r] = v.x * sD[4 * r]; h[4 * r + 1] = v.y * sD[4 * r + 1];
                 h[4 * r + 2] = v.z * sD[4 * r + 2]; h[4 * r + 3] = v.w * sD[4 * r + 3];
                 const float4 c = cp[r];
-                mv[4 * r] = (l1 - c.x) * sInvD[4 * r]; mv[4 * r + 1] = (l1 - c.y) * sInvD[4 * r + 1];
-                mv[4 * r + 2] = (l1 - c.z) * sInvD[4 * r + 2]; mv[4 * r + 3] = (l1 - c.w) * sInvD[4 * r + 3];
+                cp[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                mv[4 * r] = (p.l1 - c.x) * sInvD[4 * r]; mv[4 * r + 1] = (p.l1 - c.y) * sInvD[4 * r + 1];
+                mv[4 * r + 2] = (p.l1 - c.z) * sInvD[4 * r + 2]; mv[4 * r + 3] = (p.l1 - c.w) * sInvD[4 * r + 3];
             }
         } else {
 #pragma unroll
@@ -498,20 +591,72 @@ tc_wsolve_kernel(float *__restrict__ X, const float *__restrict__ C, const float
         }
         tc_st32(trow, mv);
     }
-    gs_push_h<false>(L, h, k);
-    const int my_sweeps = tc_block_gs(h, trow, L, k, max_iter, rel_tol);
+    gs_push_h<false>(L, h, p.k);
+    const int my_sweeps = tc_block_gs(h, trow, L, p.k, p.max_iter, p.rel_tol);
     gs_wait(L);
+    // ---- W row, its split image, the tile's Gram
+    float wmax = 0.f;
+    bool ovf = false;
+    const float scale = exp2f((float)w_exp);
+#pragma unroll
+    for (int f = 0; f < 32; ++f) {
+        h[f] *= sInvD[f];
+        ws[threadIdx.x][f] = h[f];
+        wmax = fmaxf(wmax, h[f]);
+    }
     if (valid) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
-            reinterpret_cast<float4 *>(xrow)[r] = make_float4(h[4 * r] * sInvD[4 * r], h[4 * r + 1] * sInvD[4 * r + 1],
-                                                              h[4 * r + 2] * sInvD[4 * r + 2], h[4 * r + 3] * sInvD[4 * r + 3]);
+        for (int r = 0; r < 8; ++r) reinterpret_cast<float4 *>(xrow)[r] = make_float4(h[4 * r], h[4 * r + 1], h[4 * r + 2], h[4 * r + 3]);
     }
+    if (j < p.n_pad) {
+#pragma unroll
+        for (int f = 0; f < TC_KP; ++f) {
+            float x = h[f] * scale;                 // rows past n hold h = 0
+            if (x > 60000.f) { x = 60000.f; ovf = true; }
+            const __half hi = __float2half_rn(x);
+            p.Wst[(size_t)f * p.n_pad + j] = hi;
+            p.Wst[(size_t)(TC_KP + f) * p.n_pad + j] = __float2half_rn(x - __half2float(hi));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
     int sw = valid ? my_sweeps : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sw += __shfl_xor_sync(0xffffffffu, sw, o);
-    if (lane == 0) atomicAdd(sweeps, (unsigned long long)sw);
+    if (lane == 0) {
+        atomicMax(p.state + TC_ST_WMAX + p.par, __float_as_int(wmax));
+        atomicAdd(&p.scal->sweeps_w, (unsigned long long)sw);
+    }
+    if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicOr(p.state + TC_ST_OVF, 1);
+    __syncthreads();
+    {
+        // W'W of the 128 rows: thread e owns entries e, e + 128, ... of the 32 x 32 block (a = entry / 32 is warp-uniform)
+        double *G = p.G64w + (size_t)p.par * TC_GS;
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) {
+            const int e = threadIdx.x + 128 * q, a = e >> 5, b = e & 31;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 128; ++r) acc = fmaf(ws[r][a], ws[r][b], acc);
+            if (a < p.k && b < p.k) atomicAdd(G + e, (double)acc);
+        }
+        if (threadIdx.x < p.k) {
+            float cs = 0.f;
+            for (int r = 0; r < 128; ++r) cs += ws[r][threadIdx.x];
+            atomicAdd(G + TC_KP * TC_KP + threadIdx.x, (double)cs);
+        }
+    }
     tc_fence_before();
+    if (tc_last_cta(p.state + TC_ST_CNT_W, &s_flag)) {
+        // GramPack of the H update; reset what the next kernels accumulate into
+        tc_finalize_gram(p.G64w + (size_t)p.par * TC_GS, p.pack_next, p.k, p.pen_next0, p.pen_next1, sD);
+        double *Gz = p.G64w + (size_t)(p.par ^ 1) * TC_GS;
+        for (int t = threadIdx.x; t < TC_GS; t += blockDim.x) Gz[t] = 0.0;
+        if (threadIdx.x == 0) {
+            p.state[TC_ST_HMAX + p.par] = 0;
+            p.scal->loss_part = 0.0;
+        }
+    }
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
@@ -524,7 +669,8 @@ tc_wsolve_kernel(float *__restrict__ X, const float *__restrict__ C, const float
 //
 //   warp 0       TMA producer (one elected lane): phase 1 streams (A_hi, A_lo, W) chunks of every tile, phase 3 streams
 //                (A_hi, A_lo) for one third-of-an-eighth of the genes at a time
-//   warp 1       MMA issuer (one elected lane): phase 1 C[t] = A W' into one of 6 TMEM accumulators; phase 3 D += A' H
+//   warp 1       MMA issuer (one elected lane): phase 1 C[t] = A W' into one of 5 TMEM accumulators; phase 3 D += A' H,
+//                and H H' of every solved tile from the same shared-memory image (one more accumulator)
 //   warp 2       H-tile loader: copies the split 16-bit image of a solved tile from global scratch to smem
 //   warps 4-7    drain: phase-3 accumulators -> red.add into B
 //   warps 8-23   4 solver groups x 4 warps: tensor-core block Gauss-Seidel on tiles g, g+4, ...
@@ -571,6 +717,9 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     auto MBG = [&](int g) { return bar0 + 8u * (B2 + 8 + g); };            // "block MMA of group g done"
     auto TDONE = [&](int t) { return bar0 + 8u * (B2 + 8 + TC_TGROUPS + t); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcSmem::misc);
+    int *s_flag = reinterpret_cast<int *>(smem + TcSmem::misc + 4);
+    float *s_hsum = reinterpret_cast<float *>(smem + TcSmem::misc + 64);
+    if (threadIdx.x < TC_KP) s_hsum[threadIdx.x] = 0.f;
 
     // zero the A stages once: rows of a partial tile that TMA never writes must hold finite values
     for (int i = threadIdx.x; i < (2 * TC_STAGES * TC_A_STAGE) / 16; i += blockDim.x)
@@ -619,21 +768,13 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
 
     // fp16 scale of the H images: the previous max(H) maps to [8, 16), which leaves a factor 4096 of growth before fp16
     // overflows (flagged, never silent) while entries down to 1e-9 of the max keep their value
-    int h_exp = 0;
-    {
-        const float hm = __int_as_float(*p.hmax_prev);
-        if (hm > 0.f) {
-            int e;
-            frexpf(hm, &e);
-            h_exp = max(-100, min(100, 4 - e));
-        }
-    }
+    const int h_exp = tc_exp_of(p.state[TC_ST_HMAX + (p.par ^ 1)]);
 
     if (warp >= 8) {
         // =========================== solver warps ===========================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_SOLVER));
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-        const float descale = exp2f(-(float)(p.a_exp + *p.w_exp));
+        const float descale = exp2f(-(float)(p.a_exp + tc_exp_of(p.state[TC_ST_WMAX + (p.par ^ 1)])));
         const float hscale = exp2f((float)h_exp);
         const float *sInvD = sD + TC_KP;
         // Group g (4 warps = the 4 lane quarters of a tile) solves tiles g, g+4, ...  mu' of the tile lives in its
@@ -750,6 +891,9 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
 #pragma unroll
             for (int f = 0; f < 32; ++f) {
                 hmax = fmaxf(hmax, h[f]);
+                // row sums of H (penalties, the mkl trace): one shared-memory reduction per factor
+                const float fs = warp_sum(h[f]);
+                if (lane == (f & 31)) atomicAdd(&s_hsum[f], fs);
                 float x = h[f] * hscale;
                 if (x > 60000.f) { x = 60000.f; ovf = true; }
                 const __half hi = __float2half_rn(x);
@@ -763,8 +907,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             mbar_arrive(TDONE(t));
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
-            if (lane == 0) atomicMax(p.hmax_next, __float_as_int(hmax));
-            if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicOr(p.overflow, 1);
+            if (lane == 0) atomicMax(p.state + TC_ST_HMAX + p.par, __float_as_int(hmax));
+            if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicOr(p.state + TC_ST_OVF, 1);
             if (trec) trec[4] = clock64();
             if (lane == 0 && quarter == 0 && t < 8) TC_MARK(16 + t);
         }
@@ -794,6 +938,23 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             tc_fence_before();
             mbar_arrive(DEMPTY(u & 1));
             if (quarter == 0 && lane == 0 && u < 8) TC_MARK(32 + u);
+        }
+        // H H' of this CTA's tiles (complete: the last unit's commit covers the Gram MMAs issued before it) -> fp64 sums.
+        // Lane r of quarter 0 holds row r of hi hi', of quarter 2 row r of lo hi'  (G = hi hi' + lo hi' + (lo hi')').
+        if (quarter == 0 || quarter == 2) {
+            tc_fence_after();
+            float g[32];
+            tc_ld32(tmem + TC_GRAM_COL + ((uint32_t)(quarter * 32) << 16), g);      // .sync.aligned: the whole warp
+            const float gd = exp2f(-2.f * (float)h_exp);
+            double *G = p.G64h + (size_t)p.par * TC_GS;
+#pragma unroll
+            for (int c = 0; c < TC_KP; ++c) {
+                if (c < p.k && lane < p.k) {
+                    const double v = (double)(g[c] * gd);
+                    atomicAdd(G + lane * TC_KP + c, v);
+                    if (quarter == 2) atomicAdd(G + c * TC_KP + lane, v);
+                }
+            }
         }
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SERVICE));
@@ -904,6 +1065,22 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                     mbar_wait(HFULL(hb), (use >> 1) & 1);
                     tc_fence_after();
                     const uint32_t hs = sbase + TcSmem::h + hb * TC_H_TILE;
+                    if (ps == 0) {
+                        // H H' of this tile from its image: A = the whole image as 128 K-major rows [hi c0; hi c1; lo c0; lo c1]
+                        // (c0 / c1 = cells 0..63 / 64..127), B = hi of one cell half.  With B = hi c0 rows 0..31 of the
+                        // accumulator get hi hi' and rows 64..95 lo hi' of that half; the image shifted by one sub-tile puts
+                        // the c1 half on the same rows.  Rows 32..63 and 96..127 mix cells and are never read.
+                        if (elect_one_sync()) {
+                            const uint32_t dG = tmem + TC_GRAM_COL;
+#pragma unroll
+                            for (int hc = 0; hc < 2; ++hc)
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    tc_mma_f16(dG, desc_sw128(hs + hc * TC_H_SUB + ks * 32, 16, 1024),
+                                               desc_sw128(hs + hc * TC_H_SUB + ks * 32, 16, 1024), ID_P1, (use | hc | ks) != 0);
+                        }
+                        __syncwarp();
+                    }
                     for (int mt = mt0; mt < mt1; ++mt) {
                         const uint32_t dD = tmem_d(u) + (mt - mt0) * 32;
                         for (int hc = 0; hc < 2; ++hc) {
@@ -972,6 +1149,15 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }
+    if (threadIdx.x < p.k) atomicAdd(p.G64h + (size_t)p.par * TC_GS + TC_KP * TC_KP + threadIdx.x, (double)s_hsum[threadIdx.x]);
+    if (tc_last_cta(p.state + TC_ST_CNT_P, s_flag)) {
+        // what the next W-side kernel needs: the GramPack of H H' (single GPU; with several ranks the host all-reduces the
+        // sums first), zeroed accumulators for the next iteration
+        if (p.finalize) tc_finalize_gram(p.G64h + (size_t)p.par * TC_GS, p.pack_next, p.k, p.pen_next0, p.pen_next1, s_hsum);
+        double *Gz = p.G64h + (size_t)(p.par ^ 1) * TC_GS;
+        for (int t = threadIdx.x; t < TC_GS; t += blockDim.x) Gz[t] = 0.0;
+        if (threadIdx.x == 0) p.state[TC_ST_WMAX + (p.par ^ 1)] = 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -998,36 +1184,14 @@ __global__ void tc_absmax_kernel(const float *__restrict__ X, size_t count, int 
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_int(mx));
 }
-// Wt fp32 [n][32] -> Wst fp16 [64][n_pad] (rows 0..31 hi, 32..63 lo), scaled by 2^w_exp with max -> ~2^14
-__global__ void tc_split_w_kernel(const float *__restrict__ Wt, int n, int n_pad, const int *__restrict__ max_bits,
-                                  int *__restrict__ w_exp_out, __half *__restrict__ Wst)
-{
-    const float mx = __int_as_float(*max_bits);
-    int w_exp = 0;
-    if (mx > 0.f) {
-        int e;
-        frexpf(mx, &e);
-        w_exp = 14 - e;
-    }
-    w_exp = max(-100, min(100, w_exp));
-    if (blockIdx.x == 0 && threadIdx.x == 0) *w_exp_out = w_exp;
-    const float scale = exp2f((float)w_exp);
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_pad) return;
-#pragma unroll 4
-    for (int f = 0; f < TC_KP; ++f) {
-        const float x = (g < n) ? Wt[(size_t)g * TC_KP + f] * scale : 0.f;
-        const __half h = __float2half_rn(x);
-        Wst[(size_t)f * n_pad + g] = h;
-        Wst[(size_t)(TC_KP + f) * n_pad + g] = __float2half_rn(x - __half2float(h));
-    }
-}
-
 struct TcMatrix {
     bool ready = false;
     int n = 0, m = 0, n_pad = 0, a_exp = 0, sm_count = 148;
     __half *Ahi = nullptr, *Alo = nullptr, *Wst = nullptr;
-    int *dev_ints = nullptr;   // [0] W max bits, [1] w_exp, [2] max(H) bits before the pass, [3] after, [4] overflow flag
+    int *state = nullptr;      // TC_ST_* ints of the running fit
+    double *G64w = nullptr, *G64h = nullptr;   // [2][TC_GS] fp64 sums, double buffered by iteration parity
+    float *packW = nullptr, *packH = nullptr;  // GramPacks: W'W (+beta) for the H update, H H' (+alpha) for the W update
+    const char *env_timeline = nullptr, *env_clocks = nullptr;   // SWNE_TC_TIMELINE / SWNE_TC_CLOCKS, read once per matrix
     unsigned long long *dbg = nullptr;   // timeline buffer when SWNE_TC_TIMELINE is set
     long long *clk = nullptr;            // solver clock ring when SWNE_TC_CLOCKS is set
     uint8_t *Himg = nullptr;   // split 16-bit H tile images, [grid][tiles_per_cta][TC_H_TILE]
@@ -1082,7 +1246,11 @@ static inline void tc_release(TcMatrix &tc)
     if (tc.Ahi) cudaFree(tc.Ahi);
     if (tc.Alo) cudaFree(tc.Alo);
     if (tc.Wst) cudaFree(tc.Wst);
-    if (tc.dev_ints) cudaFree(tc.dev_ints);
+    if (tc.state) cudaFree(tc.state);
+    if (tc.G64w) cudaFree(tc.G64w);
+    if (tc.G64h) cudaFree(tc.G64h);
+    if (tc.packW) cudaFree(tc.packW);
+    if (tc.packH) cudaFree(tc.packH);
     if (tc.Himg) cudaFree(tc.Himg);
     if (tc.dbg) cudaFree(tc.dbg);
     if (tc.clk) cudaFree(tc.clk);
@@ -1104,7 +1272,11 @@ static inline void tc_prepare(TcMatrix &tc, const float *dA, size_t ldA, int n, 
         CUDA_CHECK(cudaMalloc(&tc.Ahi, cnt * sizeof(__half)));
         CUDA_CHECK(cudaMalloc(&tc.Alo, cnt * sizeof(__half)));
         CUDA_CHECK(cudaMalloc(&tc.Wst, (size_t)64 * tc.n_pad * sizeof(__half)));
-        CUDA_CHECK(cudaMalloc(&tc.dev_ints, 8 * sizeof(int)));
+        CUDA_CHECK(cudaMalloc(&tc.state, TC_ST_INTS * sizeof(int)));
+        CUDA_CHECK(cudaMalloc(&tc.G64w, 2 * TC_GS * sizeof(double)));
+        CUDA_CHECK(cudaMalloc(&tc.G64h, 2 * TC_GS * sizeof(double)));
+        CUDA_CHECK(cudaMalloc(&tc.packW, gram_pack_floats(TC_KP) * sizeof(float)));
+        CUDA_CHECK(cudaMalloc(&tc.packH, gram_pack_floats(TC_KP) * sizeof(float)));
         const int groups = (m + TC_GROUP - 1) / TC_GROUP;
         tc.grid = std::min(sm_count, groups);
         const int max_groups = (groups + tc.grid - 1) / tc.grid;
@@ -1112,7 +1284,9 @@ static inline void tc_prepare(TcMatrix &tc, const float *dA, size_t ldA, int n, 
         CUDA_CHECK(cudaMalloc(&tc.Himg, (size_t)tc.grid * tc.tiles_per_cta * TC_H_TILE));
     }
     tc.src = dA;
-    CUDA_CHECK(cudaMemsetAsync(tc.dev_ints, 0, 8 * sizeof(int), st));
+    CUDA_CHECK(cudaMemsetAsync(tc.state, 0, TC_ST_INTS * sizeof(int), st));
+    tc.env_timeline = getenv("SWNE_TC_TIMELINE");
+    tc.env_clocks = getenv("SWNE_TC_CLOCKS");
     tc.a_exp = 0;
     if (a_max > 0) {
         int e;
@@ -1130,51 +1304,50 @@ static inline void tc_prepare(TcMatrix &tc, const float *dA, size_t ldA, int n, 
     tc.ready = true;
 }
 
-// W changed: re-split it (W max -> exponent -> stacked fp16 operand)
-static inline void tc_update_w(TcMatrix &tc, const float *Wt, cudaStream_t st)
+// ---- per-fit device state of the fused engine (owned by TcMatrix, reset by tc_fit_begin)
+//   state ints (TC_ST_*), G64w / G64h: [2][TC_GS] fp64 sums (double buffered by iteration parity), packW / packH: the two
+//   GramPacks (W'W + beta penalties for the H update, H H' + alpha penalties for the W update)
+
+// Start of a fit: W0 / H0 are on the device.  Zeroes the state, records max(W0) / max(H0) as the first scale references
+// and splits W0 (the pre-pass needs no W operand, but the first W-side kernel needs max(W0)).  4 small launches, once.
+static inline void tc_fit_begin(TcMatrix &tc, const float *Wt, const float *H, cudaStream_t st)
 {
-    CUDA_CHECK(cudaMemsetAsync(tc.dev_ints, 0, sizeof(int), st));
-    tc_absmax_kernel<<<32, 256, 0, st>>>(Wt, (size_t)tc.n * TC_KP, tc.dev_ints);
-    tc_split_w_kernel<<<(tc.n_pad + 127) / 128, 128, 0, st>>>(Wt, tc.n, tc.n_pad, tc.dev_ints, tc.dev_ints + 1, tc.Wst);
+    CUDA_CHECK(cudaMemsetAsync(tc.state, 0, TC_ST_INTS * sizeof(int), st));
+    CUDA_CHECK(cudaMemsetAsync(tc.G64w, 0, 2 * TC_GS * sizeof(double), st));
+    CUDA_CHECK(cudaMemsetAsync(tc.G64h, 0, 2 * TC_GS * sizeof(double), st));
+    // iteration 0 has parity 0 and reads the "previous" halves (index 1): max(W0); the pre-pass (parity 1) reads max(H0) from
+    // half 0 and writes half 1
+    tc_absmax_kernel<<<32, 256, 0, st>>>(Wt, (size_t)tc.n * TC_KP, tc.state + TC_ST_WMAX + 1);
+    tc_absmax_kernel<<<148, 256, 0, st>>>(H, (size_t)tc.m * TC_KP, tc.state + TC_ST_HMAX + 0);
     CUDA_CHECK(cudaGetLastError());
 }
 
-// one pass.  mode 0: H update (phase 1 + solve) followed by B = A H' of the new H; mode 1: B = A H' only.
-// B must be zeroed by the caller.  launches: 1 (+3 for the W split in mode 0)
-static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, float *Cscr, const float *pack, float l1, float pen_diag,
-                           float pen_all, int k, int max_iter, float rel_tol, float *B, FitScalars *scal, cudaStream_t st)
+// one pass.  mode 0: H update (phase 1 + solve) followed by B = A H' and H H' of the new H; mode 1: B = A H', H H' only.
+// par: iteration parity (the pre-pass before iteration 0 runs with par = 1).  finalize: the last CTA builds packH from
+// H H' and (alpha0, alpha1) -- single GPU; with several ranks the caller all-reduces G64h[par] and finalises itself.
+// launches: 1 kernel (+ 1 constant-bank copy of the triangular coefficients in mode 0)
+static inline void tc_pass(TcMatrix &tc, int mode, int par, bool finalize, float *H, float *Cscr, float l1, float pen_diag, float pen_all,
+                           double alpha0, double alpha1, int k, int max_iter, float rel_tol, float *B, FitScalars *scal, cudaStream_t st)
 {
-
-    if (mode == 0) {
-        tc_update_w(tc, Wt, st);
-        // max(H) of the previous pass becomes the scale reference of this one
-        CUDA_CHECK(cudaMemcpyAsync(tc.dev_ints + 2, tc.dev_ints + 3, sizeof(int), cudaMemcpyDeviceToDevice, st));
-    } else {
-        CUDA_CHECK(cudaMemsetAsync(tc.dev_ints + 2, 0, sizeof(int), st));
-        tc_absmax_kernel<<<148, 256, 0, st>>>(H, (size_t)tc.m * TC_KP, tc.dev_ints + 2);
-    }
-    CUDA_CHECK(cudaMemsetAsync(tc.dev_ints + 3, 0, sizeof(int), st));
     TcPassParams p;
     p.n = tc.n; p.m = tc.m; p.k = k;
     p.n_mtiles = (tc.n + 127) / 128;
     p.n_chunks = 2 * p.n_mtiles;
-    p.mode = mode;
-    p.pack = pack; p.l1 = l1; p.pen_diag = pen_diag; p.pen_all = pen_all; p.max_iter = max_iter; p.rel_tol = rel_tol;
+    p.mode = mode; p.par = par; p.finalize = finalize ? 1 : 0;
+    p.pack = tc.packW; p.pack_next = tc.packH; p.pen_next0 = alpha0; p.pen_next1 = alpha1;
+    p.l1 = l1; p.pen_diag = pen_diag; p.pen_all = pen_all; p.max_iter = max_iter; p.rel_tol = rel_tol;
     p.H = H; p.Cscr = Cscr; p.B = B; p.scal = scal;
-    p.w_exp = tc.dev_ints + 1;
-    p.hmax_prev = tc.dev_ints + 2;
-    p.hmax_next = tc.dev_ints + 3;
-    p.overflow = tc.dev_ints + 4;
+    p.state = tc.state; p.G64h = tc.G64h;
     p.a_exp = tc.a_exp;
     p.groups_total = (tc.m + TC_GROUP - 1) / TC_GROUP;
     p.Himg = tc.Himg;
     p.tiles_per_cta = tc.tiles_per_cta;
-    const char *tl = getenv("SWNE_TC_TIMELINE");
-    if (tl && !tc.dbg) CUDA_CHECK(cudaMalloc(&tc.dbg, sizeof(unsigned long long) * 64 * 148));
+    const char *tl = tc.env_timeline;
+    if (tl && !tc.dbg) CUDA_CHECK(cudaMalloc(&tc.dbg, sizeof(unsigned long long) * 64 * tc.grid));
     p.dbg = tl ? tc.dbg : nullptr;
-    if (p.dbg) CUDA_CHECK(cudaMemsetAsync(tc.dbg, 0, sizeof(unsigned long long) * 64 * 148, st));
-    // SWNE_TC_CLOCKS=<file>: clock64 stamps of every block update of every solver group (tools/solver_clocks.py reads it)
-    const char *ck = getenv("SWNE_TC_CLOCKS");
+    if (p.dbg) CUDA_CHECK(cudaMemsetAsync(tc.dbg, 0, sizeof(unsigned long long) * 64 * tc.grid, st));
+    // SWNE_TC_CLOCKS=<file> (builds with -DTC_SOLVER_CLOCKS only): clock64 stamps of every block update of every solver group
+    const char *ck = tc.env_clocks;
     const size_t clk_count = (size_t)tc.grid * TC_TGROUPS * TC_CLK_RECS * 8;
     if (ck && !tc.clk) CUDA_CHECK(cudaMalloc(&tc.clk, clk_count * sizeof(long long)));
     p.clk = (ck && mode == 0) ? tc.clk : nullptr;
@@ -1185,7 +1358,7 @@ static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, fl
         throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};
     }
     if (mode == 0)
-        CUDA_CHECK(cudaMemcpyToSymbolAsync(c_gram, pack, sizeof(float) * 2 * TC_KP * TC_KP, 0, cudaMemcpyDeviceToDevice, st));
+        CUDA_CHECK(cudaMemcpyToSymbolAsync(c_gram, tc.packW, sizeof(float) * TC_KP * TC_KP, 0, cudaMemcpyDeviceToDevice, st));
     tc_pass_kernel<<<grid, 768, TcSmem::total + 1024, st>>>(tc.map_ahi, tc.map_alo, tc.map_w, p);
     CUDA_CHECK(cudaGetLastError());
     if (p.clk) {
@@ -1202,7 +1375,7 @@ static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, fl
     }
     if (p.dbg && mode == 0) {
         // debug only: dump the per-CTA timeline of this launch (ns since the earliest CTA start)
-        std::vector<unsigned long long> hbuf(64 * 148);
+        std::vector<unsigned long long> hbuf(64 * (size_t)grid);
         CUDA_CHECK(cudaStreamSynchronize(st));
         CUDA_CHECK(cudaMemcpy(hbuf.data(), tc.dbg, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         unsigned long long t0 = ~0ull;
@@ -1219,14 +1392,21 @@ static inline void tc_pass(TcMatrix &tc, int mode, const float *Wt, float *H, fl
         }
     }
 }
-// W update through the tensor-core solver (k <= 32).  pack: GramPack of H H' with the alpha penalties
-static inline void tc_wsolve(float *Wt, const float *B, const float *pack, float l1, int k, int n, int max_iter, float rel_tol,
-                             unsigned long long *sweeps, cudaStream_t st)
+static inline int tc_pass_launches(int mode) { return mode == 0 ? 2 : 1; }
+
+// the W side of iteration `par`: packH (H H' + alpha) -> solve -> W, its split image, W'W -> packW (beta0, beta1).
+// B holds A H' (all-reduced) and is zeroed as it is consumed.  launches: 1 kernel + 1 constant-bank copy
+static inline void tc_wside(TcMatrix &tc, int par, float *Wt, float *B, float l1, double beta0, double beta1, int k, int max_iter,
+                            float rel_tol, FitScalars *scal, cudaStream_t st)
 {
-    CUDA_CHECK(cudaMemcpyToSymbolAsync(c_gram, pack, sizeof(float) * 2 * TC_KP * TC_KP, 0, cudaMemcpyDeviceToDevice, st));
-    tc_wsolve_kernel<<<(n + 127) / 128, 128, 0, st>>>(Wt, B, pack, l1, k, n, max_iter, rel_tol, sweeps);
+    TcWsideParams p;
+    p.X = Wt; p.C = B; p.pack = tc.packH; p.pack_next = tc.packW; p.pen_next0 = beta0; p.pen_next1 = beta1;
+    p.l1 = l1; p.k = k; p.cols = tc.n; p.n_pad = tc.n_pad; p.max_iter = max_iter; p.rel_tol = rel_tol;
+    p.Wst = tc.Wst; p.state = tc.state; p.par = par; p.G64w = tc.G64w; p.scal = scal;
+    CUDA_CHECK(cudaMemcpyToSymbolAsync(c_gram, tc.packH, sizeof(float) * TC_KP * TC_KP, 0, cudaMemcpyDeviceToDevice, st));
+    tc_wside_kernel<<<(tc.n + 127) / 128, 128, 0, st>>>(p);
     CUDA_CHECK(cudaGetLastError());
 }
-static inline int tc_pass_launches(int mode) { return mode == 0 ? 4 : 1; }
+static inline int tc_wside_launches() { return 2; }
 
 }  // namespace swne

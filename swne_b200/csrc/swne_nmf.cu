@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <type_traits>
 #include <chrono>
+#include <functional>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -20,6 +22,7 @@
 #include "linalg_small.h"
 #include "pass_tc.cuh"
 #include "contract_tc.cuh"
+#include "seed.cuh"
 
 namespace swne {
 
@@ -144,6 +147,7 @@ struct swne_nmf_handle_s {
     size_t pinned_bytes = 0;
     swne_nmf_progress_fn progress = nullptr;
     void *progress_user = nullptr;
+    int kl_flags = 0;                // KL_L2_LATE when the fit asks for the alternative reading of NNLM's KL step
 };
 
 namespace swne {
@@ -247,6 +251,7 @@ template <typename T>
 static void set_csc(swne_nmf_handle_s *h, const int *p, const int *idx, const T *x, int n, int m)
 {
     if (!p || (!idx && p[m] > 0) || (!x && p[m] > 0)) FAIL(SWNE_ERR_BAD_ARG, "CSC slot pointer is NULL");
+    if (p[0] != 0) FAIL(SWNE_ERR_BAD_ARG, "CSC column pointer must start at 0 (dgCMatrix @p)");
     for (int j = 0; j < m; ++j)
         if (p[j + 1] < p[j]) FAIL(SWNE_ERR_BAD_ARG, "CSC column pointer is not non-decreasing");
     begin_matrix(h, n, m, true);
@@ -285,6 +290,10 @@ static void set_csc(swne_nmf_handle_s *h, const int *p, const int *idx, const T 
 static void ensure_sparse(swne_nmf_handle_s *h)
 {
     if (h->sp.ready) return;
+    // the sparse views index their nonzeros with 32-bit offsets
+    if (h->stats.nnz > 0x7fffffffull)
+        FAIL(SWNE_ERR_UNSUPPORTED, "loss = mkl needs the sparse views of A, which hold at most 2^31 - 1 nonzeros (this matrix has %llu)",
+             (unsigned long long)h->stats.nnz);
     SparseView &sp = h->sp;
     const int n = h->n, m = h->m;
     cudaStream_t st = h->stream;
@@ -431,7 +440,7 @@ static void launch_kl(swne_nmf_handle_s *h, int k, int KPv, const int *ptr, cons
     const int max_nnz = (ptr == h->sp.cptr.p) ? h->sp.cmax : h->sp.gmax;
     const int avg_nnz = (int)(h->sp.nnz / (size_t)std::max(1, (ptr == h->sp.cptr.p) ? h->m : h->n));
     ops_of(KPv).kl(ptr, idx, val, h->sp.ajt.p, X, Y, sumY, (float)pen[0], (float)pen[1], (float)pen[2], k, cols, max_iter,
-                   rel_tol, sweeps, &sc->kl_part, &sc->sq_part, err, max_nnz, avg_nnz, h->stream);
+                   rel_tol, sweeps, &sc->kl_part, &sc->sq_part, err | h->kl_flags, max_nnz, avg_nnz, h->stream);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -509,8 +518,11 @@ struct HostTrace {
 // ------------------------------------------------------------------------------------------------
 // the fit (c_nnmf)
 // ------------------------------------------------------------------------------------------------
+// device_init(KPv, mean_A, m_global): when given, the start is produced on the device -- it must fill h->Wt.p [n][KPv]
+// and h->H.p [m][KPv] on the handle's stream (RunNMF's seeds: seed.cuh); W / H are then outputs only.
+typedef std::function<void(int, double, double)> DeviceInitFn;
 static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W, double *H, double *mse_tr, double *mkl_tr,
-                    double *terr_tr, double *epo_tr, int trace_len, swne_nmf_result_t *res)
+                    double *terr_tr, double *epo_tr, int trace_len, swne_nmf_result_t *res, const DeviceInitFn *device_init = nullptr)
 {
     if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident: call swne_nmf_set_matrix_* first");
     if (!pp || !W || !H) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
@@ -528,6 +540,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     if ((mse_tr || mkl_tr || terr_tr || epo_tr) && trace_len < need_len)
         FAIL(SWNE_ERR_BAD_ARG, "trace arrays need ceil(max_iter/trace)+1 = %d entries", need_len);
     if (p.loss == SWNE_LOSS_MKL && h->nranks > 1) FAIL(SWNE_ERR_UNSUPPORTED, "mkl loss is single-GPU only");
+    h->kl_flags = (p.nnlm_variant & SWNE_VARIANT_KL_L2_LATE) ? KL_L2_LATE : 0;
 
     cudaStream_t st = h->stream;
     memset(res, 0, sizeof(*res));
@@ -581,7 +594,6 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     if (p.loss == SWNE_LOSS_MKL) ensure_sparse(h);
     if (engine == SWNE_ENGINE_TC) {
         tc_prepare(h->tc, h->dA, h->ldA, n, m, (double)__builtin_bit_cast(float, h->stats.max_bits), h->sm_count, st);
-        CUDA_CHECK(cudaMemsetAsync(h->tc.dev_ints + 4, 0, sizeof(int), st));
         if (tcx) tcx_prepare(h->tcx, h->tc);
     }
     bool tc_overflow = false;
@@ -594,9 +606,13 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     // the init is validated on the device while it is converted (NNLM: negative or non-finite init is an error)
     h->flags.reserve(1);
     CUDA_CHECK(cudaMemsetAsync(h->flags.p, 0, sizeof(unsigned), st));
-    upload_factor_colmajor(h, W, h->Wt.p, k, KPv, n, h->flags.p, 1u);
-    CUDA_CHECK(cudaStreamSynchronize(st));  // stage buffer is reused
-    upload_factor_cellmajor(h, H, h->H.p, k, KPv, (size_t)m, h->flags.p, 2u);
+    if (device_init) {
+        (*device_init)(KPv, gl[0] / N, m_glob);
+    } else {
+        upload_factor_colmajor(h, W, h->Wt.p, k, KPv, n, h->flags.p, 1u);
+        CUDA_CHECK(cudaStreamSynchronize(st));  // stage buffer is reused
+        upload_factor_cellmajor(h, H, h->H.p, k, KPv, (size_t)m, h->flags.p, 2u);
+    }
     CUDA_CHECK(cudaMemsetAsync(h->dscal.p, 0, sizeof(FitScalars), st));
     cudaEventRecord(e1, st);
     {
@@ -608,6 +624,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         }
     }
 
+    const bool tcx_solve_simt = getenv("SWNE_TCX_SOLVE_SIMT") != nullptr;   // debug knob, read once per fit
     Prof prof;
     prof.on = p.profile != 0;
     prof.st = st;
@@ -615,19 +632,29 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     const float inner_tol = (float)p.inner_rel_tol;
     const bool mse = p.loss == SWNE_LOSS_MSE;
 
-    // H0 H0' (W update of iteration 0 needs it)
-    prof.begin(4);
-    launch_gram(h, KPv, h->H.p, m, h->G64h.p);
-    prof.end(4, 1);
-    if (h->nranks > 1) allreduce(h, nullptr, 0, h->G64h.p, GS);
     bool have_B = false;  // the tcgen05 pass leaves A H' of the *new* H behind for the next W update
+    // fused engine: fp64 sums and GramPacks live in the engine's double-buffered state (half = iteration parity)
+    auto g64w_of = [&](int it) { return fused ? h->tc.G64w + (size_t)(it & 1) * GS : h->G64w.p; };
+    auto g64h_of = [&](int it) { return fused ? h->tc.G64h + (size_t)(it & 1) * GS : h->G64h.p; };
     if (fused) {
+        // pre-pass (parity 1 = "iteration -1"): B = A H0', H0 H0' and the GramPack of the first W update in one launch
         prof.begin(0);
+        tc_fit_begin(h->tc, h->Wt.p, h->H.p, st);
         CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
-        tc_pass(h->tc, 1, h->Wt.p, h->H.p, h->C.p, nullptr, 0.f, 0.f, 0.f, k, p.inner_max_iter, 0.f, h->B.p, h->dscal.p, st);
-        prof.end(0, tc_pass_launches(1));
-        if (h->nranks > 1) allreduce(h, h->B.p, (size_t)n * KPv, nullptr, 0);
+        tc_pass(h->tc, 1, 1, h->nranks == 1, h->H.p, h->C.p, 0.f, 0.f, 0.f, p.alpha[0], p.alpha[1], k, p.inner_max_iter, 0.f, h->B.p,
+                h->dscal.p, st);
+        prof.end(0, 5 + tc_pass_launches(1));
+        if (h->nranks > 1) {
+            allreduce(h, h->B.p, (size_t)n * KPv, g64h_of(1), GS);
+            launch_finalize_gram(h, k, KPv, g64h_of(1), h->tc.packH, p.alpha[0], p.alpha[1]);
+        }
         have_B = true;
+    } else {
+        // H0 H0' (W update of iteration 0 needs it)
+        prof.begin(4);
+        launch_gram(h, KPv, h->H.p, m, h->G64h.p);
+        prof.end(4, 1);
+        if (h->nranks > 1) allreduce(h, nullptr, 0, h->G64h.p, GS);
     }
 
     double rel_err = p.rel_tol + 1.0, terr_last = 1e99;
@@ -646,15 +673,18 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             prof.end(4, 1);
             if (h->nranks > 1) allreduce(h, nullptr, 0, &h->dscal.p->kl_part, 1);
         }
+        // average.epochs counts the sweeps of all cells: the H-side count is rank-local until here
+        if (h->nranks > 1)
+            NCCL_CHECK(g_nccl.AllReduce(&h->dscal.p->sweeps_h, &h->dscal.p->sweeps_h, 1, ncclUint64, ncclSum, h->comm, h->stream));
         CUDA_CHECK(cudaMemcpyAsync(&ht->sc, h->dscal.p, sizeof(FitScalars), cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaMemcpyAsync(ht->G64w, h->G64w.p, sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaMemcpyAsync(ht->G64h, h->G64h.p, sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(ht->G64w, g64w_of(i), sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(ht->G64h, g64h_of(i), sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
         ht->tc_overflow = 0;
         // every rank must take the same decision (the refit is a collective): the flag is max-reduced first
         if (fused && h->nranks > 1)
-            NCCL_CHECK(g_nccl.AllReduce(h->tc.dev_ints + 4, h->tc.dev_ints + 4, 1, ncclInt32, ncclMax, h->comm, h->stream));
+            NCCL_CHECK(g_nccl.AllReduce(h->tc.state + TC_ST_OVF, h->tc.state + TC_ST_OVF, 1, ncclInt32, ncclMax, h->comm, h->stream));
         if (fused)
-            CUDA_CHECK(cudaMemcpyAsync(&ht->tc_overflow, h->tc.dev_ints + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaMemcpyAsync(&ht->tc_overflow, h->tc.state + TC_ST_OVF, sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         if (ht->tc_overflow) tc_overflow = true;
         double w2 = 0, wg = 0, w1 = 0, h2 = 0, hg = 0, h1 = 0, wwhh = 0, sum_ahat = 0;
@@ -694,11 +724,41 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         ++i_e;
         // sweeps restart after every block (total_raw_iter = 0)
         CUDA_CHECK(cudaMemsetAsync(&h->dscal.p->sweeps_w, 0, 2 * sizeof(unsigned long long), st));
-        if (h->progress && h->progress(h->progress_user, i + 1, mse_v, mkl_v, terr, rel_err)) rc = SWNE_ERR_INTERRUPTED;
+        int stop = (h->progress && h->progress(h->progress_user, i + 1, mse_v, mkl_v, terr, rel_err)) ? 1 : 0;
+        if (h->nranks > 1 && h->progress) {
+            // an interrupt on one rank must stop all of them (the next iteration is a collective; every rank that set a
+            // callback reaches this point at the same iteration)
+            double flag = (double)stop;
+            CUDA_CHECK(cudaMemcpyAsync(h->red.p, &flag, sizeof(double), cudaMemcpyHostToDevice, st));
+            NCCL_CHECK(g_nccl.AllReduce(h->red.p, h->red.p, 1, ncclFloat64, ncclMax, h->comm, h->stream));
+            CUDA_CHECK(cudaMemcpyAsync(&flag, h->red.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            stop = flag != 0.0;
+        }
+        if (stop) rc = SWNE_ERR_INTERRUPTED;
     };
 
     cudaEventRecord(e2, st);
     for (; i < p.max_iter && fabs(rel_err) > p.rel_tol && rc == SWNE_OK && !tc_overflow; ++i) {
+        if (fused) {
+            // ---------------- fused engine: two kernels per iteration (each preceded by one constant-bank copy)
+            //   W side: packH -> solve -> W, split image, W'W -> packW      H side: the pass (C = A W, solve, A H', H H' -> packH)
+            prof.begin(3);
+            tc_wside(h->tc, i & 1, h->Wt.p, h->B.p, (float)p.alpha[2], p.beta[0], p.beta[1], k, p.inner_max_iter, inner_tol, h->dscal.p, st);
+            prof.end(3, tc_wside_launches());
+            prof.begin(0);
+            tc_pass(h->tc, 0, i & 1, h->nranks == 1, h->H.p, h->C.p, (float)p.beta[2], (float)(p.beta[0] - p.beta[1]), (float)p.beta[1],
+                    p.alpha[0], p.alpha[1], k, p.inner_max_iter, inner_tol, h->B.p, h->dscal.p, st);
+            prof.end(0, tc_pass_launches(0));
+            if (h->nranks > 1) {
+                prof.begin(6);
+                allreduce(h, h->B.p, (size_t)n * KPv, g64h_of(i), GS, &h->dscal.p->loss_part, 1);
+                launch_finalize_gram(h, k, KPv, g64h_of(i), h->tc.packH, p.alpha[0], p.alpha[1]);
+                prof.end(6, 2);
+            }
+            if (i % p.trace == 0) error_block(false);
+            continue;
+        }
         // loss partials restart every iteration (only the last one before a block is read)
         CUDA_CHECK(cudaMemsetAsync(h->dscal.p, 0, 3 * sizeof(double), st));
         if (mse) {
@@ -712,9 +772,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             }
             prof.begin(3);
             launch_finalize_gram(h, k, KPv, h->G64h.p, h->pack.p, p.alpha[0], p.alpha[1]);
-            if (fused && !getenv("SWNE_TC_WSOLVE_SIMT"))
-                tc_wsolve(h->Wt.p, h->B.p, h->pack.p, (float)p.alpha[2], k, n, p.inner_max_iter, inner_tol, &h->dscal.p->sweeps_w, st);
-            else if (tcx && !getenv("SWNE_TCX_SOLVE_SIMT"))
+            if (tcx && !tcx_solve_simt)
                 tcx_solve(h->tcx, h->Wt.p, h->B.p, h->pack.p, KPv, (float)p.alpha[2], k, n, p.inner_max_iter, inner_tol,
                           &h->dscal.p->sweeps_w, nullptr, st);
             else
@@ -726,27 +784,13 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             launch_gram(h, KPv, h->Wt.p, n, h->G64w.p);
             launch_finalize_gram(h, k, KPv, h->G64w.p, h->pack.p, p.beta[0], p.beta[1]);
             prof.end(4, 2);
-            if (fused) {
-                prof.begin(0);
-                CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
-                tc_pass(h->tc, 0, h->Wt.p, h->H.p, h->C.p, h->pack.p, (float)p.beta[2], (float)(p.beta[0] - p.beta[1]), (float)p.beta[1], k,
-                        p.inner_max_iter, inner_tol, h->B.p, h->dscal.p, st);
-                prof.end(0, tc_pass_launches(0));
-                prof.begin(7);
-                launch_gram(h, KPv, h->H.p, m, h->G64h.p);
-                prof.end(7, 1);
-                if (h->nranks > 1) {
-                    prof.begin(6);
-                    allreduce(h, h->B.p, (size_t)n * KPv, h->G64h.p, GS, &h->dscal.p->loss_part, 1);
-                    prof.end(6, 1);
-                }
-            } else {
+            {
                 prof.begin(0);
                 if (tcx) tcx_contract_cells(h->tcx, h->tc, KPv, h->Wt.p, h->C.p, st);
                 else launch_contract_cells(h, KPv, h->Wt.p, h->C.p);
                 prof.end(0, tcx ? 3 : 1);
                 prof.begin(1);
-                if (tcx && !getenv("SWNE_TCX_SOLVE_SIMT"))
+                if (tcx && !tcx_solve_simt)
                     tcx_solve(h->tcx, h->H.p, h->C.p, h->pack.p, KPv, (float)p.beta[2], k, m, p.inner_max_iter, inner_tol,
                               &h->dscal.p->sweeps_h, &h->dscal.p->loss_part, st);
                 else
@@ -810,7 +854,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         if (p.verbose) fprintf(stderr, "swne_nmf: fp16 range overflow in the tcgen05 engine, refitting with the fp32 engine\n");
         swne_nmf_params_t p2 = *pp;
         p2.engine = SWNE_ENGINE_SIMT;
-        return fit_impl(h, &p2, W, H, mse_tr, mkl_tr, terr_tr, epo_tr, trace_len, res);
+        return fit_impl(h, &p2, W, H, mse_tr, mkl_tr, terr_tr, epo_tr, trace_len, res, device_init);
     }
 
     // ---- results
@@ -825,7 +869,9 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     prof.finish(res);
     res->n_iteration = i;
     res->n_trace = i_e;
-    res->not_converged = (rel_err > p.rel_tol) ? 1 : 0;
+    // NNLM warns when the iteration cap ended the loop with the tolerance not reached; rel_tol < 0 asks for a fixed
+    // number of iterations and is not a failure to converge
+    res->not_converged = (i >= p.max_iter && p.rel_tol >= 0.0 && fabs(rel_err) > p.rel_tol) ? 1 : 0;
     if (rc != SWNE_OK) { set_error("interrupted by the progress callback"); return rc; }
     return res->not_converged ? SWNE_WARN_NOT_CONVERGED : SWNE_OK;
 }
@@ -915,29 +961,166 @@ __global__ void fill_gaussian_kernel(float *x, size_t rows, int l, int KP, uint6
     }
     x[t] = v;
 }
-// X <- X R^{-1} with R'R = X'X (Cholesky QR), twice
-static void cholesky_qr2(swne_nmf_handle_s *h, int KPv, int l, float *X, int rows, double *G64dev, float *Tdev)
+// X <- X R^{-1} with R'R = X'X (Cholesky QR), twice.  The l x l factorisation runs on the device (one block), so the
+// nine re-orthonormalisations of a seed cost no host synchronisation; a rank-deficient sketch raises bit 0 of *flag.
+static void cholesky_qr2(swne_nmf_handle_s *h, int KPv, int l, float *X, int rows, bool cell_side, double *G64dev, float *Tdev,
+                         unsigned *flag)
 {
-    std::vector<double> G(KPv * KPv + KPv), R(l * l), Ri(l * l);
-    std::vector<float> T(KPv * KPv);
     for (int pass = 0; pass < 2; ++pass) {
         launch_gram(h, KPv, X, rows, G64dev);
-        if (h->nranks > 1 && rows == h->m) allreduce(h, nullptr, 0, G64dev, KPv * KPv + KPv);
-        CUDA_CHECK(cudaMemcpyAsync(G.data(), G64dev, sizeof(double) * G.size(), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_CHECK(cudaStreamSynchronize(h->stream));
-        std::vector<double> Gs(l * l);
-        for (int a = 0; a < l; ++a)
-            for (int b = 0; b < l; ++b) Gs[a * l + b] = G[a * KPv + b];
-        if (!small_cholesky_upper(Gs.data(), l, R.data())) FAIL(SWNE_ERR_BAD_ARG, "randomized SVD: rank deficient sketch (k too large for this matrix?)");
-        small_upper_inverse(R.data(), l, Ri.data());
-        std::fill(T.begin(), T.end(), 0.f);
-        for (int a = 0; a < l; ++a)
-            for (int b = 0; b < l; ++b) T[a * KPv + b] = (float)Ri[a * l + b];
-        CUDA_CHECK(cudaMemcpyAsync(Tdev, T.data(), sizeof(float) * T.size(), cudaMemcpyHostToDevice, h->stream));
+        if (h->nranks > 1 && cell_side) allreduce(h, nullptr, 0, G64dev, KPv * KPv + KPv);
+        seed_chol_inv_kernel<<<1, 64, 0, h->stream>>>(G64dev, KPv, l, Tdev, flag);
         ops_of(KPv).right_multiply(X, (size_t)rows, Tdev, l, h->stream);
         CUDA_CHECK(cudaGetLastError());
-        CUDA_CHECK(cudaStreamSynchronize(h->stream));
     }
+}
+
+// Randomized truncated SVD of the resident matrix, left on the device: U [n][KPl] (gene side, replicated on all ranks),
+// V [m][KPl] (cell side, this rank's cells), singular values on the host.  A (n x m) = U S V'.  Range finder on the gene
+// side: Y = A Omega (n x l), power iterations with CholeskyQR2, then the small problem B = Q'A (l x m) through its Gram.
+// The 2 + 2q sketch products are the same skinny contractions as the fit's; with cells sharded over ranks the gene-side
+// products and the cell-side Grams are all-reduced.
+// mu != nullptr: the SVD of the row-centred matrix A - mu 1' (gene means mu [n] on the device; the ICA seed's whitening),
+// through rank-one corrections of the sketch products -- the centred matrix is never formed.
+struct RsvdResult { int l, KPl; std::vector<double> sv; };
+static RsvdResult rsvd_device(swne_nmf_handle_s *h, int k, int oversample, int power_iters, uint64_t seed, float *Y, float *Z,
+                              const float *mu = nullptr)
+{
+    const int n = h->n, m = h->m;
+    if (oversample < 0) oversample = 10;
+    if (power_iters < 0) power_iters = 4;
+    int l = std::min(std::min(n, m), k + oversample);
+    if (l > SWNE_MAX_K) l = SWNE_MAX_K;
+    if (k > l) FAIL(SWNE_ERR_BAD_ARG, "k must be <= %d and <= min(n, m)", SWNE_MAX_K);
+    const int KPv = kp_of(l), GS = KPv * KPv + KPv;
+    cudaStream_t st = h->stream;
+    h->G.reserve((size_t)KPv * KPv); h->G64w.reserve(GS); h->flags.reserve(1);
+    CUDA_CHECK(cudaMemsetAsync(h->flags.p, 0, sizeof(unsigned), st));
+    // split-fp16 tcgen05 contractions (fp32-level accuracy) when the shape allows, else the fp32 kernels
+    const bool use_tc = n >= 128 && m >= 128 && l <= TCX_KP && !getenv("SWNE_NNSVD_SIMT");
+    if (use_tc) {
+        tc_prepare(h->tc, h->dA, h->ldA, n, m, (double)__builtin_bit_cast(float, h->stats.max_bits), h->sm_count, st);
+        tcx_prepare(h->tcx, h->tc);
+    }
+    h->red.reserve(4 * 64 + 8);
+    double *cs = h->red.p;                                    // KPv doubles: the vector of a rank-one centring correction
+    const int wgrid_n = std::min(h->sm_count * 4, std::max(1, n / 4)), wgrid_m = std::min(h->sm_count * 4, std::max(1, m / 4));
+    auto a_times = [&](const float *Zin, float *Yout) {       // Yout (n x l) = A Zin, summed over the ranks' cells
+        if (use_tc) tcx_contract_genes(h->tcx, h->tc, KPv, Zin, Yout, st);
+        else launch_contract_genes(h, KPv, Zin, Yout);
+        if (h->nranks > 1) allreduce(h, Yout, (size_t)n * KPv, nullptr, 0);
+        if (mu) {                                             // (A - mu 1') Z = A Z - mu (1'Z)
+            CUDA_CHECK(cudaMemsetAsync(cs, 0, sizeof(double) * KPv, st));
+            seed_wcolsum_kernel<<<wgrid_m, 256, 0, st>>>(Zin, (size_t)m, KPv, nullptr, cs);
+            if (h->nranks > 1) allreduce(h, nullptr, 0, cs, KPv);
+            seed_rank1_sub_kernel<<<(unsigned)(((size_t)n * KPv + 255) / 256), 256, 0, st>>>(Yout, (size_t)n, KPv, mu, cs);
+        }
+    };
+    auto at_times = [&](const float *Yin, float *Zout) {      // Zout (m x l) = A' Yin  (local cells)
+        if (use_tc) tcx_contract_cells(h->tcx, h->tc, KPv, Yin, Zout, st);
+        else launch_contract_cells(h, KPv, Yin, Zout);
+        if (mu) {                                             // (A - mu 1')' Y = A'Y - 1 (mu'Y)
+            CUDA_CHECK(cudaMemsetAsync(cs, 0, sizeof(double) * KPv, st));
+            seed_wcolsum_kernel<<<wgrid_n, 256, 0, st>>>(Yin, (size_t)n, KPv, mu, cs);
+            seed_rank1_sub_kernel<<<(unsigned)(((size_t)m * KPv + 255) / 256), 256, 0, st>>>(Zout, (size_t)m, KPv, nullptr, cs);
+        }
+    };
+    const size_t totz = (size_t)m * KPv;
+    // different ranks draw different rows of the test matrix
+    fill_gaussian_kernel<<<(unsigned)((totz + 255) / 256), 256, 0, st>>>(Z, (size_t)m, l, KPv, seed + 0x5851F42D4C957F2Dull * (uint64_t)h->rank);
+    CUDA_CHECK(cudaGetLastError());
+    a_times(Z, Y);                                          // Y = A Omega
+    cholesky_qr2(h, KPv, l, Y, n, false, h->G64w.p, h->G.p, h->flags.p);
+    for (int q = 0; q < power_iters; ++q) {
+        at_times(Y, Z);                                     // Z = A' Q
+        cholesky_qr2(h, KPv, l, Z, m, true, h->G64w.p, h->G.p, h->flags.p);
+        a_times(Z, Y);                                      // Y = A Z
+        cholesky_qr2(h, KPv, l, Y, n, false, h->G64w.p, h->G.p, h->flags.p);
+    }
+    at_times(Y, Z);                                         // Z = A' Q  (m x l) = B'
+    launch_gram(h, KPv, Z, m, h->G64w.p);                   // B B' = Z'Z
+    if (h->nranks > 1) allreduce(h, nullptr, 0, h->G64w.p, GS);
+    std::vector<double> G(GS);
+    unsigned bad = 0;
+    CUDA_CHECK(cudaMemcpyAsync(G.data(), h->G64w.p, sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(&bad, h->flags.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));      // the only host synchronisation of the seed
+    if (bad) FAIL(SWNE_ERR_BAD_ARG, "randomized SVD: rank deficient sketch (k too large for this matrix?)");
+    std::vector<double> S(l * l), evec(l * l), eval(l);
+    for (int a = 0; a < l; ++a)
+        for (int b = 0; b < l; ++b) S[a * l + b] = G[a * KPv + b];
+    small_jacobi_eigh(S.data(), l, eval.data(), evec.data());  // descending, evec columns
+    // U = Q Uhat (n x l), V = Z Uhat S^-1 (m x l): right-multiply on device (two small uploads, stream ordered)
+    std::vector<float> T(2 * KPv * KPv, 0.f);
+    for (int a = 0; a < l; ++a)
+        for (int b = 0; b < l; ++b) {
+            T[a * KPv + b] = (float)evec[a * l + b];
+            const double s = sqrt(std::max(eval[b], 0.0));
+            T[KPv * KPv + a * KPv + b] = (s > 0) ? (float)(evec[a * l + b] / s) : 0.f;
+        }
+    h->G.reserve((size_t)2 * KPv * KPv);
+    CUDA_CHECK(cudaMemcpyAsync(h->G.p, T.data(), sizeof(float) * T.size(), cudaMemcpyHostToDevice, st));
+    ops_of(KPv).right_multiply(Y, (size_t)n, h->G.p, l, st);
+    ops_of(KPv).right_multiply(Z, (size_t)m, h->G.p + KPv * KPv, l, st);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(st));      // T is a host temporary
+    RsvdResult r;
+    r.l = l; r.KPl = KPv;
+    r.sv.resize(l);
+    for (int f = 0; f < l; ++f) r.sv[f] = sqrt(std::max(eval[f], 0.0));
+    return r;
+}
+
+// NNDSVD (R/nmf.R:12-47) of the device-resident triplets: Wt_out [n][KPd], H_out [m][KPd] hold the split factors, with
+// RunNMF's zero replacement (R/nmf.R:121-127) fused in when fill_max > 0 (eps = 1e-6) and plain zeros otherwise.
+static void nnsvd_split_device(swne_nmf_handle_s *h, const RsvdResult &r, int k, const float *U, const float *V, float *Wt_out,
+                               float *H_out, int KPd, float eps, float fill_max, uint64_t seed)
+{
+    const int n = h->n, m = h->m, KPl = r.KPl;
+    cudaStream_t st = h->stream;
+    h->red.reserve(4 * 64 + 8);
+    double *norms = h->red.p;      // [u+ | u- | v+ | v-] x KPl
+    CUDA_CHECK(cudaMemsetAsync(norms, 0, sizeof(double) * 4 * KPl, st));
+    seed_posneg_kernel<<<std::min(h->sm_count * 4, (n + 3) / 4), 256, 0, st>>>(U, (size_t)n, KPl, norms);
+    seed_posneg_kernel<<<std::min(h->sm_count * 4, (m + 3) / 4), 256, 0, st>>>(V, (size_t)m, KPl, norms + 2 * KPl);
+    CUDA_CHECK(cudaGetLastError());
+    if (h->nranks > 1) allreduce(h, nullptr, 0, norms + 2 * KPl, 2 * KPl);      // V is sharded by cells, U replicated
+    std::vector<double> hn(4 * KPl);
+    CUDA_CHECK(cudaMemcpyAsync(hn.data(), norms, sizeof(double) * 4 * KPl, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    // per factor: which sign part is kept and the scale of the u and v sides (R/nmf.R:24-44; ties favour the positive part)
+    std::vector<float> coef(2 * 64, 0.f);
+    std::vector<int> mode(2 * 64, 1);
+    for (int f = 0; f < k; ++f) {
+        const double s = r.sv[f];
+        if (f == 0) {
+            coef[0] = coef[64] = (float)sqrt(s);
+            mode[0] = mode[64] = 0;
+            continue;
+        }
+        const double nup = sqrt(hn[f]), nun = sqrt(hn[KPl + f]), vp = sqrt(hn[2 * KPl + f]), vn = sqrt(hn[3 * KPl + f]);
+        const double termp = nup * vp, termn = nun * vn;
+        if (termp >= termn) {
+            const double c = sqrt(s * termp);
+            coef[f] = nup > 0 ? (float)(c / nup) : 0.f; coef[64 + f] = vp > 0 ? (float)(c / vp) : 0.f;
+            mode[f] = mode[64 + f] = 1;
+        } else {
+            const double c = sqrt(s * termn);
+            coef[f] = nun > 0 ? (float)(-c / nun) : 0.f; coef[64 + f] = vn > 0 ? (float)(-c / vn) : 0.f;
+            mode[f] = mode[64 + f] = 2;
+        }
+    }
+    h->G.reserve(4 * 64);
+    float *dcoef = h->G.p;
+    int *dmode = reinterpret_cast<int *>(h->G.p + 2 * 64);
+    CUDA_CHECK(cudaMemcpyAsync(dcoef, coef.data(), sizeof(float) * 2 * 64, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(dmode, mode.data(), sizeof(int) * 2 * 64, cudaMemcpyHostToDevice, st));
+    const size_t tw = (size_t)n * KPd, th = (size_t)m * KPd;
+    seed_apply_kernel<<<(unsigned)((tw + 255) / 256), 256, 0, st>>>(U, KPl, Wt_out, KPd, (size_t)n, k, dcoef, dmode, eps, fill_max, seed ^ 0x57ull);
+    seed_apply_kernel<<<(unsigned)((th + 255) / 256), 256, 0, st>>>(V, KPl, H_out, KPd, (size_t)m, k, dcoef + 64, dmode + 64, eps, fill_max,
+                                                                   (seed ^ 0x48ull) + 0x9E3779B97F4A7C15ull * (uint64_t)h->rank);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(st));      // coef / mode are host temporaries
 }
 
 static int nnsvd_impl(swne_nmf_handle_s *h, int k, int oversample, int power_iters, uint64_t seed, double *W, double *H,
@@ -945,118 +1128,237 @@ static int nnsvd_impl(swne_nmf_handle_s *h, int k, int oversample, int power_ite
 {
     if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident");
     if (!W || !H) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
-    if (h->nranks > 1) FAIL(SWNE_ERR_UNSUPPORTED, "nnsvd init is single-GPU only (seed on one rank, then scatter H)");
     const int n = h->n, m = h->m;
     if (k < 1 || k > std::min(n, m)) FAIL(SWNE_ERR_BAD_ARG, "k must be in 1..min(n,m)");
-    if (oversample < 0) oversample = 10;
-    if (power_iters < 0) power_iters = 4;
-    int l = std::min(std::min(n, m), k + oversample);
-    if (l > SWNE_MAX_K) l = SWNE_MAX_K;
-    if (k > l) FAIL(SWNE_ERR_BAD_ARG, "k must be <= %d", SWNE_MAX_K);
-    const int KPv = kp_of(l), GS = KPv * KPv + KPv;
+    const int lmax = std::min(std::min(std::min(n, m), k + (oversample < 0 ? 10 : oversample)), SWNE_MAX_K);
+    const int KPl = kp_of(lmax), KPd = kp_of(k);
+    h->B.reserve((size_t)n * KPl); h->C.reserve((size_t)m * KPl);
+    h->Wt.reserve((size_t)n * KPd); h->H.reserve((size_t)m * KPd);
+    const RsvdResult r = rsvd_device(h, k, oversample, power_iters, seed, h->B.p, h->C.p);
+    nnsvd_split_device(h, r, k, h->B.p, h->C.p, h->Wt.p, h->H.p, KPd, 0.f, 0.f, seed);
+    if (sv) for (int f = 0; f < k; ++f) sv[f] = r.sv[f];
+    download_factor_colmajor(h, h->Wt.p, W, k, KPd, n);
+    download_factor_cellmajor(h, h->H.p, H, k, KPd, (size_t)m);
+    return SWNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ica_init on the device (R/nmf.R:56-66).  icafast(t(A), nc = k) whitens with the top-k eigenpairs of the gene covariance
+// of the centred data; those are the leading singular triplets of A - rowMeans(A) 1' = U S V', and the whitened data are
+// sqrt(m) V.  So: centred randomized SVD (the nnsvd seed's machinery) -> FastICA fixed point on sqrt(m) V[:, :k]
+// (one pass over m x k per iteration, the k x k algebra on the host) -> S = Y R, M = U diag(s / sqrt(m)) R ->
+//   ica.fast = F:  W = M, H = S'        ica.fast = T (irlba(nv = 50) branch):  W = (A - rowMeans) S, H = S'
+// followed by RunNMF's zero replacement (negative entries count as "< 1e-6") straight into the fit's layouts.
+// Components come out up to sign and order, as they do from LAPACK in the reference.
+// ------------------------------------------------------------------------------------------------
+static void ica_seed_device(swne_nmf_handle_s *h, int k, bool ica_fast, uint64_t seed, int KPd, float fill_max, double m_glob,
+                            float eps = 1e-6f)
+{
+    const int n = h->n, m = h->m;
     cudaStream_t st = h->stream;
-    h->Wt.reserve((size_t)n * KPv); h->H.reserve((size_t)m * KPv);
-    h->G.reserve((size_t)KPv * KPv); h->G64w.reserve(GS);
-    float *Y = h->Wt.p, *Z = h->H.p;  // Y [n][KP] gene side, Z [m][KP] cell side
-    // the 2 + 2 q sketch products are the same skinny contractions as the fit's: through the tcgen05 kernels of
-    // contract_tc.cuh (split-fp16 operands, fp32-level accuracy) when the shape allows, else the fp32 kernels
-    const bool use_tc = n >= 128 && m >= 128 && l <= TCX_KP && !getenv("SWNE_NNSVD_SIMT");
-    if (use_tc) {
-        tc_prepare(h->tc, h->dA, h->ldA, n, m, (double)__builtin_bit_cast(float, h->stats.max_bits), h->sm_count, st);
-        tcx_prepare(h->tcx, h->tc);
+    if (k > std::min(n, m)) FAIL(SWNE_ERR_BAD_ARG, "ica init needs k <= min(n, m)");
+    if (ica_fast && k > 50) FAIL(SWNE_ERR_BAD_ARG, "ica.fast uses 50 principal components: k must be <= 50");
+    // ---- gene means
+    DevBuf<double> gs;
+    DevBuf<float> mu;
+    gs.reserve((size_t)n); mu.reserve((size_t)n);
+    CUDA_CHECK(cudaMemsetAsync(gs.p, 0, sizeof(double) * n, st));
+    {
+        const int cpb = std::max(256, (m + h->sm_count * 4 - 1) / (h->sm_count * 4));
+        dim3 grid((n + 255) / 256, (m + cpb - 1) / cpb);
+        seed_gene_sums_kernel<<<grid, 256, 0, st>>>(h->dA, h->ldA, n, m, cpb, gs.p);
+        if (h->nranks > 1) allreduce(h, nullptr, 0, gs.p, (size_t)n);
+        seed_scale_to_float_kernel<<<(n + 255) / 256, 256, 0, st>>>(gs.p, mu.p, n, 1.0 / m_glob);
+        CUDA_CHECK(cudaGetLastError());
     }
-    auto a_times = [&](const float *Zin, float *Yout) {       // Yout (n x l) = A Zin
-        if (use_tc) tcx_contract_genes(h->tcx, h->tc, KPv, Zin, Yout, st);
-        else launch_contract_genes(h, KPv, Zin, Yout);
-    };
-    auto at_times = [&](const float *Yin, float *Zout) {      // Zout (m x l) = A' Yin
-        if (use_tc) tcx_contract_cells(h->tcx, h->tc, KPv, Yin, Zout, st);
-        else launch_contract_cells(h, KPv, Yin, Zout);
-    };
-    const size_t totz = (size_t)m * KPv;
-    fill_gaussian_kernel<<<(unsigned)((totz + 255) / 256), 256, 0, st>>>(Z, (size_t)m, l, KPv, seed);
+    // ---- centred truncated SVD: l = k + 10 components (ica.fast: the 50 of irlba(nv = 50), capped by the library's 64)
+    const int over = ica_fast ? std::max(0, std::min(50, std::min(n, m)) - k) : 10;
+    const int lmax = std::min(std::min(std::min(n, m), k + over), SWNE_MAX_K);
+    const int KPl = kp_of(lmax), KPk = kp_of(k);
+    h->B.reserve((size_t)n * std::max(KPl, KPd)); h->C.reserve((size_t)m * std::max(KPl, KPd));
+    float *U = h->B.p, *V = h->C.p;
+    const RsvdResult r = rsvd_device(h, k, over, -1, seed, U, V, mu.p);
+    // ---- whitened data Y = sqrt(m) V[:, :k]   [m][KPk]
+    DevBuf<float> Yb, small;
+    DevBuf<double> acc;
+    Yb.reserve((size_t)m * KPk); small.reserve(4 * 64 + (size_t)2 * 64 * 64); acc.reserve((size_t)KPk * KPk + KPk);
+    float *dcoef = small.p;
+    int *dmode = reinterpret_cast<int *>(small.p + 2 * 64);
+    float *dR = small.p + 4 * 64;
+    std::vector<float> coef(2 * 64, 1.f);
+    std::vector<int> mode(2 * 64, 3);
+    for (int f = 0; f < 64; ++f) coef[f] = (float)sqrt(m_glob);
+    CUDA_CHECK(cudaMemcpyAsync(dcoef, coef.data(), sizeof(float) * 2 * 64, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(dmode, mode.data(), sizeof(int) * 2 * 64, cudaMemcpyHostToDevice, st));
+    const size_t ty = (size_t)m * KPk;
+    seed_apply_kernel<<<(unsigned)((ty + 255) / 256), 256, 0, st>>>(V, r.KPl, Yb.p, KPk, (size_t)m, k, dcoef, dmode, -INFINITY, 0.f, 0);
     CUDA_CHECK(cudaGetLastError());
-    a_times(Z, Y);                                          // Y = A Omega
-    cholesky_qr2(h, KPv, l, Y, n, h->G64w.p, h->G.p);
-    for (int q = 0; q < power_iters; ++q) {
-        at_times(Y, Z);                                     // Z = A' Q
-        cholesky_qr2(h, KPv, l, Z, m, h->G64w.p, h->G.p);
-        a_times(Z, Y);                                      // Y = A Z
-        cholesky_qr2(h, KPv, l, Y, n, h->G64w.p, h->G.p);
+    // ---- FastICA fixed point (icafast: alg "par", fun "logcosh", Rmat = I, maxit 50, tol 1e-4)
+    std::vector<double> R(k * k, 0.0), Rn(k * k), T((size_t)KPk * KPk + KPk), RtR(k * k), evec(k * k), eval(k), P(k * k);
+    for (int a = 0; a < k; ++a) R[a * k + a] = 1.0;
+    std::vector<float> Rf((size_t)KPk * KPk);
+    const int grid = std::min(h->sm_count * 2, std::max(1, (m + 31) / 32));
+    double vtol = 1.0;
+    for (int it = 0; it < 50 && vtol > 1e-4; ++it) {
+        std::fill(Rf.begin(), Rf.end(), 0.f);
+        for (int a = 0; a < k; ++a)
+            for (int b = 0; b < k; ++b) Rf[a * KPk + b] = (float)R[a * k + b];
+        CUDA_CHECK(cudaMemcpyAsync(dR, Rf.data(), sizeof(float) * Rf.size(), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemsetAsync(acc.p, 0, sizeof(double) * T.size(), st));
+        ops_of(KPk).ica_step(Yb.p, m, k, dR, acc.p, grid, st);
+        CUDA_CHECK(cudaGetLastError());
+        if (h->nranks > 1) allreduce(h, nullptr, 0, acc.p, T.size());
+        CUDA_CHECK(cudaMemcpyAsync(T.data(), acc.p, sizeof(double) * T.size(), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        // R+ = Y'g / nobs - R diag(mean(1 - g^2)), then the symmetric orthogonalisation R+ (R+' R+)^(-1/2)
+        for (int a = 0; a < k; ++a)
+            for (int b = 0; b < k; ++b) Rn[a * k + b] = T[a * KPk + b] / m_glob - R[a * k + b] * (T[(size_t)KPk * KPk + b] / m_glob);
+        for (int a = 0; a < k; ++a)
+            for (int b = 0; b < k; ++b) {
+                double sacc = 0.0;
+                for (int q = 0; q < k; ++q) sacc += Rn[q * k + a] * Rn[q * k + b];
+                RtR[a * k + b] = sacc;
+            }
+        small_jacobi_eigh(RtR.data(), k, eval.data(), evec.data());
+        for (int a = 0; a < k; ++a)
+            for (int b = 0; b < k; ++b) {
+                double sacc = 0.0;
+                for (int q = 0; q < k; ++q) sacc += evec[a * k + q] * evec[b * k + q] / sqrt(std::max(eval[q], 1e-300));
+                P[a * k + b] = sacc;
+            }
+        std::vector<double> Ro(k * k);
+        for (int a = 0; a < k; ++a)
+            for (int b = 0; b < k; ++b) {
+                double sacc = 0.0;
+                for (int q = 0; q < k; ++q) sacc += Rn[a * k + q] * P[q * k + b];
+                Ro[a * k + b] = sacc;
+            }
+        double mn = 1e300;
+        for (int b = 0; b < k; ++b) {
+            double sacc = 0.0;
+            for (int a = 0; a < k; ++a) sacc += R[a * k + b] * Ro[a * k + b];
+            mn = std::min(mn, fabs(sacc));
+        }
+        vtol = 1.0 - mn;
+        R = Ro;
     }
-    at_times(Y, Z);                                         // Z = A' Q  (m x l) = B'
-    launch_gram(h, KPv, Z, m, h->G64w.p);                   // B B' = Z'Z
-    std::vector<double> G(GS);
-    CUDA_CHECK(cudaMemcpyAsync(G.data(), h->G64w.p, sizeof(double) * GS, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    std::vector<double> S(l * l), evec(l * l), eval(l);
-    for (int a = 0; a < l; ++a)
-        for (int b = 0; b < l; ++b) S[a * l + b] = G[a * KPv + b];
-    small_jacobi_eigh(S.data(), l, eval.data(), evec.data());  // descending, evec columns
-    // U = Q Uhat (n x l), V = Z Uhat S^-1 (m x l): right-multiply on device
-    std::vector<float> T(KPv * KPv, 0.f);
-    for (int a = 0; a < l; ++a)
-        for (int b = 0; b < l; ++b) T[a * KPv + b] = (float)evec[a * l + b];
-    CUDA_CHECK(cudaMemcpyAsync(h->G.p, T.data(), sizeof(float) * T.size(), cudaMemcpyHostToDevice, st));
-    ops_of(KPv).right_multiply(Y, (size_t)n, h->G.p, l, st);
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    for (int a = 0; a < l; ++a)
-        for (int b = 0; b < l; ++b) {
-            const double s = sqrt(std::max(eval[b], 0.0));
-            T[a * KPv + b] = (s > 0) ? (float)(evec[a * l + b] / s) : 0.f;
-        }
-    CUDA_CHECK(cudaMemcpyAsync(h->G.p, T.data(), sizeof(float) * T.size(), cudaMemcpyHostToDevice, st));
-    ops_of(KPv).right_multiply(Z, (size_t)m, h->G.p, l, st);
-    CUDA_CHECK(cudaGetLastError());
-    // NNDSVD split on the host in double (O((n+m) k)), in place in the caller's buffers: the first k columns of U
-    // land in W (n x k column-major) and of V in H (k x m column-major == cell-major), so every pass is contiguous
-    // and no (k + oversample) x m temporary is touched.
-    download_factor_colmajor(h, Y, W, k, KPv, n);                  // W[i + n f] = U[i][f]
-    download_factor_cellmajor(h, Z, H, k, KPv, (size_t)m);         // H[f + k j] = V[j][f]
-    std::vector<double> nvp(k, 0.0), nvn(k, 0.0);
-    for (size_t j = 0; j < (size_t)m; ++j) {
-        const double *v = H + j * (size_t)k;
-        for (int f = 1; f < k; ++f) {
-            const double x = v[f];
-            if (x >= 0) nvp[f] += x * x; else nvn[f] += x * x;
-        }
+    // ---- order by variance accounted for: vaf_c = sum_g M[g][c]^2 = sum_a R[a][c]^2 s_a^2 / m   (U orthonormal)
+    std::vector<int> ix(k);
+    std::vector<double> vaf(k, 0.0);
+    for (int c = 0; c < k; ++c) {
+        ix[c] = c;
+        for (int a = 0; a < k; ++a) vaf[c] += R[a * k + c] * R[a * k + c] * r.sv[a] * r.sv[a] / m_glob;
     }
-    // per factor: which sign part is kept, and the scale of the u and v sides
-    std::vector<double> cv(k, 0.0);
-    std::vector<char> keep_pos(k, 1);
-    for (int f = 0; f < k; ++f) {
-        const double s = sqrt(std::max(eval[f], 0.0));
-        if (sv) sv[f] = s;
-        double *u = W + (size_t)n * f;
-        if (f == 0) {
-            for (int i = 0; i < n; ++i) u[i] = sqrt(s) * fabs(u[i]);
-            cv[0] = sqrt(s);
-            continue;
-        }
-        double nup = 0, nun = 0;
-        for (int i = 0; i < n; ++i) { if (u[i] >= 0) nup += u[i] * u[i]; else nun += u[i] * u[i]; }
-        nup = sqrt(nup); nun = sqrt(nun);
-        const double vp = sqrt(nvp[f]), vn = sqrt(nvn[f]);
-        const double termp = nup * vp, termn = nun * vn;
-        if (termp >= termn) {
-            const double c = sqrt(s * termp), cu = nup > 0 ? c / nup : 0.0;
-            for (int i = 0; i < n; ++i) u[i] = (u[i] >= 0) ? cu * u[i] : 0.0;
-            cv[f] = vp > 0 ? c / vp : 0.0;
-        } else {
-            const double c = sqrt(s * termn), cu = nun > 0 ? -c / nun : 0.0;
-            for (int i = 0; i < n; ++i) u[i] = (u[i] < 0) ? cu * u[i] : 0.0;
-            cv[f] = vn > 0 ? -c / vn : 0.0;
-            keep_pos[f] = 0;
-        }
+    std::stable_sort(ix.begin(), ix.end(), [&](int a, int b) { return vaf[a] > vaf[b]; });
+    // ---- S = Y R[:, ix]  (in place), H = S' with the zero replacement
+    std::fill(Rf.begin(), Rf.end(), 0.f);
+    for (int a = 0; a < k; ++a)
+        for (int c = 0; c < k; ++c) Rf[a * KPk + c] = (float)R[a * k + ix[c]];
+    CUDA_CHECK(cudaMemcpyAsync(dR, Rf.data(), sizeof(float) * Rf.size(), cudaMemcpyHostToDevice, st));
+    ops_of(KPk).right_multiply(Yb.p, (size_t)m, dR, k, st);
+    for (int f = 0; f < 64; ++f) coef[f] = 1.f;
+    CUDA_CHECK(cudaMemcpyAsync(dcoef, coef.data(), sizeof(float) * 2 * 64, cudaMemcpyHostToDevice, st));
+    const size_t th = (size_t)m * KPd, tw = (size_t)n * KPd;
+    if (!ica_fast) {
+        seed_apply_kernel<<<(unsigned)((th + 255) / 256), 256, 0, st>>>(Yb.p, KPk, h->H.p, KPd, (size_t)m, k, dcoef, dmode, eps, fill_max,
+                                                                       (seed ^ 0x48ull) + 0x9E3779B97F4A7C15ull * (uint64_t)h->rank);
+        // W = M = U diag(s / sqrt(m)) R[:, ix]
+        std::vector<float> T2((size_t)r.KPl * r.KPl, 0.f);
+        for (int a = 0; a < k; ++a)
+            for (int c = 0; c < k; ++c) T2[(size_t)a * r.KPl + c] = (float)(r.sv[a] / sqrt(m_glob) * R[a * k + ix[c]]);
+        DevBuf<float> dT2;
+        dT2.reserve(T2.size());
+        CUDA_CHECK(cudaMemcpyAsync(dT2.p, T2.data(), sizeof(float) * T2.size(), cudaMemcpyHostToDevice, st));
+        ops_of(r.KPl).right_multiply(U, (size_t)n, dT2.p, k, st);
+        seed_apply_kernel<<<(unsigned)((tw + 255) / 256), 256, 0, st>>>(U, r.KPl, h->Wt.p, KPd, (size_t)n, k, dcoef, dmode, eps, fill_max,
+                                                                       seed ^ 0x57ull);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        dT2.release();
+    } else {
+        // W = (A - mu 1') S = A S - mu (1'S): one more skinny contraction on the signed S (before its replacement)
+        const bool use_tc = n >= 128 && m >= 128 && KPk <= TCX_KP;
+        float *Wraw = U;                                   // [n][KPk]; U is no longer needed
+        if (use_tc) tcx_contract_genes(h->tcx, h->tc, KPk, Yb.p, Wraw, st);
+        else launch_contract_genes(h, KPk, Yb.p, Wraw);
+        if (h->nranks > 1) allreduce(h, Wraw, (size_t)n * KPk, nullptr, 0);
+        h->red.reserve(4 * 64 + 8);
+        CUDA_CHECK(cudaMemsetAsync(h->red.p, 0, sizeof(double) * KPk, st));
+        seed_wcolsum_kernel<<<std::min(h->sm_count * 4, std::max(1, m / 4)), 256, 0, st>>>(Yb.p, (size_t)m, KPk, nullptr, h->red.p);
+        if (h->nranks > 1) allreduce(h, nullptr, 0, h->red.p, KPk);
+        seed_rank1_sub_kernel<<<(unsigned)(((size_t)n * KPk + 255) / 256), 256, 0, st>>>(Wraw, (size_t)n, KPk, mu.p, h->red.p);
+        seed_apply_kernel<<<(unsigned)((tw + 255) / 256), 256, 0, st>>>(Wraw, KPk, h->Wt.p, KPd, (size_t)n, k, dcoef, dmode, eps, fill_max,
+                                                                       seed ^ 0x57ull);
+        seed_apply_kernel<<<(unsigned)((th + 255) / 256), 256, 0, st>>>(Yb.p, KPk, h->H.p, KPd, (size_t)m, k, dcoef, dmode, eps, fill_max,
+                                                                       (seed ^ 0x48ull) + 0x9E3779B97F4A7C15ull * (uint64_t)h->rank);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaStreamSynchronize(st));
     }
-    for (size_t j = 0; j < (size_t)m; ++j) {
-        double *hj = H + j * (size_t)k;
-        hj[0] = cv[0] * fabs(hj[0]);
-        for (int f = 1; f < k; ++f) {
-            const double x = hj[f];
-            hj[f] = keep_pos[f] ? ((x >= 0) ? cv[f] * x : 0.0) : ((x < 0) ? cv[f] * x : 0.0);
-        }
+    gs.release(); mu.release(); Yb.release(); small.release(); acc.release();
+}
+
+// ------------------------------------------------------------------------------------------------
+// RunNMF in one call (R/nmf.R:96-134): seed on the device -> zero replacement -> fit.  Nothing crosses the host
+// between the seed and the fit.
+// ------------------------------------------------------------------------------------------------
+static int run_nmf_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, int init, uint64_t seed, double *W, double *H,
+                        double *mse_tr, double *mkl_tr, double *terr_tr, double *epo_tr, int trace_len, swne_nmf_result_t *res)
+{
+    if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident: call swne_nmf_set_matrix_* first");
+    if (!pp || !W || !H) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    if (init == SWNE_INIT_GIVEN) return fit_impl(h, pp, W, H, mse_tr, mkl_tr, terr_tr, epo_tr, trace_len, res);
+    const int k = pp->k, n = h->n, m = h->m;
+    if (k < 1 || k > SWNE_MAX_K) FAIL(SWNE_ERR_BAD_ARG, "k must be in 1..%d", SWNE_MAX_K);
+    cudaStream_t st = h->stream;
+    DeviceInitFn fn;
+    if (init == SWNE_INIT_RANDOM) {
+        // NNLM's own start: U(0,1) * 0.01.  W identical on every rank, H per shard.
+        fn = [=](int KPv, double, double) {
+            const size_t tw = (size_t)n * KPv, th = (size_t)m * KPv;
+            seed_uniform_kernel<<<(unsigned)((tw + 255) / 256), 256, 0, st>>>(h->Wt.p, (size_t)n, k, KPv, 0.01f, seed ^ 0x57ull);
+            seed_uniform_kernel<<<(unsigned)((th + 255) / 256), 256, 0, st>>>(h->H.p, (size_t)m, k, KPv, 0.01f,
+                                                                            (seed ^ 0x48ull) + 0x9E3779B97F4A7C15ull * (uint64_t)h->rank);
+            CUDA_CHECK(cudaGetLastError());
+        };
+    } else if (init == SWNE_INIT_NNSVD) {
+        if (k > std::min(n, m)) FAIL(SWNE_ERR_BAD_ARG, "nnsvd init needs k <= min(n, m)");
+        fn = [=](int KPv, double mean_a, double) {
+            const int lmax = std::min(std::min(std::min(n, m), k + 10), SWNE_MAX_K);
+            const int KPl = kp_of(lmax);
+            h->B.reserve((size_t)n * std::max(KPl, KPv)); h->C.reserve((size_t)m * std::max(KPl, KPv));
+            const RsvdResult r = rsvd_device(h, k, -1, -1, seed, h->B.p, h->C.p);
+            // R/nmf.R:121-127: entries below 1e-6 -> 0, zeros -> runif(0, mean(A) / 100)
+            nnsvd_split_device(h, r, k, h->B.p, h->C.p, h->Wt.p, h->H.p, KPv, 1e-6f, (float)(mean_a / 100.0), seed);
+        };
+    } else if (init == SWNE_INIT_ICA || init == SWNE_INIT_ICA_FAST) {
+        fn = [=](int KPv, double mean_a, double m_glob) {
+            ica_seed_device(h, k, init == SWNE_INIT_ICA_FAST, seed, KPv, (float)(mean_a / 100.0), m_glob);
+        };
+    } else {
+        FAIL(SWNE_ERR_BAD_ARG, "Invalid initialization method");
     }
+    return fit_impl(h, pp, W, H, mse_tr, mkl_tr, terr_tr, epo_tr, trace_len, res, &fn);
+}
+
+// ica_init (R/nmf.R:56-66) as a stand-alone call: the signed W (n x k) and H (k x m), before RunNMF's zero replacement
+static int ica_init_impl(swne_nmf_handle_s *h, int k, int ica_fast, uint64_t seed, double *W, double *H)
+{
+    if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident");
+    if (!W || !H) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    if (k < 1 || k > SWNE_MAX_K) FAIL(SWNE_ERR_BAD_ARG, "k must be in 1..%d", SWNE_MAX_K);
+    const int n = h->n, m = h->m, KPd = kp_of(k);
+    h->Wt.reserve((size_t)n * KPd); h->H.reserve((size_t)m * KPd);
+    double m_glob = (double)m;
+    if (h->nranks > 1) {
+        h->red.reserve(8);
+        CUDA_CHECK(cudaMemcpyAsync(h->red.p, &m_glob, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        allreduce(h, nullptr, 0, h->red.p, 1);
+        CUDA_CHECK(cudaMemcpyAsync(&m_glob, h->red.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    }
+    ica_seed_device(h, k, ica_fast != 0, seed, KPd, 0.f, m_glob, -INFINITY);
+    download_factor_colmajor(h, h->Wt.p, W, k, KPd, n);
+    download_factor_cellmajor(h, h->H.p, H, k, KPd, (size_t)m);
     return SWNE_OK;
 }
 
@@ -1211,6 +1513,7 @@ void swne_nmf_default_params(swne_nmf_params_t *p, int k)
     p->engine = SWNE_ENGINE_AUTO;
     p->full_traces = 0;
     p->profile = 0;
+    p->nnlm_variant = 0;
 }
 
 int swne_nmf_create(swne_nmf_handle_t *out, int device)
@@ -1290,8 +1593,16 @@ int swne_nmf_comm_init(swne_nmf_handle_t h, const void *id128, int rank, int nra
     API_END
 }
 
+// The solvers read the Gram's triangular coefficients from __constant__ memory, which is per device, not per handle:
+// compute entry points of handles on the same device are serialised (different devices run concurrently).
+static std::mutex &device_mutex(int device)
+{
+    static std::mutex m[64];
+    return m[device & 63];
+}
 #define HANDLE_GUARD(h)                                               \
     if (!(h)) FAIL(SWNE_ERR_BAD_ARG, "NULL handle");                  \
+    std::lock_guard<std::mutex> _dev_lock(device_mutex((h)->device)); \
     DeviceGuard _guard((h)->device)
 
 int swne_nmf_set_matrix_dense_f64(swne_nmf_handle_t h, const double *A, int n, int m)
@@ -1383,18 +1694,16 @@ int swne_nmf_fit_dense_f64(swne_nmf_handle_t h, const swne_nmf_params_t *p, cons
 {
     API_BEGIN
     HANDLE_GUARD(h);
-    cudaEvent_t a, b;
-    cudaEventCreate(&a); cudaEventCreate(&b);
-    cudaEventRecord(a, h->stream);
+    FitEvents ev;       // destroyed on every exit path
+    cudaEventRecord(ev.e[0], h->stream);
     set_dense<double>(h, A, n, m);
-    cudaEventRecord(b, h->stream);
+    cudaEventRecord(ev.e[1], h->stream);
     swne_nmf_result_t local;
     swne_nmf_result_t *r = res ? res : &local;
     const int rc = fit_impl(h, p, W, H, mse, mkl, target_loss, average_epochs, trace_len, r);
     float ms = 0;
-    cudaEventElapsedTime(&ms, a, b);
+    cudaEventElapsedTime(&ms, ev.e[0], ev.e[1]);
     r->upload_ms += ms;
-    cudaEventDestroy(a); cudaEventDestroy(b);
     return rc;
     API_END
 }
@@ -1408,6 +1717,16 @@ int swne_nmf_fit_csc_f64(swne_nmf_handle_t h, const swne_nmf_params_t *p, const 
     set_csc<double>(h, cp, ci, cx, n, m);
     swne_nmf_result_t local;
     return fit_impl(h, p, W, H, mse, mkl, target_loss, average_epochs, trace_len, res ? res : &local);
+    API_END
+}
+
+int swne_run_nmf(swne_nmf_handle_t h, const swne_nmf_params_t *p, int init, uint64_t seed, double *W, double *H, double *mse,
+                 double *mkl, double *target_loss, double *average_epochs, int trace_len, swne_nmf_result_t *res)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    swne_nmf_result_t local;
+    return run_nmf_impl(h, p, init, seed, W, H, mse, mkl, target_loss, average_epochs, trace_len, res ? res : &local);
     API_END
 }
 
@@ -1426,6 +1745,14 @@ int swne_nnsvd_init(swne_nmf_handle_t h, int k, int oversample, int power_iters,
     API_BEGIN
     HANDLE_GUARD(h);
     return nnsvd_impl(h, k, oversample, power_iters, seed, W, H, singular_values);
+    API_END
+}
+
+int swne_ica_init(swne_nmf_handle_t h, int k, int ica_fast, uint64_t seed, double *W, double *H)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    return ica_init_impl(h, k, ica_fast, seed, W, H);
     API_END
 }
 

@@ -63,6 +63,8 @@ class NMFHandle:
     def set_matrix(self, A):
         """A: numpy (n x m, any float dtype), scipy.sparse CSC (dgCMatrix analogue), or a torch CUDA
         float32 tensor of shape (m, n) (cell-major == R column-major n x m) that is used in place."""
+        if not (hasattr(A, "data_ptr") and hasattr(A, "is_cuda")):
+            self._keep = None       # a previously borrowed device tensor is released once the library owns a copy again
         if _is_csc(A):
             n, m = A.shape
             p = np.ascontiguousarray(A.indptr, dtype=np.int32)
@@ -101,19 +103,27 @@ class NMFHandle:
         return dict(n=n.value, m=m.value, nnz=nnz.value, sum=s.value, sumsq=s2.value)
 
     # ---- NNLM::nnmf on the resident matrix
-    def fit(self, k, W0, H0, alpha=0.0, beta=0.0, loss="mse", max_iter=500, rel_tol=1e-4, inner_max_iter=0,
+    def fit(self, k, W0=None, H0=None, alpha=0.0, beta=0.0, loss="mse", max_iter=500, rel_tol=1e-4, inner_max_iter=0,
             inner_rel_tol=1e-9, trace=0, verbose=0, engine="auto", full_traces=False, profile=False,
-            show_warning=False):
+            show_warning=False, kl_l2_late=False, init="given", seed=0):
+        """NNLM::nnmf on the resident matrix from the init (W0, H0), or -- init in {"random", "nnsvd", "ica", "ica_fast"} --
+        RunNMF's seed computed on the device and handed to the fit without a host round trip (swne_run_nmf)."""
         if loss not in C.LOSS:
             raise ValueError("loss must be 'mse' or 'mkl'")
+        if init not in C.INIT:
+            raise ValueError("Invalid initialization method")
         if self.n == 0:
             raise C.SwneError(C.SWNE_ERR_NO_MATRIX, "set_matrix first")
         n, m = self.n, self.m
-        # one copy each, straight into R's column-major layout (the library overwrites them with the result)
-        W = np.array(W0, dtype=np.float64, order="F", copy=True)
-        H = np.array(H0, dtype=np.float64, order="F", copy=True)
-        if W.shape != (n, k) or H.shape != (k, m):
-            raise ValueError("init shapes must be W %s and H %s" % ((n, k), (k, m)))
+        if init == "given":
+            # one copy each, straight into R's column-major layout (the library overwrites them with the result)
+            W = np.array(W0, dtype=np.float64, order="F", copy=True)
+            H = np.array(H0, dtype=np.float64, order="F", copy=True)
+            if W.shape != (n, k) or H.shape != (k, m):
+                raise ValueError("init shapes must be W %s and H %s" % ((n, k), (k, m)))
+        else:
+            W = np.empty((n, k), dtype=np.float64, order="F")
+            H = np.empty((k, m), dtype=np.float64, order="F")
         p = C.Params()
         self._lib.swne_nmf_default_params(ctypes.byref(p), int(k))
         p.alpha[:] = list(C.pad3(alpha)); p.beta[:] = list(C.pad3(beta))
@@ -121,14 +131,15 @@ class NMFHandle:
         p.inner_max_iter = int(inner_max_iter); p.inner_rel_tol = float(inner_rel_tol); p.trace = int(trace)
         p.verbose = int(verbose); p.engine = C.ENGINE[engine]; p.full_traces = int(full_traces)
         p.profile = int(bool(profile))
+        p.nnlm_variant = C.VARIANT_KL_L2_LATE if kl_l2_late else 0
         imi = p.inner_max_iter if p.inner_max_iter > 0 else (50 if loss == "mse" else 1)
         tr = p.trace if p.trace > 0 else max(1, 100 // imi)
         L = -(-int(max_iter) // tr) + 1
         mse = np.zeros(L); mkl = np.zeros(L); terr = np.zeros(L); epo = np.zeros(L)
         res = C.Result()
         t0 = time.perf_counter()
-        code = C.check(self._lib.swne_nmf_fit(self._h, ctypes.byref(p), C.dptr(W), C.dptr(H), C.dptr(mse), C.dptr(mkl),
-                                             C.dptr(terr), C.dptr(epo), L, ctypes.byref(res)))
+        code = C.check(self._lib.swne_run_nmf(self._h, ctypes.byref(p), C.INIT[init], ctypes.c_uint64(int(seed) & (2**64 - 1)), C.dptr(W),
+                                             C.dptr(H), C.dptr(mse), C.dptr(mkl), C.dptr(terr), C.dptr(epo), L, ctypes.byref(res)))
         wall = time.perf_counter() - t0
         if code == C.SWNE_WARN_NOT_CONVERGED and show_warning:
             import warnings
@@ -168,6 +179,13 @@ class NMFHandle:
         C.check(self._lib.swne_nnsvd_init(self._h, int(k), int(oversample), int(power_iters), int(seed), C.dptr(W),
                                           C.dptr(H), C.dptr(sv)))
         return W, H, sv
+
+    def ica_init(self, k, ica_fast=False, seed=1):
+        """ica_init (R/nmf.R:56-66) of the resident matrix on the device: signed W (n x k), H (k x m)."""
+        n, m = self.n, self.m
+        W = np.zeros((n, k), order="F"); H = np.zeros((k, m), order="F")
+        C.check(self._lib.swne_ica_init(self._h, int(k), int(bool(ica_fast)), ctypes.c_uint64(int(seed)), C.dptr(W), C.dptr(H)))
+        return W, H
 
     def recon_error(self, W, H):
         W = np.asfortranarray(W, dtype=np.float64); H = np.asfortranarray(H, dtype=np.float64)
@@ -227,40 +245,14 @@ def nnsvd_init(A, k, handle=None, **kw):
     return dict(W=W, H=H)
 
 
-def _icafast(X, nc, maxit=100, tol=1e-6):
-    """ica::icafast(alg='par', fun='logcosh') -- host side (SURVEY.md section 8 a8: 'ica stays host')."""
-    X = np.asarray(X, dtype=np.float64)
-    nobs = X.shape[0]
-    X = X - X.mean(axis=0, keepdims=True)
-    vals, vecs = np.linalg.eigh(X.T @ X / nobs)
-    vals, vecs = vals[::-1][:nc], vecs[:, ::-1][:, :nc]
-    Mprt = np.sqrt(vals)[:, None] * vecs.T
-    Xw = X @ (vecs / np.sqrt(vals)[None, :])
-    R = np.eye(nc)
-    it, vtol = 0, 1.0
-    while vtol > tol and it < maxit:
-        g = np.tanh(Xw @ R)
-        Rn = Xw.T @ g / nobs - R * np.mean(1.0 - g * g, axis=0)[None, :]
-        u, _, vt = np.linalg.svd(Rn)
-        Rn = u @ vt
-        vtol = 1.0 - np.min(np.abs(np.sum(R * Rn, axis=0)))
-        R = Rn
-        it += 1
-    M = R.T @ Mprt
-    ix = np.argsort(-np.sum(M * M, axis=1), kind="stable")
-    return Xw @ R[:, ix], M[ix].T
-
-
-def ica_init(A, k, ica_fast=False):
-    """ica_init (R/nmf.R:56-66)."""
-    A = np.asarray(A, dtype=np.float64)
-    if ica_fast:
-        Ac = A - A.mean(axis=1, keepdims=True)
-        u, _, _ = np.linalg.svd(Ac.T, full_matrices=False)
-        S, _ = _icafast(u[:, :50], k, maxit=50, tol=1e-4)
-        return dict(W=Ac @ S, H=S.T)
-    S, M = _icafast(A.T, k, maxit=50, tol=1e-4)
-    return dict(W=M, H=S.T)
+def ica_init(A, k, ica_fast=False, handle=None, seed=1):
+    """ica_init (R/nmf.R:56-66) on the device: centred randomized SVD for the whitening + the FastICA fixed point
+    (swne_ica_init).  Components are defined up to sign and order (as LAPACK's eigenvector signs are in the reference)."""
+    h = handle or default_handle()
+    if A is not None:
+        h.set_matrix(A)
+    W, H = h.ica_init(k, ica_fast=ica_fast, seed=seed)
+    return dict(W=W, H=H)
 
 
 def zero_replace(init, A_mean, rng, zero_eps=1e-6):
@@ -302,8 +294,15 @@ def RunNMF(A, k, alpha=0, init="ica", n_cores=1, loss="mse", max_iter=500, ica_f
            **kw):
     """RunNMF(A, k, alpha, init, n.cores, loss, max.iter, ica.fast) -- R/nmf.R:96-134.  Same checks and
     error messages; returns the nnmf list with factor names factor_1..factor_k."""
-    dense = None if _is_csc(A) else np.asarray(A)
-    if (A.data.min() if _is_csc(A) and A.data.size else (dense.min() if dense is not None else 0)) < 0:
+    # A: numpy (genes x cells), scipy CSC (dgCMatrix), or a CUDA float32 tensor of shape (cells, genes) -- the transpose of
+    # the numpy orientation, because that is R's column-major genes x cells matrix as it sits in memory (set_matrix)
+    if _is_csc(A):
+        amin = A.data.min() if A.data.size else 0
+    elif hasattr(A, "is_cuda"):
+        amin = float(A.min()) if A.numel() else 0
+    else:
+        amin = np.asarray(A).min()
+    if amin < 0:
         raise ValueError("The input matrix contains negative elements !")
     if k < 3:
         raise ValueError("k must be greater than or equal to 3 to create a viable SWNE plot")
@@ -314,18 +313,10 @@ def RunNMF(A, k, alpha=0, init="ica", n_cores=1, loss="mse", max_iter=500, ica_f
     h = handle or default_handle()
     h.set_matrix(A)
     rng = np.random.default_rng(seed)
-    if init == "random":
-        nmf_init = None
-    else:
-        if init == "ica":
-            nmf_init = ica_init(A.toarray() if _is_csc(A) else dense, k, ica_fast=ica_fast)
-        else:
-            W0, H0, _ = h.nnsvd_init(k, seed=int(rng.integers(1, 2**31)))
-            nmf_init = dict(W=W0, H=H0)
-        info = h.matrix_info()
-        nmf_init = zero_replace(nmf_init, info["sum"] / (float(info["n"]) * info["m"]), rng)
-    res = nnmf(None, k, alpha=alpha, init=nmf_init, loss=loss, max_iter=max_iter, n_threads=n_cores,
-               seed=None if seed is None else seed + 1, handle=h, **kw)
+    # the seed (R/nmf.R:108-127: ica_init / nnsvd_init / NNLM's random start, then the zero replacement) is computed on the
+    # device inside the same library call as the fit
+    mode = {"random": "random", "nnsvd": "nnsvd", "ica": "ica_fast" if ica_fast else "ica"}[init]
+    res = h.fit(k, alpha=alpha, loss=loss, max_iter=max_iter, init=mode, seed=int(rng.integers(1, 2**62)), **kw)
     res["factor_names"] = ["factor_%d" % (i + 1) for i in range(k)]
     return res
 

@@ -147,6 +147,81 @@ def test_mkl_vs_oracle_with_self_noise(handle):
     assert rel_fro(r["W"], ref["W"]) < tol and rel_fro(r["H"], ref["H"]) < tol
 
 
+def test_unpinned_nnlm_details_both_readings(handle):
+    """The two details of NNLM that Appendix A recalls without certainty are switches on both sides (oracle and C-ABI): the
+    CUDA path must match the oracle under BOTH readings, so a future golden from real NNLM decides with no code change.
+      1. the default of `trace` (2 = 100 / inner.max.iter, or 10 as in NNLM 0.4.1): it sets where the stopping rule is tested
+      2. scd_kl_update's Newton step with an L2 penalty (a += beta0 before or after b += a*h)"""
+    from oracle import nnmf_ref
+    A = small_matrix(300, 500, 6, 4)
+    W0, H0 = seeded_init(A, 8, 4)
+    handle.set_matrix(A)
+    for trace in (2, 10):
+        ref = nnmf_ref(A, 8, W0, H0, trace=trace)                 # NNLM's stopping rule, 500 / 1e-4
+        r = handle.fit(8, W0, H0, trace=trace)
+        assert abs(r["n_iteration"] - ref["n_iteration"]) <= trace   # the test sits on a 1e-4 threshold, checked every `trace`
+        assert abs(r["target_loss"][-1] - ref["target_loss"][-1]) / ref["target_loss"][-1] < 1e-4
+        assert r["options"]["trace"] == trace
+    refs = {}
+    for late in (False, True):
+        kw = dict(loss="mkl", alpha=[0.2, 0, 0], beta=[0.1, 0, 0.05], max_iter=30, trace=1, rel_tol=-1.0)
+        refs[late] = nnmf_ref(A, 8, W0, H0, kl_l2_late=late, **kw)
+        r = handle.fit(8, W0, H0, kl_l2_late=late, **kw)
+        assert max_rel(r["target_loss"], refs[late]["target_loss"]) < LOSS_TOL
+        assert rel_fro(r["W"], refs[late]["W"]) < 2e-2 and rel_fro(r["H"], refs[late]["H"]) < 2e-2
+    # the two readings are distinguishable on this input (otherwise the test above proves nothing)
+    assert rel_fro(refs[True]["H"], refs[False]["H"]) > 1e-3
+
+
+def _match_components(S, Sref):
+    """|correlation| of every reference component with its best match among S (components are defined up to sign/order)"""
+    S = (S - S.mean(axis=1, keepdims=True)); Sref = (Sref - Sref.mean(axis=1, keepdims=True))
+    S /= np.linalg.norm(S, axis=1, keepdims=True); Sref /= np.linalg.norm(Sref, axis=1, keepdims=True)
+    return np.max(np.abs(Sref @ S.T), axis=1)
+
+
+def test_device_ica_init_vs_oracle(handle):
+    """ica_init on the device (centred randomized SVD + FastICA fixed point) against the oracle's icafast restatement
+    (exact eigen-decomposition): same independent components up to sign and order, same mixing matrix."""
+    from oracle import ica_init_ref
+    A = small_matrix(300, 2000, 5, 13, density_scale=2.0)
+    k = 5
+    Wr, Hr = ica_init_ref(A, k)
+    handle.set_matrix(A)
+    W, H = handle.ica_init(k, seed=3)
+    c = _match_components(H.copy(), Hr.copy())
+    assert c.min() > 0.999, c
+    cw = _match_components(W.T.copy(), Wr.T.copy())
+    assert cw.min() > 0.999, cw
+    # scale: icafast's sources have unit variance
+    assert np.max(np.abs(H.std(axis=1) - 1.0)) < 1e-3
+    # ica.fast = T: the reference picks k of 50 equal-eigenvalue directions (numerically arbitrary); the device version
+    # takes the k leading ones.  Property checks: unit-variance sources, W = (A - rowMeans) S
+    Wf, Hf = handle.ica_init(k, ica_fast=True, seed=3)
+    assert np.max(np.abs(Hf.std(axis=1) - 1.0)) < 1e-3
+    assert rel_fro(Wf, (A - A.mean(axis=1, keepdims=True)) @ Hf.T) < 1e-3
+
+
+def test_run_nmf_device_seeds(handle):
+    """RunNMF with every seed computed on the device (swne_run_nmf): the fit must start from a valid point (monotone
+    loss from iteration 1) and end as well as the oracle's RunNMF with the same kind of seed."""
+    from oracle import run_nmf_ref
+    from swne_b200 import RunNMF
+    A = small_matrix(300, 1500, 6, 14, density_scale=2.0)
+    k = 6
+    for init in ("random", "nnsvd", "ica"):
+        r = RunNMF(A, k, init=init, max_iter=60, seed=2, handle=handle, rel_tol=-1.0, trace=1)
+        t = r["target_loss"]
+        assert r["W"].shape == (300, k) and r["H"].shape == (k, 1500) and r["W"].min() >= 0 and r["H"].min() >= 0
+        assert np.all(np.diff(t) <= 1e-6 * t[:-1])
+        ref = run_nmf_ref(A, k, init=init, max_iter=60, seed=2, rel_tol=-1.0, trace=1)
+        assert t[-1] < 1.02 * ref["target_loss"][-1], (init, t[-1], ref["target_loss"][-1])
+    # the NNDSVD start is far better than the random one after one iteration (that is its point)
+    r1 = RunNMF(A, k, init="nnsvd", max_iter=1, seed=2, handle=handle, rel_tol=-1.0, trace=1)
+    r2 = RunNMF(A, k, init="random", max_iter=1, seed=2, handle=handle, rel_tol=-1.0, trace=1)
+    assert r1["target_loss"][0] < r2["target_loss"][0]
+
+
 def test_csc_input_equals_dense(handle):
     A = small_matrix(150, 220, 5, 7)
     W0, H0 = seeded_init(A, 5, 7)

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_capi.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.swne_nmf_abi_version() == 1
+    assert lib.swne_nmf_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
@@ -33,7 +33,7 @@ def test_struct_layout_matches_header():
     p = _capi.Params()
     lib.swne_nmf_default_params(ctypes.byref(p), 7)
     assert p.k == 7 and p.max_iter == 500 and abs(p.rel_tol - 1e-4) < 1e-20 and abs(p.inner_rel_tol - 1e-9) < 1e-20
-    assert p.loss == 0 and p.engine == 0 and list(p.alpha) == [0, 0, 0]
+    assert p.loss == 0 and p.engine == 0 and list(p.alpha) == [0, 0, 0] and p.profile == 0 and p.nnlm_variant == 0
 
 
 def test_no_cpu_fallback():
@@ -56,16 +56,31 @@ def test_zero_replace_host_entry():
     assert out["W"][0, 0] <= 0.02 and out["H"][0, 0] <= 0.02
 
 
-def test_host_sammon_and_ica_match_oracle():
-    from oracle import ica_init_ref, sammon_ref
-    from swne_b200 import ica_init, sammon
+def test_host_sammon_matches_oracle():
+    from oracle import sammon_ref
+    from swne_b200 import sammon
     rng = np.random.default_rng(4)
     P = rng.uniform(size=(8, 2))
     D = np.sqrt(((P[:, None] - P[None]) ** 2).sum(-1)) + 0.05 * (1 - np.eye(8))
     assert np.max(np.abs(sammon(D) - sammon_ref(D))) < 1e-9
+
+
+def test_ica_whitening_is_the_truncated_svd_of_the_centred_matrix():
+    """the identity the device ICA seed rests on (swne_nmf.cu ica_seed_device): icafast's whitened data, built from the
+    eigenpairs of the gene covariance, are sqrt(m) V of the SVD A - rowMeans(A) 1' = U S V' (up to column signs), and its
+    mixing matrix is U diag(s / sqrt(m)) R."""
     A = small_matrix(40, 120, 4, 9)
-    a, (W, H) = ica_init(A, 4), ica_init_ref(A, 4)
-    assert rel_fro(a["W"], W) < 1e-9 and rel_fro(a["H"], H) < 1e-9
+    n, m = A.shape
+    k = 4
+    X = A.T - A.T.mean(axis=0, keepdims=True)
+    vals, vecs = np.linalg.eigh(X.T @ X / m)
+    order = np.argsort(vals)[::-1][:k]
+    Xw = X @ (vecs[:, order] / np.sqrt(vals[order])[None, :])
+    U, s, Vt = np.linalg.svd(A - A.mean(axis=1, keepdims=True), full_matrices=False)
+    Y = np.sqrt(m) * Vt[:k].T
+    sign = np.sign(np.sum(Xw * Y, axis=0))
+    assert np.max(np.abs(Xw - Y * sign[None, :])) < 1e-8
+    assert np.max(np.abs(vals[order] - s[:k] ** 2 / m)) < 1e-10
 
 
 def test_shard_bounds():
