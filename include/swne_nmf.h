@@ -163,6 +163,14 @@ int swne_run_nmf(swne_nmf_handle_t h, const swne_nmf_params_t *p, int init, uint
                  double *mse, double *mkl, double *target_loss, double *average_epochs, int trace_len,
                  swne_nmf_result_t *res);
 
+/* ---- FindNumFactors (R/nmf.R:157-205) on the resident matrix in one call: for every k in k_range two mse fits from
+ * NNLM's random start (max_iter, rel_tol 1e-4) -- on A and on a random permutation of all its entries (R/nmf.R:163) --
+ * and their reconstruction errors (loss_metric SWNE_LOSS_MSE: mean squared error, SWNE_LOSS_MKL: mean kl_div,
+ * R/nmf.R:71-75,170-181).  k_err: 2 x nk row-major (row 0: A, row 1: permuted); err_diff (nk - 1, may be NULL) and
+ * k_pick (may be NULL) follow R/nmf.R:186-194.  The permuted matrix, seeds, W and H never leave the device. */
+int swne_find_num_factors(swne_nmf_handle_t h, const int *k_range, int nk, int loss_metric, int max_iter, uint64_t seed,
+                          int engine, double *k_err, int *k_pick, double *err_diff);
+
 /* ---- NNLM::nnlm on the resident matrix: side 0 solves H (k x m) given W (ProjectSamples),
  * side 1 solves W (n x k) given H (ProjectFeatures on the fitted genes).  coef holds the init. */
 int swne_nnlm(swne_nmf_handle_t h, int side, int k, const double *X, double *coef, const double *alpha3,

@@ -34,7 +34,7 @@ SYMBOLS = (
     "swne_nmf_create", "swne_nmf_destroy", "swne_nmf_set_progress", "swne_nmf_comm_unique_id", "swne_nmf_comm_init",
     "swne_nmf_set_matrix_dense_f64", "swne_nmf_set_matrix_dense_f32", "swne_nmf_set_matrix_csc_f64",
     "swne_nmf_set_matrix_csc_f32", "swne_nmf_set_matrix_dense_f32_device", "swne_nmf_matrix_info", "swne_nmf_fit",
-    "swne_nmf_fit_dense_f64", "swne_nmf_fit_csc_f64", "swne_run_nmf", "swne_nnlm", "swne_nnsvd_init", "swne_ica_init", "swne_zero_replace",
+    "swne_nmf_fit_dense_f64", "swne_nmf_fit_csc_f64", "swne_run_nmf", "swne_find_num_factors", "swne_nnlm", "swne_nnsvd_init", "swne_ica_init", "swne_zero_replace",
     "swne_sample_coords", "swne_factor_distance", "swne_recon_error",
 )
 
@@ -101,6 +101,7 @@ def load(build_if_missing=True):
     lib.swne_nmf_fit_csc_f64.argtypes = [vp, ctypes.POINTER(Params), ip, ip, dp, c_int, c_int, dp, dp, dp, dp, dp, dp,
                                          c_int, ctypes.POINTER(Result)]
     lib.swne_run_nmf.argtypes = [vp, ctypes.POINTER(Params), c_int, ctypes.c_uint64, dp, dp, dp, dp, dp, dp, c_int, ctypes.POINTER(Result)]
+    lib.swne_find_num_factors.argtypes = [vp, ip, c_int, c_int, c_int, ctypes.c_uint64, c_int, dp, ip, dp]
     lib.swne_nnlm.argtypes = [vp, c_int, c_int, dp, dp, dp, c_int, c_int, c_dbl, ctypes.POINTER(ctypes.c_longlong)]
     lib.swne_nnsvd_init.argtypes = [vp, c_int, c_int, c_int, ctypes.c_uint64, dp, dp, dp]
     lib.swne_ica_init.argtypes = [vp, c_int, c_int, ctypes.c_uint64, dp, dp]

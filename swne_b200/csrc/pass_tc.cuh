@@ -49,9 +49,10 @@ constexpr int TC_DELTA_COL = 192;
 constexpr int TC_D_COL = 320;
 constexpr int TC_MT_PER_PASS = 3;                       // 128-gene accumulators per phase-3 unit (3 * 32 TMEM columns, two regions)
 // device-side state of a fit (ints): scales and counters that used to be separate memset / absmax / copy launches
-//   [0,1] max(W) float bits of the even / odd iteration   [2,3] max(H) likewise   [4] fp16 overflow flag
+//   [0] max(W) float bits of the running W-side kernel   [1] fp16 scale exponent of the current split image of W
+//   [2,3] max(H) float bits of the even / odd iteration   [4] fp16 overflow flag (H images)
 //   [5] ticket counter of the W-side kernel   [6] ticket counter of the pass kernel
-constexpr int TC_ST_WMAX = 0, TC_ST_HMAX = 2, TC_ST_OVF = 4, TC_ST_CNT_W = 5, TC_ST_CNT_P = 6, TC_ST_INTS = 8;
+constexpr int TC_ST_WMAX = 0, TC_ST_WEXP = 1, TC_ST_HMAX = 2, TC_ST_OVF = 4, TC_ST_CNT_W = 5, TC_ST_CNT_P = 6, TC_ST_INTS = 8;
 constexpr int TC_GS = TC_KP * TC_KP + TC_KP;            // doubles of one Gram + sums buffer
 constexpr int TC_MAX_TILES = 128;                       // tiles per CTA (one mbarrier each)
 constexpr int TC_GOP = 1024;                            // one [32 x 8] tf32 operand of G' (per block, hi / lo)
@@ -515,9 +516,11 @@ __device__ __forceinline__ bool tc_last_cta(int *counter, int *s_flag)
 // ------------------------------------------------------------------------------------------------
 // The W side of one outer iteration in ONE kernel (one CTA of 4 warps per 128 genes):
 //   solve the 128 columns with the tensor-core sweeps (X [cols][32] in/out, C = A H' the contraction, pack = GramPack of
-//   H H', c_gram its triangular coefficients), write W and its split-fp16 image for the pass (scale from the previous
-//   iteration's max(W)), add this tile's W'W and column sums into the fp64 sums, zero the consumed rows of C (the pass
-//   accumulates the next A H' into them), and let the last CTA build the GramPack of the H update.
+//   H H', c_gram its triangular coefficients), write W, add this tile's W'W, column sums and max into the device state,
+//   zero the consumed rows of C (the pass accumulates the next A H' into them), and let the last CTA build the GramPack
+//   of the H update and the split-fp16 image of W for the pass (exact power-of-two scale from the global max: 96 K
+//   entries, a few microseconds on one SM -- a scale guessed from the previous iteration would cost the small entries
+//   of W five bits, measured as 2.5x the W/H error).
 // Replaces, per iteration: finalize_gram, tc_wsolve, zero_fill, gram(W), finalize_gram, absmax, split_w and three
 // memsets (round 1: 0.15 ms of serial launches).
 // ------------------------------------------------------------------------------------------------
@@ -557,7 +560,6 @@ __global__ void __launch_bounds__(128, 1) tc_wside_kernel(const TcWsideParams p)
     }
     tc_fill_gops(gops, p.pack, threadIdx.x, blockDim.x);
     if (threadIdx.x < 2 * TC_KP) sD[threadIdx.x] = p.pack[2 * TC_KP * TC_KP + threadIdx.x];
-    const int w_exp = tc_exp_of(p.state[TC_ST_WMAX + (p.par ^ 1)]);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
@@ -596,8 +598,6 @@ __global__ void __launch_bounds__(128, 1) tc_wside_kernel(const TcWsideParams p)
     gs_wait(L);
     // ---- W row, its split image, the tile's Gram
     float wmax = 0.f;
-    bool ovf = false;
-    const float scale = exp2f((float)w_exp);
 #pragma unroll
     for (int f = 0; f < 32; ++f) {
         h[f] *= sInvD[f];
@@ -608,26 +608,15 @@ __global__ void __launch_bounds__(128, 1) tc_wside_kernel(const TcWsideParams p)
 #pragma unroll
         for (int r = 0; r < 8; ++r) reinterpret_cast<float4 *>(xrow)[r] = make_float4(h[4 * r], h[4 * r + 1], h[4 * r + 2], h[4 * r + 3]);
     }
-    if (j < p.n_pad) {
-#pragma unroll
-        for (int f = 0; f < TC_KP; ++f) {
-            float x = h[f] * scale;                 // rows past n hold h = 0
-            if (x > 60000.f) { x = 60000.f; ovf = true; }
-            const __half hi = __float2half_rn(x);
-            p.Wst[(size_t)f * p.n_pad + j] = hi;
-            p.Wst[(size_t)(TC_KP + f) * p.n_pad + j] = __float2half_rn(x - __half2float(hi));
-        }
-    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
     int sw = valid ? my_sweeps : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sw += __shfl_xor_sync(0xffffffffu, sw, o);
     if (lane == 0) {
-        atomicMax(p.state + TC_ST_WMAX + p.par, __float_as_int(wmax));
+        atomicMax(p.state + TC_ST_WMAX, __float_as_int(wmax));
         atomicAdd(&p.scal->sweeps_w, (unsigned long long)sw);
     }
-    if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicOr(p.state + TC_ST_OVF, 1);
     __syncthreads();
     {
         // W'W of the 128 rows: thread e owns entries e, e + 128, ... of the 32 x 32 block (a = entry / 32 is warp-uniform)
@@ -652,7 +641,36 @@ __global__ void __launch_bounds__(128, 1) tc_wside_kernel(const TcWsideParams p)
         tc_finalize_gram(p.G64w + (size_t)p.par * TC_GS, p.pack_next, p.k, p.pen_next0, p.pen_next1, sD);
         double *Gz = p.G64w + (size_t)(p.par ^ 1) * TC_GS;
         for (int t = threadIdx.x; t < TC_GS; t += blockDim.x) Gz[t] = 0.0;
+        // split image of the whole W: Wst [64][n_pad] (rows 0..31 hi, 32..63 lo), scaled by 2^w_exp with max(W) -> [2^13, 2^14)
+        int w_exp = 0;
+        {
+            const float mx = __int_as_float(__ldcg(p.state + TC_ST_WMAX));
+            if (mx > 0.f) {
+                int e;
+                frexpf(mx, &e);
+                w_exp = max(-100, min(100, 14 - e));
+            }
+        }
+        const float scale = exp2f((float)w_exp);
+        for (int g = threadIdx.x; g < p.n_pad; g += blockDim.x) {
+            float w[TC_KP];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g < p.cols) v = __ldcg(reinterpret_cast<const float4 *>(p.X + (size_t)g * TC_KP) + r);
+                w[4 * r] = v.x; w[4 * r + 1] = v.y; w[4 * r + 2] = v.z; w[4 * r + 3] = v.w;
+            }
+#pragma unroll
+            for (int f = 0; f < TC_KP; ++f) {
+                const float x = w[f] * scale;
+                const __half hi = __float2half_rn(x);
+                p.Wst[(size_t)f * p.n_pad + g] = hi;
+                p.Wst[(size_t)(TC_KP + f) * p.n_pad + g] = __float2half_rn(x - __half2float(hi));
+            }
+        }
         if (threadIdx.x == 0) {
+            p.state[TC_ST_WEXP] = w_exp;
+            p.state[TC_ST_WMAX] = 0;
             p.state[TC_ST_HMAX + p.par] = 0;
             p.scal->loss_part = 0.0;
         }
@@ -774,7 +792,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         // =========================== solver warps ===========================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_SOLVER));
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-        const float descale = exp2f(-(float)(p.a_exp + tc_exp_of(p.state[TC_ST_WMAX + (p.par ^ 1)])));
+        const float descale = exp2f(-(float)(p.a_exp + p.state[TC_ST_WEXP]));
         const float hscale = exp2f((float)h_exp);
         const float *sInvD = sD + TC_KP;
         // Group g (4 warps = the 4 lane quarters of a tile) solves tiles g, g+4, ...  mu' of the tile lives in its
@@ -1156,7 +1174,6 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         if (p.finalize) tc_finalize_gram(p.G64h + (size_t)p.par * TC_GS, p.pack_next, p.k, p.pen_next0, p.pen_next1, s_hsum);
         double *Gz = p.G64h + (size_t)(p.par ^ 1) * TC_GS;
         for (int t = threadIdx.x; t < TC_GS; t += blockDim.x) Gz[t] = 0.0;
-        if (threadIdx.x == 0) p.state[TC_ST_WMAX + (p.par ^ 1)] = 0;
     }
 }
 
@@ -1308,16 +1325,15 @@ static inline void tc_prepare(TcMatrix &tc, const float *dA, size_t ldA, int n, 
 //   state ints (TC_ST_*), G64w / G64h: [2][TC_GS] fp64 sums (double buffered by iteration parity), packW / packH: the two
 //   GramPacks (W'W + beta penalties for the H update, H H' + alpha penalties for the W update)
 
-// Start of a fit: W0 / H0 are on the device.  Zeroes the state, records max(W0) / max(H0) as the first scale references
-// and splits W0 (the pre-pass needs no W operand, but the first W-side kernel needs max(W0)).  4 small launches, once.
+// Start of a fit: W0 / H0 are on the device.  Zeroes the state and records max(H0) as the first scale reference of the
+// H images (the pre-pass needs no W operand).  Once per fit.
 static inline void tc_fit_begin(TcMatrix &tc, const float *Wt, const float *H, cudaStream_t st)
 {
     CUDA_CHECK(cudaMemsetAsync(tc.state, 0, TC_ST_INTS * sizeof(int), st));
     CUDA_CHECK(cudaMemsetAsync(tc.G64w, 0, 2 * TC_GS * sizeof(double), st));
     CUDA_CHECK(cudaMemsetAsync(tc.G64h, 0, 2 * TC_GS * sizeof(double), st));
-    // iteration 0 has parity 0 and reads the "previous" halves (index 1): max(W0); the pre-pass (parity 1) reads max(H0) from
-    // half 0 and writes half 1
-    tc_absmax_kernel<<<32, 256, 0, st>>>(Wt, (size_t)tc.n * TC_KP, tc.state + TC_ST_WMAX + 1);
+    // the pre-pass (parity 1) reads max(H0) from half 0 and writes half 1; iteration 0 (parity 0) then reads half 1
+    (void)Wt;
     tc_absmax_kernel<<<148, 256, 0, st>>>(H, (size_t)tc.m * TC_KP, tc.state + TC_ST_HMAX + 0);
     CUDA_CHECK(cudaGetLastError());
 }

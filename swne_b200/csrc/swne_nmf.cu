@@ -23,6 +23,7 @@
 #include "pass_tc.cuh"
 #include "contract_tc.cuh"
 #include "seed.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 namespace swne {
 
@@ -148,6 +149,7 @@ struct swne_nmf_handle_s {
     swne_nmf_progress_fn progress = nullptr;
     void *progress_user = nullptr;
     int kl_flags = 0;                // KL_L2_LATE when the fit asks for the alternative reading of NNLM's KL step
+    int last_KPv = 0;                // row stride of Wt / H as the last fit left them on the device
 };
 
 namespace swne {
@@ -525,7 +527,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
                     double *terr_tr, double *epo_tr, int trace_len, swne_nmf_result_t *res, const DeviceInitFn *device_init = nullptr)
 {
     if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident: call swne_nmf_set_matrix_* first");
-    if (!pp || !W || !H) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    if (!pp || ((!W || !H) && !device_init)) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
     swne_nmf_params_t p = *pp;
     const int k = p.k, n = h->n, m = h->m;
     if (k < 1 || k > SWNE_MAX_K) FAIL(SWNE_ERR_BAD_ARG, "k must be in 1..%d", SWNE_MAX_K);
@@ -643,7 +645,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
         tc_pass(h->tc, 1, 1, h->nranks == 1, h->H.p, h->C.p, 0.f, 0.f, 0.f, p.alpha[0], p.alpha[1], k, p.inner_max_iter, 0.f, h->B.p,
                 h->dscal.p, st);
-        prof.end(0, 5 + tc_pass_launches(1));
+        prof.end(0, 1 + tc_pass_launches(1));
         if (h->nranks > 1) {
             allreduce(h, h->B.p, (size_t)n * KPv, g64h_of(1), GS);
             launch_finalize_gram(h, k, KPv, g64h_of(1), h->tc.packH, p.alpha[0], p.alpha[1]);
@@ -857,9 +859,10 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         return fit_impl(h, &p2, W, H, mse_tr, mkl_tr, terr_tr, epo_tr, trace_len, res, device_init);
     }
 
-    // ---- results
-    download_factor_colmajor(h, h->Wt.p, W, k, KPv, n);
-    download_factor_cellmajor(h, h->H.p, H, k, KPv, (size_t)m);
+    // ---- results (a device-seeded fit may leave them on the device: FindNumFactors only needs the errors)
+    h->last_KPv = KPv;
+    if (W) download_factor_colmajor(h, h->Wt.p, W, k, KPv, n);
+    if (H) download_factor_cellmajor(h, h->H.p, H, k, KPv, (size_t)m);
     cudaEventRecord(e4, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
     float ms = 0.f;
@@ -1305,7 +1308,7 @@ static int run_nmf_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, int i
                         double *mse_tr, double *mkl_tr, double *terr_tr, double *epo_tr, int trace_len, swne_nmf_result_t *res)
 {
     if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident: call swne_nmf_set_matrix_* first");
-    if (!pp || !W || !H) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    if (!pp) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
     if (init == SWNE_INIT_GIVEN) return fit_impl(h, pp, W, H, mse_tr, mkl_tr, terr_tr, epo_tr, trace_len, res);
     const int k = pp->k, n = h->n, m = h->m;
     if (k < 1 || k > SWNE_MAX_K) FAIL(SWNE_ERR_BAD_ARG, "k must be in 1..%d", SWNE_MAX_K);
@@ -1360,6 +1363,120 @@ static int ica_init_impl(swne_nmf_handle_s *h, int k, int ica_fast, uint64_t see
     download_factor_colmajor(h, h->Wt.p, W, k, KPd, n);
     download_factor_cellmajor(h, h->H.p, H, k, KPd, (size_t)m);
     return SWNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FindNumFactors (R/nmf.R:157-205) on the resident matrix, as one library call: for every k two mse fits from NNLM's
+// random start (R/nmf.R:167-168; `loss` only selects the error metric) -- on A and on
+// matrix(A[sample(length(A))], nrow(A)) (R/nmf.R:163) -- and the reconstruction errors (R/nmf.R:170-181).  A, the
+// permuted copy, every seed, W and H stay on the device; only 2 x |k.range| doubles come back.
+// ------------------------------------------------------------------------------------------------
+__global__ void fnf_keys_kernel(uint64_t *keys, size_t count, uint64_t seed)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (t + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    keys[t] = z ^ (z >> 31);
+}
+// compact [m][n] <-> padded [m][ldA]
+__global__ void fnf_repad_kernel(const float *src, size_t src_ld, float *dst, size_t dst_ld, int n, size_t m)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * dst_ld) return;
+    const size_t j = t / dst_ld, g = t % dst_ld;
+    dst[t] = (g < (size_t)n && g < src_ld) ? src[j * src_ld + g] : 0.f;
+}
+
+static int find_num_factors_impl(swne_nmf_handle_s *h, const int *k_range, int nk, int loss_metric, int max_iter, uint64_t seed,
+                                 int engine, double *k_err, int *k_pick, double *err_diff)
+{
+    if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident");
+    if (!k_range || !k_err) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    if (nk < 3) FAIL(SWNE_ERR_BAD_ARG, "k.range sequence must have at least 3 values");
+    if (loss_metric != SWNE_LOSS_MSE && loss_metric != SWNE_LOSS_MKL) FAIL(SWNE_ERR_BAD_ARG, "Invalid loss function");
+    if (h->nranks > 1) FAIL(SWNE_ERR_UNSUPPORTED, "FindNumFactors runs its fits as replicas: call it on a single-GPU handle per k subset");
+    for (int c = 0; c < nk; ++c)
+        if (k_range[c] < 1 || k_range[c] > SWNE_MAX_K) FAIL(SWNE_ERR_BAD_ARG, "k must be in 1..%d", SWNE_MAX_K);
+    const int n = h->n, m = h->m;
+    cudaStream_t st = h->stream;
+    if (max_iter <= 0) max_iter = 250;
+    // ---- the permuted matrix: sort the entries by random 64-bit keys
+    const size_t count = (size_t)n * m;
+    DevBuf<float> Arand, vin, vout;
+    DevBuf<uint64_t> kin, kout;
+    DevBuf<unsigned char> tmp;
+    Arand.reserve((size_t)m * h->ldA);
+    kin.reserve(count); kout.reserve(count); vout.reserve(count);
+    const float *vals = h->dA;
+    if (h->ldA != (size_t)n) {
+        vin.reserve(count);
+        fnf_repad_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(h->dA, h->ldA, vin.p, (size_t)n, n, (size_t)m);
+        vals = vin.p;
+    }
+    fnf_keys_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(kin.p, count, seed ^ 0xA5A5A5A5ull);
+    CUDA_CHECK(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    if (count > 0x7fffffffull) FAIL(SWNE_ERR_UNSUPPORTED, "FindNumFactors: more than 2^31 - 1 matrix entries");
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kin.p, kout.p, vals, vout.p, (int)count, 0, 64, st));
+    tmp.reserve(tmp_bytes);
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, kin.p, kout.p, vals, vout.p, (int)count, 0, 64, st));
+    fnf_repad_kernel<<<(unsigned)(((size_t)m * h->ldA + 255) / 256), 256, 0, st>>>(vout.p, (size_t)n, Arand.p, h->ldA, n, (size_t)m);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    kin.release(); kout.release(); vin.release(); vout.release(); tmp.release();
+
+    swne_nmf_params_t p;
+    swne_nmf_default_params(&p, 0);
+    p.loss = SWNE_LOSS_MSE; p.max_iter = max_iter; p.engine = engine; p.full_traces = -1;
+    float *const dA_orig = h->dA;
+    const bool own_orig = h->own_A;
+    int rc_all = SWNE_OK;
+    try {
+        for (int which = 0; which < 2; ++which) {
+            if (which == 1) {
+                // the permutation keeps every statistic of the matrix (sum, sum of squares, nnz, max): only the data pointer changes
+                h->dA = Arand.p;
+                h->own_A = false;
+                h->tc.ready = false; h->sp.ready = false;
+            }
+            for (int c = 0; c < nk; ++c) {
+                p.k = k_range[c];
+                swne_nmf_result_t res;
+                const int rc = run_nmf_impl(h, &p, SWNE_INIT_RANDOM, seed + 7919ull * (uint64_t)(2 * c + which), nullptr, nullptr, nullptr, nullptr,
+                                            nullptr, nullptr, 0, &res);
+                if (rc < 0) { rc_all = rc; throw ArgError{rc}; }
+                h->red.reserve(8);
+                CUDA_CHECK(cudaMemsetAsync(h->red.p, 0, 2 * sizeof(double), st));
+                ops_of(h->last_KPv).recon_error(h->dA, h->ldA, n, m, h->Wt.p, h->H.p, p.k, h->red.p, std::min(m, h->sm_count * 8), st);
+                CUDA_CHECK(cudaGetLastError());
+                double r2[2];
+                CUDA_CHECK(cudaMemcpyAsync(r2, h->red.p, sizeof(r2), cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaStreamSynchronize(st));
+                k_err[(size_t)which * nk + c] = r2[loss_metric == SWNE_LOSS_MSE ? 0 : 1] / ((double)n * m);
+            }
+        }
+    } catch (...) {
+        h->dA = dA_orig; h->own_A = own_orig; h->tc.ready = false; h->sp.ready = false;
+        Arand.release();
+        throw;
+    }
+    h->dA = dA_orig; h->own_A = own_orig; h->tc.ready = false; h->sp.ready = false;
+    Arand.release();
+    // ---- the pick (R/nmf.R:186-194): first k where the permuted data gain more from the next factor than the real data
+    int pick = -1;
+    double best = 1e300;
+    int best_i = 0;
+    for (int c = 0; c + 1 < nk; ++c) {
+        const double d = (k_err[c] - k_err[c + 1]) - (k_err[nk + c] - k_err[nk + c + 1]);
+        if (err_diff) err_diff[c] = d;
+        if (d < 0 && pick < 0) pick = c;
+        if (d < best) { best = d; best_i = c; }
+    }
+    if (pick < 0) pick = best_i + 1;
+    if (k_pick) *k_pick = k_range[pick];
+    return rc_all;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1727,6 +1844,15 @@ int swne_run_nmf(swne_nmf_handle_t h, const swne_nmf_params_t *p, int init, uint
     HANDLE_GUARD(h);
     swne_nmf_result_t local;
     return run_nmf_impl(h, p, init, seed, W, H, mse, mkl, target_loss, average_epochs, trace_len, res ? res : &local);
+    API_END
+}
+
+int swne_find_num_factors(swne_nmf_handle_t h, const int *k_range, int nk, int loss_metric, int max_iter, uint64_t seed, int engine,
+                          double *k_err, int *k_pick, double *err_diff)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    return find_num_factors_impl(h, k_range, nk, loss_metric, max_iter, seed, engine, k_err, k_pick, err_diff);
     API_END
 }
 
