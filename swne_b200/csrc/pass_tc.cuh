@@ -33,7 +33,7 @@ namespace swne {
 constexpr int TC_KP = 32;             // padded factor count handled by this engine (k <= 32)
 constexpr int TC_TILE = 128;          // cells per tile (MMA M in phase 1, K in phase 3)
 constexpr int TC_CHUNK = 64;          // genes per stage (128 B of fp16: one swizzle-128B row)
-constexpr int TC_STAGES = 3;                  // 3 x 40 KB: the CTA stays under 164 KB of shared memory, which leaves ~90 KB of L1 (local-memory traffic of the solver then hits L1)
+constexpr int TC_STAGES = 4;                  // A stages of 16 KB hi + 16 KB lo (+ 8 KB of W in phase 1)
 constexpr int TC_GROUP = 32;          // cells per TMA box / work granule
 constexpr int TC_A_STAGE = TC_TILE * TC_CHUNK * 2;      // 16 KB
 constexpr int TC_W_STAGE = 64 * TC_CHUNK * 2;           // 8 KB  (rows 0..31 W_hi, 32..63 W_lo)
@@ -62,11 +62,16 @@ struct TcSmem {
     static constexpr int a_hi = 0;
     static constexpr int a_lo = a_hi + TC_STAGES * TC_A_STAGE;
     static constexpr int w = a_lo + TC_STAGES * TC_A_STAGE;
-    static constexpr int h = w + TC_STAGES * TC_W_STAGE;
-    static constexpr int gops = h + 2 * TC_H_TILE;       // 8 tf32 operands of G' (8 KB)
+    // The two H tile images of phase 3 overlay the W stages of phase 1 (4 x 8 KB = 2 x 16 KB): the MMA / TMA warps run
+    // phase 1 to completion before phase 3 starts, so the two are never live together (the loader waits for P1DONE).
+    // This keeps the CTA at ~170 KB of shared memory, i.e. under the 196 KB carve-out, which leaves 60 KB of L1 for the
+    // solver's local-memory traffic (with 28 KB of L1 its spills missed half of the time, round 2 ncu).
+    static constexpr int h = w;
+    static_assert(2 * TC_H_TILE <= TC_STAGES * TC_W_STAGE, "H images must fit the W stage area");
+    static constexpr int gops = w + TC_STAGES * TC_W_STAGE;       // 8 tf32 operands of G' (8 KB)
     static constexpr int dvec = gops + 8 * TC_GOP;       // sqrt(diag), 1/sqrt(diag)
     static constexpr int bars = dvec + 2 * TC_KP * 4;
-    static constexpr int n_bars = 2 * TC_STAGES + 2 * TC_CBUF + 2 + 2 + 4 + TC_TGROUPS + TC_MAX_TILES;
+    static constexpr int n_bars = 2 * TC_STAGES + 2 * TC_CBUF + 2 + 2 + 4 + TC_TGROUPS + 1 + TC_MAX_TILES;
     static constexpr int misc = bars + n_bars * 8;       // [0] TMEM base, [4] last-CTA flag, [64,192) row sums of H (fp32)
     static constexpr int total = misc + 256;
 };
@@ -232,6 +237,16 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&a)[8], con
         : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_st16_nowait(uint32_t taddr, const float (&a)[8], const float (&b)[8])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+        "r"(__float_as_uint(a[4])), "r"(__float_as_uint(a[5])), "r"(__float_as_uint(a[6])), "r"(__float_as_uint(a[7])),
+        "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])), "r"(__float_as_uint(b[2])), "r"(__float_as_uint(b[3])),
+        "r"(__float_as_uint(b[4])), "r"(__float_as_uint(b[5])), "r"(__float_as_uint(b[6])), "r"(__float_as_uint(b[7]))
+        : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16])
 {
     uint32_t r[16];
@@ -347,15 +362,22 @@ __device__ __forceinline__ void gs_push(GsLink &L, const float (&h)[32], const f
 {
     constexpr uint32_t ID_TF32 = idesc_tf32(128, 32);
     {
-        // columns [0,16): hi (tf32-exact), [16,32): lo
-        float hl[32];
+        // columns [0,16): hi (tf32-exact), [16,32): lo -- stored in two halves: 16 live registers instead of 32 next to h'
+        const uint32_t tq = L.tdelta + ((uint32_t)(L.quarter * 32) << 16);
+        float a8[8], b8[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float v = from_h ? h[16 * BLK + i] : d[i];
-            hl[i] = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-            hl[16 + i] = v - hl[i];
+        for (int i = 0; i < 8; ++i) {
+            a8[i] = __uint_as_float(__float_as_uint(from_h ? h[16 * BLK + i] : d[i]) & 0xffffe000u);
+            b8[i] = __uint_as_float(__float_as_uint(from_h ? h[16 * BLK + 8 + i] : d[8 + i]) & 0xffffe000u);
         }
-        tc_st32(L.tdelta + ((uint32_t)(L.quarter * 32) << 16), hl);
+        tc_st16_nowait(tq, a8, b8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            a8[i] = (from_h ? h[16 * BLK + i] : d[i]) - a8[i];
+            b8[i] = (from_h ? h[16 * BLK + 8 + i] : d[8 + i]) - b8[i];
+        }
+        tc_st16_nowait(tq + 16, a8, b8);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     named_bar_sync(L.bar_id, 128);
@@ -537,18 +559,23 @@ struct TcWsideParams {
     int *state;
     int par;
     double *G64w;             // [2][TC_GS]
+    float *partial;           // [grid][TC_GS] per-CTA partial W'W and column sums
     FitScalars *scal;
+    unsigned long long *dbg;  // optional timeline (SWNE_TC_TIMELINE): 16 globaltimer slots per CTA
 };
+#define TCW_MARK(slot) do { if (p.dbg && threadIdx.x == 0) p.dbg[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
 
-__global__ void __launch_bounds__(128, 1) tc_wside_kernel(const TcWsideParams p)
+constexpr int TC_WSIDE_THREADS = 256;     // warps 0-3 solve (one per TMEM lane quarter), warps 4-7 help with the Gram and the tail
+__global__ void __launch_bounds__(TC_WSIDE_THREADS, 1) tc_wside_kernel(const TcWsideParams p)
 {
     __shared__ __align__(1024) uint8_t gops[8 * TC_GOP];
     __shared__ float sD[2 * TC_KP];
-    __shared__ float ws[128][TC_KP + 1];
+    __shared__ __align__(16) float ws[128][TC_KP + 2];     // the tile's W rows (stride 34: 8-byte aligned pairs); reused as the split staging
     __shared__ __align__(8) uint64_t mbar_store;
     __shared__ uint32_t tmem_slot;
     __shared__ int s_flag;
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31, quarter = warp;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31, quarter = warp & 3;
+    TCW_MARK(0);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(64));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -566,119 +593,168 @@ __global__ void __launch_bounds__(128, 1) tc_wside_kernel(const TcWsideParams p)
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const float *sInvD = sD + TC_KP;
-    const int j = blockIdx.x * 128 + threadIdx.x;
-    const bool valid = j < p.cols;
-    float *xrow = p.X + (size_t)(valid ? j : 0) * TC_KP;
-    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
-    GsLink L{tmem, tmem + 32, smem_u32(gops), mbar, 0u, false, 1, quarter};
-    float h[32];
-    {
-        // mu'_0 = (l1 - c) / d; the G' h' part is added by the tensor core
-        float mv[32];
-        if (valid) {
-            float4 *cp = reinterpret_cast<float4 *>(p.C + (size_t)j * TC_KP);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const float4 v = reinterpret_cast<const float4 *>(xrow)[r];
-                h[4 * r] = v.x * sD[4 * r]; h[4 * r + 1] = v.y * sD[4 * r + 1];
-                h[4 * r + 2] = v.z * sD[4 * r + 2]; h[4 * r + 3] = v.w * sD[4 * r + 3];
-                const float4 c = cp[r];
-                cp[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                mv[4 * r] = (p.l1 - c.x) * sInvD[4 * r]; mv[4 * r + 1] = (p.l1 - c.y) * sInvD[4 * r + 1];
-                mv[4 * r + 2] = (p.l1 - c.z) * sInvD[4 * r + 2]; mv[4 * r + 3] = (p.l1 - c.w) * sInvD[4 * r + 3];
-            }
-        } else {
-#pragma unroll
-            for (int f = 0; f < 32; ++f) { h[f] = 0.f; mv[f] = 0.f; }
-        }
-        tc_st32(trow, mv);
-    }
-    gs_push_h<false>(L, h, p.k);
-    const int my_sweeps = tc_block_gs(h, trow, L, p.k, p.max_iter, p.rel_tol);
-    gs_wait(L);
-    // ---- W row, its split image, the tile's Gram
-    float wmax = 0.f;
-#pragma unroll
-    for (int f = 0; f < 32; ++f) {
-        h[f] *= sInvD[f];
-        ws[threadIdx.x][f] = h[f];
-        wmax = fmaxf(wmax, h[f]);
-    }
-    if (valid) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) reinterpret_cast<float4 *>(xrow)[r] = make_float4(h[4 * r], h[4 * r + 1], h[4 * r + 2], h[4 * r + 3]);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    int sw = valid ? my_sweeps : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sw += __shfl_xor_sync(0xffffffffu, sw, o);
-    if (lane == 0) {
-        atomicMax(p.state + TC_ST_WMAX, __float_as_int(wmax));
-        atomicAdd(&p.scal->sweeps_w, (unsigned long long)sw);
-    }
-    __syncthreads();
-    {
-        // W'W of the 128 rows: thread e owns entries e, e + 128, ... of the 32 x 32 block (a = entry / 32 is warp-uniform)
-        double *G = p.G64w + (size_t)p.par * TC_GS;
-#pragma unroll 1
-        for (int q = 0; q < 8; ++q) {
-            const int e = threadIdx.x + 128 * q, a = e >> 5, b = e & 31;
-            float acc = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < 128; ++r) acc = fmaf(ws[r][a], ws[r][b], acc);
-            if (a < p.k && b < p.k) atomicAdd(G + e, (double)acc);
-        }
-        if (threadIdx.x < p.k) {
-            float cs = 0.f;
-            for (int r = 0; r < 128; ++r) cs += ws[r][threadIdx.x];
-            atomicAdd(G + TC_KP * TC_KP + threadIdx.x, (double)cs);
-        }
-    }
-    tc_fence_before();
-    if (tc_last_cta(p.state + TC_ST_CNT_W, &s_flag)) {
-        // GramPack of the H update; reset what the next kernels accumulate into
-        tc_finalize_gram(p.G64w + (size_t)p.par * TC_GS, p.pack_next, p.k, p.pen_next0, p.pen_next1, sD);
-        double *Gz = p.G64w + (size_t)(p.par ^ 1) * TC_GS;
-        for (int t = threadIdx.x; t < TC_GS; t += blockDim.x) Gz[t] = 0.0;
-        // split image of the whole W: Wst [64][n_pad] (rows 0..31 hi, 32..63 lo), scaled by 2^w_exp with max(W) -> [2^13, 2^14)
-        int w_exp = 0;
+    TCW_MARK(1);
+    if (warp < 4) {
+        const int j = blockIdx.x * 128 + threadIdx.x;
+        const bool valid = j < p.cols;
+        float *xrow = p.X + (size_t)(valid ? j : 0) * TC_KP;
+        const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+        GsLink L{tmem, tmem + 32, smem_u32(gops), mbar, 0u, false, 1, quarter};
+        float h[32];
         {
-            const float mx = __int_as_float(__ldcg(p.state + TC_ST_WMAX));
-            if (mx > 0.f) {
-                int e;
-                frexpf(mx, &e);
-                w_exp = max(-100, min(100, 14 - e));
-            }
-        }
-        const float scale = exp2f((float)w_exp);
-        for (int g = threadIdx.x; g < p.n_pad; g += blockDim.x) {
-            float w[TC_KP];
+            // mu'_0 = (l1 - c) / d; the G' h' part is added by the tensor core
+            float mv[32];
+            if (valid) {
+                float4 *cp = reinterpret_cast<float4 *>(p.C + (size_t)j * TC_KP);
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g < p.cols) v = __ldcg(reinterpret_cast<const float4 *>(p.X + (size_t)g * TC_KP) + r);
-                w[4 * r] = v.x; w[4 * r + 1] = v.y; w[4 * r + 2] = v.z; w[4 * r + 3] = v.w;
-            }
+                for (int r = 0; r < 8; ++r) {
+                    const float4 v = reinterpret_cast<const float4 *>(xrow)[r];
+                    h[4 * r] = v.x * sD[4 * r]; h[4 * r + 1] = v.y * sD[4 * r + 1];
+                    h[4 * r + 2] = v.z * sD[4 * r + 2]; h[4 * r + 3] = v.w * sD[4 * r + 3];
+                    const float4 c = cp[r];
+                    cp[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    mv[4 * r] = (p.l1 - c.x) * sInvD[4 * r]; mv[4 * r + 1] = (p.l1 - c.y) * sInvD[4 * r + 1];
+                    mv[4 * r + 2] = (p.l1 - c.z) * sInvD[4 * r + 2]; mv[4 * r + 3] = (p.l1 - c.w) * sInvD[4 * r + 3];
+                }
+            } else {
 #pragma unroll
-            for (int f = 0; f < TC_KP; ++f) {
-                const float x = w[f] * scale;
-                const __half hi = __float2half_rn(x);
-                p.Wst[(size_t)f * p.n_pad + g] = hi;
-                p.Wst[(size_t)(TC_KP + f) * p.n_pad + g] = __float2half_rn(x - __half2float(hi));
+                for (int f = 0; f < 32; ++f) { h[f] = 0.f; mv[f] = 0.f; }
             }
+            tc_st32(trow, mv);
         }
-        if (threadIdx.x == 0) {
-            p.state[TC_ST_WEXP] = w_exp;
-            p.state[TC_ST_WMAX] = 0;
-            p.state[TC_ST_HMAX + p.par] = 0;
-            p.scal->loss_part = 0.0;
+        gs_push_h<false>(L, h, p.k);
+        TCW_MARK(2);
+        const int my_sweeps = tc_block_gs(h, trow, L, p.k, p.max_iter, p.rel_tol);
+        gs_wait(L);
+        TCW_MARK(3);
+        // ---- W row, the tile's maximum and rows for the Gram
+        float wmax = 0.f;
+#pragma unroll
+        for (int f = 0; f < 32; ++f) {
+            h[f] *= sInvD[f];
+            ws[threadIdx.x][f] = h[f];
+            wmax = fmaxf(wmax, h[f]);
         }
+        if (valid) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) reinterpret_cast<float4 *>(xrow)[r] = make_float4(h[4 * r], h[4 * r + 1], h[4 * r + 2], h[4 * r + 3]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        int sw = valid ? my_sweeps : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sw += __shfl_xor_sync(0xffffffffu, sw, o);
+        if (lane == 0) {
+            atomicMax(p.state + TC_ST_WMAX, __float_as_int(wmax));
+            atomicAdd(&p.scal->sweeps_w, (unsigned long long)sw);
+        }
+        tc_fence_before();
     }
     __syncthreads();
+    {
+        // W'W of the 128 rows: thread e owns entries e, e + 256, ... of the 32 x 32 block (a = entry / 32 is warp-uniform).
+        // Every CTA leaves its partial sums in its own slot (no atomics: 24 CTAs finishing together on the same 1056
+        // addresses cost 6 us); the last CTA adds the slots up in fp64.
+        float *slot = p.partial + (size_t)blockIdx.x * TC_GS;
+        // 2 x 2 register blocks: thread t owns rows a0, a0 + 1 and columns b0, b0 + 1 of the 32 x 32 Gram (two 8-byte
+        // shared-memory loads feed four FMAs; the one-entry-per-thread form was bound by the shared-memory pipe: 6 us)
+        const int a0 = 2 * (threadIdx.x >> 4), b0 = 2 * (threadIdx.x & 15);
+        float g00 = 0.f, g01 = 0.f, g10 = 0.f, g11 = 0.f, csum = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 128; ++r) {
+            const float2 wa = *reinterpret_cast<const float2 *>(&ws[r][a0]);
+            const float2 wb = *reinterpret_cast<const float2 *>(&ws[r][b0]);
+            g00 = fmaf(wa.x, wb.x, g00); g01 = fmaf(wa.x, wb.y, g01);
+            g10 = fmaf(wa.y, wb.x, g10); g11 = fmaf(wa.y, wb.y, g11);
+        }
+        slot[a0 * TC_KP + b0] = g00; slot[a0 * TC_KP + b0 + 1] = g01;
+        slot[(a0 + 1) * TC_KP + b0] = g10; slot[(a0 + 1) * TC_KP + b0 + 1] = g11;
+        // column sums: thread (part, f) adds 16 rows, the first warp folds the 8 parts
+        {
+            const int f = threadIdx.x & 31, part = threadIdx.x >> 5;
+            for (int r = 16 * part; r < 16 * part + 16; ++r) csum += ws[r][f];
+            __syncthreads();
+            float *cpart = &ws[0][0];          // the rows are consumed: reuse the first 256 floats
+            cpart[part * 32 + f] = csum;
+            __syncthreads();
+            if (threadIdx.x < TC_KP) {
+                float cs = 0.f;
+#pragma unroll
+                for (int q = 0; q < TC_WSIDE_THREADS / 32; ++q) cs += cpart[q * 32 + threadIdx.x];
+                slot[TC_KP * TC_KP + threadIdx.x] = cs;
+            }
+        }
+    }
+    TCW_MARK(4);
+    __syncthreads();
+    TCW_MARK(8);
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+    }
+}
+
+// The W side's second, tiny kernel (one CTA per 128 genes, right behind tc_wside_kernel on the stream): CTA 0 adds up the
+// per-CTA partial sums into W'W (fp64) and builds the GramPack of the H update; every CTA writes the split-fp16 image of
+// its 128 genes with the exact power-of-two scale of max(W).  As the serial tail of the solve kernel's last CTA this
+// took 45 us (L2 round trips of a single CTA); spread over the CTAs it is a few microseconds.
+__global__ void __launch_bounds__(1024, 1) tc_wfinish_kernel(const TcWsideParams p, int n_slots)
+{
+    __shared__ __align__(16) __half stg[64 * 128];
+    __shared__ float sInv[64];
+    // ---- split image of this CTA's genes: Wst [64][n_pad] (rows 0..31 hi, 32..63 lo), max(W) -> [2^13, 2^14)
+    int w_exp = 0;
+    {
+        const float mx = __int_as_float(p.state[TC_ST_WMAX]);
+        if (mx > 0.f) {
+            int e;
+            frexpf(mx, &e);
+            w_exp = max(-100, min(100, 14 - e));
+        }
+    }
+    const float scale = exp2f((float)w_exp);
+    {
+        const int gi = threadIdx.x >> 3, fq = threadIdx.x & 7;    // gene within the tile, which 4 factors
+        const int g = blockIdx.x * 128 + gi;
+        const float4 v = (g < p.cols) ? reinterpret_cast<const float4 *>(p.X + (size_t)g * TC_KP)[fq] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int f = 4 * fq + e;
+            const float x = w4[e] * scale;
+            const __half hi = __float2half_rn(x);
+            stg[f * 128 + gi] = hi;
+            stg[(TC_KP + f) * 128 + gi] = __float2half_rn(x - __half2float(hi));
+        }
+        __syncthreads();
+        // one 16-byte store per thread: row = thread / 16, 8 genes per piece
+        const int row = threadIdx.x >> 4, piece = threadIdx.x & 15;
+        const int g0 = blockIdx.x * 128 + 8 * piece;
+        if (g0 < p.n_pad)
+            *reinterpret_cast<uint4 *>(p.Wst + (size_t)row * p.n_pad + g0) = *reinterpret_cast<const uint4 *>(stg + row * 128 + 8 * piece);
+    }
+    if (blockIdx.x != 0) return;
+    // ---- CTA 0: W'W + column sums of the whole W (fp64, one entry per thread), the GramPack of the H update, state
+    double *G = p.G64w + (size_t)p.par * TC_GS;
+    for (int t = threadIdx.x; t < TC_GS; t += blockDim.x) {
+        double acc = 0.0;
+        for (int c0 = 0; c0 < n_slots; c0 += 8) {
+            float v8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v8[u] = (c0 + u < n_slots) ? p.partial[(size_t)(c0 + u) * TC_GS + t] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += (double)v8[u];
+        }
+        const int a = t >> 5, b = t & 31;
+        G[t] = (t < TC_KP * TC_KP) ? ((a < p.k && b < p.k) ? acc : 0.0) : ((t - TC_KP * TC_KP < p.k) ? acc : 0.0);
+    }
+    __threadfence();
+    __syncthreads();
+    tc_finalize_gram(G, p.pack_next, p.k, p.pen_next0, p.pen_next1, sInv);
+    if (threadIdx.x == 0) {
+        p.state[TC_ST_WEXP] = w_exp;
+        p.state[TC_ST_HMAX + p.par] = 0;
+        p.scal->loss_part = 0.0;
     }
 }
 
@@ -733,7 +809,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     auto DFULL = [&](int r) { return bar0 + 8u * (B2 + 4 + r); };
     auto DEMPTY = [&](int r) { return bar0 + 8u * (B2 + 6 + r); };
     auto MBG = [&](int g) { return bar0 + 8u * (B2 + 8 + g); };            // "block MMA of group g done"
-    auto TDONE = [&](int t) { return bar0 + 8u * (B2 + 8 + TC_TGROUPS + t); };
+    const uint32_t P1DONE = bar0 + 8u * (B2 + 8 + TC_TGROUPS);              // all phase-1 MMAs complete (W stages free)
+    auto TDONE = [&](int t) { return bar0 + 8u * (B2 + 8 + TC_TGROUPS + 1 + t); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcSmem::misc);
     int *s_flag = reinterpret_cast<int *>(smem + TcSmem::misc + 4);
     float *s_hsum = reinterpret_cast<float *>(smem + TcSmem::misc + 64);
@@ -749,6 +826,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         for (int r = 0; r < 2; ++r) { mbar_init(DFULL(r), 1); mbar_init(DEMPTY(r), 128); }
         for (int t = 0; t < n_tiles; ++t) mbar_init(TDONE(t), 128);
         for (int g = 0; g < TC_TGROUPS; ++g) mbar_init(MBG(g), 1);
+        mbar_init(P1DONE, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -1068,6 +1146,9 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                     }
                 }
             }
+            // the W stages are free once every phase-1 MMA has completed: the H tile loader may overwrite them
+            if (elect_one_sync()) tc_commit(P1DONE);
+            __syncwarp();
             if (lane == 0) TC_MARK(2);
             int use = 0;  // H tile buffer uses
             for (int u = 0; u < n_waves * n_pass; ++u) {
@@ -1138,6 +1219,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             }
         } else if (warp == 2) {
             // =========================== H tile loader ===========================
+            mbar_wait(P1DONE, 0);
             int use = 0;
             for (int u = 0; u < n_waves * n_pass; ++u) {
                 const int wv = u / n_pass;
@@ -1174,6 +1256,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         if (p.finalize) tc_finalize_gram(p.G64h + (size_t)p.par * TC_GS, p.pack_next, p.k, p.pen_next0, p.pen_next1, s_hsum);
         double *Gz = p.G64h + (size_t)(p.par ^ 1) * TC_GS;
         for (int t = threadIdx.x; t < TC_GS; t += blockDim.x) Gz[t] = 0.0;
+        if (threadIdx.x == 0) p.state[TC_ST_WMAX] = 0;       // the next W-side kernel takes the maximum of its W afresh
     }
 }
 
@@ -1207,9 +1290,11 @@ struct TcMatrix {
     __half *Ahi = nullptr, *Alo = nullptr, *Wst = nullptr;
     int *state = nullptr;      // TC_ST_* ints of the running fit
     double *G64w = nullptr, *G64h = nullptr;   // [2][TC_GS] fp64 sums, double buffered by iteration parity
+    float *w_partial = nullptr;                // [ceil(n/128)][TC_GS] per-CTA partial sums of the W-side kernel
     float *packW = nullptr, *packH = nullptr;  // GramPacks: W'W (+beta) for the H update, H H' (+alpha) for the W update
     const char *env_timeline = nullptr, *env_clocks = nullptr;   // SWNE_TC_TIMELINE / SWNE_TC_CLOCKS, read once per matrix
     unsigned long long *dbg = nullptr;   // timeline buffer when SWNE_TC_TIMELINE is set
+    unsigned long long *dbg_w = nullptr; // the same for the W-side kernel
     long long *clk = nullptr;            // solver clock ring when SWNE_TC_CLOCKS is set
     uint8_t *Himg = nullptr;   // split 16-bit H tile images, [grid][tiles_per_cta][TC_H_TILE]
     int grid = 0, tiles_per_cta = 0;
@@ -1266,10 +1351,12 @@ static inline void tc_release(TcMatrix &tc)
     if (tc.state) cudaFree(tc.state);
     if (tc.G64w) cudaFree(tc.G64w);
     if (tc.G64h) cudaFree(tc.G64h);
+    if (tc.w_partial) cudaFree(tc.w_partial);
     if (tc.packW) cudaFree(tc.packW);
     if (tc.packH) cudaFree(tc.packH);
     if (tc.Himg) cudaFree(tc.Himg);
     if (tc.dbg) cudaFree(tc.dbg);
+    if (tc.dbg_w) cudaFree(tc.dbg_w);
     if (tc.clk) cudaFree(tc.clk);
     tc = TcMatrix();
 }
@@ -1292,6 +1379,7 @@ static inline void tc_prepare(TcMatrix &tc, const float *dA, size_t ldA, int n, 
         CUDA_CHECK(cudaMalloc(&tc.state, TC_ST_INTS * sizeof(int)));
         CUDA_CHECK(cudaMalloc(&tc.G64w, 2 * TC_GS * sizeof(double)));
         CUDA_CHECK(cudaMalloc(&tc.G64h, 2 * TC_GS * sizeof(double)));
+        CUDA_CHECK(cudaMalloc(&tc.w_partial, (size_t)((n + 127) / 128) * TC_GS * sizeof(float)));
         CUDA_CHECK(cudaMalloc(&tc.packW, gram_pack_floats(TC_KP) * sizeof(float)));
         CUDA_CHECK(cudaMalloc(&tc.packH, gram_pack_floats(TC_KP) * sizeof(float)));
         const int groups = (m + TC_GROUP - 1) / TC_GROUP;
@@ -1418,11 +1506,34 @@ static inline void tc_wside(TcMatrix &tc, int par, float *Wt, float *B, float l1
     TcWsideParams p;
     p.X = Wt; p.C = B; p.pack = tc.packH; p.pack_next = tc.packW; p.pen_next0 = beta0; p.pen_next1 = beta1;
     p.l1 = l1; p.k = k; p.cols = tc.n; p.n_pad = tc.n_pad; p.max_iter = max_iter; p.rel_tol = rel_tol;
-    p.Wst = tc.Wst; p.state = tc.state; p.par = par; p.G64w = tc.G64w; p.scal = scal;
+    p.Wst = tc.Wst; p.state = tc.state; p.par = par; p.G64w = tc.G64w; p.partial = tc.w_partial; p.scal = scal;
+    const int grid = (tc.n + 127) / 128;
+    const char *tl = tc.env_timeline;
+    if (tl && !tc.dbg_w) CUDA_CHECK(cudaMalloc(&tc.dbg_w, sizeof(unsigned long long) * 16 * grid));
+    p.dbg = tl ? tc.dbg_w : nullptr;
+    if (p.dbg) CUDA_CHECK(cudaMemsetAsync(tc.dbg_w, 0, sizeof(unsigned long long) * 16 * grid, st));
     CUDA_CHECK(cudaMemcpyToSymbolAsync(c_gram, tc.packH, sizeof(float) * TC_KP * TC_KP, 0, cudaMemcpyDeviceToDevice, st));
-    tc_wside_kernel<<<(tc.n + 127) / 128, 128, 0, st>>>(p);
+    tc_wside_kernel<<<grid, TC_WSIDE_THREADS, 0, st>>>(p);
+    tc_wfinish_kernel<<<(tc.n_pad + 127) / 128, 1024, 0, st>>>(p, grid);
     CUDA_CHECK(cudaGetLastError());
+    if (p.dbg) {
+        // debug only: per-CTA marks of this launch (ns since the earliest CTA start), next to the pass timeline
+        std::vector<unsigned long long> hbuf(16 * (size_t)grid);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(cudaMemcpy(hbuf.data(), tc.dbg_w, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull;
+        for (int c = 0; c < grid; ++c) if (hbuf[c * 16]) t0 = std::min(t0, hbuf[c * 16]);
+        FILE *f = fopen((std::string(tl) + ".wside").c_str(), "w");
+        if (f) {
+            for (int c = 0; c < grid; ++c) {
+                fprintf(f, "cta %d", c);
+                for (int q = 0; q < 12; ++q) fprintf(f, " %lld", hbuf[c * 16 + q] ? (long long)(hbuf[c * 16 + q] - t0) : -1ll);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
 }
-static inline int tc_wside_launches() { return 2; }
+static inline int tc_wside_launches() { return 3; }
 
 }  // namespace swne

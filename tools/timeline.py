@@ -19,3 +19,9 @@ for s, nm in names.items():
     print("%-12s min %.1f med %.1f max %.1f" % (nm, v.min(), np.median(v), v.max()))
 for c_ in (0, 73, 147):
     print("cta", c_, "job pick", a[c_, 8:16].round(0), "job done", a[c_, 16:24].round(0), "ps0 tile done", a[c_, 24:32].round(0))
+wpath = os.environ["SWNE_TC_TIMELINE"] + ".wside"
+if os.path.exists(wpath):
+    w = np.array([list(map(int, l.split()[2:])) for l in open(wpath)], dtype=float) / 1000.0
+    print("W-side kernel marks (us): start, prologue done, init pushes done, sweeps done, gram atomics done, [last CTA:] ticket, finalize, split, end")
+    for c_ in range(w.shape[0]):
+        print("  cta %2d" % c_, w[c_].round(1))
