@@ -342,6 +342,185 @@ def run_ours(args, cfg):
         td.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# --config cfg5: BASELINE.json configuration 5 as specified -- 3000 genes x 1.3 M cells, k = 40, mse, the matrix handed over
+# as CSC (dgCMatrix slots: int32 p / i, float32 x), cells sharded over the ranks by EQUAL NNZ (dist.shard_bounds_nnz).
+# The synthetic matrix is a concatenation of independently generated 20 000-cell chunks (chunk c: generator seed + c), so
+# any rank can produce any cell range without holding the whole matrix.
+# ------------------------------------------------------------------------------------------------
+CFG5_CHUNK = 20000
+
+
+def cfg5_chunk(cfg, c, m, device):
+    from swne_b200 import synth
+    mc = min(CFG5_CHUNK, m - c * CFG5_CHUNK)
+    return synth.make_matrix_torch(cfg["n"], mc, cfg["kt"], cfg["scale"], cfg["seed"] + c, device=device)
+
+
+def cfg5_csc_range(cfg, m, lo, hi, device):
+    """CSC slots (p int32, i int32, x float32) of cells [lo, hi) of the synthetic matrix"""
+    import torch
+    ps, iis, xs = [np.zeros(1, dtype=np.int64)], [], []
+    for c in range(lo // CFG5_CHUNK, (hi - 1) // CFG5_CHUNK + 1):
+        D = cfg5_chunk(cfg, c, m, device)                           # (cells, genes)
+        a, b = max(lo, c * CFG5_CHUNK) - c * CFG5_CHUNK, min(hi, (c + 1) * CFG5_CHUNK) - c * CFG5_CHUNK
+        D = D[a:b]
+        nz = D != 0
+        ps.append(nz.sum(dim=1).cpu().numpy().astype(np.int64))
+        iis.append(nz.nonzero()[:, 1].to(torch.int32).cpu().numpy())
+        xs.append(D[nz].cpu().numpy())
+        del D, nz
+    p = np.cumsum(np.concatenate(ps))
+    assert p[-1] < 2**31
+    return p.astype(np.int32), np.concatenate(iis), np.concatenate(xs)
+
+
+def run_cfg5(args):
+    import scipy.sparse
+    import torch
+    import torch.distributed as td
+    from swne_b200 import NMFHandle, synth
+    from swne_b200.dist import init_comm, shard_bounds, shard_bounds_nnz
+    cfg = dict(synth.CONFIGS["cfg5"])
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n, m, k = cfg["n"], args.cells or cfg["m"], cfg["k"]
+    metric = "RunNMF iterations/s (%d genes x %d cells, k=%d, mse, CSC input)" % (n, m, k)
+    config = {"workload": "cfg5: %d genes x %d cells, k=%d, mse, sparse CSC input (int32 p/i, float32 x), cells sharded by equal nnz, "
+                          "random init U(0,1)*0.01, timed from the state after the warm-up iterations" % (n, m, k),
+              "genes": n, "cells": m, "k": k, "loss": "mse",
+              "l2": "input (%.1f GB dense fp32 on the device) larger than L2" % (4.0 * n * m / 1e9)}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # restated NNLM on a 100 000-cell slice (dense fp64: the full matrix would be 31 GB twice), scaled by cells: flagged
+        cells = min(m, 100000)
+        _, iis, xs = None, None, None
+        p_, i_, x_ = cfg5_csc_range(cfg, m, 0, cells, "cuda" if torch.cuda.is_available() else "cpu")
+        A64 = np.asfortranarray(scipy.sparse.csc_matrix((x_.astype(np.float64), i_, p_), shape=(n, cells)).toarray())
+        W0 = synth.random_init(n, 1, k, 0)[0]
+        H0 = synth.random_init(n, cells, k, 100)[1]
+        cores = host_cores()
+        val, dt, loss = cpu_oracle_run(A64, k, W0, H0, min(args.warmup, 1), min(max(args.steps, 1), 4), cores)
+        val *= cells / m
+        line = {"metric": metric, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": min(max(args.steps, 1), 4), "warmup": min(args.warmup, 1),
+                "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "impl": "reference", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": "EXTRAPOLATED: first %d of %d cells (dense fp64), value scaled by %d/%d; %.1f s timed" % (cells, m, cells, m, dt)},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+    torch.cuda.set_device(local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- pass 1: nnz per cell of an equal-cell range, all-gathered -> the global column pointer -> equal-nnz bounds
+    b0 = shard_bounds(m, world)
+    cnt = torch.zeros(m, dtype=torch.int64, device="cuda")
+    for c in range(b0[rank] // CFG5_CHUNK, (b0[rank + 1] - 1) // CFG5_CHUNK + 1):
+        lo, hi = max(b0[rank], c * CFG5_CHUNK), min(b0[rank + 1], (c + 1) * CFG5_CHUNK)
+        D = cfg5_chunk(cfg, c, m, "cuda")
+        cnt[lo:hi] = (D[lo - c * CFG5_CHUNK:hi - c * CFG5_CHUNK] != 0).sum(dim=1)
+        del D
+    if world > 1:
+        td.all_reduce(cnt)
+    indptr = np.concatenate([[0], np.cumsum(cnt.cpu().numpy())])
+    b = shard_bounds_nnz(indptr, world)
+    lo, hi = b[rank], b[rank + 1]
+    # ---- pass 2: this rank's cells as CSC on the host (pinned), handed to the library as dgCMatrix slots
+    p_, i_, x_ = cfg5_csc_range(cfg, m, lo, hi, "cuda")
+    m_loc = hi - lo
+    S = scipy.sparse.csc_matrix((x_, i_, p_), shape=(n, m_loc))
+    torch.cuda.empty_cache()
+    h = NMFHandle(local)
+    if world > 1:
+        init_comm(h)
+    barrier()
+    t0 = time.perf_counter()
+    h.set_matrix(S)
+    barrier()
+    ingest_s = maxr(time.perf_counter() - t0)
+    info = h.matrix_info()
+    W0 = synth.random_init(n, 1, k, 0)[0]
+    H0 = synth.random_init(n, m_loc, k, 100 + rank)[1]
+    warm = h.fit(k, W0, H0, max_iter=max(args.warmup, 3), rel_tol=-1.0, engine=args.engine, full_traces=-1)
+    barrier()
+    with ClockSampler(local) as clk:
+        time.sleep(0.2)
+        clk.mark()
+        r = h.fit(k, warm.W, warm.H, max_iter=args.steps, rel_tol=-1.0, engine=args.engine, full_traces=-1)
+        barrier()
+        t_load = time.perf_counter()
+        while True:
+            more = clk.n_loaded() < 8 and time.perf_counter() - t_load < 3.0
+            if world > 1:
+                flag = torch.tensor([1 if more else 0], dtype=torch.int32, device="cuda")
+                td.all_reduce(flag, op=td.ReduceOp.MAX)
+                more = bool(flag.item())
+            if not more:
+                break
+            h.fit(k, r.W, r.H, max_iter=max(args.steps, 10), rel_tol=-1.0, engine=args.engine, full_traces=-1)
+    loop_ms = maxr(r.stats["loop_ms"])
+    ms_per_step = loop_ms / args.steps
+    pr = h.fit(k, r.W, r.H, max_iter=min(args.steps, 6), rel_tol=-1.0, engine=args.engine, profile=True, full_traces=-1)
+    prof_ms = [x / max(pr.n_iteration, 1) for x in pr.stats["prof_ms"]]
+    peak, peak_src = peaks()
+    # dense algorithmic bytes per iteration on this rank (SURVEY 8d): A once + W, H read and written
+    alg = 4.0 * n * m_loc + 4.0 * k * (2 * m_loc + 2 * n)
+    dom = int(np.argmax(prof_ms[:4]))
+    names = ("contract W'A (tcx_cells)", "solve H", "contract A H' (tcx_genes)", "solve W")
+    a_bytes = 4.0 * n * m_loc
+    roofline = {"bound": "hbm", "achieved": a_bytes / (prof_ms[dom] * 1e-3) / 1e9 if dom in (0, 2) else None, "peak": peak, "unit": "GB/s",
+                "frac": (a_bytes / (prof_ms[dom] * 1e-3) / 1e9) / peak if dom in (0, 2) else None, "traffic": None,
+                "kernel": names[dom], "kernel_ms": prof_ms[dom], "peak_source": peak_src,
+                "iteration_frac_of_hbm_roofline": (alg / (ms_per_step * 1e-3) / 1e9) / peak,
+                "profiled_ms_per_iteration": {nm: round(v, 4) for nm, v in zip(("contract_H", "solve_H", "contract_W", "solve_W", "gram_loss", "mkl", "allreduce", "other"), prof_ms)}}
+    # ---- end to end: CSC slots from host memory -> device (dense + split copy) -> K iterations -> W, H back
+    barrier()
+    t0 = time.perf_counter()
+    h.set_matrix(S)
+    re = h.fit(k, warm.W, warm.H, max_iter=args.steps, rel_tol=-1.0, engine=args.engine, full_traces=-1)
+    barrier()
+    e2e_s = maxr(time.perf_counter() - t0)
+    h2d = p_.nbytes + i_.nbytes + x_.nbytes + 8.0 * (n * k + k * m_loc)
+    e2e = {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": 8.0 * (n * k + k * m_loc) / args.steps,
+           "wall_s": e2e_s, "note": "dgCMatrix slots (host) -> device ingest + K iterations + W, H read back"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cells = min(m_loc, 40000)
+        A64 = np.asfortranarray(S[:, :cells].toarray().astype(np.float64))
+        cores = host_cores()
+        val, dt, _ = cpu_oracle_run(A64, k, W0, H0[:, :cells], 1, 3, cores)
+        cpu = {"value": val * cells / m, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "EXTRAPOLATED: first %d of %d cells, 1 warm-up + 3 timed iterations (%.1f s), value scaled by %d/%d" % (cells, m, dt, cells, m)}
+    if rank == 0:
+        line = {"metric": metric, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "run": {"cells_this_rank": m_loc, "nnz_this_rank": int(info["nnz"]), "nnz_bounds": [int(x) for x in b], "engine": pr.options["engine"],
+                        "csc_ingest_s": ingest_s, "parallelism": "cells sharded by equal nnz over %d GPU(s)" % world},
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(r.stats["gpu_launches"]), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        td.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -354,8 +533,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-tol", action="store_true")
+    ap.add_argument("--config", default="cfg3", choices=["cfg3", "cfg5"], help="cfg3: the headline (default); cfg5: 1.3 M cells, k=40, CSC input")
     args = ap.parse_args()
     from swne_b200 import synth
+    if args.config == "cfg5":
+        run_cfg5(args)
+        return
     cfg = dict(synth.CONFIGS["cfg3"])
     if args.impl == "reference":
         run_reference(args, cfg)

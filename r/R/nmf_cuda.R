@@ -1,17 +1,27 @@
-## r/R/nmf_cuda.R -- drop-in overlay for R/nmf.R:96-134 (RunNMF).  COMPILE-UNTESTED here (no R in the image).
-## Same formals and return layout; only the NNLM::nnmf call is replaced by the CUDA path.  n.cores is accepted
-## and ignored.  options(swne.cuda.device = 0) selects the GPU.
+## r/R/nmf_cuda.R -- drop-in overlay for R/nmf.R (RunNMF :96-134, FindNumFactors :157-205, ProjectFeatures :222-225,
+## ProjectSamples :241-249, nnsvd_init :12-47, ica_init :56-66) and for the two hot helpers of R/swne_plotting.R
+## (get_sample_coords :70-84, the distance block of get_factor_coords :43-52).  COMPILE-UNTESTED here (no R in the image).
+## Same formals and return layouts; only the NNLM / ica / irlba calls are replaced by the CUDA path.  n.cores is accepted
+## and ignored.  options(swne.cuda.device = 0) selects the GPU.  R's own RNG only provides one seed per call (the device
+## generator is keyed by it), so set.seed() still makes runs reproducible.
 
+.swne_dev <- function() as.integer(getOption("swne.cuda.device", 0L))
+.swne_seed <- function() floor(runif(1, 1, 2^52))
+.swne_mat <- function(A) if (methods::is(A, "dgCMatrix")) A else as.matrix(A)   # no as.matrix() densify of a dgCMatrix (R/nmf.R:105)
+.swne_init_mode <- c(given = 0L, random = 1L, nnsvd = 2L, ica = 3L, ica_fast = 4L)
+
+## NNLM::nnmf(A, k, alpha, beta, init, method = "scd", loss, max.iter, rel.tol, ...) on the GPU
 .nnmf_cuda <- function(A, k, alpha = rep(0, 3), beta = rep(0, 3), init = NULL, loss = "mse", max.iter = 500,
                        rel.tol = 1e-4, inner.max.iter = ifelse(loss == "mse", 50, 1), inner.rel.tol = 1e-9,
-                       trace = 100 / inner.max.iter, verbose = 0) {
+                       trace = 100 / inner.max.iter, verbose = 0, init.mode = NULL) {
   alpha <- c(as.double(alpha), 0, 0, 0)[1:3]; beta <- c(as.double(beta), 0, 0, 0)[1:3]   # NNLM's padding
-  if (is.null(init)) init <- list(W = matrix(runif(nrow(A) * k) * 0.01, nrow(A), k),
-                                  H = matrix(runif(k * ncol(A)) * 0.01, k, ncol(A)))       # NNLM's random start
+  if (is.null(init.mode)) init.mode <- if (is.null(init)) "random" else "given"          # NNLM's random start: U(0,1) * 0.01
+  Wi <- if (is.null(init)) matrix(0, 0, 0) else init$W
+  Hi <- if (is.null(init)) matrix(0, 0, 0) else init$H
   t0 <- proc.time()
-  out <- swne_nmf_cuda(A, k, init$W, init$H, alpha, beta, as.integer(max.iter), rel.tol, as.integer(inner.max.iter),
-                       inner.rel.tol, ifelse(loss == "mse", 1L, 3L), as.integer(trace),
-                       as.integer(getOption("swne.cuda.device", 0L)))
+  out <- swne_nmf_cuda(.swne_mat(A), k, Wi, Hi, alpha, beta, as.integer(max.iter), rel.tol, as.integer(inner.max.iter),
+                       inner.rel.tol, ifelse(loss == "mse", 1L, 3L), as.integer(trace), .swne_init_mode[[init.mode]],
+                       .swne_seed(), .swne_dev())
   dimnames(out$W) <- list(rownames(A), NULL); dimnames(out$H) <- list(NULL, colnames(A))
   structure(list(W = out$W, H = out$H, mse = out$mse_error, mkl = out$mkl_error, target.loss = out$target_error,
                  average.epochs = out$average_epoch, n.iteration = out$n_iteration, run.time = proc.time() - t0,
@@ -24,23 +34,73 @@ RunNMF <- function(A, k, alpha = 0, init = "ica", n.cores = 1, loss = "mse", max
   if (any(A < 0)) stop('The input matrix contains negative elements !')
   if (k < 3) stop("k must be greater than or equal to 3 to create a viable SWNE plot")
   if (!init %in% c("ica", "nnsvd", "random")) stop("Invalid initialization method")
-  sparse <- methods::is(A, "dgCMatrix")        # new: no as.matrix() densify on the host (R/nmf.R:105)
-  if (!sparse) A <- as.matrix(A)
-  if (init == "ica") {
-    nmf.init <- ica_init(as.matrix(A), k, ica.fast = ica.fast)
-  } else if (init == "nnsvd") {
-    nmf.init <- nnsvd_init(as.matrix(A), k, LINPACK = T)   # or the GPU rSVD: swne_nnsvd_init through a second shim
-  } else {
-    nmf.init <- NULL
-  }
-  if (!is.null(nmf.init)) {
-    A.mean <- mean(A); zero.eps <- 1e-6
-    nmf.init$W[nmf.init$W < zero.eps] <- 0; nmf.init$H[nmf.init$H < zero.eps] <- 0
-    zero.idx.w <- which(nmf.init$W == 0); zero.idx.h <- which(nmf.init$H == 0)
-    nmf.init$W[zero.idx.w] <- runif(length(zero.idx.w), 0, A.mean/100)
-    nmf.init$H[zero.idx.h] <- runif(length(zero.idx.h), 0, A.mean/100)
-  }
-  nmf.res <- .nnmf_cuda(A, k = k, alpha = alpha, init = nmf.init, loss = loss, max.iter = max.iter)
+  ## the seed (ica_init / nnsvd_init / NNLM's random start) and the zero replacement of R/nmf.R:121-127 are computed on the
+  ## device inside the same call as the fit
+  mode <- if (init == "ica" && ica.fast) "ica_fast" else init
+  nmf.res <- .nnmf_cuda(A, k = k, alpha = alpha, init = NULL, loss = loss, max.iter = max.iter, init.mode = mode)
   colnames(nmf.res$W) <- rownames(nmf.res$H) <- sapply(1:ncol(nmf.res$W), function(i) paste("factor", i, sep = "_"))
   return(nmf.res)
+}
+
+nnsvd_init <- function(A, k, LINPACK = T, eps = 1e-10) {     # LINPACK / eps kept for the signature (R/nmf.R:12)
+  swne_seed_cuda(.swne_mat(A), as.integer(k), .swne_init_mode[["nnsvd"]], .swne_seed(), .swne_dev())
+}
+
+ica_init <- function(A, k, ica.fast = F) {
+  swne_seed_cuda(.swne_mat(A), as.integer(k), .swne_init_mode[[if (ica.fast) "ica_fast" else "ica"]], .swne_seed(), .swne_dev())
+}
+
+FindNumFactors <- function(A, k.range = seq(2, 12, 2), n.cores = 1, do.plot = T, seed = NULL, loss = "mse", max.iter = 250) {
+  if (!is.null(seed)) set.seed(seed)
+  if (!loss %in% c("mse", "mkl")) stop("Invalid loss function")
+  if (length(k.range) < 3) stop("k.range sequence must have at least 3 values")
+  if (ncol(A) > 15000) print("Warning: This function can be slow for very large datasets")
+  ## R/nmf.R:163-181 (the permuted matrix, the 2 x length(k.range) mse fits, their errors) in one device call
+  k.err.mat <- swne_find_num_factors_cuda(.swne_mat(A), as.integer(k.range), ifelse(loss == "mse", 0L, 1L), as.integer(max.iter),
+                                          .swne_seed(), .swne_dev())
+  rownames(k.err.mat) <- c("Decomp", "RandomDecomp"); colnames(k.err.mat) <- k.range
+  ## R/nmf.R:183-204, unchanged
+  err.del <- sapply(1:(ncol(k.err.mat) - 1), function(i) k.err.mat[, i] - k.err.mat[, i + 1])
+  colnames(err.del) <- colnames(k.err.mat)[-1]
+  err.del.diff <- err.del[1, ] - err.del[2, ]
+  if (sum(err.del.diff < 0) > 0) {
+    min.idx <- which.max(err.del.diff < 0) - 1
+  } else {
+    min.idx <- which.min(err.del.diff)
+  }
+  res <- list()
+  res$err <- err.del.diff
+  res$k <- as.numeric(names(err.del.diff)[[min.idx]])
+  if (do.plot) print(PlotFactorSelection(res, font.size = 12))
+  return(res)
+}
+
+## NNLM::nnlm(x, y, alpha, method = "scd", loss) on the GPU: coefficients ncol(x) x ncol(y)
+.nnlm_cuda <- function(A, X, side, alpha, loss) {
+  alpha <- c(as.double(alpha), 0, 0, 0)[1:3]
+  k <- if (side == 0L) ncol(X) else nrow(X)
+  init <- if (side == 0L) matrix(runif(k * ncol(A)) * 0.01, k, ncol(A)) else matrix(runif(nrow(A) * k) * 0.01, nrow(A), k)
+  swne_nnlm_cuda(.swne_mat(A), X, init, side, alpha, ifelse(loss == "mse", 0L, 1L), 10000L, 1e-12, .swne_dev())
+}
+
+ProjectFeatures <- function(newdata, H, alpha = rep(0, 3), loss = "mse", n.cores = 1) {   # R/nmf.R:222-225
+  W <- .nnlm_cuda(newdata, H, 1L, alpha, loss)           # nnlm(t(H), t(newdata)) transposed: features x factors
+  rownames(W) <- rownames(newdata); colnames(W) <- rownames(H)
+  return(W)
+}
+
+ProjectSamples <- function(newdata, W, features.use = NULL, alpha = rep(0, 3), loss = "mse", n.cores = 1) {   # R/nmf.R:241-249
+  if (is.null(features.use)) features.use <- intersect(rownames(newdata), rownames(W))
+  H <- .nnlm_cuda(newdata[features.use, ], W[features.use, ], 0L, alpha, loss)
+  rownames(H) <- colnames(W); colnames(H) <- colnames(newdata)
+  return(H)
+}
+
+## get_sample_coords (R/swne_plotting.R:70-84): one device call instead of an sapply over all cells
+get_sample_coords <- function(H, H.coords, alpha = 1, n_pull = NULL) {
+  if (n_pull < 3 || is.null(n_pull)) n_pull <- 3
+  if (n_pull > nrow(H)) n_pull <- nrow(H)
+  sample.coords <- swne_sample_coords_cuda(as.matrix(H), as.matrix(H.coords), alpha, as.integer(n_pull), .swne_dev())
+  colnames(sample.coords) <- c("x", "y"); rownames(sample.coords) <- colnames(H)
+  return(sample.coords)
 }

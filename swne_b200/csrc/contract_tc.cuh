@@ -20,6 +20,7 @@
 namespace swne {
 
 constexpr int TCX_KP = 64;
+constexpr int TCX_STAGES = 3;                             // 3 x (32 KB A + 16 KB W): leaves shared memory for co-resident solve CTAs (slab pipeline)
 constexpr int TCX_W_STAGE = 2 * TCX_KP * TC_CHUNK * 2;   // 16 KB: rows 0..63 W_hi, 64..127 W_lo, 64 genes each
 constexpr int TCX_H_SUB = TCX_KP * 64 * 2;               // 8 KB: [64 factors][64 cells] fp16, K-major
 constexpr int TCX_H_TILE = 4 * TCX_H_SUB;                // hi cells 0..63, hi cells 64..127, lo, lo
@@ -28,19 +29,19 @@ constexpr int TCX_THREADS_GENES = 8 * 32;                // producer, MMA, H loa
 
 struct TcxSmemCells {
     static constexpr int a_hi = 0;
-    static constexpr int a_lo = a_hi + TC_STAGES * TC_A_STAGE;
-    static constexpr int w = a_lo + TC_STAGES * TC_A_STAGE;
-    static constexpr int bars = w + TC_STAGES * TCX_W_STAGE;
-    static constexpr int n_bars = 2 * TC_STAGES + 4;
+    static constexpr int a_lo = a_hi + TCX_STAGES * TC_A_STAGE;
+    static constexpr int w = a_lo + TCX_STAGES * TC_A_STAGE;
+    static constexpr int bars = w + TCX_STAGES * TCX_W_STAGE;
+    static constexpr int n_bars = 2 * TCX_STAGES + 4;
     static constexpr int misc = bars + n_bars * 8;
     static constexpr int total = misc + 64;
 };
 struct TcxSmemGenes {
     static constexpr int a_hi = 0;
-    static constexpr int a_lo = a_hi + TC_STAGES * TC_A_STAGE;
-    static constexpr int h = a_lo + TC_STAGES * TC_A_STAGE;
+    static constexpr int a_lo = a_hi + TCX_STAGES * TC_A_STAGE;
+    static constexpr int h = a_lo + TCX_STAGES * TC_A_STAGE;
     static constexpr int bars = h + 2 * TCX_H_TILE;
-    static constexpr int n_bars = 2 * TC_STAGES + 8;
+    static constexpr int n_bars = 2 * TCX_STAGES + 8;
     static constexpr int misc = bars + n_bars * 8;
     static constexpr int total = misc + 64;
 };
@@ -50,7 +51,8 @@ struct TcxParams {
     int ld;                // row stride (= padded factor count KP, a multiple of 8, <= 64) of C, B, Wt and H
     int n_chunks;          // 64-gene chunks of the split copy (n_pad / 64)
     int n_mtiles;          // ceil(n / 128)
-    int tiles_total;       // ceil(m / 128)
+    int tiles_total;       // number of 128-cell tiles this launch covers
+    int tile0;             // first of them (a launch may cover a slab of the cells)
     float *C;              // [m][ld] fp32 out (cells kernel)
     float *B;              // [n][ld] fp32, accumulated with red.add (genes kernel; zeroed by the caller)
     const uint8_t *Himg;   // [tiles_total][TCX_H_TILE] split images of H (genes kernel)
@@ -58,10 +60,10 @@ struct TcxParams {
     int a_exp;
 };
 
-__device__ __forceinline__ void tcx_my_tiles(int tiles_total, int &t_begin, int &t_count)
+__device__ __forceinline__ void tcx_my_tiles(int tiles_total, int tile0, int &t_begin, int &t_count)
 {
     const int base = tiles_total / (int)gridDim.x, rem = tiles_total % (int)gridDim.x;
-    t_begin = (int)blockIdx.x * base + min((int)blockIdx.x, rem);
+    t_begin = tile0 + (int)blockIdx.x * base + min((int)blockIdx.x, rem);
     t_count = base + ((int)blockIdx.x < rem ? 1 : 0);
 }
 
@@ -77,20 +79,20 @@ tcx_cells_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t_begin, n_tiles;
-    tcx_my_tiles(p.tiles_total, t_begin, n_tiles);
+    tcx_my_tiles(p.tiles_total, p.tile0, t_begin, n_tiles);
 
     const uint32_t bar0 = sbase + TcxSmemCells::bars;
     auto FULL = [&](int s) { return bar0 + 8u * s; };
-    auto EMPTY = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
-    auto CFULL = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + b); };
-    auto CEMPTY = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + 2 + b); };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (TCX_STAGES + s); };
+    auto CFULL = [&](int b) { return bar0 + 8u * (2 * TCX_STAGES + b); };
+    auto CEMPTY = [&](int b) { return bar0 + 8u * (2 * TCX_STAGES + 2 + b); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcxSmemCells::misc);
 
     // rows of a partial tile that TMA never writes only feed C rows that are not stored, but keep them finite
-    for (int i = threadIdx.x; i < (2 * TC_STAGES * TC_A_STAGE) / 16; i += blockDim.x)
+    for (int i = threadIdx.x; i < (2 * TCX_STAGES * TC_A_STAGE) / 16; i += blockDim.x)
         reinterpret_cast<uint4 *>(smem + TcxSmemCells::a_hi)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        for (int s = 0; s < TCX_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(CFULL(b), 1); mbar_init(CEMPTY(b), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -122,7 +124,7 @@ tcx_cells_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                 } else if (lane == 2 * nbox) {
                     tma_load_2d(sbase + TcxSmemCells::w + stage * TCX_W_STAGE, &map_w, ch * TC_CHUNK, 0, FULL(stage));
                 }
-                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == TCX_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -149,7 +151,7 @@ tcx_cells_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                         tc_mma_f16(dC, desc_sw128(alo + ks * 32, 16, 1024), dw_hi, ID, 1);
                     }
                     tc_commit(EMPTY(stage));
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == TCX_STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(CFULL(b));
             }
@@ -202,13 +204,13 @@ tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t_begin, n_tiles;
-    tcx_my_tiles(p.tiles_total, t_begin, n_tiles);
+    tcx_my_tiles(p.tiles_total, p.tile0, t_begin, n_tiles);
     const int n_pass = (p.n_mtiles + TC_MT_PER_PASS - 1) / TC_MT_PER_PASS;
 
     const uint32_t bar0 = sbase + TcxSmemGenes::bars;
     auto FULL = [&](int s) { return bar0 + 8u * s; };
-    auto EMPTY = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
-    constexpr int B2 = 2 * TC_STAGES;
+    auto EMPTY = [&](int s) { return bar0 + 8u * (TCX_STAGES + s); };
+    constexpr int B2 = 2 * TCX_STAGES;
     auto HFULL = [&](int b) { return bar0 + 8u * (B2 + b); };
     auto HEMPTY = [&](int b) { return bar0 + 8u * (B2 + 2 + b); };
     auto DFULL = [&](int r) { return bar0 + 8u * (B2 + 4 + r); };
@@ -216,10 +218,10 @@ tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcxSmemGenes::misc);
 
     // cells of a partial tile that TMA never writes meet zero rows of the H image: they must be finite
-    for (int i = threadIdx.x; i < (2 * TC_STAGES * TC_A_STAGE) / 16; i += blockDim.x)
+    for (int i = threadIdx.x; i < (2 * TCX_STAGES * TC_A_STAGE) / 16; i += blockDim.x)
         reinterpret_cast<uint4 *>(smem + TcxSmemGenes::a_hi)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        for (int s = 0; s < TCX_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(HFULL(b), 1); mbar_init(HEMPTY(b), 1); }
         for (int r = 0; r < 2; ++r) { mbar_init(DFULL(r), 1); mbar_init(DEMPTY(r), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -259,7 +261,7 @@ tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                                             (2 * mt + gh) * TC_CHUNK, cell0 + (2 * hc + cg) * TC_GROUP, FULL(stage));
                             }
                         }
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == TCX_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -301,7 +303,7 @@ tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                                 tc_mma_f16(dD, da_lo, dh_hi, ID, 1);
                             }
                             tc_commit(EMPTY(stage));
-                            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                            if (++stage == TCX_STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
                     tc_commit(HEMPTY(hb));
@@ -393,14 +395,15 @@ __global__ void tcx_split_w_kernel(const float *__restrict__ Wt, int ld, int n, 
 // H fp32 [m][ld] -> per 128-cell tile the smem-ready split image: four K-major [64 factors][64 cells] sub-tiles
 // (hi cells 0..63, hi cells 64..127, lo, lo) with 128 B rows in the 128B-swizzle pattern.  One block per tile.
 __global__ void __launch_bounds__(128) tcx_split_h_kernel(const float *__restrict__ H, int ld, int m, const int *__restrict__ max_bits,
-                                                          int *__restrict__ h_exp_out, uint8_t *__restrict__ Himg)
+                                                          int *__restrict__ h_exp_out, uint8_t *__restrict__ Himg, int tile0)
 {
     const int h_exp = tcx_exp_of(*max_bits);
     if (blockIdx.x == 0 && threadIdx.x == 0) *h_exp_out = h_exp;
     const float scale = exp2f((float)h_exp);
     const int lc = threadIdx.x;
-    const int cell = blockIdx.x * TC_TILE + lc;
-    uint8_t *img = Himg + (size_t)blockIdx.x * TCX_H_TILE + (lc >> 6) * TCX_H_SUB;
+    const int tile = tile0 + blockIdx.x;
+    const int cell = tile * TC_TILE + lc;
+    uint8_t *img = Himg + (size_t)tile * TCX_H_TILE + (lc >> 6) * TCX_H_SUB;
     const int cc = lc & 63;
     const float4 *row = reinterpret_cast<const float4 *>(H + (size_t)min(cell, m - 1) * ld);
 #pragma unroll 4
@@ -450,7 +453,7 @@ tcx_solve_kernel(float *__restrict__ X, const float *__restrict__ C, const float
     __shared__ __align__(8) uint64_t mbar_store;
     __shared__ uint32_t tmem_slot;
     __shared__ double scratch[32];
-    const int warp = threadIdx.x >> 5, quarter = warp;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), quarter = warp;     // warp-uniform for the compiler
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -494,18 +497,23 @@ tcx_solve_kernel(float *__restrict__ X, const float *__restrict__ C, const float
     auto issue_update = [&](int blk) {
         tc_fence_before();
         named_bar_sync(1, 128);
-        if (threadIdx.x == 0) {
-            tc_fence_after();
+        if (warp == 0) {
+            // elect.sync in warp-uniform control flow: the six UTCHMMA issue back to back (under `threadIdx.x == 0` each is
+            // wrapped in an ELECT / BRA.U.ANY loop, ~80 cycles per instruction; tools/micro/gs_bench.cu)
+            if (elect_one_sync()) {
+                tc_fence_after();
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                const int b8 = 2 * blk + ks;
-                const uint64_t g_hi = desc_nosw(gop_u + (2 * b8) * TCX_GOP, 128, 256);
-                const uint64_t g_lo = desc_nosw(gop_u + (2 * b8 + 1) * TCX_GOP, 128, 256);
-                tc_mma_tf32_ts(tmu, tdelta + 8 * ks, g_hi, ID_TF32, 1);
-                tc_mma_tf32_ts(tmu, tdelta + 8 * ks, g_lo, ID_TF32, 1);
-                tc_mma_tf32_ts(tmu, tdelta + 16 + 8 * ks, g_hi, ID_TF32, 1);
+                for (int ks = 0; ks < 2; ++ks) {
+                    const int b8 = 2 * blk + ks;
+                    const uint64_t g_hi = desc_nosw(gop_u + (2 * b8) * TCX_GOP, 128, 256);
+                    const uint64_t g_lo = desc_nosw(gop_u + (2 * b8 + 1) * TCX_GOP, 128, 256);
+                    tc_mma_tf32_ts(tmu, tdelta + 8 * ks, g_hi, ID_TF32, 1);
+                    tc_mma_tf32_ts(tmu, tdelta + 8 * ks, g_lo, ID_TF32, 1);
+                    tc_mma_tf32_ts(tmu, tdelta + 16 + 8 * ks, g_hi, ID_TF32, 1);
+                }
+                tc_commit(mbar);
             }
-            tc_commit(mbar);
+            __syncwarp();
         }
         pending = true;
     };
@@ -631,7 +639,7 @@ struct TcxState {
     int n_pad = 0, tiles_total = 0;
     __half *Wst = nullptr;       // [128][n_pad]
     uint8_t *Himg = nullptr;     // [tiles_total][TCX_H_TILE]
-    int *ints = nullptr;         // [0] W max bits, [1] w_exp, [2] H max bits, [3] h_exp
+    int *ints = nullptr;         // [0] W max bits, [1] w_exp, [2 + 2 s] H max bits, [3 + 2 s] h_exp of slab slot s (0..3)
     float *gram64 = nullptr;     // G' and G0 repacked to row stride 64 (source of c_gram and of the tf32 operands)
     CUtensorMap map_w;
     bool attr = false;
@@ -661,58 +669,83 @@ static inline void tcx_prepare(TcxState &x, const TcMatrix &tc)
     x.n_pad = tc.n_pad; x.tiles_total = tiles_total;
     CUDA_CHECK(cudaMalloc(&x.Wst, (size_t)2 * TCX_KP * tc.n_pad * sizeof(__half)));
     CUDA_CHECK(cudaMalloc(&x.Himg, (size_t)tiles_total * TCX_H_TILE));
-    CUDA_CHECK(cudaMalloc(&x.ints, 8 * sizeof(int)));
+    CUDA_CHECK(cudaMalloc(&x.ints, 16 * sizeof(int)));
     CUDA_CHECK(cudaMalloc(&x.gram64, 2 * 64 * 64 * sizeof(float)));
     tc_make_map(&x.map_w, x.Wst, (uint64_t)tc.n_pad, 2 * TCX_KP, (uint64_t)tc.n_pad * sizeof(__half), TC_CHUNK, 2 * TCX_KP);
     CUDA_CHECK(cudaFuncSetAttribute(tcx_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcxSmemCells::total + 1024));
     CUDA_CHECK(cudaFuncSetAttribute(tcx_genes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcxSmemGenes::total + 1024));
 }
 
-static inline TcxParams tcx_params(const TcxState &x, const TcMatrix &tc, int ld)
+static inline TcxParams tcx_params(const TcxState &x, const TcMatrix &tc, int ld, int tile0, int ntiles)
 {
     TcxParams p;
     p.n = tc.n; p.m = tc.m; p.ld = ld;
     p.n_chunks = tc.n_pad / TC_CHUNK;
     p.n_mtiles = (tc.n + 127) / 128;
-    p.tiles_total = x.tiles_total;
+    p.tiles_total = ntiles; p.tile0 = tile0;
     p.C = nullptr; p.B = nullptr; p.Himg = x.Himg; p.x_exp = nullptr;
     p.a_exp = tc.a_exp;
     return p;
 }
 
-// C[m][ld] = A Wt.  launches: 3
-static inline void tcx_contract_cells(TcxState &x, const TcMatrix &tc, int ld, const float *Wt, float *C, cudaStream_t st)
+// W changed: its split image (max -> exponent -> stacked fp16 operand).  launches: 2
+static inline void tcx_split_w(TcxState &x, const TcMatrix &tc, int ld, const float *Wt, cudaStream_t st)
 {
     CUDA_CHECK(cudaMemsetAsync(x.ints, 0, sizeof(int), st));
     tc_absmax_kernel<<<32, 256, 0, st>>>(Wt, (size_t)tc.n * ld, x.ints);
     tcx_split_w_kernel<<<(tc.n_pad + 127) / 128, 128, 0, st>>>(Wt, ld, tc.n, tc.n_pad, x.ints, x.ints + 1, x.Wst);
-    TcxParams p = tcx_params(x, tc, ld);
+    CUDA_CHECK(cudaGetLastError());
+}
+// C[cells of the slab][ld] = A Wt for the tiles [tile0, tile0 + ntiles); the split image of W must be current.  launches: 1
+static inline void tcx_cells_slab(TcxState &x, const TcMatrix &tc, int ld, float *C, int tile0, int ntiles, cudaStream_t st)
+{
+    TcxParams p = tcx_params(x, tc, ld, tile0, ntiles);
     p.C = C; p.x_exp = x.ints + 1;
-    const int grid = std::min(tc.sm_count, x.tiles_total);
+    const int grid = std::min(tc.sm_count, ntiles);
     tcx_cells_kernel<<<grid, TCX_THREADS_CELLS, TcxSmemCells::total + 1024, st>>>(tc.map_ahi, tc.map_alo, x.map_w, p);
     CUDA_CHECK(cudaGetLastError());
 }
-// B[n][ld] += A' H (B zeroed here).  launches: 3
-static inline void tcx_contract_genes(TcxState &x, const TcMatrix &tc, int ld, const float *H, float *B, cudaStream_t st)
+// B[n][ld] += A' H over the cells of the slab (B is NOT zeroed here).  slot: which pair of x.ints holds this slab's max / exponent
+// (slabs in flight on different streams use different slots: 0..3).  launches: 3
+static inline void tcx_genes_slab(TcxState &x, const TcMatrix &tc, int ld, const float *H, float *B, int tile0, int ntiles, int slot,
+                                  cudaStream_t st)
 {
-    CUDA_CHECK(cudaMemsetAsync(B, 0, sizeof(float) * (size_t)tc.n * ld, st));
-    CUDA_CHECK(cudaMemsetAsync(x.ints + 2, 0, sizeof(int), st));
-    tc_absmax_kernel<<<148, 256, 0, st>>>(H, (size_t)tc.m * ld, x.ints + 2);
-    tcx_split_h_kernel<<<x.tiles_total, 128, 0, st>>>(H, ld, tc.m, x.ints + 2, x.ints + 3, x.Himg);
-    TcxParams p = tcx_params(x, tc, ld);
-    p.B = B; p.x_exp = x.ints + 3;
-    const int grid = std::min(tc.sm_count, x.tiles_total);
+    int *mx = x.ints + 2 + 2 * slot;
+    const int cell0 = tile0 * TC_TILE, cells = std::min(tc.m - cell0, ntiles * TC_TILE);
+    CUDA_CHECK(cudaMemsetAsync(mx, 0, sizeof(int), st));
+    tc_absmax_kernel<<<148, 256, 0, st>>>(H + (size_t)cell0 * ld, (size_t)cells * ld, mx);
+    tcx_split_h_kernel<<<ntiles, 128, 0, st>>>(H, ld, tc.m, mx, mx + 1, x.Himg, tile0);
+    TcxParams p = tcx_params(x, tc, ld, tile0, ntiles);
+    p.B = B; p.x_exp = mx + 1;
+    const int grid = std::min(tc.sm_count, ntiles);
     tcx_genes_kernel<<<grid, TCX_THREADS_GENES, TcxSmemGenes::total + 1024, st>>>(tc.map_ahi, tc.map_alo, p);
     CUDA_CHECK(cudaGetLastError());
 }
 
-// per-column NNLS solves (H side: cols = cells, loss partial wanted; W side: cols = genes).  pack: GramPack at row
-// stride ld.  launches: 2
-static inline void tcx_solve(TcxState &x, float *X, const float *C, const float *pack, int ld, float l1, int k, int cols,
-                             int max_iter, float rel_tol, unsigned long long *sweeps, double *loss_part, cudaStream_t st)
+// C[m][ld] = A Wt.  launches: 3
+static inline void tcx_contract_cells(TcxState &x, const TcMatrix &tc, int ld, const float *Wt, float *C, cudaStream_t st)
+{
+    tcx_split_w(x, tc, ld, Wt, st);
+    tcx_cells_slab(x, tc, ld, C, 0, x.tiles_total, st);
+}
+// B[n][ld] = A' H (B zeroed here).  launches: 4
+static inline void tcx_contract_genes(TcxState &x, const TcMatrix &tc, int ld, const float *H, float *B, cudaStream_t st)
+{
+    CUDA_CHECK(cudaMemsetAsync(B, 0, sizeof(float) * (size_t)tc.n * ld, st));
+    tcx_genes_slab(x, tc, ld, H, B, 0, x.tiles_total, 0, st);
+}
+
+// per-column NNLS solves (H side: cols = cells, loss partial wanted; W side: cols = genes).  pack: GramPack at row stride ld.
+// tcx_solve_prepare puts the Grams where the kernel reads them (once per half step); tcx_solve_run may then be launched on
+// several column ranges (streams) of the same half step.
+static inline void tcx_solve_prepare(TcxState &x, const float *pack, int ld, cudaStream_t st)
 {
     tcx_repack_gram_kernel<<<8, 1024, 0, st>>>(pack, ld, x.gram64);
     CUDA_CHECK(cudaMemcpyToSymbolAsync(c_gram, x.gram64, sizeof(float) * 2 * 64 * 64, 0, cudaMemcpyDeviceToDevice, st));
+}
+static inline void tcx_solve_run(TcxState &x, float *X, const float *C, const float *pack, int ld, float l1, int k, int cols, int max_iter,
+                                 float rel_tol, unsigned long long *sweeps, double *loss_part, cudaStream_t st)
+{
     const float *dvec = pack + 2 * ld * ld;
     const int grid = (cols + 127) / 128;
     if (k <= 48)
@@ -720,6 +753,12 @@ static inline void tcx_solve(TcxState &x, float *X, const float *C, const float 
     else
         tcx_solve_kernel<4><<<grid, 128, 0, st>>>(X, C, x.gram64, dvec, ld, l1, k, cols, max_iter, rel_tol, sweeps, loss_part);
     CUDA_CHECK(cudaGetLastError());
+}
+static inline void tcx_solve(TcxState &x, float *X, const float *C, const float *pack, int ld, float l1, int k, int cols,
+                             int max_iter, float rel_tol, unsigned long long *sweeps, double *loss_part, cudaStream_t st)
+{
+    tcx_solve_prepare(x, pack, ld, st);
+    tcx_solve_run(x, X, C, pack, ld, l1, k, cols, max_iter, rel_tol, sweeps, loss_part, st);
 }
 
 }  // namespace swne

@@ -148,6 +148,8 @@ struct swne_nmf_handle_s {
     size_t pinned_bytes = 0;
     swne_nmf_progress_fn progress = nullptr;
     void *progress_user = nullptr;
+    cudaStream_t aux[2] = {nullptr, nullptr};   // slab pipeline of the wide engine: solves of one slab under the contraction of the next
+    cudaEvent_t ev_ready = nullptr, ev_done[2] = {nullptr, nullptr};
     int kl_flags = 0;                // KL_L2_LATE when the fit asks for the alternative reading of NNLM's KL step
     int last_KPv = 0;                // row stride of Wt / H as the last fit left them on the device
 };
@@ -627,6 +629,21 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     }
 
     const bool tcx_solve_simt = getenv("SWNE_TCX_SOLVE_SIMT") != nullptr;   // debug knob, read once per fit
+    // slabs of the wide engine's H update: enough tiles per slab to keep every SM's contraction CTA busy (>= 4 tiles per SM)
+    int tcx_slabs = 1;
+    if (tcx) {
+        const char *e = getenv("SWNE_TCX_SLABS");
+        tcx_slabs = e ? atoi(e) : std::max(1, std::min(8, h->tcx.tiles_total / (h->sm_count * 4)));
+        if (h->nranks > 1) {
+            // every rank must take the same path (the collectives differ): the smallest count wins
+            double v = -(double)tcx_slabs;
+            CUDA_CHECK(cudaMemcpyAsync(h->red.p, &v, sizeof(double), cudaMemcpyHostToDevice, st));
+            NCCL_CHECK(g_nccl.AllReduce(h->red.p, h->red.p, 1, ncclFloat64, ncclMax, h->comm, h->stream));
+            CUDA_CHECK(cudaMemcpyAsync(&v, h->red.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            tcx_slabs = (int)(-v);
+        }
+    }
     Prof prof;
     prof.on = p.profile != 0;
     prof.st = st;
@@ -670,6 +687,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             // nothing extra
         } else {
             prof.begin(4);
+            CUDA_CHECK(cudaMemsetAsync(&h->dscal.p->kl_part, 0, sizeof(double), st));
             ops_of(KPv).kl_trace(h->dA, h->ldA, n, m, h->H.p, h->Wt.p, k, &h->dscal.p->kl_part, st);
             CUDA_CHECK(cudaGetLastError());
             prof.end(4, 1);
@@ -786,7 +804,43 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             launch_gram(h, KPv, h->Wt.p, n, h->G64w.p);
             launch_finalize_gram(h, k, KPv, h->G64w.p, h->pack.p, p.beta[0], p.beta[1]);
             prof.end(4, 2);
-            {
+            if (tcx && !tcx_solve_simt && tcx_slabs > 1) {
+                // ---- wide engine, slab pipeline: the cells go in slabs over two auxiliary streams, each slab running
+                // contraction -> solves -> A H' of the new H.  The contractions are HBM-bound and the solves latency-bound, so
+                // the solves of one slab run under the contraction of the next (profile slots are wall shares here).
+                prof.begin(0);
+                tcx_split_w(h->tcx, h->tc, KPv, h->Wt.p, st);
+                tcx_solve_prepare(h->tcx, h->pack.p, KPv, st);
+                CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
+                CUDA_CHECK(cudaEventRecord(h->ev_ready, st));
+                const int tiles = h->tcx.tiles_total, per = (tiles + tcx_slabs - 1) / tcx_slabs;
+                for (int sl = 0; sl < tcx_slabs; ++sl) {
+                    const int t0 = sl * per, nt = std::min(per, tiles - t0);
+                    if (nt <= 0) break;
+                    cudaStream_t q = h->aux[sl & 1];
+                    if (sl < 2) CUDA_CHECK(cudaStreamWaitEvent(q, h->ev_ready, 0));
+                    const size_t c0 = (size_t)t0 * TC_TILE;
+                    const int cells = std::min(m - (int)c0, nt * TC_TILE);
+                    tcx_cells_slab(h->tcx, h->tc, KPv, h->C.p, t0, nt, q);
+                    tcx_solve_run(h->tcx, h->H.p + c0 * KPv, h->C.p + c0 * KPv, h->pack.p, KPv, (float)p.beta[2], k, cells, p.inner_max_iter,
+                                  inner_tol, &h->dscal.p->sweeps_h, &h->dscal.p->loss_part, q);
+                    tcx_genes_slab(h->tcx, h->tc, KPv, h->H.p, h->B.p, t0, nt, sl & 3, q);
+                }
+                for (int q = 0; q < 2; ++q) {
+                    CUDA_CHECK(cudaEventRecord(h->ev_done[q], h->aux[q]));
+                    CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_done[q], 0));
+                }
+                prof.end(0, 2 + 5 * tcx_slabs);
+                prof.begin(4);
+                launch_gram(h, KPv, h->H.p, m, h->G64h.p);
+                prof.end(4, 1);
+                if (h->nranks > 1) {
+                    prof.begin(6);
+                    allreduce(h, h->B.p, (size_t)n * KPv, h->G64h.p, GS, &h->dscal.p->loss_part, 1);
+                    prof.end(6, 1);
+                }
+                have_B = true;      // A H' of the new H is in place for the next W update
+            } else {
                 prof.begin(0);
                 if (tcx) tcx_contract_cells(h->tcx, h->tc, KPv, h->Wt.p, h->C.p, st);
                 else launch_contract_cells(h, KPv, h->Wt.p, h->C.p);
@@ -1649,6 +1703,11 @@ int swne_nmf_create(swne_nmf_handle_t *out, int device)
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; ++q) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&h->aux[q], cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_done[q], cudaEventDisableTiming));
+    }
+    CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
     *out = h;
     return SWNE_OK;
     API_END
@@ -1669,6 +1728,11 @@ int swne_nmf_destroy(swne_nmf_handle_t h)
     h->Wt.release(); h->H.release(); h->C.release(); h->B.release(); h->G.release(); h->pack.release();
     h->G64w.release(); h->G64h.release(); h->stage.release(); h->dstats.release(); h->dscal.release(); h->red.release(); h->flags.release();
     if (h->pinned) cudaFreeHost(h->pinned);
+    for (int q = 0; q < 2; ++q) {
+        if (h->aux[q]) { cudaStreamSynchronize(h->aux[q]); cudaStreamDestroy(h->aux[q]); }
+        if (h->ev_done[q]) cudaEventDestroy(h->ev_done[q]);
+    }
+    if (h->ev_ready) cudaEventDestroy(h->ev_ready);
     cudaStreamDestroy(h->stream);
     delete h;
     return SWNE_OK;

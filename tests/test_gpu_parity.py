@@ -74,9 +74,11 @@ def test_tcgen05_engine_vs_oracle(handle, n, m, kt, k, seed):
     assert r.options["engine"] == "tc"
     _check_against(r, ref)
     assert r["H"].min() >= 0 and r["W"].min() >= 0
-    # penalties go through the same pass
+    # penalties go through the same pass; with full traces the mkl of the mse fit is evaluated at every block
     kw = dict(alpha=[0.05, 0.02, 0.01], beta=[0.03, 0.01, 0.02], max_iter=8, trace=1, rel_tol=-1.0)
-    _check_against(handle.fit(k, W0, H0, engine="tc", **kw), nnmf_ref(A, k, W0, H0, **kw))
+    rp, refp = handle.fit(k, W0, H0, engine="tc", full_traces=True, **kw), nnmf_ref(A, k, W0, H0, **kw)
+    _check_against(rp, refp)
+    assert max_rel(rp["mkl"], refp["mkl"]) < LOSS_TOL and max_rel(rp["mse"], refp["mse"]) < LOSS_TOL
 
 
 @pytest.mark.parametrize("n,m,kt,k,seed", [(300, 700, 12, 40, 31), (520, 1000, 20, 64, 32), (257, 385, 10, 33, 33)])
