@@ -20,6 +20,9 @@
 namespace swne {
 
 constexpr int TCX_KP = 64;
+constexpr int TCX_MT_PER_PASS = 3;                        // 128-gene accumulators (64 TMEM columns each) per sub-pass, two regions = 384 columns
+                                                          // (2 per sub-pass = 256 columns would let solve CTAs sit next to a genes CTA, but
+                                                          // the extra sub-passes re-read the H images: measured slower, round 2)
 constexpr int TCX_STAGES = 3;                             // 3 x (32 KB A + 16 KB W): leaves shared memory for co-resident solve CTAs (slab pipeline)
 constexpr int TCX_W_STAGE = 2 * TCX_KP * TC_CHUNK * 2;   // 16 KB: rows 0..63 W_hi, 64..127 W_lo, 64 genes each
 constexpr int TCX_H_SUB = TCX_KP * 64 * 2;               // 8 KB: [64 factors][64 cells] fp16, K-major
@@ -205,7 +208,7 @@ tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t_begin, n_tiles;
     tcx_my_tiles(p.tiles_total, p.tile0, t_begin, n_tiles);
-    const int n_pass = (p.n_mtiles + TC_MT_PER_PASS - 1) / TC_MT_PER_PASS;
+    const int n_pass = (p.n_mtiles + TCX_MT_PER_PASS - 1) / TCX_MT_PER_PASS;
 
     const uint32_t bar0 = sbase + TcxSmemGenes::bars;
     auto FULL = [&](int s) { return bar0 + 8u * s; };
@@ -235,12 +238,12 @@ tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    auto tmem_d = [&](int u) { return tmem + (u & 1) * (TC_MT_PER_PASS * TCX_KP); };
+    auto tmem_d = [&](int u) { return tmem + (u & 1) * (TCX_MT_PER_PASS * TCX_KP); };
 
     if (warp == 0) {
         int stage = 0, phase = 0;
         for (int u = 0; u < n_pass; ++u) {
-            const int mt0 = u * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
+            const int mt0 = u * TCX_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TCX_MT_PER_PASS);
             for (int i = 0; i < n_tiles; ++i) {
                 const int cell0 = (t_begin + i) * TC_TILE;
                 const int nbox = (min(TC_TILE, p.m - cell0) + TC_GROUP - 1) / TC_GROUP;
@@ -271,7 +274,7 @@ tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
             constexpr uint32_t ID = idesc_f16(128, TCX_KP, 1, 0, 0);
             int stage = 0, phase = 0, use = 0;
             for (int u = 0; u < n_pass; ++u) {
-                const int mt0 = u * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
+                const int mt0 = u * TCX_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TCX_MT_PER_PASS);
                 const int r = u & 1;
                 mbar_wait(DEMPTY(r), ((u >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -331,7 +334,7 @@ tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
         const int quarter = warp & 3;
         const float descale = exp2f(-(float)(p.a_exp + *p.x_exp));
         for (int u = 0; u < n_pass; ++u) {
-            const int mt0 = u * TC_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TC_MT_PER_PASS);
+            const int mt0 = u * TCX_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TCX_MT_PER_PASS);
             mbar_wait(DFULL(u & 1), (u >> 1) & 1);
             tc_fence_after();
             for (int mt = mt0; mt < mt1; ++mt) {
@@ -674,6 +677,13 @@ static inline void tcx_prepare(TcxState &x, const TcMatrix &tc)
     tc_make_map(&x.map_w, x.Wst, (uint64_t)tc.n_pad, 2 * TCX_KP, (uint64_t)tc.n_pad * sizeof(__half), TC_CHUNK, 2 * TCX_KP);
     CUDA_CHECK(cudaFuncSetAttribute(tcx_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcxSmemCells::total + 1024));
     CUDA_CHECK(cudaFuncSetAttribute(tcx_genes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcxSmemGenes::total + 1024));
+    // The slab pipeline wants solve CTAs (25 KB of shared memory each) resident NEXT TO a contraction CTA.  An SM's shared
+    // memory carve-out is fixed while CTAs are resident, and by default it is the smallest one that fits the first kernel
+    // (164 KB for 145 KB): ask for the largest carve-out so that the co-resident CTAs fit.
+    CUDA_CHECK(cudaFuncSetAttribute(tcx_cells_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_CHECK(cudaFuncSetAttribute(tcx_genes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_CHECK(cudaFuncSetAttribute(tcx_solve_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_CHECK(cudaFuncSetAttribute(tcx_solve_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 }
 
 static inline TcxParams tcx_params(const TcxState &x, const TcMatrix &tc, int ld, int tile0, int ntiles)
