@@ -28,3 +28,14 @@ def rel_fro(X, Y):
 def max_rel(a, b):
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+MEASURED = []   # (test id, quantity, measured value, bar) of every recorded parity check; conftest writes them out
+
+
+def within(name, value, bar):
+    """assert value < bar, and keep the measured value next to its bar (-> gpurun_out/parity_measured.json)"""
+    import os
+    value = float(value)
+    MEASURED.append({"test": os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0], "what": name, "measured": value, "bar": float(bar)})
+    assert value < bar, "%s: measured %.3e, bar %.3e" % (name, value, bar)

@@ -46,6 +46,34 @@ for (n, m, kt, k, engine) in [(300, 1000, 5, 8, "simt"), (1000, 4000, 6, 16, "tc
         print("%s n=%d m=%d k=%d engine=%s ranks=%d: W identical on ranks %s | vs 1 GPU: loss %.2e mkl %.2e W %.2e H %.2e | "
               "vs oracle: loss %.2e W %.2e H %.2e epochs %.2e" % ("PASS" if good else "FAIL", n, m, k, r.options["engine"], world,
                                                                 same_w, e_loss, e_mkl, e_w, e_h, o_loss, o_w, o_h, o_ep), flush=True)
+# device-side seeds on the sharded matrix (RunNMF's init = nnsvd / ica / NNLM's random start): the sketch and the ICA
+# moments are all-reduced, W is replicated; the seeds draw different random numbers than a 1-GPU run, so the comparison is
+# the quality of the fit, not the factors
+n, m, kt, k = 1000, 4000, 6, 12
+A = small_matrix(n, m, kt, 5)
+b = shard_bounds(m, world)
+for init in ("nnsvd", "ica", "random"):
+    h = NMFHandle(local)
+    init_comm(h)
+    h.set_matrix(np.asfortranarray(A[:, b[rank]:b[rank + 1]]))
+    r = h.fit(k, init=init, seed=11, max_iter=30, trace=1, rel_tol=-1.0)
+    Ws = [None] * world
+    td.all_gather_object(Ws, r.W)
+    H = gather_H(r.H)
+    h.close()
+    if rank == 0:
+        h1 = NMFHandle(local)
+        h1.set_matrix(A)
+        r1 = h1.fit(k, init=init, seed=11, max_iter=30, trace=1, rel_tol=-1.0)
+        h1.close()
+        t = np.asarray(r.target_loss)
+        direct = 0.5 * np.mean((A - r.W @ H) ** 2)
+        same_w = all(np.array_equal(Ws[0], w) for w in Ws)
+        good = (same_w and np.all(np.diff(t) <= 1e-6 * t[:-1]) and abs(direct - t[-1]) < 1e-4 * direct
+                and t[-1] < 1.02 * r1.target_loss[-1] and r.W.min() >= 0 and H.min() >= 0)
+        ok &= good
+        print("%s device seed %s ranks=%d: W identical %s | final loss %.6e (1 GPU %.6e) | loss recomputed from W,H rel %.1e"
+              % ("PASS" if good else "FAIL", init, world, same_w, t[-1], r1.target_loss[-1], abs(direct - t[-1]) / direct), flush=True)
 td.barrier()
 td.destroy_process_group()
 sys.exit(0 if ok else 1)
