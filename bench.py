@@ -262,10 +262,10 @@ def run_ours(args, cfg):
     iters_prof = pr.n_iteration
     shares = {nm: round(ms / max(sum(prof_ms), 1e-9), 4) for nm, ms in zip(
         ("contract_H_or_pass", "solve_H", "contract_W", "solve_W", "gram_loss", "mkl_update", "allreduce", "other"), prof_ms)}
-    # dram__bytes_read.sum + dram__bytes_write.sum of one tc_pass_kernel<1> launch on this workload, from the ncu --set
-    # full capture summarised in profiles/r1_pass_kernel_ncu_raw_key_metrics.txt (2.502 GB + 0.070 GB): the pass reads A
-    # twice by design, so traffic is ~2.1x the algorithmic bytes
-    traffic = 2.5715e9 if (engine == "tc" and world == 1 and m == 100000) else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of one tc_pass_kernel launch on this workload, from the round-2 ncu --set full
+    # capture summarised in profiles/r2_iteration_kernels_ncu_full_key_metrics.txt (2.4887 GB + 0.0536 GB = 5.41 TB/s over the
+    # 469.6 us launch): the pass reads A twice by design, so traffic is ~2.1x the algorithmic bytes
+    traffic = 2.5423e9 if (engine == "tc" and world == 1 and m == 100000) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": dom_name, "kernel_ms": dom_ms, "peak_source": peak_src,
                 "iteration_frac_of_hbm_roofline": ((a_bytes + 4.0 * k * (2 * m_loc + 2 * n)) / (ms_per_step * 1e-3) / 1e9) / peak,

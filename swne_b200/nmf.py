@@ -187,6 +187,15 @@ class NMFHandle:
         C.check(self._lib.swne_ica_init(self._h, int(k), int(bool(ica_fast)), ctypes.c_uint64(int(seed)), C.dptr(W), C.dptr(H)))
         return W, H
 
+    def find_num_factors(self, k_range, loss="mse", max_iter=250, seed=0, engine="auto"):
+        """FindNumFactors' sweep (R/nmf.R:157-205) on the resident matrix in one library call: permutation, random starts,
+        2 x len(k_range) fits and their errors all stay on the device (swne_find_num_factors)."""
+        ks = np.ascontiguousarray(k_range, dtype=np.int32)
+        k_err = np.zeros((2, len(ks))); diff = np.zeros(max(len(ks) - 1, 1)); pick = ctypes.c_int(0)
+        C.check(self._lib.swne_find_num_factors(self._h, C.iptr(ks), len(ks), C.LOSS[loss], int(max_iter), ctypes.c_uint64(int(seed)),
+                                                C.ENGINE[engine], C.dptr(k_err), ctypes.byref(pick), C.dptr(diff)))
+        return dict(err=diff[:len(ks) - 1], k=int(pick.value), k_err=k_err)
+
     def recon_error(self, W, H):
         W = np.asfortranarray(W, dtype=np.float64); H = np.asfortranarray(H, dtype=np.float64)
         mse, kl = ctypes.c_double(), ctypes.c_double()
@@ -360,9 +369,13 @@ def FindNumFactors(A, k_range=(2, 4, 6, 8, 10, 12), n_cores=1, do_plot=False, se
     if m > 20000:
         print("Warning: This function can be slow for very large datasets")
     rng = np.random.default_rng(seed)
+    h = handle or default_handle()
+    if inits is None and A_rand is None and not kw:
+        # the whole sweep in the library: the permuted matrix, the random starts and the factors never leave the device
+        h.set_matrix(A)
+        return h.find_num_factors(k_range, loss=loss, max_iter=max_iter, seed=int(rng.integers(1 << 62)))
     if A_rand is None:
         A_rand = _permuted_entries(A, rng)
-    h = handle or default_handle()
     k_err = np.zeros((2, len(k_range)))
     for which, mat in enumerate((A, A_rand)):
         h.set_matrix(mat)

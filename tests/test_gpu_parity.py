@@ -41,9 +41,8 @@ def test_golden_mkl(handle, path):
     handle.set_matrix(g["A"])
     r = handle.fit(int(g["k"]), g["W0"], g["H0"], alpha=g["alpha"], beta=g["beta"], loss="mkl",
                    max_iter=int(g["max_iter"]), trace=int(g["trace"]), rel_tol=-1.0)
-    # the KL coordinate step is ill-conditioned where a row collapses: loss at the bar, W/H looser
-    _check_against(r, g, factor_tol=2e-2)
-    within("mse of the mkl fit, max rel", max_rel(r["mse"], g["mse"]), 1e-3)
+    _check_against(r, g)          # measured round 2: loss 7e-7, W/H 4e-6 (profiles/r2_parity_measured.json)
+    within("mse of the mkl fit, max rel", max_rel(r["mse"], g["mse"]), LOSS_TOL)
 
 
 @pytest.mark.parametrize("n,m,kt,k,seed", [(200, 300, 5, 5, 1), (2000, 3000, 9, 16, 1), (301, 517, 6, 30, 2), (128, 257, 6, 40, 3)])
@@ -172,8 +171,8 @@ def test_unpinned_nnlm_details_both_readings(handle):
         refs[late] = nnmf_ref(A, 8, W0, H0, kl_l2_late=late, **kw)
         r = handle.fit(8, W0, H0, kl_l2_late=late, **kw)
         within("mkl target_loss, max rel (kl_l2_late=%d)" % late, max_rel(r["target_loss"], refs[late]["target_loss"]), LOSS_TOL)
-        within("W rel Frobenius (kl_l2_late=%d)" % late, rel_fro(r["W"], refs[late]["W"]), 2e-2)
-        within("H rel Frobenius (kl_l2_late=%d)" % late, rel_fro(r["H"], refs[late]["H"]), 2e-2)
+        within("W rel Frobenius (kl_l2_late=%d)" % late, rel_fro(r["W"], refs[late]["W"]), FACTOR_TOL)
+        within("H rel Frobenius (kl_l2_late=%d)" % late, rel_fro(r["H"], refs[late]["H"]), FACTOR_TOL)
     # the two readings are distinguishable on this input (otherwise the test above proves nothing)
     assert rel_fro(refs[True]["H"], refs[False]["H"]) > 1e-3
 
@@ -283,7 +282,7 @@ def test_nnlm_vs_oracle(handle):
     # mkl projection
     refk = nnlm_ref(g["W"], A, loss="mkl", init=np.full((5, 90), 0.005), max_iter=200)
     rk = handle.nnlm(0, g["W"], init=np.full((5, 90), 0.005), loss="mkl", max_iter=200)
-    within("nnlm mkl coefficients", rel_fro(rk["coefficients"], refk["coefficients"]), 5e-3)
+    within("nnlm mkl coefficients", rel_fro(rk["coefficients"], refk["coefficients"]), FACTOR_TOL)
 
 
 def test_project_features_and_samples(handle):
@@ -305,14 +304,14 @@ def test_nnsvd_init_vs_lapack(handle):
     handle.set_matrix(A)
     W, H, sv = handle.nnsvd_init(6, oversample=10, power_iters=6, seed=3)
     S = np.linalg.svd(A, compute_uv=False)[:6]
-    within("singular values vs LAPACK, max rel", max_rel(sv, S), 1e-4)
+    within("singular values vs LAPACK, max rel", max_rel(sv, S), 1e-5)
     assert W.min() >= 0 and H.min() >= 0
     # leading (well separated) factors match the LAPACK-based NNDSVD
     for f in range(6):
         gap = (S[f] - S[f + 1]) / S[f] if f + 1 < len(S) else 1.0
         if f == 0 or gap > 0.05:
-            within("NNDSVD column %d of W vs LAPACK" % f, rel_fro(W[:, f], Wr[:, f]), 2e-2)
-            within("NNDSVD row %d of H vs LAPACK" % f, rel_fro(H[f], Hr[f]), 2e-2)
+            within("NNDSVD column %d of W vs LAPACK" % f, rel_fro(W[:, f], Wr[:, f]), 2e-4)
+            within("NNDSVD row %d of H vs LAPACK" % f, rel_fro(H[f], Hr[f]), 2e-4)
     # and it seeds an equally good fit
     from oracle import nnmf_ref
     ref = nnmf_ref(A, 6, *seeded_init(A, 6, 10), max_iter=30, rel_tol=-1.0)
@@ -359,11 +358,35 @@ def test_find_num_factors_vs_oracle(handle):
                  rng.uniform(size=(120, k)) * 0.01, rng.uniform(size=(k, 200)) * 0.01) for k in ks}
     ref = find_num_factors_ref(A, ks, inits, A_rand, max_iter=40)
     r = FindNumFactors(A, ks, inits=inits, A_rand=A_rand, max_iter=40, handle=handle)
-    within("FindNumFactors k_err (mse), max rel", max_rel(r["k_err"], ref["k_err"]), 2e-3)   # different stopping iteration is possible at the 1e-4 rule
+    within("FindNumFactors k_err (mse), max rel", max_rel(r["k_err"], ref["k_err"]), LOSS_TOL)
     assert r["k"] == ref["k"]
     rk = FindNumFactors(A, ks, inits=inits, A_rand=A_rand, max_iter=40, loss="mkl", handle=handle)
     refk = find_num_factors_ref(A, ks, inits, A_rand, max_iter=40, loss="mkl")
-    within("FindNumFactors k_err (mkl), max rel", max_rel(rk["k_err"], refk["k_err"]), 5e-3)
+    within("FindNumFactors k_err (mkl), max rel", max_rel(rk["k_err"], refk["k_err"]), LOSS_TOL)
+
+
+def test_find_num_factors_in_library_sweep(handle):
+    """swne_find_num_factors: permutation, random starts, fits and errors on the device (what FindNumFactors calls when
+    nothing is injected).  Its random numbers differ from numpy's, so it is compared with the host-orchestrated sweep
+    (which the test above pins to the oracle) statistically, and with R/nmf.R:186-194's selection rule exactly."""
+    from swne_b200 import FindNumFactors
+    A = small_matrix(300, 500, 4, 21, density_scale=2.0)
+    ks = [2, 3, 4, 5, 6, 8]
+    for loss in ("mse", "mkl"):
+        r = FindNumFactors(A, ks, seed=5, loss=loss, max_iter=60, handle=handle)
+        rng = np.random.default_rng(7)
+        inits = {k: (rng.uniform(size=(300, k)) * 0.01, rng.uniform(size=(k, 500)) * 0.01,
+                     rng.uniform(size=(300, k)) * 0.01, rng.uniform(size=(k, 500)) * 0.01) for k in ks}
+        A_rand = np.asfortranarray(rng.permutation(A.ravel()).reshape(A.shape))
+        rh = FindNumFactors(A, ks, inits=inits, A_rand=A_rand, loss=loss, max_iter=60, handle=handle)
+        within("in-library sweep vs host-orchestrated sweep, k_err on A (%s)" % loss, max_rel(r["k_err"][0], rh["k_err"][0]), 1e-2)
+        within("in-library sweep vs host-orchestrated sweep, k_err on permuted A (%s)" % loss, max_rel(r["k_err"][1], rh["k_err"][1]), 1e-2)
+        assert np.all(np.diff(r["k_err"][0]) < 0) and np.all(r["k_err"][1] > r["k_err"][0])
+        d = (r["k_err"][0, :-1] - r["k_err"][0, 1:]) - (r["k_err"][1, :-1] - r["k_err"][1, 1:])
+        assert np.allclose(r["err"], d, rtol=0, atol=1e-15)
+        neg = np.nonzero(d < 0)[0]
+        assert r["k"] == ks[int(neg[0]) if neg.size else int(np.argmin(d)) + 1]
+        assert r["k"] == rh["k"]
 
 
 def test_run_nmf_front_end(handle):
@@ -471,10 +494,12 @@ def test_cfg2_mkl_at_size_vs_oracle(handle):
         tag = "beta L1" if "beta" in kw else "alpha L2"
         within("mkl target_loss, max rel (%s)" % tag, max_rel(r["target_loss"], ref["target_loss"]), LOSS_TOL)
         within("mkl trace, max rel (%s)" % tag, max_rel(r["mkl"], ref["mkl"]), LOSS_TOL)
-        within("mse of the mkl fit, max rel (%s)" % tag, max_rel(r["mse"], ref["mse"]), 1e-3)
-        # the KL coordinate step amplifies rounding where a factor row collapses; W/H are held to the looser bar
-        within("W rel Frobenius (%s)" % tag, rel_fro(r["W"], ref["W"]), 2e-2)
-        within("H rel Frobenius (%s)" % tag, rel_fro(r["H"], ref["H"]), 2e-2)
+        within("mse of the mkl fit, max rel (%s)" % tag, max_rel(r["mse"], ref["mse"]), LOSS_TOL)
+        # the KL coordinate step amplifies rounding where a factor row collapses (40 iterations at this size:
+        # measured 8e-4 with the L1 penalty, 2.4e-3 with the L2 one, i.e. fp32's 6e-8 amplified ~4e4 times -- the oracle's own
+        # summation-order noise is amplified by the same factor, test_mkl_vs_oracle_with_self_noise); bar = 3x measured
+        within("W rel Frobenius (%s)" % tag, rel_fro(r["W"], ref["W"]), 8e-3)
+        within("H rel Frobenius (%s)" % tag, rel_fro(r["H"], ref["H"]), 8e-3)
 
 
 def test_csc_ingest_at_size_equals_dense(handle):
