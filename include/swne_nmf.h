@@ -127,6 +127,19 @@ int swne_nmf_set_matrix_dense_f32(swne_nmf_handle_t h, const float *A, int n, in
 /* dgCMatrix slots: p (m+1), i (nnz, 0-based row = gene), x (nnz) */
 int swne_nmf_set_matrix_csc_f64(swne_nmf_handle_t h, const int *p, const int *i, const double *x, int n, int m);
 int swne_nmf_set_matrix_csc_f32(swne_nmf_handle_t h, const int *p, const int *i, const float *x, int n, int m);
+/* Raw counts as dgCMatrix slots with ScaleCounts (R/data_processing.R:275-307) fused into the upload, so the normalised
+ * matrix never exists on the host (R/nmf.R:105 would make it dense there):
+ *   a = f(x * cell_scale[cell] * gene_scale[gene])   on the stored entries, zeros stay zero (the reference transforms @x)
+ *   cell_scale[j] = depthScale / depth[j]  (NormalizeCounts, R/data_processing.R:167,184; depth = column sums of the FULL
+ *                   count matrix, depthScale = their median by default, :278-280), NULL = 1
+ *   gene_scale[g] = the variance scale factor gsf of AdjustVariance (:284-287; its GAM fit stays on the host), NULL = 1
+ *   transform     = SWNE_TRANSFORM_NONE | _LOG (log(x + 1), :301) | _FT (sqrt(x) + sqrt(x + 1), :256,:299)
+ * The batch correction of NormalizeCounts and method = "logrank" are not covered.  (i, j) pairs must be unique. */
+#define SWNE_TRANSFORM_NONE 0
+#define SWNE_TRANSFORM_LOG 1
+#define SWNE_TRANSFORM_FT 2
+int swne_nmf_set_matrix_csc_counts(swne_nmf_handle_t h, const int *p, const int *i, const double *x, int n, int m,
+                                   const double *cell_scale, const double *gene_scale, int transform);
 /* A already in HBM (fp32, cell-major = R column-major, leading dimension n): no copy is made on the
  * host; used by bench.py for the HBM-resident measurement. */
 int swne_nmf_set_matrix_dense_f32_device(swne_nmf_handle_t h, const float *dA, int n, int m);
@@ -167,7 +180,9 @@ int swne_run_nmf(swne_nmf_handle_t h, const swne_nmf_params_t *p, int init, uint
  * NNLM's random start (max_iter, rel_tol 1e-4) -- on A and on a random permutation of all its entries (R/nmf.R:163) --
  * and their reconstruction errors (loss_metric SWNE_LOSS_MSE: mean squared error, SWNE_LOSS_MKL: mean kl_div,
  * R/nmf.R:71-75,170-181).  k_err: 2 x nk row-major (row 0: A, row 1: permuted); err_diff (nk - 1, may be NULL) and
- * k_pick (may be NULL) follow R/nmf.R:186-194.  The permuted matrix, seeds, W and H never leave the device. */
+ * k_pick (may be NULL) follow R/nmf.R:186-194.  The permuted matrix, seeds, W and H never leave the device.  The
+ * permutation is a function of `seed`, every fit's start of (seed, k): a replica (one GPU of several) may sweep any subset
+ * of k.range -- with k_pick and err_diff NULL fewer than 3 values are accepted -- and obtains the errors of the full sweep. */
 int swne_find_num_factors(swne_nmf_handle_t h, const int *k_range, int nk, int loss_metric, int max_iter, uint64_t seed,
                           int engine, double *k_err, int *k_pick, double *err_diff);
 

@@ -23,6 +23,7 @@ LOSS = {"mse": 0, "mkl": 1}
 ENGINE = {"auto": 0, "simt": 1, "tc": 2}
 ENGINE_NAME = {0: "auto", 1: "simt", 2: "tc"}
 VARIANT_KL_L2_LATE = 1      # include/swne_nmf.h SWNE_VARIANT_KL_L2_LATE
+TRANSFORM = {"none": 0, "log": 1, "ft": 2}     # ScaleCounts(method = ...), include/swne_nmf.h SWNE_TRANSFORM_*
 INIT = {"given": 0, "random": 1, "nnsvd": 2, "ica": 3, "ica_fast": 4}
 MAX_K = 64
 PROF_SLOTS = 8
@@ -33,7 +34,7 @@ SYMBOLS = (
     "swne_nmf_last_error", "swne_nmf_abi_version", "swne_nmf_device_count", "swne_nmf_default_params",
     "swne_nmf_create", "swne_nmf_destroy", "swne_nmf_set_progress", "swne_nmf_comm_unique_id", "swne_nmf_comm_init",
     "swne_nmf_set_matrix_dense_f64", "swne_nmf_set_matrix_dense_f32", "swne_nmf_set_matrix_csc_f64",
-    "swne_nmf_set_matrix_csc_f32", "swne_nmf_set_matrix_dense_f32_device", "swne_nmf_matrix_info", "swne_nmf_fit",
+    "swne_nmf_set_matrix_csc_f32", "swne_nmf_set_matrix_csc_counts", "swne_nmf_set_matrix_dense_f32_device", "swne_nmf_matrix_info", "swne_nmf_fit",
     "swne_nmf_fit_dense_f64", "swne_nmf_fit_csc_f64", "swne_run_nmf", "swne_find_num_factors", "swne_nnlm", "swne_nnsvd_init", "swne_ica_init", "swne_zero_replace",
     "swne_sample_coords", "swne_factor_distance", "swne_recon_error",
 )
@@ -93,6 +94,7 @@ def load(build_if_missing=True):
     lib.swne_nmf_set_matrix_dense_f32.argtypes = [vp, fp, c_int, c_int]
     lib.swne_nmf_set_matrix_csc_f64.argtypes = [vp, ip, ip, dp, c_int, c_int]
     lib.swne_nmf_set_matrix_csc_f32.argtypes = [vp, ip, ip, fp, c_int, c_int]
+    lib.swne_nmf_set_matrix_csc_counts.argtypes = [vp, ip, ip, dp, c_int, c_int, dp, dp, c_int]
     lib.swne_nmf_set_matrix_dense_f32_device.argtypes = [vp, vp, c_int, c_int]
     lib.swne_nmf_matrix_info.argtypes = [vp, ip, ip, ctypes.POINTER(ctypes.c_longlong), dp, dp]
     lib.swne_nmf_fit.argtypes = [vp, ctypes.POINTER(Params), dp, dp, dp, dp, dp, dp, c_int, ctypes.POINTER(Result)]

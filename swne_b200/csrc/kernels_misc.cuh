@@ -58,7 +58,8 @@ __global__ void ingest_dense_kernel(const T *__restrict__ src, size_t src_ld, fl
 template <typename T>
 __global__ void ingest_csc_kernel(const int *__restrict__ p, const int *__restrict__ idx, const T *__restrict__ x,
                                   float *__restrict__ dst, size_t dst_ld, int n, int col0, int cols, int base,
-                                  MatStats *st)
+                                  MatStats *st, const double *__restrict__ cell_scale = nullptr,
+                                  const double *__restrict__ gene_scale = nullptr, int transform = 0)
 {
     __shared__ double scratch[32];
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -70,8 +71,15 @@ __global__ void ingest_csc_kernel(const int *__restrict__ p, const int *__restri
         const int b = p[col0 + j] - base, e = p[col0 + j + 1] - base;
         for (int q = b + lane; q < e; q += 32) {
             const int g = idx[q];
-            const double v = (double)x[q];
+            double v = (double)x[q];
             if (g < 0 || g >= n) { bad |= 4u; continue; }
+            // ScaleCounts fused into the upload (R/data_processing.R:275-307): depth scaling per cell (NormalizeCounts,
+            // :184), the variance scale factor per gene (:284-287), then log(x + 1) (:301) or Freeman-Tukey (:256,:299) on
+            // the stored entries only, as the reference transforms the @x slot
+            if (cell_scale) v *= cell_scale[col0 + j];
+            if (gene_scale) v *= gene_scale[g];
+            if (transform == 1) v = log1p(v);
+            else if (transform == 2) v = sqrt(v) + sqrt(v + 1.0);
             if (!(v >= 0.0)) bad |= (v < 0.0) ? 1u : 2u;
             if (isinf(v) || isinf((float)v)) bad |= 2u;      // also a finite double beyond the fp32 range
             // duplicate (i, j) entries add up, as in a dgCMatrix built by Matrix::sparseMatrix (the statistics below count

@@ -252,8 +252,10 @@ static void set_dense(swne_nmf_handle_s *h, const T *A, int n, int m)
 }
 
 template <typename T>
-static void set_csc(swne_nmf_handle_s *h, const int *p, const int *idx, const T *x, int n, int m)
+static void set_csc(swne_nmf_handle_s *h, const int *p, const int *idx, const T *x, int n, int m, const double *cell_scale = nullptr,
+                    const double *gene_scale = nullptr, int transform = 0)
 {
+    if (transform < 0 || transform > 2) FAIL(SWNE_ERR_BAD_ARG, "transform must be 0 (none), 1 (log) or 2 (ft)");
     if (!p || (!idx && p[m] > 0) || (!x && p[m] > 0)) FAIL(SWNE_ERR_BAD_ARG, "CSC slot pointer is NULL");
     if (p[0] != 0) FAIL(SWNE_ERR_BAD_ARG, "CSC column pointer must start at 0 (dgCMatrix @p)");
     for (int j = 0; j < m; ++j)
@@ -262,8 +264,17 @@ static void set_csc(swne_nmf_handle_s *h, const int *p, const int *idx, const T 
     CUDA_CHECK(cudaMemsetAsync(h->dA, 0, (size_t)m * h->ldA * sizeof(float), h->stream));
     DevBuf<int> dp, di;
     DevBuf<T> dx;
+    DevBuf<double> dcs, dgs;
     dp.reserve((size_t)m + 1);
     CUDA_CHECK(cudaMemcpyAsync(dp.p, p, ((size_t)m + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (cell_scale) {
+        dcs.reserve((size_t)m);
+        CUDA_CHECK(cudaMemcpyAsync(dcs.p, cell_scale, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    if (gene_scale) {
+        dgs.reserve((size_t)n);
+        CUDA_CHECK(cudaMemcpyAsync(dgs.p, gene_scale, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
     // upload the nonzeros in column chunks of <= 64M entries
     const long long chunk_nnz = 64ll << 20;
     int c0 = 0;
@@ -278,7 +289,8 @@ static void set_csc(swne_nmf_handle_s *h, const int *p, const int *idx, const T 
             const int cols = c1 - c0;
             const int grid = std::min((cols + 7) / 8, h->sm_count * 8);
             ingest_csc_kernel<T><<<grid, 256, 0, h->stream>>>(dp.p, di.p, dx.p, h->dA + (size_t)c0 * h->ldA, h->ldA, n, c0,
-                                                              cols, p[c0], h->dstats.p);
+                                                              cols, p[c0], h->dstats.p, cell_scale ? dcs.p : nullptr,
+                                                              gene_scale ? dgs.p : nullptr, transform);
             CUDA_CHECK(cudaGetLastError());
             CUDA_CHECK(cudaStreamSynchronize(h->stream));
         }
@@ -288,7 +300,7 @@ static void set_csc(swne_nmf_handle_s *h, const int *p, const int *idx, const T 
     check_stats(h);
     const double zeros = (double)n * (double)m - (double)h->stats.nnz;
     h->stats.klc += zeros * (TINY_NUM_D * log(TINY_NUM_D));
-    dp.release(); di.release(); dx.release();
+    dp.release(); di.release(); dx.release(); dcs.release(); dgs.release();
 }
 
 static void ensure_sparse(swne_nmf_handle_s *h)
@@ -943,7 +955,10 @@ static int nnlm_impl(swne_nmf_handle_s *h, int side, int k, const double *X, dou
     if (!X || !coef) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
     if (k < 1 || k > SWNE_MAX_K) FAIL(SWNE_ERR_BAD_ARG, "k must be in 1..%d", SWNE_MAX_K);
     if (side != 0 && side != 1) FAIL(SWNE_ERR_BAD_ARG, "side must be 0 (solve H) or 1 (solve W)");
-    if (side == 1 && h->nranks > 1) FAIL(SWNE_ERR_UNSUPPORTED, "nnlm side 1 is single-GPU only");
+    // cells sharded over ranks: side 0 is local (W replicated); side 1 sums H H' and A H' over the ranks (mse), every rank
+    // then solves all genes (identical results everywhere, like the W update of a fit)
+    if (side == 1 && h->nranks > 1 && loss != SWNE_LOSS_MSE)
+        FAIL(SWNE_ERR_UNSUPPORTED, "nnlm side 1 with mkl loss is single-GPU only");
     if (max_iter <= 0) max_iter = 10000;
     if (rel_tol <= 0) rel_tol = 1e-12;
     double pen[3] = {0, 0, 0};
@@ -971,10 +986,14 @@ static int nnlm_impl(swne_nmf_handle_s *h, int side, int k, const double *X, dou
         fixed = h->H.p; solve = h->Wt.p; fixed_rows = m; cols = n;
     }
     launch_gram(h, KPv, fixed, fixed_rows, h->G64w.p);
+    if (side == 1 && h->nranks > 1) allreduce(h, nullptr, 0, h->G64w.p, GS);
     if (loss == SWNE_LOSS_MSE) {
         launch_finalize_gram(h, k, KPv, h->G64w.p, h->pack.p, pen[0], pen[1]);
         if (side == 0) launch_contract_cells(h, KPv, fixed, h->C.p);
-        else launch_contract_genes(h, KPv, fixed, h->C.p);
+        else {
+            launch_contract_genes(h, KPv, fixed, h->C.p);
+            if (h->nranks > 1) allreduce(h, h->C.p, (size_t)n * KPv, nullptr, 0);
+        }
         launch_solve(h, k, KPv, solve, h->C.p, h->pack.p, (float)pen[2], cols, max_iter, (float)rel_tol,
                      &h->dscal.p->sweeps_h, nullptr);
     } else if (loss == SWNE_LOSS_MKL) {
@@ -1448,7 +1467,9 @@ static int find_num_factors_impl(swne_nmf_handle_s *h, const int *k_range, int n
 {
     if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident");
     if (!k_range || !k_err) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
-    if (nk < 3) FAIL(SWNE_ERR_BAD_ARG, "k.range sequence must have at least 3 values");
+    // R/nmf.R:158's rule belongs to the selection; a replica that only wants the errors of its share of k.range (k_pick and
+    // err_diff NULL) may pass fewer values
+    if (nk < 1 || (nk < 3 && (k_pick || err_diff))) FAIL(SWNE_ERR_BAD_ARG, "k.range sequence must have at least 3 values");
     if (loss_metric != SWNE_LOSS_MSE && loss_metric != SWNE_LOSS_MKL) FAIL(SWNE_ERR_BAD_ARG, "Invalid loss function");
     if (h->nranks > 1) FAIL(SWNE_ERR_UNSUPPORTED, "FindNumFactors runs its fits as replicas: call it on a single-GPU handle per k subset");
     for (int c = 0; c < nk; ++c)
@@ -1498,7 +1519,7 @@ static int find_num_factors_impl(swne_nmf_handle_s *h, const int *k_range, int n
             for (int c = 0; c < nk; ++c) {
                 p.k = k_range[c];
                 swne_nmf_result_t res;
-                const int rc = run_nmf_impl(h, &p, SWNE_INIT_RANDOM, seed + 7919ull * (uint64_t)(2 * c + which), nullptr, nullptr, nullptr, nullptr,
+                const int rc = run_nmf_impl(h, &p, SWNE_INIT_RANDOM, seed + 7919ull * (uint64_t)(2 * k_range[c] + which), nullptr, nullptr, nullptr, nullptr,
                                             nullptr, nullptr, 0, &res);
                 if (rc < 0) { rc_all = rc; throw ArgError{rc}; }
                 h->red.reserve(8);
@@ -1815,6 +1836,15 @@ int swne_nmf_set_matrix_csc_f32(swne_nmf_handle_t h, const int *p, const int *i,
     API_BEGIN
     HANDLE_GUARD(h);
     set_csc<float>(h, p, i, x, n, m);
+    return SWNE_OK;
+    API_END
+}
+int swne_nmf_set_matrix_csc_counts(swne_nmf_handle_t h, const int *p, const int *i, const double *x, int n, int m,
+                                   const double *cell_scale, const double *gene_scale, int transform)
+{
+    API_BEGIN
+    HANDLE_GUARD(h);
+    set_csc<double>(h, p, i, x, n, m, cell_scale, gene_scale, transform);
     return SWNE_OK;
     API_END
 }

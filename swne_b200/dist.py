@@ -47,3 +47,27 @@ def gather_H(H_local, group=None):
     parts = [None] * world
     td.all_gather_object(parts, np.ascontiguousarray(H_local), group=group)
     return np.concatenate(parts, axis=1)
+
+
+def find_num_factors_replicas(handle, A, k_range, loss="mse", max_iter=250, seed=0, group=None):
+    """FindNumFactors (R/nmf.R:157-205) over the ranks as replicas: its 2 x len(k_range) fits are independent, so every
+    rank holds the whole matrix on its own (communicator-free) handle and sweeps a strided subset of k_range; the permuted
+    matrix and the random starts are functions of (seed, k) only, so the errors are those of the single-GPU sweep.  No data-path collective; k_err is gathered on the host."""
+    import torch.distributed as td
+    rank, world = td.get_rank(group), td.get_world_size(group)
+    ks = [int(k) for k in k_range]
+    if len(ks) < 3:
+        raise ValueError("k.range sequence must have at least 3 values")
+    handle.set_matrix(A)
+    k_err = np.zeros((2, len(ks)))
+    mine = list(range(rank, len(ks), world))
+    if mine:
+        r = handle.find_num_factors([ks[c] for c in mine], loss=loss, max_iter=max_iter, seed=seed, errors_only=True)
+        k_err[:, mine] = r["k_err"]
+    parts = [None] * world
+    td.all_gather_object(parts, k_err, group=group)
+    k_err = np.sum(parts, axis=0)
+    err_del = k_err[:, :-1] - k_err[:, 1:]
+    diff = err_del[0] - err_del[1]
+    neg = np.nonzero(diff < 0)[0]
+    return dict(err=diff, k=ks[int(neg[0]) if neg.size else int(np.argmin(diff)) + 1], k_err=k_err)

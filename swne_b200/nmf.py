@@ -94,6 +94,31 @@ class NMFHandle:
                 C.check(self._lib.swne_nmf_set_matrix_dense_f64(self._h, C.dptr(Af), n, m))
         self.n, self.m = n, m
 
+    def set_matrix_counts(self, counts, depth=None, scale_factor=None, gene_scale=None, method="log"):
+        """Raw counts (scipy CSC, genes x cells) -> ScaleCounts(method = "log" | "ft" | "none") fused into the upload
+        (R/data_processing.R:275-307 without the batch correction; swne_nmf_set_matrix_csc_counts): the normalised matrix
+        never exists on the host.  depth = column sums of the FULL count matrix (default: of `counts`), scale_factor =
+        median depth by default, gene_scale = AdjustVariance's gsf per gene (None: adj.var = F)."""
+        if not _is_csc(counts):
+            raise ValueError("counts must be a scipy.sparse CSC matrix (dgCMatrix)")
+        if method not in C.TRANSFORM:
+            raise ValueError("method must be 'log', 'ft' or 'none'")
+        n, m = counts.shape
+        depth = np.asarray(counts.sum(axis=0)).ravel() if depth is None else np.asarray(depth, dtype=np.float64).ravel()
+        if depth.shape != (m,):
+            raise ValueError("depth must have one entry per cell")
+        sf = float(np.median(depth)) if scale_factor is None else float(scale_factor)
+        cs = np.ascontiguousarray(sf / depth, dtype=np.float64)
+        gs = None if gene_scale is None else np.ascontiguousarray(gene_scale, dtype=np.float64)
+        if gs is not None and gs.shape != (n,):
+            raise ValueError("gene_scale must have one entry per gene")
+        p = np.ascontiguousarray(counts.indptr, dtype=np.int32); i = np.ascontiguousarray(counts.indices, dtype=np.int32)
+        x = np.ascontiguousarray(counts.data, dtype=np.float64)
+        self._keep = None
+        C.check(self._lib.swne_nmf_set_matrix_csc_counts(self._h, C.iptr(p), C.iptr(i), C.dptr(x), n, m, C.dptr(cs),
+                                                         None if gs is None else C.dptr(gs), C.TRANSFORM[method]))
+        self.n, self.m = n, m
+
     def matrix_info(self):
         n, m = ctypes.c_int(), ctypes.c_int()
         nnz = ctypes.c_longlong()
@@ -187,11 +212,17 @@ class NMFHandle:
         C.check(self._lib.swne_ica_init(self._h, int(k), int(bool(ica_fast)), ctypes.c_uint64(int(seed)), C.dptr(W), C.dptr(H)))
         return W, H
 
-    def find_num_factors(self, k_range, loss="mse", max_iter=250, seed=0, engine="auto"):
+    def find_num_factors(self, k_range, loss="mse", max_iter=250, seed=0, engine="auto", errors_only=False):
         """FindNumFactors' sweep (R/nmf.R:157-205) on the resident matrix in one library call: permutation, random starts,
-        2 x len(k_range) fits and their errors all stay on the device (swne_find_num_factors)."""
+        2 x len(k_range) fits and their errors all stay on the device (swne_find_num_factors).  The permutation depends on
+        `seed` only and every fit's start on (seed, k) only, so a replica may sweep any subset of k.range (errors_only)."""
         ks = np.ascontiguousarray(k_range, dtype=np.int32)
-        k_err = np.zeros((2, len(ks))); diff = np.zeros(max(len(ks) - 1, 1)); pick = ctypes.c_int(0)
+        k_err = np.zeros((2, len(ks)))
+        if errors_only:
+            C.check(self._lib.swne_find_num_factors(self._h, C.iptr(ks), len(ks), C.LOSS[loss], int(max_iter), ctypes.c_uint64(int(seed)),
+                                                    C.ENGINE[engine], C.dptr(k_err), None, None))
+            return dict(k_err=k_err)
+        diff = np.zeros(max(len(ks) - 1, 1)); pick = ctypes.c_int(0)
         C.check(self._lib.swne_find_num_factors(self._h, C.iptr(ks), len(ks), C.LOSS[loss], int(max_iter), ctypes.c_uint64(int(seed)),
                                                 C.ENGINE[engine], C.dptr(k_err), ctypes.byref(pick), C.dptr(diff)))
         return dict(err=diff[:len(ks) - 1], k=int(pick.value), k_err=k_err)

@@ -74,6 +74,42 @@ for init in ("nnsvd", "ica", "random"):
         ok &= good
         print("%s device seed %s ranks=%d: W identical %s | final loss %.6e (1 GPU %.6e) | loss recomputed from W,H rel %.1e"
               % ("PASS" if good else "FAIL", init, world, same_w, t[-1], r1.target_loss[-1], abs(direct - t[-1]) / direct), flush=True)
+# ProjectFeatures on a sharded matrix (nnlm side 1, R/nmf.R:222-225): H H' and A H' are summed over the ranks
+from oracle import nnlm_ref
+n, m, k = 400, 1500, 6
+A = small_matrix(n, m, 5, 9)
+Hfix = np.random.default_rng(4).gamma(0.5, 1.0, size=(k, m))
+b = shard_bounds(m, world)
+h = NMFHandle(local)
+init_comm(h)
+h.set_matrix(np.asfortranarray(A[:, b[rank]:b[rank + 1]]))
+rW = h.nnlm(1, Hfix[:, b[rank]:b[rank + 1]], init=np.full((n, k), 0.005))["coefficients"]
+rH = h.nnlm(0, rW, init=np.full((k, b[rank + 1] - b[rank]), 0.005))["coefficients"]      # ProjectSamples: local
+Hs = gather_H(rH)
+h.close()
+if rank == 0:
+    refW = nnlm_ref(Hfix.T, A.T, init=np.full((k, n), 0.005))["coefficients"].T
+    refH = nnlm_ref(refW, A, init=np.full((k, m), 0.005))["coefficients"]
+    e_w, e_h = rel_fro(rW, refW), rel_fro(Hs, refH)
+    good = e_w < 1e-3 and e_h < 1e-3
+    ok &= good
+    print("%s nnlm on the sharded matrix ranks=%d: gene side (ProjectFeatures) W %.2e | cell side (ProjectSamples) H %.2e" % (
+        "PASS" if good else "FAIL", world, e_w, e_h), flush=True)
+
+# FindNumFactors as replicas: every rank sweeps a share of k.range on the whole matrix, no collective on the data path
+from swne_b200.dist import find_num_factors_replicas
+A = small_matrix(300, 500, 4, 21, density_scale=2.0)
+ks = [2, 3, 4, 5, 6, 8, 10]
+h = NMFHandle(local)
+rr = find_num_factors_replicas(h, A, ks, max_iter=60, seed=5)
+if rank == 0:
+    r1 = h.find_num_factors(ks, max_iter=60, seed=5)
+    e = max_rel(rr["k_err"], r1["k_err"])
+    good = e < 2e-3 and rr["k"] == r1["k"]       # same seeds; atomics reorder sums, and the 1e-4 stopping test sits on a threshold
+    ok &= good
+    print("%s FindNumFactors replicas ranks=%d: k_err vs the 1-GPU sweep %.2e, k = %d (1 GPU: %d)" % ("PASS" if good else "FAIL", world, e, rr["k"], r1["k"]),
+          flush=True)
+h.close()
 td.barrier()
 td.destroy_process_group()
 sys.exit(0 if ok else 1)

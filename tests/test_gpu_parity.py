@@ -253,6 +253,34 @@ def test_csc_input_equals_dense(handle):
     assert rel_fro(r32t["H"], rdd["H"]) < 1e-4 and rel_fro(r32t["W"], rdd["W"]) < 1e-4
 
 
+def test_counts_ingest_fuses_scale_counts(handle):
+    """swne_nmf_set_matrix_csc_counts: ScaleCounts (R/data_processing.R:275-307: depth scaling, gene variance factor, log or
+    Freeman-Tukey on the stored entries) applied during the upload gives the matrix the host-side transform gives."""
+    rng = np.random.default_rng(8)
+    n, m = 150, 260
+    full = rng.poisson(rng.gamma(0.3, 2.0, size=(400, m)))           # all genes: defines the depth
+    counts = scipy.sparse.csc_matrix(full[:n].astype(np.float64))   # the variable genes handed to RunNMF
+    depth = full.sum(axis=0).astype(np.float64)
+    gsf = rng.uniform(0.5, 2.0, size=n)
+    W0, H0 = rng.uniform(size=(n, 5)) * 0.01, rng.uniform(size=(5, m)) * 0.01
+    for method, f in (("log", np.log1p), ("ft", lambda v: np.sqrt(v) + np.sqrt(v + 1.0)), ("none", lambda v: v)):
+        for gs in (None, gsf):
+            norm = full[:n] / depth[None, :] * np.median(depth) * (1.0 if gs is None else gs[:, None])
+            ref = np.where(full[:n] > 0, f(norm), 0.0)                # the reference transforms the @x slot only
+            handle.set_matrix(ref)
+            info_r = handle.matrix_info()
+            rr = handle.fit(5, W0, H0, max_iter=8, trace=1, rel_tol=-1.0, engine="simt")
+            handle.set_matrix_counts(counts, depth=depth, gene_scale=gs, method=method)
+            info_c = handle.matrix_info()
+            rc = handle.fit(5, W0, H0, max_iter=8, trace=1, rel_tol=-1.0, engine="simt")
+            assert info_c["nnz"] == info_r["nnz"] == counts.nnz
+            within("fused ScaleCounts(%s%s): sum of A" % (method, ", gsf" if gs is not None else ""), abs(info_c["sum"] - info_r["sum"]) / info_r["sum"], 1e-7)
+            within("fused ScaleCounts(%s%s): loss trace" % (method, ", gsf" if gs is not None else ""), max_rel(rc["target_loss"], rr["target_loss"]), 1e-5)
+            within("fused ScaleCounts(%s%s): H" % (method, ", gsf" if gs is not None else ""), rel_fro(rc["H"], rr["H"]), 1e-4)
+    with pytest.raises(ValueError):
+        handle.set_matrix_counts(counts, method="logrank")
+
+
 def test_float32_and_device_resident_inputs(handle):
     import torch
     A = small_matrix(120, 200, 4, 8)
