@@ -171,7 +171,7 @@ def run_reference(args, cfg):
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "final_target_loss": loss, "input_generated_on": device,
             "wall_s": time.perf_counter() - t_all}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args, cfg):
@@ -337,7 +337,7 @@ def run_ours(args, cfg):
                 "roofline": roofline, "cpu_baseline": cpu, "time_to_tolerance": ttt, "time_to_tolerance_nnsvd_seed": ttt_nnsvd,
                 "timed_region": {"wall_s_incl_upload_download": wall, "loop_ms_cuda_events_max_over_ranks": loop_ms,
                                  "final_target_loss": float(r.target_loss[-1])}}
-        print(json.dumps(line))
+        emit(line)
     h.close()
     if world > 1:
         td.destroy_process_group()
@@ -411,7 +411,7 @@ def run_cfg5(args):
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                  "sample": "EXTRAPOLATED: first %d of %d cells (dense fp64), value scaled by %d/%d; %.1f s timed" % (cells, m, cells, m, dt)},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
     torch.cuda.set_device(local)
     if world > 1:
@@ -516,13 +516,30 @@ def run_cfg5(args):
                 "run": {"cells_this_rank": m_loc, "nnz_this_rank": int(info["nnz"]), "nnz_bounds": [int(x) for x in b], "engine": pr.options["engine"],
                         "csc_ingest_s": ingest_s, "parallelism": "cells sharded by equal nnz over %d GPU(s)" % world},
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(r.stats["gpu_launches"]), "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit(line)
     h.close()
     if world > 1:
         td.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line, on the process's real stdout (everything else this process or its libraries print goes to stderr)"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # NCCL prints its version banner on stdout when the first communicator is created: keep stdout for the JSON line
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
