@@ -61,6 +61,9 @@ struct TcxParams {
     const uint8_t *Himg;   // [tiles_total][TCX_H_TILE] split images of H (genes kernel)
     const int *x_exp;      // device: exponent the W (cells kernel) or H (genes kernel) operand was scaled by
     int a_exp;
+    int regions;           // genes kernel: accumulator regions in TMEM.  2 (512 columns): the drain of one gene sub-pass overlaps the
+                           // MMAs of the next; 1 (256 columns): leaves TMEM for two co-resident solve CTAs (slab pipeline), the
+                           // drain bubble is negligible when a sub-pass covers many cells
 };
 
 __device__ __forceinline__ void tcx_my_tiles(int tiles_total, int tile0, int &t_begin, int &t_count)
@@ -209,6 +212,8 @@ tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     int t_begin, n_tiles;
     tcx_my_tiles(p.tiles_total, p.tile0, t_begin, n_tiles);
     const int n_pass = (p.n_mtiles + TCX_MT_PER_PASS - 1) / TCX_MT_PER_PASS;
+    const int regions = p.regions;
+    const uint32_t tmem_cols = regions == 2 ? 512u : 256u;
 
     const uint32_t bar0 = sbase + TcxSmemGenes::bars;
     auto FULL = [&](int s) { return bar0 + 8u * s; };
@@ -230,7 +235,7 @@ tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -238,7 +243,10 @@ tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    auto tmem_d = [&](int u) { return tmem + (u & 1) * (TCX_MT_PER_PASS * TCX_KP); };
+    // unit u accumulates into region u % regions; its barriers' phase advances every `regions` units
+    auto reg_of = [&](int u) { return regions == 2 ? (u & 1) : 0; };
+    auto ph_of = [&](int u) { return regions == 2 ? ((u >> 1) & 1) : (u & 1); };
+    auto tmem_d = [&](int u) { return tmem + reg_of(u) * (TCX_MT_PER_PASS * TCX_KP); };
 
     if (warp == 0) {
         int stage = 0, phase = 0;
@@ -275,8 +283,8 @@ tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
             int stage = 0, phase = 0, use = 0;
             for (int u = 0; u < n_pass; ++u) {
                 const int mt0 = u * TCX_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TCX_MT_PER_PASS);
-                const int r = u & 1;
-                mbar_wait(DEMPTY(r), ((u >> 1) & 1) ^ 1);
+                const int r = reg_of(u);
+                mbar_wait(DEMPTY(r), ph_of(u) ^ 1);
                 tc_fence_after();
                 for (int i = 0; i < n_tiles; ++i, ++use) {
                     const int hb = use & 1;
@@ -335,7 +343,7 @@ tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
         const float descale = exp2f(-(float)(p.a_exp + *p.x_exp));
         for (int u = 0; u < n_pass; ++u) {
             const int mt0 = u * TCX_MT_PER_PASS, mt1 = min(p.n_mtiles, mt0 + TCX_MT_PER_PASS);
-            mbar_wait(DFULL(u & 1), (u >> 1) & 1);
+            mbar_wait(DFULL(reg_of(u)), ph_of(u));
             tc_fence_after();
             for (int mt = mt0; mt < mt1; ++mt) {
                 const int gene = mt * 128 + quarter * 32 + lane;
@@ -354,14 +362,14 @@ tcx_genes_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                 }
             }
             tc_fence_before();
-            mbar_arrive(DEMPTY(u & 1));
+            mbar_arrive(DEMPTY(reg_of(u)));
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
     }
 }
 
@@ -695,6 +703,7 @@ static inline TcxParams tcx_params(const TcxState &x, const TcMatrix &tc, int ld
     p.tiles_total = ntiles; p.tile0 = tile0;
     p.C = nullptr; p.B = nullptr; p.Himg = x.Himg; p.x_exp = nullptr;
     p.a_exp = tc.a_exp;
+    p.regions = 2;
     return p;
 }
 
@@ -718,7 +727,7 @@ static inline void tcx_cells_slab(TcxState &x, const TcMatrix &tc, int ld, float
 // B[n][ld] += A' H over the cells of the slab (B is NOT zeroed here).  slot: which pair of x.ints holds this slab's max / exponent
 // (slabs in flight on different streams use different slots: 0..3).  launches: 3
 static inline void tcx_genes_slab(TcxState &x, const TcMatrix &tc, int ld, const float *H, float *B, int tile0, int ntiles, int slot,
-                                  cudaStream_t st)
+                                  cudaStream_t st, int regions = 2)
 {
     int *mx = x.ints + 2 + 2 * slot;
     const int cell0 = tile0 * TC_TILE, cells = std::min(tc.m - cell0, ntiles * TC_TILE);
@@ -726,7 +735,7 @@ static inline void tcx_genes_slab(TcxState &x, const TcMatrix &tc, int ld, const
     tc_absmax_kernel<<<148, 256, 0, st>>>(H + (size_t)cell0 * ld, (size_t)cells * ld, mx);
     tcx_split_h_kernel<<<ntiles, 128, 0, st>>>(H, ld, tc.m, mx, mx + 1, x.Himg, tile0);
     TcxParams p = tcx_params(x, tc, ld, tile0, ntiles);
-    p.B = B; p.x_exp = mx + 1;
+    p.B = B; p.x_exp = mx + 1; p.regions = regions;
     const int grid = std::min(tc.sm_count, ntiles);
     tcx_genes_kernel<<<grid, TCX_THREADS_GENES, TcxSmemGenes::total + 1024, st>>>(tc.map_ahi, tc.map_alo, p);
     CUDA_CHECK(cudaGetLastError());

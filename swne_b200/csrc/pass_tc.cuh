@@ -539,18 +539,17 @@ __device__ __forceinline__ bool tc_last_cta(int *counter, int *s_flag)
 // The W side of one outer iteration in ONE kernel (one CTA of 4 warps per 128 genes):
 //   solve the 128 columns with the tensor-core sweeps (X [cols][32] in/out, C = A H' the contraction, pack = GramPack of
 //   H H', c_gram its triangular coefficients), write W, add this tile's W'W, column sums and max into the device state,
-//   zero the consumed rows of C (the pass accumulates the next A H' into them), and let the last CTA build the GramPack
-//   of the H update and the split-fp16 image of W for the pass (exact power-of-two scale from the global max: 96 K
-//   entries, a few microseconds on one SM -- a scale guessed from the previous iteration would cost the small entries
-//   of W five bits, measured as 2.5x the W/H error).
-// Replaces, per iteration: finalize_gram, tc_wsolve, zero_fill, gram(W), finalize_gram, absmax, split_w and three
-// memsets (round 1: 0.15 ms of serial launches).
+//   zero the consumed rows of C (the pass accumulates the next A H' into them).  The GramPack of the H update and the
+//   split-fp16 image of W (exact power-of-two scale from the global max -- a scale guessed from the previous iteration would
+//   cost the small entries of W five bits, measured as 2.5x the W/H error) are built by tc_wfinish_kernel right behind it.
+// Together the two replace, per iteration: finalize_gram, tc_wsolve, zero_fill, gram(W), finalize_gram, absmax, split_w and
+// three memsets (round 1: 0.15 ms of serial launches).
 // ------------------------------------------------------------------------------------------------
 struct TcWsideParams {
     float *X;                 // Wt [n][32]
     float *C;                 // B [n][32] = A H' (all-reduced); rows zeroed after they are read
     const float *pack;        // GramPack of H H' (alpha penalties)
-    float *pack_next;         // GramPack of W'W (beta penalties), written by the last CTA
+    float *pack_next;         // GramPack of W'W (beta penalties), written by CTA 0 of tc_wfinish_kernel
     double pen_next0, pen_next1;
     float l1;
     int k, cols, n_pad, max_iter;

@@ -14,6 +14,7 @@
 #include <chrono>
 #include <functional>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -148,8 +149,9 @@ struct swne_nmf_handle_s {
     size_t pinned_bytes = 0;
     swne_nmf_progress_fn progress = nullptr;
     void *progress_user = nullptr;
-    cudaStream_t aux[2] = {nullptr, nullptr};   // slab pipeline of the wide engine: solves of one slab under the contraction of the next
-    cudaEvent_t ev_ready = nullptr, ev_done[2] = {nullptr, nullptr};
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // slab pipeline of the wide engine: [0] C = A W, [1] solves (low priority), [2] A H'
+    cudaEvent_t ev_ready = nullptr, ev_done[3] = {nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_slab;           // [2 s] contraction of slab s done, [2 s + 1] its solve done
     int kl_flags = 0;                // KL_L2_LATE when the fit asks for the alternative reading of NNLM's KL step
     int last_KPv = 0;                // row stride of Wt / H as the last fit left them on the device
 };
@@ -641,11 +643,16 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     }
 
     const bool tcx_solve_simt = getenv("SWNE_TCX_SOLVE_SIMT") != nullptr;   // debug knob, read once per fit
+    const bool slab_timeline = getenv("SWNE_TCX_TIMELINE") != nullptr;
+    const bool three_streams = getenv("SWNE_TCX_STREAMS2") == nullptr;     // debug knob: both contractions on one stream
     // slabs of the wide engine's H update: enough tiles per slab to keep every SM's contraction CTA busy (>= 4 tiles per SM)
     int tcx_slabs = 1;
     if (tcx) {
         const char *e = getenv("SWNE_TCX_SLABS");
-        tcx_slabs = e ? atoi(e) : std::max(1, std::min(8, h->tcx.tiles_total / (h->sm_count * 4)));
+        // measured (round 2, three streams): 650 k cells 1 / 2 / 3 / 4 / 8 slabs = 4.92 / 4.39 / 4.27 / 4.31 / 4.51 ms per iteration:
+        // slabs of about 10 tiles per contraction CTA
+        const int tiles = h->tcx.tiles_total;
+        tcx_slabs = e ? atoi(e) : (tiles >= h->sm_count * 8 ? std::max(2, std::min(8, (2 * tiles + h->sm_count * 21 / 2) / (h->sm_count * 21))) : 1);
         if (h->nranks > 1) {
             // every rank must take the same path (the collectives differ): the smallest count wins
             double v = -(double)tcx_slabs;
@@ -824,28 +831,82 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
                 tcx_split_w(h->tcx, h->tc, KPv, h->Wt.p, st);
                 tcx_solve_prepare(h->tcx, h->pack.p, KPv, st);
                 CUDA_CHECK(cudaMemsetAsync(h->B.p, 0, sizeof(float) * (size_t)n * KPv, st));
+                dev_zero(h->G64h.p, sizeof(double) * (size_t)GS, st);
                 CUDA_CHECK(cudaEventRecord(h->ev_ready, st));
                 const int tiles = h->tcx.tiles_total, per = (tiles + tcx_slabs - 1) / tcx_slabs;
-                for (int sl = 0; sl < tcx_slabs; ++sl) {
-                    const int t0 = sl * per, nt = std::min(per, tiles - t0);
-                    if (nt <= 0) break;
-                    cudaStream_t q = h->aux[sl & 1];
-                    if (sl < 2) CUDA_CHECK(cudaStreamWaitEvent(q, h->ev_ready, 0));
-                    const size_t c0 = (size_t)t0 * TC_TILE;
-                    const int cells = std::min(m - (int)c0, nt * TC_TILE);
-                    tcx_cells_slab(h->tcx, h->tc, KPv, h->C.p, t0, nt, q);
-                    tcx_solve_run(h->tcx, h->H.p + c0 * KPv, h->C.p + c0 * KPv, h->pack.p, KPv, (float)p.beta[2], k, cells, p.inner_max_iter,
-                                  inner_tol, &h->dscal.p->sweeps_h, &h->dscal.p->loss_part, q);
-                    tcx_genes_slab(h->tcx, h->tc, KPv, h->H.p, h->B.p, t0, nt, sl & 3, q);
+                const int n_sl = (tiles + per - 1) / per;
+                while ((int)h->ev_slab.size() < 2 * n_sl) {
+                    cudaEvent_t e;
+                    CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    h->ev_slab.push_back(e);
                 }
-                for (int q = 0; q < 2; ++q) {
+                cudaStream_t qc = h->aux[0], qs = h->aux[1];
+                CUDA_CHECK(cudaStreamWaitEvent(qc, h->ev_ready, 0));
+                CUDA_CHECK(cudaStreamWaitEvent(qs, h->ev_ready, 0));
+                // SWNE_TCX_TIMELINE: event marks around every kernel of iteration 3 (debug: where the two streams overlap)
+                std::vector<std::pair<std::string, cudaEvent_t>> marks;
+                const bool tl_on = slab_timeline && i == 3;
+                auto mark = [&](cudaStream_t q, const char *what, int sl) {
+                    if (!tl_on) return;
+                    cudaEvent_t e;
+                    cudaEventCreate(&e);
+                    cudaEventRecord(e, q);
+                    marks.emplace_back(std::string(what) + " " + std::to_string(sl), e);
+                };
+                mark(qc, "begin", 0);
+                auto slab = [&](int sl, int &t0, int &nt, size_t &c0, int &cells) {
+                    t0 = sl * per; nt = std::min(per, tiles - t0);
+                    c0 = (size_t)t0 * TC_TILE; cells = std::min(m - (int)c0, nt * TC_TILE);
+                };
+                auto enqueue_cells = [&](int sl) {
+                    int t0, nt, cells; size_t c0;
+                    slab(sl, t0, nt, c0, cells);
+                    mark(qc, "cells  start", sl);
+                    tcx_cells_slab(h->tcx, h->tc, KPv, h->C.p, t0, nt, qc);
+                    mark(qc, "cells  end  ", sl);
+                    CUDA_CHECK(cudaEventRecord(h->ev_slab[2 * sl], qc));
+                    // the solve of the slab, on the low-priority stream
+                    CUDA_CHECK(cudaStreamWaitEvent(qs, h->ev_slab[2 * sl], 0));
+                    mark(qs, "solve  start", sl);
+                    tcx_solve_run(h->tcx, h->H.p + c0 * KPv, h->C.p + c0 * KPv, h->pack.p, KPv, (float)p.beta[2], k, cells, p.inner_max_iter,
+                                  inner_tol, &h->dscal.p->sweeps_h, &h->dscal.p->loss_part, qs);
+                    mark(qs, "solve  end  ", sl);
+                    CUDA_CHECK(cudaEventRecord(h->ev_slab[2 * sl + 1], qs));
+                    // H H' and the row sums of this slab's H (fp64 atomics into the zeroed sums), beside the next contraction
+                    ops_of(KPv).gram(h->H.p + c0 * KPv, cells, h->G64h.p, h->G64h.p + KPv * KPv, qs);
+                    CUDA_CHECK(cudaGetLastError());
+                    mark(qs, "gramH  end  ", sl);
+                };
+                // contraction stream: C(0), C(1), then A H'(s) as soon as solve(s) is done, each followed by C(s + 2): the stream
+                // always has HBM-bound work queued while the solves of the two slabs in between run beside it
+                // (three_streams: A H' on its own stream, every C = A W queued up front -- the two contractions then share the SMs)
+                cudaStream_t qg = three_streams ? h->aux[2] : qc;
+                if (three_streams) CUDA_CHECK(cudaStreamWaitEvent(qg, h->ev_ready, 0));
+                const int ahead = three_streams ? n_sl : 2;
+                for (int sl = 0; sl < std::min(ahead, n_sl); ++sl) enqueue_cells(sl);
+                for (int sl = 0; sl < n_sl; ++sl) {
+                    int t0, nt, cells; size_t c0;
+                    slab(sl, t0, nt, c0, cells);
+                    CUDA_CHECK(cudaStreamWaitEvent(qg, h->ev_slab[2 * sl + 1], 0));
+                    mark(qg, "genes  start", sl);
+                    tcx_genes_slab(h->tcx, h->tc, KPv, h->H.p, h->B.p, t0, nt, sl & 3, qg, 1);
+                    mark(qg, "genes  end  ", sl);
+                    if (sl + ahead < n_sl) enqueue_cells(sl + ahead);
+                }
+                for (int q = 0; q < 3; ++q) {
                     CUDA_CHECK(cudaEventRecord(h->ev_done[q], h->aux[q]));
                     CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_done[q], 0));
                 }
-                prof.end(0, 2 + 5 * tcx_slabs);
-                prof.begin(4);
-                launch_gram(h, KPv, h->H.p, m, h->G64h.p);
-                prof.end(4, 1);
+                if (tl_on) {
+                    CUDA_CHECK(cudaStreamSynchronize(st));
+                    for (size_t q = 1; q < marks.size(); ++q) {
+                        float ms = 0.f;
+                        cudaEventElapsedTime(&ms, marks[0].second, marks[q].second);
+                        fprintf(stderr, "[tcx timeline] %-16s %8.3f ms\n", marks[q].first.c_str(), ms);
+                    }
+                    for (auto &mk : marks) cudaEventDestroy(mk.second);
+                }
+                prof.end(0, 3 + 6 * tcx_slabs);
                 if (h->nranks > 1) {
                     prof.begin(6);
                     allreduce(h, h->B.p, (size_t)n * KPv, h->G64h.p, GS, &h->dscal.p->loss_part, 1);
@@ -1724,8 +1785,12 @@ int swne_nmf_create(swne_nmf_handle_t *out, int device)
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    for (int q = 0; q < 2; ++q) {
-        CUDA_CHECK(cudaStreamCreateWithFlags(&h->aux[q], cudaStreamNonBlocking));
+    // aux[0] and aux[2] carry the HBM-bound contractions of the slab pipeline at high priority, aux[1] the latency-bound solves at
+    // low priority: when an SM frees resources the block scheduler places a waiting contraction CTA before more solve CTAs
+    int prio_least = 0, prio_greatest = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    for (int q = 0; q < 3; ++q) {
+        CUDA_CHECK(cudaStreamCreateWithPriority(&h->aux[q], cudaStreamNonBlocking, q == 1 ? prio_least : prio_greatest));
         CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_done[q], cudaEventDisableTiming));
     }
     CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
@@ -1749,9 +1814,10 @@ int swne_nmf_destroy(swne_nmf_handle_t h)
     h->Wt.release(); h->H.release(); h->C.release(); h->B.release(); h->G.release(); h->pack.release();
     h->G64w.release(); h->G64h.release(); h->stage.release(); h->dstats.release(); h->dscal.release(); h->red.release(); h->flags.release();
     if (h->pinned) cudaFreeHost(h->pinned);
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < 3; ++q) {
         if (h->aux[q]) { cudaStreamSynchronize(h->aux[q]); cudaStreamDestroy(h->aux[q]); }
         if (h->ev_done[q]) cudaEventDestroy(h->ev_done[q]);
+        if (q == 0) for (cudaEvent_t e : h->ev_slab) cudaEventDestroy(e);
     }
     if (h->ev_ready) cudaEventDestroy(h->ev_ready);
     cudaStreamDestroy(h->stream);

@@ -635,6 +635,15 @@ def test_debug_variants_of_the_wide_engine_and_the_seed(handle):
         del os.environ["SWNE_TCX_SOLVE_SIMT"]
     assert r.options["engine"] == "tc"
     _check_against(r, ref)
+    # the slab pipeline of the wide engine (contractions on a high-priority stream, solves on a low-priority one, one
+    # accumulator region in the second contraction) is chosen by size; forced here on 8 tiles cut into 3 and 8 slabs
+    for slabs in ("3", "8"):
+        os.environ["SWNE_TCX_SLABS"] = slabs
+        try:
+            rs = handle.fit(36, W0, H0, max_iter=8, trace=1, rel_tol=-1.0, engine="tc")
+        finally:
+            del os.environ["SWNE_TCX_SLABS"]
+        _check_against(rs, ref)
     # the un-fused kernels also serve k <= 32 (their job when a shard is too long for the fused pass)
     W0s, H0s = seeded_init(A, 16, 42)
     refs = nnmf_ref(A, 16, W0s, H0s, max_iter=8, trace=1, rel_tol=-1.0)
