@@ -332,7 +332,9 @@ def run_ours(args, cfg):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": workload_config(n, m, k),
-                "run": {"cells_per_gpu": m_loc, "engine": engine, "parallelism": "cells sharded over %d GPU(s)" % world},
+                "run": {"cells_per_gpu": m_loc, "engine": engine, "parallelism": "cells sharded over %d GPU(s)" % world,
+                        "exchange": (None if world == 1 else ("NVLink peer memory (one-shot all-reduce kernels)" if h.comm_info()["peer_exchange"]
+                                                               else "NCCL all-reduce"))},
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(r.stats["gpu_launches"]),
                 "roofline": roofline, "cpu_baseline": cpu, "time_to_tolerance": ttt, "time_to_tolerance_nnsvd_seed": ttt_nnsvd,
                 "timed_region": {"wall_s_incl_upload_download": wall, "loop_ms_cuda_events_max_over_ranks": loop_ms,

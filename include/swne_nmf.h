@@ -118,6 +118,10 @@ int swne_nmf_set_progress(swne_nmf_handle_t h, swne_nmf_progress_fn fn, void *us
  * other ranks by the caller (torch.distributed / MPI / R parallel). */
 int swne_nmf_comm_unique_id(void *id128);
 int swne_nmf_comm_init(swne_nmf_handle_t h, const void *id128, int rank, int nranks);
+/* rank / number of ranks of the handle, and whether the per-iteration sums of the fused engine travel over NVLink peer
+ * memory (1: CUDA IPC mappings of every rank's exchange region, set up at the first sharded fit; 0: NCCL all-reduces --
+ * no peer access, SWNE_PEER_XCHG=0, or no sharded fit yet) */
+int swne_nmf_comm_info(swne_nmf_handle_t h, int *rank, int *nranks, int *peer_exchange);
 
 /* ---- the data matrix (this rank's cells).  m is the LOCAL number of cells. Values must be finite and
  * >= 0 (RunNMF R/nmf.R:98,106). The matrix stays resident until replaced, so several fits

@@ -32,7 +32,7 @@ PROF_NAMES = ("contract_H_or_pass", "solve_H", "contract_W", "solve_W", "gram_lo
 # every symbol include/swne_nmf.h declares (tests check the .so exports all of them)
 SYMBOLS = (
     "swne_nmf_last_error", "swne_nmf_abi_version", "swne_nmf_device_count", "swne_nmf_default_params",
-    "swne_nmf_create", "swne_nmf_destroy", "swne_nmf_set_progress", "swne_nmf_comm_unique_id", "swne_nmf_comm_init",
+    "swne_nmf_create", "swne_nmf_destroy", "swne_nmf_set_progress", "swne_nmf_comm_unique_id", "swne_nmf_comm_init", "swne_nmf_comm_info",
     "swne_nmf_set_matrix_dense_f64", "swne_nmf_set_matrix_dense_f32", "swne_nmf_set_matrix_csc_f64",
     "swne_nmf_set_matrix_csc_f32", "swne_nmf_set_matrix_csc_counts", "swne_nmf_set_matrix_dense_f32_device", "swne_nmf_matrix_info", "swne_nmf_fit",
     "swne_nmf_fit_dense_f64", "swne_nmf_fit_csc_f64", "swne_run_nmf", "swne_find_num_factors", "swne_nnlm", "swne_nnsvd_init", "swne_ica_init", "swne_zero_replace",
@@ -90,6 +90,7 @@ def load(build_if_missing=True):
     lib.swne_nmf_set_progress.argtypes = [vp, PROGRESS_FN, vp]
     lib.swne_nmf_comm_unique_id.argtypes = [vp]
     lib.swne_nmf_comm_init.argtypes = [vp, vp, c_int, c_int]
+    lib.swne_nmf_comm_info.argtypes = [vp, ip, ip, ip]
     lib.swne_nmf_set_matrix_dense_f64.argtypes = [vp, dp, c_int, c_int]
     lib.swne_nmf_set_matrix_dense_f32.argtypes = [vp, fp, c_int, c_int]
     lib.swne_nmf_set_matrix_csc_f64.argtypes = [vp, ip, ip, dp, c_int, c_int]

@@ -24,6 +24,7 @@
 #include "pass_tc.cuh"
 #include "contract_tc.cuh"
 #include "seed.cuh"
+#include "peer_xchg.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 namespace swne {
@@ -55,6 +56,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -77,6 +79,7 @@ static void load_nccl()
     LOADSYM(CommInitRank, "ncclCommInitRank");
     LOADSYM(CommDestroy, "ncclCommDestroy");
     LOADSYM(AllReduce, "ncclAllReduce");
+    LOADSYM(AllGather, "ncclAllGather");
     LOADSYM(GroupStart, "ncclGroupStart");
     LOADSYM(GroupEnd, "ncclGroupEnd");
     LOADSYM(GetErrorString, "ncclGetErrorString");
@@ -151,6 +154,7 @@ struct swne_nmf_handle_s {
     void *progress_user = nullptr;
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // slab pipeline of the wide engine: [0] C = A W, [1] solves (low priority), [2] A H'
     cudaEvent_t ev_ready = nullptr, ev_done[3] = {nullptr, nullptr, nullptr};
+    swne::PeerXchg xchg;                               // NVLink peer-memory exchange of the fused engine's per-iteration sums
     std::vector<cudaEvent_t> ev_slab;           // [2 s] contraction of slab s done, [2 s + 1] its solve done
     int kl_flags = 0;                // KL_L2_LATE when the fit asks for the alternative reading of NNLM's KL step
     int last_KPv = 0;                // row stride of Wt / H as the last fit left them on the device
@@ -510,6 +514,93 @@ static void allreduce(swne_nmf_handle_s *h, float *f, size_t nf, double *d, size
     NCCL_CHECK(g_nccl.GroupEnd());
 }
 
+// ---- peer-memory exchange (peer_xchg.cuh): set-up is a collective over the handle's communicator
+static void xchg_release(swne_nmf_handle_s *h, bool collective)
+{
+    PeerXchg &x = h->xchg;
+    if (!x.region && x.opened.empty()) { x.ready = false; return; }
+    cudaStreamSynchronize(h->stream);
+    for (void *q : x.opened) cudaIpcCloseMemHandle(q);
+    x.opened.clear();
+    if (collective && h->comm && h->nranks > 1) {
+        // nobody may free a region a peer still has mapped: barrier between closing and freeing
+        h->red.reserve(8);
+        cudaMemsetAsync(h->red.p, 0, sizeof(double), h->stream);
+        g_nccl.AllReduce(h->red.p, h->red.p, 1, ncclFloat64, ncclSum, h->comm, h->stream);
+        cudaStreamSynchronize(h->stream);
+    }
+    if (x.region) cudaFree(x.region);
+    if (x.peers_dev) cudaFree(x.peers_dev);
+    x.region = nullptr; x.peers_dev = nullptr; x.ready = false; x.payload = 0; x.epoch = 0;
+}
+
+// returns true when every rank mapped every other rank's region (all ranks return the same answer)
+static bool xchg_setup(swne_nmf_handle_s *h, size_t payload)
+{
+    PeerXchg &x = h->xchg;
+    if (x.tried && x.payload == payload) return x.ready;
+    xchg_release(h, true);
+    x.tried = true; x.payload = payload; x.nranks = h->nranks; x.rank = h->rank;
+    cudaStream_t st = h->stream;
+    const int R = h->nranks;
+    x.flags_off = 2 * (size_t)R * payload;
+    x.total = x.flags_off + 2 * (size_t)R * 8 + 64;
+    int ok = 1;
+    if (getenv("SWNE_PEER_XCHG") && atoi(getenv("SWNE_PEER_XCHG")) == 0) ok = 0;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok) {
+        if (cudaMalloc(&x.region, x.total) != cudaSuccess) { cudaGetLastError(); x.region = nullptr; ok = 0; }
+        else {
+            CUDA_CHECK(cudaMemsetAsync(x.region, 0, x.total, st));
+            if (cudaIpcGetMemHandle(&mine, x.region) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        }
+    }
+    // swap the handles (64 bytes each) and the "I could allocate" bits
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    DevBuf<unsigned char> hb;
+    hb.reserve(rec * R);
+    std::vector<unsigned char> host(rec * R, 0);
+    memcpy(host.data() + rec * h->rank, &mine, sizeof(mine));
+    host[rec * h->rank + sizeof(mine)] = (unsigned char)ok;
+    CUDA_CHECK(cudaMemcpyAsync(hb.p + rec * h->rank, host.data() + rec * h->rank, rec, cudaMemcpyHostToDevice, st));
+    NCCL_CHECK(g_nccl.AllGather(hb.p + rec * h->rank, hb.p, rec, ncclUint8, h->comm, st));
+    CUDA_CHECK(cudaMemcpyAsync(host.data(), hb.p, rec * R, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int r = 0; r < R; ++r) ok &= host[rec * r + sizeof(mine)];
+    std::vector<uint8_t *> peers(R, nullptr);
+    if (ok) {
+        for (int r = 0; r < R && ok; ++r) {
+            if (r == h->rank) { peers[r] = x.region; continue; }
+            cudaIpcMemHandle_t mh;
+            memcpy(&mh, host.data() + rec * r, sizeof(mh));
+            void *q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, mh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            x.opened.push_back(q);
+            peers[r] = (uint8_t *)q;
+        }
+    }
+    // every rank must have mapped every region (this all-reduce is also the barrier behind which the zeroed flags are safe to use)
+    double v = ok ? 1.0 : 0.0;
+    h->red.reserve(8);
+    CUDA_CHECK(cudaMemcpyAsync(h->red.p, &v, sizeof(double), cudaMemcpyHostToDevice, st));
+    NCCL_CHECK(g_nccl.AllReduce(h->red.p, h->red.p, 1, ncclFloat64, ncclMin, h->comm, st));
+    CUDA_CHECK(cudaMemcpyAsync(&v, h->red.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (v < 0.5) {
+        const size_t keep = x.payload;
+        xchg_release(h, true);
+        x.payload = keep; x.tried = true; x.ready = false;
+        return false;
+    }
+    CUDA_CHECK(cudaMalloc(&x.peers_dev, sizeof(uint8_t *) * R));
+    CUDA_CHECK(cudaMemcpyAsync(x.peers_dev, peers.data(), sizeof(uint8_t *) * R, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    x.epoch = 0;
+    x.ready = true;
+    return true;
+}
+
 static void validate_init(const double *x, size_t len, const char *name)
 {
     for (size_t i = 0; i < len; ++i)
@@ -529,6 +620,7 @@ struct FitEvents {
 struct HostTrace {
     FitScalars sc;
     int tc_overflow;   // the tcgen05 engine's "a scaled H entry left the fp16 range" flag
+    int xchg_err;      // peer-memory exchange: a rank's flag did not arrive in time
     double G64w[SWNE_MAX_K * SWNE_MAX_K + SWNE_MAX_K];  // W'W and column sums of W
     double G64h[SWNE_MAX_K * SWNE_MAX_K + SWNE_MAX_K];  // H H' and row sums of H (global)
 };
@@ -671,6 +763,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     const bool mse = p.loss == SWNE_LOSS_MSE;
 
     bool have_B = false;  // the tcgen05 pass leaves A H' of the *new* H behind for the next W update
+    bool peer_x = false;  // fused engine, several ranks: the per-iteration sums go over NVLink peer memory
     // fused engine: fp64 sums and GramPacks live in the engine's double-buffered state (half = iteration parity)
     auto g64w_of = [&](int it) { return fused ? h->tc.G64w + (size_t)(it & 1) * GS : h->G64w.p; };
     auto g64h_of = [&](int it) { return fused ? h->tc.G64h + (size_t)(it & 1) * GS : h->G64h.p; };
@@ -683,8 +776,16 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
                 h->dscal.p, st);
         prof.end(0, 1 + tc_pass_launches(1));
         if (h->nranks > 1) {
-            allreduce(h, h->B.p, (size_t)n * KPv, g64h_of(1), GS);
-            launch_finalize_gram(h, k, KPv, g64h_of(1), h->tc.packH, p.alpha[0], p.alpha[1]);
+            // the sums of the ranks: over NVLink peer memory (peer_xchg.cuh) when every rank could map every other's region,
+            // else three grouped NCCL all-reduces and the finalize kernel
+            peer_x = xchg_setup(h, xchg_payload_bytes((size_t)n * KPv, (size_t)GS));
+            if (peer_x)
+                xchg_launch(h->xchg, h->B.p, (size_t)n * KPv, g64h_of(1), (size_t)GS, nullptr, h->tc.packH, k, p.alpha[0], p.alpha[1],
+                            h->sm_count, st);
+            else {
+                allreduce(h, h->B.p, (size_t)n * KPv, g64h_of(1), GS);
+                launch_finalize_gram(h, k, KPv, g64h_of(1), h->tc.packH, p.alpha[0], p.alpha[1]);
+            }
         }
         have_B = true;
     } else {
@@ -724,7 +825,12 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             NCCL_CHECK(g_nccl.AllReduce(h->tc.state + TC_ST_OVF, h->tc.state + TC_ST_OVF, 1, ncclInt32, ncclMax, h->comm, h->stream));
         if (fused)
             CUDA_CHECK(cudaMemcpyAsync(&ht->tc_overflow, h->tc.state + TC_ST_OVF, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ht->xchg_err = 0;
+        if (peer_x)
+            CUDA_CHECK(cudaMemcpyAsync(&ht->xchg_err, h->xchg.region + h->xchg.flags_off + 2 * (size_t)h->nranks * 8 + 8, sizeof(int),
+                                       cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
+        if (ht->xchg_err) FAIL(SWNE_ERR_NCCL, "peer-memory exchange: a rank did not publish its partial sums within 5 s");
         if (ht->tc_overflow) tc_overflow = true;
         double w2 = 0, wg = 0, w1 = 0, h2 = 0, hg = 0, h1 = 0, wwhh = 0, sum_ahat = 0;
         for (int a = 0; a < k; ++a) {
@@ -791,8 +897,13 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             prof.end(0, tc_pass_launches(0));
             if (h->nranks > 1) {
                 prof.begin(6);
-                allreduce(h, h->B.p, (size_t)n * KPv, g64h_of(i), GS, &h->dscal.p->loss_part, 1);
-                launch_finalize_gram(h, k, KPv, g64h_of(i), h->tc.packH, p.alpha[0], p.alpha[1]);
+                if (peer_x)
+                    xchg_launch(h->xchg, h->B.p, (size_t)n * KPv, g64h_of(i), (size_t)GS, &h->dscal.p->loss_part, h->tc.packH, k, p.alpha[0],
+                                p.alpha[1], h->sm_count, st);
+                else {
+                    allreduce(h, h->B.p, (size_t)n * KPv, g64h_of(i), GS, &h->dscal.p->loss_part, 1);
+                    launch_finalize_gram(h, k, KPv, g64h_of(i), h->tc.packH, p.alpha[0], p.alpha[1]);
+                }
                 prof.end(6, 2);
             }
             if (i % p.trace == 0) error_block(false);
@@ -1805,6 +1916,7 @@ int swne_nmf_destroy(swne_nmf_handle_t h)
     if (!h) return SWNE_OK;
     DeviceGuard g(h->device);
     cudaStreamSynchronize(h->stream);
+    xchg_release(h, true);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     h->A_store.release();
     h->sp.cptr.release(); h->sp.cidx.release(); h->sp.gptr.release(); h->sp.gidx.release();
@@ -1857,6 +1969,17 @@ int swne_nmf_comm_init(swne_nmf_handle_t h, const void *id128, int rank, int nra
     memcpy(&id, id128, sizeof(id));
     NCCL_CHECK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
     h->rank = rank; h->nranks = nranks;
+    return SWNE_OK;
+    API_END
+}
+
+int swne_nmf_comm_info(swne_nmf_handle_t h, int *rank, int *nranks, int *peer_exchange)
+{
+    API_BEGIN
+    if (!h) FAIL(SWNE_ERR_BAD_ARG, "NULL handle");
+    if (rank) *rank = h->rank;
+    if (nranks) *nranks = h->nranks;
+    if (peer_exchange) *peer_exchange = h->xchg.ready ? 1 : 0;
     return SWNE_OK;
     API_END
 }

@@ -60,6 +60,12 @@ class NMFHandle:
         self.rank, self.nranks = rank, nranks
 
     # ---- matrix
+    def comm_info(self):
+        """rank, number of ranks, and whether the fused engine's per-iteration sums go over NVLink peer memory (else NCCL)."""
+        r, n, x = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        C.check(self._lib.swne_nmf_comm_info(self._h, ctypes.byref(r), ctypes.byref(n), ctypes.byref(x)))
+        return dict(rank=r.value, nranks=n.value, peer_exchange=bool(x.value))
+
     def set_matrix(self, A):
         """A: numpy (n x m, any float dtype), scipy.sparse CSC (dgCMatrix analogue), or a torch CUDA
         float32 tensor of shape (m, n) (cell-major == R column-major n x m) that is used in place."""

@@ -27,6 +27,7 @@ for (n, m, kt, k, engine) in [(300, 1000, 5, 8, "simt"), (1000, 4000, 6, 16, "tc
     H = gather_H(r.H)
     Ws = [None] * world
     td.all_gather_object(Ws, r.W)
+    peer = h.comm_info()["peer_exchange"]
     h.close()
     if rank == 0:
         from oracle import nnmf_ref
@@ -43,9 +44,9 @@ for (n, m, kt, k, engine) in [(300, 1000, 5, 8, "simt"), (1000, 4000, 6, 16, "tc
         good = (same_w and e_loss < 1e-4 and e_mkl < 1e-4 and e_w < 1e-3 and e_h < 1e-3
                 and o_loss < 1e-4 and o_w < 1e-3 and o_h < 1e-3 and o_ep < 0.35)
         ok &= good
-        print("%s n=%d m=%d k=%d engine=%s ranks=%d: W identical on ranks %s | vs 1 GPU: loss %.2e mkl %.2e W %.2e H %.2e | "
+        print("%s n=%d m=%d k=%d engine=%s ranks=%d exchange=%s: W identical on ranks %s | vs 1 GPU: loss %.2e mkl %.2e W %.2e H %.2e | "
               "vs oracle: loss %.2e W %.2e H %.2e epochs %.2e" % ("PASS" if good else "FAIL", n, m, k, r.options["engine"], world,
-                                                                same_w, e_loss, e_mkl, e_w, e_h, o_loss, o_w, o_h, o_ep), flush=True)
+                                                                "nvlink-peer" if peer else "nccl", same_w, e_loss, e_mkl, e_w, e_h, o_loss, o_w, o_h, o_ep), flush=True)
 # device-side seeds on the sharded matrix (RunNMF's init = nnsvd / ica / NNLM's random start): the sketch and the ICA
 # moments are all-reduced, W is replicated; the seeds draw different random numbers than a 1-GPU run, so the comparison is
 # the quality of the fit, not the factors
