@@ -737,6 +737,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     const bool tcx_solve_simt = getenv("SWNE_TCX_SOLVE_SIMT") != nullptr;   // debug knob, read once per fit
     const bool slab_timeline = getenv("SWNE_TCX_TIMELINE") != nullptr;
     const bool three_streams = getenv("SWNE_TCX_STREAMS2") == nullptr;     // debug knob: both contractions on one stream
+    const int genes_regions = getenv("SWNE_TCX_REGIONS") ? atoi(getenv("SWNE_TCX_REGIONS")) : 1;   // debug knob: 2 = double-buffered accumulators
     // slabs of the wide engine's H update: enough tiles per slab to keep every SM's contraction CTA busy (>= 4 tiles per SM)
     int tcx_slabs = 1;
     if (tcx) {
@@ -744,7 +745,8 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         // measured (round 2, three streams): 650 k cells 1 / 2 / 3 / 4 / 8 slabs = 4.92 / 4.39 / 4.27 / 4.31 / 4.51 ms per iteration:
         // slabs of about 10 tiles per contraction CTA
         const int tiles = h->tcx.tiles_total;
-        tcx_slabs = e ? atoi(e) : (tiles >= h->sm_count * 8 ? std::max(2, std::min(8, (2 * tiles + h->sm_count * 21 / 2) / (h->sm_count * 21))) : 1);
+        // (a 162.5 k-cell shard: 1 / 2 / 3 slabs = 1.47 / 1.44 / 1.37 ms)
+        tcx_slabs = e ? atoi(e) : (tiles >= h->sm_count * 8 ? std::max(3, std::min(8, (2 * tiles + h->sm_count * 21 / 2) / (h->sm_count * 21))) : 1);
         if (h->nranks > 1) {
             // every rank must take the same path (the collectives differ): the smallest count wins
             double v = -(double)tcx_slabs;
@@ -1000,7 +1002,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
                     slab(sl, t0, nt, c0, cells);
                     CUDA_CHECK(cudaStreamWaitEvent(qg, h->ev_slab[2 * sl + 1], 0));
                     mark(qg, "genes  start", sl);
-                    tcx_genes_slab(h->tcx, h->tc, KPv, h->H.p, h->B.p, t0, nt, sl & 3, qg, 1);
+                    tcx_genes_slab(h->tcx, h->tc, KPv, h->H.p, h->B.p, t0, nt, sl & 3, qg, genes_regions == 2 ? 2 : 1);
                     mark(qg, "genes  end  ", sl);
                     if (sl + ahead < n_sl) enqueue_cells(sl + ahead);
                 }
