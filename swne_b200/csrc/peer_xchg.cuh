@@ -26,7 +26,7 @@ struct PeerXchg {
     bool ready = false;
     bool tried = false;               // set-up attempted for the current payload size (a failed attempt is not repeated)
     int nranks = 0, rank = 0;
-    size_t payload = 0;               // bytes per slot, multiple of 16
+    size_t payload = 0;               // bytes per slot (capacity: the largest payload of this matrix), multiple of 16
     size_t flags_off = 0, total = 0;  // flags: [2][nranks] uint64 behind the slots; then the two ticket / error ints
     uint8_t *region = nullptr;        // this rank's region
     uint8_t **peers_dev = nullptr;    // device array [nranks]: base of every rank's region as mapped here
@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(XCHG_THREADS) xchg_reduce_kernel(const uint8_t
             else if (loss) *loss = acc.x;
         }
     }
-    if (tc_last_cta(ticket, &s_flag)) tc_finalize_gram(reinterpret_cast<const double *>(G), pack_next, k, pen0, pen1, s_inv);
+    // (pack_next == nullptr: the wide engine, whose W update builds its GramPack itself at another row stride)
+    if (pack_next != nullptr && tc_last_cta(ticket, &s_flag))
+        tc_finalize_gram(reinterpret_cast<const double *>(G), pack_next, k, pen0, pen1, s_inv);
 }
 
 // host side ------------------------------------------------------------------------------------------------------------

@@ -780,7 +780,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         if (h->nranks > 1) {
             // the sums of the ranks: over NVLink peer memory (peer_xchg.cuh) when every rank could map every other's region,
             // else three grouped NCCL all-reduces and the finalize kernel
-            peer_x = xchg_setup(h, xchg_payload_bytes((size_t)n * KPv, (size_t)GS));
+            peer_x = xchg_setup(h, xchg_payload_bytes((size_t)n * SWNE_MAX_K, (size_t)SWNE_MAX_K * SWNE_MAX_K + SWNE_MAX_K));
             if (peer_x)
                 xchg_launch(h->xchg, h->B.p, (size_t)n * KPv, g64h_of(1), (size_t)GS, nullptr, h->tc.packH, k, p.alpha[0], p.alpha[1],
                             h->sm_count, st);
@@ -828,7 +828,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
         if (fused)
             CUDA_CHECK(cudaMemcpyAsync(&ht->tc_overflow, h->tc.state + TC_ST_OVF, sizeof(int), cudaMemcpyDeviceToHost, st));
         ht->xchg_err = 0;
-        if (peer_x)
+        if (h->xchg.ready)
             CUDA_CHECK(cudaMemcpyAsync(&ht->xchg_err, h->xchg.region + h->xchg.flags_off + 2 * (size_t)h->nranks * 8 + 8, sizeof(int),
                                        cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
@@ -1022,7 +1022,11 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
                 prof.end(0, 3 + 6 * tcx_slabs);
                 if (h->nranks > 1) {
                     prof.begin(6);
-                    allreduce(h, h->B.p, (size_t)n * KPv, h->G64h.p, GS, &h->dscal.p->loss_part, 1);
+                    if (xchg_setup(h, xchg_payload_bytes((size_t)n * SWNE_MAX_K, (size_t)SWNE_MAX_K * SWNE_MAX_K + SWNE_MAX_K)))
+                        xchg_launch(h->xchg, h->B.p, (size_t)n * KPv, h->G64h.p, (size_t)GS, &h->dscal.p->loss_part, nullptr, k, 0.0, 0.0,
+                                    h->sm_count, st);
+                    else
+                        allreduce(h, h->B.p, (size_t)n * KPv, h->G64h.p, GS, &h->dscal.p->loss_part, 1);
                     prof.end(6, 1);
                 }
                 have_B = true;      // A H' of the new H is in place for the next W update

@@ -20,6 +20,11 @@ for (n, m, kt, k, engine) in [(300, 1000, 5, 8, "simt"), (1000, 4000, 6, 16, "tc
     A = small_matrix(n, m, kt, 3)
     W0, H0 = seeded_init(A, k, 3)
     b = shard_bounds(m, world)
+    # the wide engine's slab pipeline (with its own use of the peer-memory exchange) is chosen by size: force it on this small case
+    if k > 32:
+        os.environ["SWNE_TCX_SLABS"] = "3"
+    else:
+        os.environ.pop("SWNE_TCX_SLABS", None)
     h = NMFHandle(local)
     init_comm(h)
     h.set_matrix(np.asfortranarray(A[:, b[rank]:b[rank + 1]]))
@@ -47,6 +52,7 @@ for (n, m, kt, k, engine) in [(300, 1000, 5, 8, "simt"), (1000, 4000, 6, 16, "tc
         print("%s n=%d m=%d k=%d engine=%s ranks=%d exchange=%s: W identical on ranks %s | vs 1 GPU: loss %.2e mkl %.2e W %.2e H %.2e | "
               "vs oracle: loss %.2e W %.2e H %.2e epochs %.2e" % ("PASS" if good else "FAIL", n, m, k, r.options["engine"], world,
                                                                 "nvlink-peer" if peer else "nccl", same_w, e_loss, e_mkl, e_w, e_h, o_loss, o_w, o_h, o_ep), flush=True)
+os.environ.pop("SWNE_TCX_SLABS", None)
 # device-side seeds on the sharded matrix (RunNMF's init = nnsvd / ica / NNLM's random start): the sketch and the ICA
 # moments are all-reduced, W is replicated; the seeds draw different random numbers than a 1-GPU run, so the comparison is
 # the quality of the fit, not the factors
