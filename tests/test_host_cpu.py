@@ -136,6 +136,52 @@ def test_sharded_algorithm_equals_unsharded_gloo(tmp_path):
     assert np.max(np.abs(r0["terr"] - ref["target_loss"]) / ref["target_loss"]) < 1e-10
 
 
+REPLICA_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as td
+sys.path.insert(0, sys.argv[1])
+from swne_b200.dist import find_num_factors_replicas
+td.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+
+class FakeHandle:
+    """stands in for NMFHandle: the errors are a fixed function of k, as they are for the library (fits seeded by (seed, k))"""
+    def __init__(self): self.calls = []
+    def set_matrix(self, A): self.shape = A.shape
+    def find_num_factors(self, ks, loss="mse", max_iter=250, seed=0, errors_only=False):
+        assert errors_only
+        self.calls.append(list(ks))
+        ks = np.asarray(ks, dtype=float)
+        return dict(k_err=np.stack([10.0 / ks + 0.3 * (ks > 5), 12.0 / np.sqrt(ks)]))
+
+h = FakeHandle()
+r = find_num_factors_replicas(h, np.zeros((4, 6)), [2, 3, 4, 5, 6, 8, 10], seed=3)
+np.savez(sys.argv[4] + ".%d.npz" % td.get_rank(), k_err=r["k_err"], err=r["err"], k=r["k"], mine=np.array(h.calls[0]))
+td.destroy_process_group()
+'''
+
+
+def test_find_num_factors_replicas_gloo(tmp_path):
+    """FindNumFactors over two ranks as replicas (dist.find_num_factors_replicas): every rank sweeps a strided share of
+    k.range, the errors are gathered, and all ranks apply R/nmf.R:186-194's selection to the same table."""
+    port = 31000 + os.getpid() % 2000
+    script = tmp_path / "replica_worker.py"
+    script.write_text(REPLICA_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), str(tmp_path / "rep")]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    r0, r1 = np.load(str(tmp_path / "rep") + ".0.npz"), np.load(str(tmp_path / "rep") + ".1.npz")
+    ks = np.array([2, 3, 4, 5, 6, 8, 10], dtype=float)
+    want = np.stack([10.0 / ks + 0.3 * (ks > 5), 12.0 / np.sqrt(ks)])
+    assert list(r0["mine"]) == [2, 4, 6, 10] and list(r1["mine"]) == [3, 5, 8]
+    for r in (r0, r1):
+        assert np.allclose(r["k_err"], want, rtol=0, atol=1e-15)
+        d = (want[0, :-1] - want[0, 1:]) - (want[1, :-1] - want[1, 1:])
+        assert np.allclose(r["err"], d)
+        neg = np.nonzero(d < 0)[0]
+        assert int(r["k"]) == int(ks[int(neg[0]) if neg.size else int(np.argmin(d)) + 1])
+
+
 def test_build_digest_is_location_independent(tmp_path):
     """the tree is copied to another absolute path on the GPU box: the shipped .so must still count as current there
     (a rebuild on the box costs GPU minutes, and eight ranks rebuilding at once used to race)"""
