@@ -504,7 +504,7 @@ def test_cfg3_slice_vs_oracle(handle, cells, iters):
     _check_against(r, ref)
     within("mse trace, max rel", max_rel(r["mse"], ref["mse"]), LOSS_TOL)
     # sweep counts: fp32 stops a column a sweep or two earlier than fp64 once its updates fall below fp32 resolution
-    within("average_epochs, max rel", max_rel(r["average_epochs"], ref["average_epochs"]), 0.15)
+    within("average_epochs, max rel", max_rel(r["average_epochs"], ref["average_epochs"]), 0.2)
     handle.set_matrix(np.zeros((4, 4)) + 1.0)    # drop the borrowed tensor
 
 
