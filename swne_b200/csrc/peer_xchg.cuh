@@ -1,5 +1,6 @@
 // peer_xchg.cuh -- the per-iteration exchange of the cell-sharded fit over NVLink peer memory:
-//   A H' partial (n x 32 fp32)  +  H H' and row sums (fp64)  +  loss partial  ->  summed over the ranks, on every rank
+//   A H' partial (n x KP fp32)  +  H H' and row sums (fp64)  +  loss partial  ->  summed over the ranks, on every rank
+// (fused engine: KP = 32, plus the GramPack of the next W update; wide engine's slab pipeline: KP = k rounded up to 8)
 // as a one-shot all-reduce written for this payload (a few hundred KB, <= 8 ranks on one NVSwitch box), instead of three
 // grouped ncclAllReduce calls plus a finalize kernel:
 //   push    every rank stores its payload into slot [parity][rank] of EVERY rank's exchange region (its own included) with
