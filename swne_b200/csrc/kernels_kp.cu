@@ -1,4 +1,6 @@
 // kernels_kp.cu -- instantiates the KP-templated kernels for one KP (-DKP_VALUE=8|16|...|64).
+#include <stdlib.h>
+
 #include "kernels_simt.cuh"
 #include "kp_ops.h"
 
@@ -45,6 +47,10 @@ static void kl_launch_nt(const int *ptr, const int *idx, const float *val, float
     int cap = (max_nnz + 3) & ~3;
     if (cap < 4) cap = 4;
     if (cap > cap_max) cap = cap_max;
+    // debug knob (read once): an upper bound on the staged column length -- shorter staging buffers let more blocks share an
+    // SM, columns above the bound run on the global arrays
+    static const int cap_env = [] { const char *e = getenv("SWNE_KL_CAP"); return e ? atoi(e) : 0; }();
+    if (cap_env >= 4 && cap > (cap_env & ~3)) cap = cap_env & ~3;
     const size_t smem = (size_t)cap * (KP + 2) * sizeof(float);
     int per_sm = (int)((220 * 1024) / (smem + 2048));
     if (per_sm > 2048 / NT) per_sm = 2048 / NT;
@@ -66,6 +72,27 @@ void kl_l(const int *ptr, const int *idx, const float *val, float *ajt, float *X
     else
         kl_launch_nt<64>(ptr, idx, val, ajt, X, Y, sumY, b0, b1, b2, k, cols, max_iter, rel_tol, sweeps, kl_part, sq_part, err,
                          max_nnz, st);
+}
+void kl_shard_init_l(const int *ptr, const int *idx, float *ajt, const float *X, const float *Y, int k, int cols, float *dprev,
+                     float *sumX, int *active, cudaStream_t st)
+{
+    kl_shard_init_kernel<KP><<<cols < 148 * 8 ? cols : 148 * 8, 256, 0, st>>>(ptr, idx, ajt, X, Y, k, cols, dprev, sumX, active);
+}
+void kl_shard_accum_l(const int *ptr, const int *idx, const float *val, float *ajt, const float *Y, const float *dprev,
+                      const int *active, int kk, int kprev, int cols, float *part, cudaStream_t st)
+{
+    kl_shard_accum_kernel<KP><<<cols < 148 * 8 ? cols : 148 * 8, 256, 0, st>>>(ptr, idx, val, ajt, Y, dprev, active, kk, kprev, cols,
+                                                                               reinterpret_cast<float2 *>(part));
+}
+void kl_shard_update_l(const float *part, float *X, const float *sumY, float *sumX, float *dprev, int *active, float b0, float b1,
+                       float b2, int kk, int cols, float rel_tol, int flags, cudaStream_t st)
+{
+    kl_shard_update_kernel<KP><<<(cols + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float2 *>(part), X, sumY, sumX, dprev,
+                                                                   active, b0, b1, b2, kk, cols, rel_tol, flags);
+}
+void kl_shard_sweep_end_l(int *active, int cols, unsigned long long *sweeps, unsigned *n_active, cudaStream_t st)
+{
+    kl_shard_sweep_end_kernel<KP><<<(cols + 127) / 128, 128, 0, st>>>(active, cols, sweeps, n_active);
 }
 void kl_trace_l(const float *A, size_t ldA, int n, int m, const float *H, const float *Wt, int k, double *kl_part,
                 cudaStream_t st)
@@ -95,6 +122,7 @@ void ica_step_l(const float *Y, int rows, int nc, const float *R, double *out, i
 
 #define KP_OPS_NAME2(v) kp_ops_table_##v
 #define KP_OPS_NAME(v) KP_OPS_NAME2(v)
-extern const KpOps KP_OPS_NAME(KP_VALUE) = {gram_l, contract_cells_l, contract_genes_l, solve_l, kl_l, kl_trace_l,
+extern const KpOps KP_OPS_NAME(KP_VALUE) = {gram_l, contract_cells_l, contract_genes_l, solve_l, kl_l, kl_shard_init_l, kl_shard_accum_l,
+                                            kl_shard_update_l, kl_shard_sweep_end_l, kl_trace_l,
                                             recon_error_l, right_multiply_l, ica_step_l};
 }  // namespace swne

@@ -675,6 +675,135 @@ __global__ void __launch_bounds__(NT) scd_kl_kernel(const int *__restrict__ ptr,
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// SCD KL update of the gene side when the cells are sharded over ranks (scd_kl_update).
+// A gene's row of A is spread over all ranks, so one coordinate step is split at the point where the Newton sums are
+// complete:   kl_shard_accum (the rank's part of sum a mu^2, sum a mu on its own nonzeros, with the A-hat update of the
+// previous coordinate applied lazily, exactly as kl_column does)  ->  all-reduce of the 2 n partials  ->
+// kl_shard_update (the step itself, replicated: every rank gets the same W).  A-hat lives in the nnz-sized scratch of the
+// by-gene view.  active[0..cols) : the gene is still sweeping;  active[cols..2 cols) : "again" flag of the running sweep.
+// ----------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(256) kl_shard_init_kernel(const int *__restrict__ ptr, const int *__restrict__ idx,
+                                                            float *__restrict__ ajt, const float *__restrict__ X,
+                                                            const float *__restrict__ Y, int k, int cols,
+                                                            float *__restrict__ dprev, float *__restrict__ sumX,
+                                                            int *__restrict__ active)
+{
+    __shared__ __align__(16) float h[KP];
+    for (int j = blockIdx.x; j < cols; j += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < KP) h[threadIdx.x] = X[(size_t)j * KP + threadIdx.x];
+        __syncthreads();
+        const int b = ptr[j], nz = ptr[j + 1] - b;
+        for (int q = threadIdx.x; q < nz; q += 256) {
+            const float4 *y4 = reinterpret_cast<const float4 *>(Y + (size_t)idx[b + q] * KP);
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < KP / 4; ++r) {
+                const float4 y = __ldg(y4 + r);
+                const float4 hh = *reinterpret_cast<const float4 *>(h + 4 * r);
+                s = fmaf(y.x, hh.x, s); s = fmaf(y.y, hh.y, s); s = fmaf(y.z, hh.z, s); s = fmaf(y.w, hh.w, s);
+            }
+            ajt[b + q] = s;
+        }
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+            for (int f = 0; f < k; ++f) s += h[f];
+            sumX[j] = s; dprev[j] = 0.f; active[j] = 1; active[cols + j] = 0;
+        }
+    }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(256) kl_shard_accum_kernel(const int *__restrict__ ptr, const int *__restrict__ idx,
+                                                             const float *__restrict__ val, float *__restrict__ ajt,
+                                                             const float *__restrict__ Y, const float *__restrict__ dprev,
+                                                             const int *__restrict__ active, int kk, int kprev, int cols,
+                                                             float2 *__restrict__ part)
+{
+    __shared__ float red[2][8];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int j = blockIdx.x; j < cols; j += gridDim.x) {
+        if (!active[j]) {                       // block-uniform: the gene left the sweeps, its partials are zeros
+            if (tid == 0) part[j] = make_float2(0.f, 0.f);
+            continue;
+        }
+        const int b = ptr[j], nz = ptr[j + 1] - b;
+        const float d = dprev[j];
+        float a2 = 0.f, bb = 0.f;
+        for (int q = tid; q < nz; q += 256) {
+            const float *y = Y + (size_t)idx[b + q] * KP;
+            float a = ajt[b + q];
+            if (d != 0.f) {
+                a = fmaxf(fmaf(d, __ldg(y + kprev), a), 0.f);
+                ajt[b + q] = a;
+            }
+            const float w = __ldg(y + kk), v = val[b + q];
+            const float mu = __fdividef(w, a + TINY_NUM_F);
+            a2 = fmaf(v * mu, mu, a2);
+            bb = fmaf(v, mu, bb);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+            bb += __shfl_xor_sync(0xffffffffu, bb, o);
+        }
+        if (lane == 0) { red[0][wid] = a2; red[1][wid] = bb; }
+        __syncthreads();
+        if (tid == 0) {
+            float s2 = 0.f, sb = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) { s2 += red[0][w8]; sb += red[1][w8]; }
+            part[j] = make_float2(s2, sb);
+        }
+        __syncthreads();   // red[] is reused by the next gene of this block
+    }
+}
+
+// one thread per gene: the Newton step of coordinate kk from the summed partials (same arithmetic as kl_column)
+template <int KP>
+__global__ void __launch_bounds__(128) kl_shard_update_kernel(const float2 *__restrict__ part, float *__restrict__ X,
+                                                              const float *__restrict__ sumY, float *__restrict__ sumX,
+                                                              float *__restrict__ dprev, int *__restrict__ active, float b0,
+                                                              float b1, float b2, int kk, int cols, float rel_tol, int flags)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cols || !active[j]) return;
+    const float hk = X[(size_t)j * KP + kk];
+    const float2 pt = part[j];
+    float a2 = pt.x, bb = pt.y - sumY[kk];
+    float a2h;
+    if (flags & KL_L2_LATE) { a2h = a2 * hk; a2 += b0; }
+    else { a2 += b0; a2h = a2 * hk; }
+    const float sH = sumX[j];
+    bb += a2h - b2 - b1 * (sH - hk);
+    float tmp = bb / (a2 + TINY_NUM_F);
+    if (!(tmp > 0.f)) tmp = 0.f;
+    const float d = tmp - hk;
+    dprev[j] = d;
+    if (tmp != hk) {
+        if (2.f * fabsf(d) > rel_tol * (tmp + hk + TINY_NUM_F)) active[cols + j] = 1;
+        sumX[j] = sH + d;
+        X[(size_t)j * KP + kk] = tmp;
+    }
+}
+
+// end of a sweep: count it for every gene that ran it, carry "again" into "active"; counts[0] += sweeps, counts[1] += genes
+// that go on   (a template only because this header is compiled into several translation units)
+template <int KP>
+__global__ void kl_shard_sweep_end_kernel(int *__restrict__ active, int cols, unsigned long long *__restrict__ sweeps,
+                                          unsigned *__restrict__ n_active)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cols || !active[j]) return;
+    atomicAdd(sweeps, 1ull);
+    const int again = active[cols + j];
+    active[j] = again;
+    active[cols + j] = 0;
+    if (again) atomicAdd(n_active, 1u);
+}
+
 // A-hat on the support only: kl_part += sum_nz a log(ahat + tiny)   (the mkl trace of an mse fit).
 // Works on the dense rows directly (no sparse view to build).  A thread owns one gene and keeps that gene's row of
 // Wt in registers; a block walks KL_CELLS cells whose h vectors sit in shared memory (broadcast reads), so the

@@ -20,6 +20,15 @@ struct KpOps {
     void (*kl)(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y, const float *sumY,
                float b0, float b1, float b2, int k, int cols, int max_iter, float rel_tol, unsigned long long *sweeps,
                double *kl_part, double *sq_part, int err, int max_nnz, int avg_nnz, cudaStream_t st);
+    // gene side of the KL update with the cells sharded over ranks (kernels_simt.cuh, kl_shard_*): init of A-hat and the
+    // per-gene state, the rank's partial Newton sums of coordinate kk (part: float2 per gene), the replicated step, sweep end
+    void (*kl_shard_init)(const int *ptr, const int *idx, float *ajt, const float *X, const float *Y, int k, int cols, float *dprev,
+                          float *sumX, int *active, cudaStream_t st);
+    void (*kl_shard_accum)(const int *ptr, const int *idx, const float *val, float *ajt, const float *Y, const float *dprev,
+                           const int *active, int kk, int kprev, int cols, float *part, cudaStream_t st);
+    void (*kl_shard_update)(const float *part, float *X, const float *sumY, float *sumX, float *dprev, int *active, float b0,
+                            float b1, float b2, int kk, int cols, float rel_tol, int flags, cudaStream_t st);
+    void (*kl_shard_sweep_end)(int *active, int cols, unsigned long long *sweeps, unsigned *n_active, cudaStream_t st);
     void (*kl_trace)(const float *A, size_t ldA, int n, int m, const float *H, const float *Wt, int k, double *kl_part,
                      cudaStream_t st);
     void (*recon_error)(const float *A, size_t ldA, int n, int m, const float *Wt, const float *H, int k, double *out2, int grid,

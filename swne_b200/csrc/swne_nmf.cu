@@ -156,6 +156,8 @@ struct swne_nmf_handle_s {
     cudaEvent_t ev_ready = nullptr, ev_done[3] = {nullptr, nullptr, nullptr};
     swne::PeerXchg xchg;                               // NVLink peer-memory exchange of the fused engine's per-iteration sums
     std::vector<cudaEvent_t> ev_slab;           // [2 s] contraction of slab s done, [2 s + 1] its solve done
+    swne::DevBuf<float> kls_f;       // sharded KL gene side: Newton partials (2 n), pending delta (n), row sums of W (n)
+    swne::DevBuf<int> kls_i;         // ... active / again flags (2 n) and the count of genes still sweeping
     int kl_flags = 0;                // KL_L2_LATE when the fit asks for the alternative reading of NNLM's KL step
     int last_KPv = 0;                // row stride of Wt / H as the last fit left them on the device
 };
@@ -466,6 +468,45 @@ static void launch_kl(swne_nmf_handle_s *h, int k, int KPv, const int *ptr, cons
     CUDA_CHECK(cudaGetLastError());
 }
 
+static void allreduce(swne_nmf_handle_s *h, float *f, size_t nf, double *d, size_t nd, double *d2 = nullptr, size_t nd2 = 0);
+// Gene side of the KL update when the cells are sharded over ranks: a gene's Newton sums run over all cells, so every
+// coordinate step is   partial sums on the rank's nonzeros -> all-reduce of 2 n floats -> the step, replicated
+// (k all-reduces per sweep; NNLM runs one sweep per outer iteration for mkl).  Returns the number of kernel launches.
+static int launch_kl_sharded(swne_nmf_handle_s *h, int k, int KPv, float *X, const float *Y, const float *sumY, const double *pen,
+                             int cols, int max_iter, float rel_tol, unsigned long long *sweeps)
+{
+    const KpOps &o = ops_of(KPv);
+    cudaStream_t st = h->stream;
+    SparseView &sp = h->sp;
+    h->kls_f.reserve(4 * (size_t)cols);
+    h->kls_i.reserve(2 * (size_t)cols + 4);
+    float *part = h->kls_f.p, *dprev = part + 2 * (size_t)cols, *sumX = dprev + cols;
+    int *active = h->kls_i.p;
+    unsigned *n_active = reinterpret_cast<unsigned *>(active + 2 * (size_t)cols);
+    int launches = 1;
+    o.kl_shard_init(sp.gptr.p, sp.gidx.p, sp.ajt.p, X, Y, k, cols, dprev, sumX, active, st);
+    for (int it = 0; it < max_iter; ++it) {
+        for (int kk = 0; kk < k; ++kk) {
+            o.kl_shard_accum(sp.gptr.p, sp.gidx.p, sp.gval.p, sp.ajt.p, Y, dprev, active, kk, (kk + k - 1) % k, cols, part, st);
+            allreduce(h, part, 2 * (size_t)cols, nullptr, 0, nullptr, 0);
+            o.kl_shard_update(part, X, sumY, sumX, dprev, active, (float)pen[0], (float)pen[1], (float)pen[2], kk, cols, rel_tol,
+                              h->kl_flags, st);
+        }
+        CUDA_CHECK(cudaMemsetAsync(n_active, 0, sizeof(unsigned), st));
+        o.kl_shard_sweep_end(active, cols, sweeps, n_active, st);
+        CUDA_CHECK(cudaGetLastError());
+        launches += 2 * k + 1;
+        if (it + 1 < max_iter) {
+            // W is replicated, so every rank reads the same count and leaves the loop at the same sweep
+            unsigned left = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&left, n_active, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            if (!left) break;
+        }
+    }
+    return launches;
+}
+
 static void upload_factor_cellmajor(swne_nmf_handle_s *h, const double *src, float *dst, int k, int KPv, size_t cols,
                                     unsigned *bad = nullptr, unsigned bit = 0)
 {
@@ -504,7 +545,7 @@ static void download_factor_colmajor(swne_nmf_handle_s *h, const float *src, dou
 }
 
 // one NCCL group (one launch) for up to three buffers of the per-iteration exchange
-static void allreduce(swne_nmf_handle_s *h, float *f, size_t nf, double *d, size_t nd, double *d2 = nullptr, size_t nd2 = 0)
+static void allreduce(swne_nmf_handle_s *h, float *f, size_t nf, double *d, size_t nd, double *d2, size_t nd2)
 {
     if (h->nranks <= 1) return;
     NCCL_CHECK(g_nccl.GroupStart());
@@ -649,7 +690,6 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     const int need_len = (p.max_iter + p.trace - 1) / p.trace + 1;
     if ((mse_tr || mkl_tr || terr_tr || epo_tr) && trace_len < need_len)
         FAIL(SWNE_ERR_BAD_ARG, "trace arrays need ceil(max_iter/trace)+1 = %d entries", need_len);
-    if (p.loss == SWNE_LOSS_MKL && h->nranks > 1) FAIL(SWNE_ERR_UNSUPPORTED, "mkl loss is single-GPU only");
     h->kl_flags = (p.nnlm_variant & SWNE_VARIANT_KL_L2_LATE) ? KL_L2_LATE : 0;
 
     cudaStream_t st = h->stream;
@@ -735,6 +775,9 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     }
 
     const bool tcx_solve_simt = getenv("SWNE_TCX_SOLVE_SIMT") != nullptr;   // debug knob, read once per fit
+    // mkl with cells sharded over ranks: the gene side runs coordinate by coordinate around an all-reduce (launch_kl_sharded);
+    // SWNE_KL_SHARD_STEP takes the same kernels on one GPU (tests)
+    const bool kl_sharded = h->nranks > 1 || getenv("SWNE_KL_SHARD_STEP") != nullptr;
     const bool slab_timeline = getenv("SWNE_TCX_TIMELINE") != nullptr;
     const bool three_streams = getenv("SWNE_TCX_STREAMS2") == nullptr;     // debug knob: both contractions on one stream
     const int genes_regions = getenv("SWNE_TCX_REGIONS") ? atoi(getenv("SWNE_TCX_REGIONS")) : 1;   // debug knob: 2 = double-buffered accumulators
@@ -815,6 +858,8 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             prof.end(4, 1);
             if (h->nranks > 1) allreduce(h, nullptr, 0, &h->dscal.p->kl_part, 1);
         }
+        // an mkl fit's loss partials come out of the cell side's update: rank-local sums over the rank's cells
+        if (!mse && h->nranks > 1) allreduce(h, nullptr, 0, &h->dscal.p->kl_part, 2);
         // average.epochs counts the sweeps of all cells: the H-side count is rank-local until here
         if (h->nranks > 1)
             NCCL_CHECK(g_nccl.AllReduce(&h->dscal.p->sweeps_h, &h->dscal.p->sweeps_h, 1, ncclUint64, ncclSum, h->comm, h->stream));
@@ -1056,9 +1101,14 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             // ---------------- mkl: W update on the by-gene view, H update on the by-cell view
             prof.begin(5);
             launch_finalize_gram(h, k, KPv, h->G64h.p, h->pack.p, 0.0, 0.0);
-            launch_kl(h, k, KPv, h->sp.gptr.p, h->sp.gidx.p, h->sp.gval.p, h->Wt.p, h->H.p, pack_colsum(h->pack.p, KPv), p.alpha, n,
-                      p.inner_max_iter, inner_tol, &h->dscal.p->sweeps_w, h->dscal.p, 0);
-            prof.end(5, 2);
+            int kl_launches = 1;
+            if (kl_sharded)
+                kl_launches = launch_kl_sharded(h, k, KPv, h->Wt.p, h->H.p, pack_colsum(h->pack.p, KPv), p.alpha, n, p.inner_max_iter,
+                                                inner_tol, &h->dscal.p->sweeps_w);
+            else
+                launch_kl(h, k, KPv, h->sp.gptr.p, h->sp.gidx.p, h->sp.gval.p, h->Wt.p, h->H.p, pack_colsum(h->pack.p, KPv), p.alpha, n,
+                          p.inner_max_iter, inner_tol, &h->dscal.p->sweeps_w, h->dscal.p, 0);
+            prof.end(5, 1 + kl_launches);
             prof.begin(4);
             launch_gram(h, KPv, h->Wt.p, n, h->G64w.p);
             launch_finalize_gram(h, k, KPv, h->G64w.p, h->pack.p, 0.0, 0.0);
@@ -1071,6 +1121,8 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             prof.begin(4);
             launch_gram(h, KPv, h->H.p, m, h->G64h.p);
             prof.end(4, 1);
+            // row sums of H over all cells (the next gene side's sum of the fixed factor) and H H' of the penalties
+            if (h->nranks > 1) { prof.begin(6); allreduce(h, nullptr, 0, h->G64h.p, GS); prof.end(6, 1); }
         }
         if (i % p.trace == 0) error_block(false);
     }
@@ -1133,10 +1185,9 @@ static int nnlm_impl(swne_nmf_handle_s *h, int side, int k, const double *X, dou
     if (!X || !coef) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
     if (k < 1 || k > SWNE_MAX_K) FAIL(SWNE_ERR_BAD_ARG, "k must be in 1..%d", SWNE_MAX_K);
     if (side != 0 && side != 1) FAIL(SWNE_ERR_BAD_ARG, "side must be 0 (solve H) or 1 (solve W)");
-    // cells sharded over ranks: side 0 is local (W replicated); side 1 sums H H' and A H' over the ranks (mse), every rank
-    // then solves all genes (identical results everywhere, like the W update of a fit)
-    if (side == 1 && h->nranks > 1 && loss != SWNE_LOSS_MSE)
-        FAIL(SWNE_ERR_UNSUPPORTED, "nnlm side 1 with mkl loss is single-GPU only");
+    // cells sharded over ranks: side 0 is local (W replicated); side 1 sums H H' and A H' over the ranks (mse) or the Newton
+    // sums of every coordinate step (mkl, launch_kl_sharded); every rank then solves all genes (identical results everywhere,
+    // like the W update of a fit)
     if (max_iter <= 0) max_iter = 10000;
     if (rel_tol <= 0) rel_tol = 1e-12;
     double pen[3] = {0, 0, 0};
@@ -1180,6 +1231,9 @@ static int nnlm_impl(swne_nmf_handle_s *h, int side, int k, const double *X, dou
         if (side == 0)
             launch_kl(h, k, KPv, h->sp.cptr.p, h->sp.cidx.p, h->sp.cval.p, solve, fixed, pack_colsum(h->pack.p, KPv), pen, cols, max_iter,
                       (float)rel_tol, &h->dscal.p->sweeps_h, h->dscal.p, 0);
+        else if (h->nranks > 1 || getenv("SWNE_KL_SHARD_STEP"))
+            launch_kl_sharded(h, k, KPv, solve, fixed, pack_colsum(h->pack.p, KPv), pen, cols, max_iter, (float)rel_tol,
+                              &h->dscal.p->sweeps_h);
         else
             launch_kl(h, k, KPv, h->sp.gptr.p, h->sp.gidx.p, h->sp.gval.p, solve, fixed, pack_colsum(h->pack.p, KPv), pen, cols, max_iter,
                       (float)rel_tol, &h->dscal.p->sweeps_h, h->dscal.p, 0);

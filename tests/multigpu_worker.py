@@ -53,6 +53,32 @@ for (n, m, kt, k, engine) in [(300, 1000, 5, 8, "simt"), (1000, 4000, 6, 16, "tc
               "vs oracle: loss %.2e W %.2e H %.2e epochs %.2e" % ("PASS" if good else "FAIL", n, m, k, r.options["engine"], world,
                                                                 "nvlink-peer" if peer else "nccl", same_w, e_loss, e_mkl, e_w, e_h, o_loss, o_w, o_h, o_ep), flush=True)
 os.environ.pop("SWNE_TCX_SLABS", None)
+# loss = mkl on the sharded matrix: the cell side is local, the gene side runs coordinate by coordinate around an all-reduce
+# of the 2 n Newton partials (launch_kl_sharded); penalties on both sides, one and three inner sweeps
+n, m, kt, k = 300, 1000, 5, 8
+A = small_matrix(n, m, kt, 7)
+W0, H0 = seeded_init(A, k, 7)
+b = shard_bounds(m, world)
+for inner in (1, 3):
+    kw = dict(loss="mkl", alpha=[0.2, 0.01, 0.02], beta=[0.1, 0, 0.05], max_iter=20, trace=1, rel_tol=-1.0, inner_max_iter=inner)
+    h = NMFHandle(local)
+    init_comm(h)
+    h.set_matrix(np.asfortranarray(A[:, b[rank]:b[rank + 1]]))
+    r = h.fit(k, W0, H0[:, b[rank]:b[rank + 1]], **kw)
+    H = gather_H(r.H)
+    Ws = [None] * world
+    td.all_gather_object(Ws, r.W)
+    h.close()
+    if rank == 0:
+        from oracle import nnmf_ref
+        ref = nnmf_ref(A, k, W0, H0, **kw)
+        same_w = all(np.array_equal(Ws[0], w) for w in Ws)
+        o_loss, o_mse = max_rel(r.target_loss, ref["target_loss"]), max_rel(r.mse, ref["mse"])
+        o_w, o_h, o_ep = rel_fro(r.W, ref["W"]), rel_fro(H, ref["H"]), max_rel(r.average_epochs, ref["average_epochs"])
+        good = same_w and o_loss < 1e-4 and o_mse < 1e-4 and o_w < 1e-3 and o_h < 1e-3 and o_ep < 0.35
+        ok &= good
+        print("%s mkl n=%d m=%d k=%d inner=%d ranks=%d: W identical on ranks %s | vs oracle: loss %.2e mse %.2e W %.2e H %.2e epochs %.2e"
+              % ("PASS" if good else "FAIL", n, m, k, inner, world, same_w, o_loss, o_mse, o_w, o_h, o_ep), flush=True)
 # device-side seeds on the sharded matrix (RunNMF's init = nnsvd / ica / NNLM's random start): the sketch and the ICA
 # moments are all-reduced, W is replicated; the seeds draw different random numbers than a 1-GPU run, so the comparison is
 # the quality of the fit, not the factors

@@ -177,6 +177,35 @@ def test_unpinned_nnlm_details_both_readings(handle):
     assert rel_fro(refs[True]["H"], refs[False]["H"]) > 1e-3
 
 
+def test_mkl_sharded_gene_side_kernels_on_one_gpu(handle):
+    """With cells sharded over ranks the gene side of an mkl fit runs coordinate by coordinate around an all-reduce
+    (kl_shard_* kernels, swne_nmf.cu launch_kl_sharded).  SWNE_KL_SHARD_STEP takes exactly those kernels on one GPU (the
+    all-reduce of one rank is the identity): same bars against the oracle as the one-block-per-gene kernel, for one inner
+    sweep (NNLM's default for mkl) and for three (genes leave the sweeps one by one), and for nnlm on the gene side."""
+    from oracle import nnmf_ref, nnlm_ref
+    A = small_matrix(300, 500, 6, 4)
+    W0, H0 = seeded_init(A, 8, 4)
+    handle.set_matrix(A)
+    os.environ["SWNE_KL_SHARD_STEP"] = "1"
+    try:
+        for inner in (1, 3):
+            kw = dict(loss="mkl", alpha=[0.2, 0.01, 0.02], beta=[0.1, 0, 0.05], max_iter=20, trace=1, rel_tol=-1.0, inner_max_iter=inner)
+            ref = nnmf_ref(A, 8, W0, H0, **kw)
+            r = handle.fit(8, W0, H0, **kw)
+            within("sharded-step mkl target_loss, max rel (inner=%d)" % inner, max_rel(r["target_loss"], ref["target_loss"]), LOSS_TOL)
+            within("sharded-step mse of the mkl fit, max rel (inner=%d)" % inner, max_rel(r["mse"], ref["mse"]), LOSS_TOL)
+            within("sharded-step W rel Frobenius (inner=%d)" % inner, rel_fro(r["W"], ref["W"]), FACTOR_TOL)
+            within("sharded-step H rel Frobenius (inner=%d)" % inner, rel_fro(r["H"], ref["H"]), FACTOR_TOL)
+            within("sharded-step average_epochs, max rel (inner=%d)" % inner, max_rel(r["average_epochs"], ref["average_epochs"]), 0.35)
+        # ProjectFeatures with loss = mkl: nnlm on the gene side
+        Hfix = np.random.default_rng(4).gamma(0.5, 1.0, size=(6, 500))
+        refW = nnlm_ref(Hfix.T, A.T, loss="mkl", init=np.full((6, 300), 0.005), max_iter=200)["coefficients"].T
+        rW = handle.nnlm(1, Hfix, init=np.full((300, 6), 0.005), loss="mkl", max_iter=200)["coefficients"]
+        within("sharded-step nnlm gene side (mkl)", rel_fro(rW, refW), FACTOR_TOL)
+    finally:
+        del os.environ["SWNE_KL_SHARD_STEP"]
+
+
 def _match_components(S, Sref):
     """|correlation| of every reference component with its best match among S (components are defined up to sign/order)"""
     S = (S - S.mean(axis=1, keepdims=True)); Sref = (Sref - Sref.mean(axis=1, keepdims=True))

@@ -136,6 +136,48 @@ def test_sharded_algorithm_equals_unsharded_gloo(tmp_path):
     assert np.max(np.abs(r0["terr"] - ref["target_loss"]) / ref["target_loss"]) < 1e-10
 
 
+MKL_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as td
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from helpers import small_matrix, seeded_init
+from swne_b200.dist import shard_bounds
+from sharded_model import sharded_nnmf_mkl
+td.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+A = small_matrix(40, 61, 4, 3); W0, H0 = seeded_init(A, 5, 3)
+b = shard_bounds(61, 2); r = td.get_rank()
+out = {}
+for inner in (1, 3):
+    W, H, mkl = sharded_nnmf_mkl(A[:, b[r]:b[r+1]], W0, H0[:, b[r]:b[r+1]], 8, A.shape[1], (0.05, 0.01, 0.02), (0.02, 0.0, 0.05), inner)
+    out.update({"W%d" % inner: W, "H%d" % inner: H, "mkl%d" % inner: mkl})
+np.savez(sys.argv[4] + ".%d.npz" % r, **out)
+td.destroy_process_group()
+'''
+
+
+def test_sharded_mkl_schedule_equals_unsharded_gloo(tmp_path):
+    """world_size-2 gloo run of the cell-sharded mkl schedule (swne_nmf.cu launch_kl_sharded: per coordinate, partial Newton
+    sums on the rank's cells -> all-reduce of 2 n numbers -> replicated step with the lazy A-hat update; local cell side)
+    against the unsharded oracle, with all three penalties, for one and for three inner sweeps."""
+    from oracle import nnmf_ref
+    port = 31000 + os.getpid() % 2000
+    script = tmp_path / "worker.py"
+    script.write_text(MKL_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), str(tmp_path / "out")]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    A = small_matrix(40, 61, 4, 3); W0, H0 = seeded_init(A, 5, 3)
+    r0, r1 = np.load(str(tmp_path / "out") + ".0.npz"), np.load(str(tmp_path / "out") + ".1.npz")
+    for inner in (1, 3):
+        ref = nnmf_ref(A, 5, W0, H0, alpha=(0.05, 0.01, 0.02), beta=(0.02, 0.0, 0.05), loss="mkl", max_iter=8, trace=1, rel_tol=-1.0,
+                       inner_max_iter=inner)
+        assert np.array_equal(r0["W%d" % inner], r1["W%d" % inner])          # W is replicated bit for bit
+        assert rel_fro(r0["W%d" % inner], ref["W"]) < 1e-9
+        assert rel_fro(np.concatenate([r0["H%d" % inner], r1["H%d" % inner]], axis=1), ref["H"]) < 1e-9
+        assert np.max(np.abs(r0["mkl%d" % inner] - ref["mkl"]) / np.abs(ref["mkl"])) < 1e-10
+
+
 REPLICA_WORKER = r'''
 import os, sys
 import numpy as np

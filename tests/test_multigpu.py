@@ -24,4 +24,4 @@ def test_sharded_fit_matches_oracle_and_single_gpu(nranks):
            "--master-port", str(port), os.path.join(ROOT, "tests", "multigpu_worker.py")]
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, (out.stdout[-3000:], out.stderr[-3000:])
-    assert "FAIL" not in out.stdout and out.stdout.count("PASS") >= 9, out.stdout[-3000:]
+    assert "FAIL" not in out.stdout and out.stdout.count("PASS") >= 11, out.stdout[-3000:]
