@@ -42,7 +42,7 @@ RunNMF <- function(A, k, alpha = 0, init = "ica", n.cores = 1, loss = "mse", max
   return(nmf.res)
 }
 
-nnsvd_init <- function(A, k, LINPACK = T, eps = 1e-10) {     # LINPACK / eps kept for the signature (R/nmf.R:12)
+nnsvd_init <- function(A, k, LINPACK) {     # LINPACK kept for the signature (R/nmf.R:12), unused
   swne_seed_cuda(.swne_mat(A), as.integer(k), .swne_init_mode[["nnsvd"]], .swne_seed(), .swne_dev())
 }
 
@@ -51,10 +51,10 @@ ica_init <- function(A, k, ica.fast = F) {
 }
 
 FindNumFactors <- function(A, k.range = seq(2, 12, 2), n.cores = 1, do.plot = T, seed = NULL, loss = "mse", max.iter = 250) {
-  if (!is.null(seed)) set.seed(seed)
   if (!loss %in% c("mse", "mkl")) stop("Invalid loss function")
+  if (ncol(A) > 20000) print("Warning: This function can be slow for very large datasets")
+  if (!is.null(seed)) set.seed(seed)
   if (length(k.range) < 3) stop("k.range sequence must have at least 3 values")
-  if (ncol(A) > 15000) print("Warning: This function can be slow for very large datasets")
   ## R/nmf.R:163-181 (the permuted matrix, the 2 x length(k.range) mse fits, their errors) in one device call
   k.err.mat <- swne_find_num_factors_cuda(.swne_mat(A), as.integer(k.range), ifelse(loss == "mse", 0L, 1L), as.integer(max.iter),
                                           .swne_seed(), .swne_dev())
@@ -97,9 +97,9 @@ ProjectSamples <- function(newdata, W, features.use = NULL, alpha = rep(0, 3), l
 }
 
 ## get_sample_coords (R/swne_plotting.R:70-84): one device call instead of an sapply over all cells
-get_sample_coords <- function(H, H.coords, alpha = 1, n_pull = NULL) {
-  if (n_pull < 3 || is.null(n_pull)) n_pull <- 3
-  if (n_pull > nrow(H)) n_pull <- nrow(H)
+get_sample_coords <- function(H, H.coords, alpha, n_pull) {
+  if (n_pull < 3) { n_pull <- 3 }
+  if (is.null(n_pull) || n_pull > nrow(H.coords)) { n_pull <- nrow(H.coords) }
   sample.coords <- swne_sample_coords_cuda(as.matrix(H), as.matrix(H.coords), alpha, as.integer(n_pull), .swne_dev())
   colnames(sample.coords) <- c("x", "y"); rownames(sample.coords) <- colnames(H)
   return(sample.coords)

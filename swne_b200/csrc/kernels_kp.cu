@@ -47,9 +47,10 @@ static void kl_launch_nt(const int *ptr, const int *idx, const float *val, float
     int cap = (max_nnz + 3) & ~3;
     if (cap < 4) cap = 4;
     if (cap > cap_max) cap = cap_max;
-    // debug knob (read once): an upper bound on the staged column length -- shorter staging buffers let more blocks share an
-    // SM, columns above the bound run on the global arrays
-    static const int cap_env = [] { const char *e = getenv("SWNE_KL_CAP"); return e ? atoi(e) : 0; }();
+    // debug knob (read at launch, so a test can flip it in-process): an upper bound on the staged column length -- shorter
+    // staging buffers let more blocks share an SM, columns above the bound run on the global arrays
+    const char *cap_e = getenv("SWNE_KL_CAP");
+    const int cap_env = cap_e ? atoi(cap_e) : 0;
     if (cap_env >= 4 && cap > (cap_env & ~3)) cap = cap_env & ~3;
     const size_t smem = (size_t)cap * (KP + 2) * sizeof(float);
     int per_sm = (int)((220 * 1024) / (smem + 2048));

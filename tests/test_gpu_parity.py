@@ -186,17 +186,22 @@ def test_mkl_sharded_gene_side_kernels_on_one_gpu(handle):
     A = small_matrix(300, 500, 6, 4)
     W0, H0 = seeded_init(A, 8, 4)
     handle.set_matrix(A)
+    # three inner sweeps start from the oracle's state after 30 default iterations: from the NNDSVD start a second sweep drives
+    # a-hat to ~1e-16 on entries with a > 0, where a log(a-hat) turns 1e-7 of fp32 rounding into 1e-3 of loss (measured on
+    # both kernels; the reported loss equals the fp64 loss of the returned W, H to 3e-9 -- conditioning, not bookkeeping)
+    pen = dict(alpha=[0.2, 0.01, 0.02], beta=[0.1, 0, 0.05])
+    warm = nnmf_ref(A, 8, W0, H0, loss="mkl", max_iter=30, trace=1, rel_tol=-1.0, **pen)
     os.environ["SWNE_KL_SHARD_STEP"] = "1"
     try:
-        for inner in (1, 3):
-            kw = dict(loss="mkl", alpha=[0.2, 0.01, 0.02], beta=[0.1, 0, 0.05], max_iter=20, trace=1, rel_tol=-1.0, inner_max_iter=inner)
-            ref = nnmf_ref(A, 8, W0, H0, **kw)
-            r = handle.fit(8, W0, H0, **kw)
+        for inner, Wi, Hi, iters in ((1, W0, H0, 20), (3, warm["W"], warm["H"], 10)):
+            kw = dict(loss="mkl", max_iter=iters, trace=1, rel_tol=-1.0, inner_max_iter=inner, **pen)
+            ref = nnmf_ref(A, 8, Wi, Hi, **kw)
+            r = handle.fit(8, Wi, Hi, **kw)
             within("sharded-step mkl target_loss, max rel (inner=%d)" % inner, max_rel(r["target_loss"], ref["target_loss"]), LOSS_TOL)
             within("sharded-step mse of the mkl fit, max rel (inner=%d)" % inner, max_rel(r["mse"], ref["mse"]), LOSS_TOL)
             within("sharded-step W rel Frobenius (inner=%d)" % inner, rel_fro(r["W"], ref["W"]), FACTOR_TOL)
             within("sharded-step H rel Frobenius (inner=%d)" % inner, rel_fro(r["H"], ref["H"]), FACTOR_TOL)
-            within("sharded-step average_epochs, max rel (inner=%d)" % inner, max_rel(r["average_epochs"], ref["average_epochs"]), 0.35)
+            within("sharded-step average_epochs, max rel (inner=%d)" % inner, max_rel(r["average_epochs"], ref["average_epochs"]), 0.05)
         # ProjectFeatures with loss = mkl: nnlm on the gene side
         Hfix = np.random.default_rng(4).gamma(0.5, 1.0, size=(6, 500))
         refW = nnlm_ref(Hfix.T, A.T, loss="mkl", init=np.full((6, 300), 0.005), max_iter=200)["coefficients"].T

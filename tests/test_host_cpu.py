@@ -381,3 +381,29 @@ def test_bench_clock_sampler_summary_and_peaks(tmp_path, monkeypatch):
     assert bench.peaks() == (6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)")
     (tmp_path / "MEASURED_PEAKS.json").write_text('{"hbm_gbs": 6549.1, "bf16_tflops": 1645}')
     assert bench.peaks()[0] == 6549.1
+
+
+def test_rcpp_shim_type_checks_against_the_c_abi():
+    """r/src/swne_nmf_cuda.cpp (the Rcpp glue a maintainer adds next to src/swne_cpp_funcs.cpp) cannot be built here -- no
+    R -- but every call it makes into include/swne_nmf.h can be type-checked: g++ -fsyntax-only against a declarations-only
+    stand-in for <Rcpp.h> (tests/rcpp_stub).  A changed C-ABI signature that the shim does not follow fails here."""
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "rcpp_stub"),
+           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "r", "src", "swne_nmf_cuda.cpp")]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+
+
+def test_r_overlay_keeps_the_reference_formals():
+    """The R overlay (r/R/nmf_cuda.R) must keep the formals of the functions it replaces: compared as text with
+    the signatures in R/nmf.R:96-97, :157-158, :222, :241-242 and R/swne_plotting.R:69 (recorded here: the reference tree is
+    not available on the GPU box)."""
+    src = open(os.path.join(ROOT, "r", "R", "nmf_cuda.R")).read()
+    squeeze = lambda s: "".join(s.split())
+    for sig in ('RunNMF <- function(A, k, alpha = 0, init = "ica", n.cores = 1, loss = "mse", max.iter = 500, ica.fast = F)',
+                'FindNumFactors <- function(A, k.range = seq(2, 12, 2), n.cores = 1, do.plot = T, seed = NULL, loss = "mse", max.iter = 250)',
+                'ProjectFeatures <- function(newdata, H, alpha = rep(0, 3), loss = "mse", n.cores = 1)',
+                'ProjectSamples <- function(newdata, W, features.use = NULL, alpha = rep(0, 3), loss = "mse", n.cores = 1)',
+                'get_sample_coords <- function(H, H.coords, alpha, n_pull)',
+                'nnsvd_init <- function(A, k, LINPACK)',
+                'ica_init <- function(A, k, ica.fast = F)'):
+        assert squeeze(sig) in squeeze(src), sig
