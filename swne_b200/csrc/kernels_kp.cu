@@ -34,10 +34,19 @@ void solve_l(float *X, const float *C, const float *pack, float l1, int k, int c
     const int bs = cols <= 148 * 64 ? 32 : 128;
     scd_ls_solve_kernel<KP><<<(cols + bs - 1) / bs, bs, 0, st>>>(X, C, pack, l1, k, cols, max_iter, rel_tol, sweeps, loss_part);
 }
+// blocks of scd_kl_kernel<KP, NT> that share an SM when a column of up to `cap` nonzeros is staged: (KP + 2) floats each
+static int kl_per_sm(int cap, int NT)
+{
+    const size_t smem = (size_t)cap * (KP + 2) * sizeof(float);
+    int per_sm = (int)((220 * 1024) / (smem + 2048));
+    if (per_sm > 2048 / NT) per_sm = 2048 / NT;
+    return per_sm < 1 ? 1 : per_sm;
+}
 template <int NT>
 static void kl_launch_nt(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y,
                          const float *sumY, float b0, float b1, float b2, int k, int cols, int max_iter, float rel_tol,
-                         unsigned long long *sweeps, double *kl_part, double *sq_part, int err, int max_nnz, cudaStream_t st)
+                         unsigned long long *sweeps, double *kl_part, double *sq_part, int err, int max_nnz, const int *order,
+                         const int *sorted_cnt, cudaStream_t st)
 {
     // shared-memory staging of one column: (KP + 2) floats per nonzero; columns longer than cap run on global arrays
     // set on every launch: the attribute is per device, and one process may drive several GPUs (one handle each)
@@ -52,27 +61,64 @@ static void kl_launch_nt(const int *ptr, const int *idx, const float *val, float
     const char *cap_e = getenv("SWNE_KL_CAP");
     const int cap_env = cap_e ? atoi(cap_e) : 0;
     if (cap_env >= 4 && cap > (cap_env & ~3)) cap = cap_env & ~3;
-    const size_t smem = (size_t)cap * (KP + 2) * sizeof(float);
-    int per_sm = (int)((220 * 1024) / (smem + 2048));
-    if (per_sm > 2048 / NT) per_sm = 2048 / NT;
-    if (per_sm < 1) per_sm = 1;
-    const int grid = cols < 148 * per_sm ? cols : 148 * per_sm;
-    scd_kl_kernel<KP, NT><<<grid, NT, smem, st>>>(ptr, idx, val, ajt, X, Y, sumY, b0, b1, b2, k, cols, max_iter, rel_tol,
-                                                  sweeps, kl_part, sq_part, err, cap);
+    // The sweeps are latency-bound chains, so what counts is how many columns an SM works on at once, and that is set by the
+    // staging buffer of the LONGEST column of the launch (cfg2's gene side: longest 1804 of mean 684 nonzeros -> one block
+    // per SM).  With the columns sorted by length the launch is cut in two: the long columns with the big buffer, the rest
+    // with a buffer sized for P blocks per SM; P and the cut minimise the number of block rounds (one extra round is charged
+    // for the second launch's tail).  SWNE_KL_SPLIT=0 keeps the single launch.
+    int n_long = 0, cap_short = cap;
+    const char *split_e = getenv("SWNE_KL_SPLIT");
+    if (order && sorted_cnt && cols > 148 && !(split_e && atoi(split_e) == 0) && cap_env < 4) {
+        const int p_long = kl_per_sm(cap, NT);
+        double best = (double)cols / (148.0 * p_long);
+        for (int P = p_long + 1; P <= 2048 / NT; ++P) {
+            int cap_p = (int)(((220 * 1024) / P - 2048) / ((KP + 2) * sizeof(float))) & ~3;
+            if (cap_p < 4) break;
+            // columns longer than cap_p: sorted_cnt is descending
+            int lo = 0, hi = cols;
+            while (lo < hi) { const int mid = (lo + hi) / 2; if (sorted_cnt[mid] > cap_p) lo = mid + 1; else hi = mid; }
+            const double rounds = (double)lo / (148.0 * p_long) + (double)(cols - lo) / (148.0 * P) + (lo ? 1.0 : 0.0);
+            if (rounds < best) { best = rounds; n_long = lo; cap_short = lo < cols ? ((sorted_cnt[lo] + 3) & ~3) : 4; }
+        }
+        if (cap_short < 4) cap_short = 4;
+    }
+    for (int part = 0; part < 2; ++part) {
+        const int first = part == 0 ? 0 : n_long;
+        const int count = part == 0 ? (cap_short == cap ? cols : n_long) : cols - n_long;
+        if (part == 1 && cap_short == cap) break;
+        if (count <= 0) continue;
+        const int cap_l = part == 0 ? cap : cap_short;
+        const size_t smem = (size_t)cap_l * (KP + 2) * sizeof(float);
+        const int per_sm = kl_per_sm(cap_l, NT);
+        const int grid = count < 148 * per_sm ? count : 148 * per_sm;
+        scd_kl_kernel<KP, NT><<<grid, NT, smem, st>>>(ptr, idx, val, ajt, X, Y, sumY, b0, b1, b2, k, count, max_iter, rel_tol,
+                                                      sweeps, kl_part, sq_part, err, cap_l, order, first);
+    }
 }
 void kl_l(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y, const float *sumY, float b0,
           float b1, float b2, int k, int cols, int max_iter, float rel_tol, unsigned long long *sweeps, double *kl_part,
-          double *sq_part, int err, int max_nnz, int avg_nnz, cudaStream_t st)
+          double *sq_part, int err, int max_nnz, int avg_nnz, const int *order, const int *sorted_cnt, cudaStream_t st)
 {
-    if (avg_nnz > 320)
-        kl_launch_nt<512>(ptr, idx, val, ajt, X, Y, sumY, b0, b1, b2, k, cols, max_iter, rel_tol, sweeps, kl_part, sq_part, err,
-                          max_nnz, st);
-    else if (avg_nnz > 96)
-        kl_launch_nt<256>(ptr, idx, val, ajt, X, Y, sumY, b0, b1, b2, k, cols, max_iter, rel_tol, sweeps, kl_part, sq_part, err,
-                          max_nnz, st);
-    else
-        kl_launch_nt<64>(ptr, idx, val, ajt, X, Y, sumY, b0, b1, b2, k, cols, max_iter, rel_tol, sweeps, kl_part, sq_part, err,
-                         max_nnz, st);
+    // Threads per column.  Every warp of the block pays the per-coordinate reduction (two butterflies, a barrier, the Newton
+    // step) whatever the column length, so a thread should own several nonzeros: at cfg2 (456 / 684 nonzeros per column,
+    // k = 16) 512 threads per column executed ~150 warp instructions per 32 nonzero-coordinates and ran issue-bound (65 %
+    // issue slots, ncu); measured per iteration, both sides: NT 512 / 256 / 128 / 64 = 307 / 239 / 232 / 308 us.
+    int nt = avg_nnz > 2048 ? 512 : (avg_nnz > 1024 ? 256 : (avg_nnz > 96 ? 128 : 64));
+    const char *nt_e = getenv("SWNE_KL_NT");     // debug knob, read at launch: threads per column
+    if (nt_e) nt = atoi(nt_e);
+#define KL_NT_CASE(NTV)                                                                                                         \
+    case NTV:                                                                                                                   \
+        kl_launch_nt<NTV>(ptr, idx, val, ajt, X, Y, sumY, b0, b1, b2, k, cols, max_iter, rel_tol, sweeps, kl_part, sq_part, err, \
+                          max_nnz, order, sorted_cnt, st);                                                                      \
+        break;
+    switch (nt) {
+        KL_NT_CASE(64)
+        KL_NT_CASE(128)
+        KL_NT_CASE(256)
+        default:
+        KL_NT_CASE(512)
+    }
+#undef KL_NT_CASE
 }
 void kl_shard_init_l(const int *ptr, const int *idx, float *ajt, const float *X, const float *Y, int k, int cols, float *dprev,
                      float *sumX, int *active, cudaStream_t st)

@@ -515,6 +515,7 @@ __global__ void __launch_bounds__(128) scd_ls_solve_kernel(float *__restrict__ X
 // every thread owns one or two nonzeros: the per-coordinate chain is latency bound, not work bound).  (scd_kl_update)
 //   ptr/idx/val : the sparse view whose "columns" are the columns being solved
 //   X  [cols][KP] in/out;  Y [rows][KP] the fixed factor (row r = factors of entity r);  sumY[KP]
+//   order / sorted_cnt : the columns by descending length (device) and their lengths (host), or null
 //   err: bit 0 (KL_ERR) add sum a log(ahat+tiny) and sum a^2-2 a ahat;  bit 1 (KL_L2_LATE) the other reading of NNLM's
 //        Newton step with an L2 penalty (see kl_column)
 // A column with at most `cap` nonzeros is staged once in shared memory -- the gathered rows of Y
@@ -642,7 +643,8 @@ __global__ void __launch_bounds__(NT) scd_kl_kernel(const int *__restrict__ ptr,
                                                     float *__restrict__ X, const float *__restrict__ Y,
                                                     const float *__restrict__ sumY, float b0, float b1, float b2, int k,
                                                     int cols, int max_iter, float rel_tol, unsigned long long *sweeps,
-                                                    double *kl_part, double *sq_part, int err, int cap)
+                                                    double *kl_part, double *sq_part, int err, int cap,
+                                                    const int *__restrict__ order, int first)
 {
     extern __shared__ __align__(16) float kl_dyn[];   // Yt[KP][cap] | aj[cap] | av[cap]
     __shared__ __align__(16) float h[KP];
@@ -651,7 +653,10 @@ __global__ void __launch_bounds__(NT) scd_kl_kernel(const int *__restrict__ ptr,
     float *Yt = kl_dyn, *aj = kl_dyn + (size_t)KP * cap, *av = aj + cap;
     unsigned long long its = 0;
     double klp = 0.0, sqp = 0.0;
-    for (int j = blockIdx.x; j < cols; j += gridDim.x) {
+    // `cols` columns of this launch: order[first .. first + cols) (columns sorted by length, so that one launch holds
+    // columns of similar length and its staging buffers are sized for them), or first .. first + cols when order is null
+    for (int t = blockIdx.x; t < cols; t += gridDim.x) {
+        const int j = order ? order[first + t] : first + t;
         __syncthreads();
         if (threadIdx.x < KP) h[threadIdx.x] = X[(size_t)j * KP + threadIdx.x];
         __syncthreads();

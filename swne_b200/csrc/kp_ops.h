@@ -19,7 +19,8 @@ struct KpOps {
                   unsigned long long *sweeps, double *loss_part, cudaStream_t st);
     void (*kl)(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y, const float *sumY,
                float b0, float b1, float b2, int k, int cols, int max_iter, float rel_tol, unsigned long long *sweeps,
-               double *kl_part, double *sq_part, int err, int max_nnz, int avg_nnz, cudaStream_t st);
+               double *kl_part, double *sq_part, int err, int max_nnz, int avg_nnz, const int *order, const int *sorted_cnt_host,
+               cudaStream_t st);
     // gene side of the KL update with the cells sharded over ranks (kernels_simt.cuh, kl_shard_*): init of A-hat and the
     // per-gene state, the rank's partial Newton sums of coordinate kk (part: float2 per gene), the replicated step, sweep end
     void (*kl_shard_init)(const int *ptr, const int *idx, float *ajt, const float *X, const float *Y, int k, int cols, float *dprev,

@@ -118,6 +118,8 @@ struct SparseView {
     bool ready = false;
     DevBuf<int> cptr, cidx, gptr, gidx;
     DevBuf<float> cval, gval, ajt;
+    DevBuf<int> corder, gorder;                 // columns of each view by descending length (the KL solver's launch classes)
+    std::vector<int> ccnt_sorted, gcnt_sorted;  // their lengths, host side
     size_t nnz = 0;
     int cmax = 0, gmax = 0;   // longest column of each view (sizes the shared-memory staging of the KL solver)
 };
@@ -353,6 +355,21 @@ static void ensure_sparse(swne_nmf_handle_s *h)
         CUDA_CHECK(cudaStreamSynchronize(st));
         sp.cmax = m ? *std::max_element(hc.begin(), hc.end()) : 0;
         sp.gmax = n ? *std::max_element(hg.begin(), hg.end()) : 0;
+        // the columns of each view by descending length: the KL solver sizes its staging buffers per launch, and runs the
+        // few long columns apart from the many short ones (kernels_kp.cu, kl_launch_nt)
+        auto sorted_order = [&](const std::vector<int> &cntv, DevBuf<int> &order, std::vector<int> &sorted) {
+            std::vector<int> ord(cntv.size());
+            for (size_t q = 0; q < ord.size(); ++q) ord[q] = (int)q;
+            std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return cntv[a] > cntv[b]; });
+            sorted.resize(ord.size());
+            for (size_t q = 0; q < ord.size(); ++q) sorted[q] = cntv[ord[q]];
+            order.reserve(ord.size());
+            if (!ord.empty())
+                CUDA_CHECK(cudaMemcpyAsync(order.p, ord.data(), sizeof(int) * ord.size(), cudaMemcpyHostToDevice, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));   // ord is a local
+        };
+        sorted_order(hc, sp.corder, sp.ccnt_sorted);
+        sorted_order(hg, sp.gorder, sp.gcnt_sorted);
     }
     cnt.release(); cnt2.release(); tot.release();
     sp.ready = true;
@@ -461,10 +478,12 @@ static void launch_kl(swne_nmf_handle_s *h, int k, int KPv, const int *ptr, cons
                       const float *Y, const float *sumY, const double *pen, int cols, int max_iter, float rel_tol,
                       unsigned long long *sweeps, FitScalars *sc, int err)
 {
-    const int max_nnz = (ptr == h->sp.cptr.p) ? h->sp.cmax : h->sp.gmax;
-    const int avg_nnz = (int)(h->sp.nnz / (size_t)std::max(1, (ptr == h->sp.cptr.p) ? h->m : h->n));
+    const bool by_cell = ptr == h->sp.cptr.p;
+    const int max_nnz = by_cell ? h->sp.cmax : h->sp.gmax;
+    const int avg_nnz = (int)(h->sp.nnz / (size_t)std::max(1, by_cell ? h->m : h->n));
     ops_of(KPv).kl(ptr, idx, val, h->sp.ajt.p, X, Y, sumY, (float)pen[0], (float)pen[1], (float)pen[2], k, cols, max_iter,
-                   rel_tol, sweeps, &sc->kl_part, &sc->sq_part, err | h->kl_flags, max_nnz, avg_nnz, h->stream);
+                   rel_tol, sweeps, &sc->kl_part, &sc->sq_part, err | h->kl_flags, max_nnz, avg_nnz,
+                   by_cell ? h->sp.corder.p : h->sp.gorder.p, by_cell ? h->sp.ccnt_sorted.data() : h->sp.gcnt_sorted.data(), h->stream);
     CUDA_CHECK(cudaGetLastError());
 }
 

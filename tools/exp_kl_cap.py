@@ -1,6 +1,7 @@
 """mkl at BASELINE cfg2 (2000 x 3000, k = 16): time per iteration and GPU-vs-GPU agreement for several bounds on the staged
-column length of scd_kl_kernel (SWNE_KL_CAP; 0 = the longest column), and for the coordinate-stepped gene side that a
-cell-sharded fit uses (SWNE_KL_SHARD_STEP)."""
+column length of scd_kl_kernel (SWNE_KL_CAP: longer columns run on the global arrays), for the default two-class launch
+(columns sorted by length, long ones apart) against a single launch (SWNE_KL_SPLIT=0), and for the coordinate-stepped gene
+side that a cell-sharded fit uses (SWNE_KL_SHARD_STEP)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -20,9 +21,10 @@ info = h.matrix_info()
 ini = zero_replace(dict(W=Wn, H=Hn), info["sum"] / (float(info["n"]) * info["m"]), np.random.default_rng(0))
 kw = dict(loss="mkl", beta=[0, 0, 0.1], rel_tol=-1.0)
 base = None
-for name, env in [("default", {}), ("cap 400", {"SWNE_KL_CAP": "400"}), ("cap 600", {"SWNE_KL_CAP": "600"}),
-                  ("cap 800", {"SWNE_KL_CAP": "800"}), ("cap 1000", {"SWNE_KL_CAP": "1000"}), ("cap 1400", {"SWNE_KL_CAP": "1400"}),
-                  ("cap 2000", {"SWNE_KL_CAP": "2000"}), ("sharded step", {"SWNE_KL_SHARD_STEP": "1"})]:
+for name, env in [("default", {}), ("NT 64", {"SWNE_KL_NT": "64"}), ("NT 128", {"SWNE_KL_NT": "128"}), ("NT 256", {"SWNE_KL_NT": "256"}),
+                  ("NT 512", {"SWNE_KL_NT": "512"}), ("NT 128 one launch", {"SWNE_KL_NT": "128", "SWNE_KL_SPLIT": "0"}),
+                  ("NT 64 one launch", {"SWNE_KL_NT": "64", "SWNE_KL_SPLIT": "0"}), ("one launch", {"SWNE_KL_SPLIT": "0"}),
+                  ("sharded step", {"SWNE_KL_SHARD_STEP": "1"})]:
     os.environ.update(env)
     try:
         h.fit(c["k"], ini["W"], ini["H"], max_iter=5, trace=100, **kw)
@@ -33,6 +35,6 @@ for name, env in [("default", {}), ("cap 400", {"SWNE_KL_CAP": "400"}), ("cap 60
             del os.environ[e]
     if base is None:
         base = p
-    print("cfg2 mkl %-13s %.1f us/iteration | vs default after 40 iterations: loss %.1e W %.1e H %.1e" % (
+    print("cfg2 mkl %-18s %.1f us/iteration | vs default after 40 iterations: loss %.1e W %.1e H %.1e" % (
         name, 1e3 * r.stats["loop_ms"] / 200, max_rel(p.target_loss, base.target_loss), rel_fro(p.W, base.W), rel_fro(p.H, base.H)), flush=True)
 h.close()
