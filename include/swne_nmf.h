@@ -95,7 +95,8 @@ typedef struct swne_nmf_result {
     double download_ms;    /* device->host time of W/H */
     long long gpu_launches;/* kernels launched inside the loop */
     /* profile==1: per kernel family summed event time and launch count.
-       slot 0 pass/contract-H, 1 solve-H, 2 contract-W, 3 solve-W, 4 gram/loss, 5 mkl update, 6 allreduce */
+       slot 0 pass/contract-H, 1 solve-H (mkl: the cell side's KL update), 2 contract-W, 3 solve-W, 4 gram/loss,
+       5 mkl: the gene side's KL update, 6 allreduce */
     double prof_ms[SWNE_PROF_SLOTS];
     long long prof_launches[SWNE_PROF_SLOTS];
 } swne_nmf_result_t;

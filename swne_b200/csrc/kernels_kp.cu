@@ -46,8 +46,10 @@ template <int NT>
 static void kl_launch_nt(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y,
                          const float *sumY, float b0, float b1, float b2, int k, int cols, int max_iter, float rel_tol,
                          unsigned long long *sweeps, double *kl_part, double *sq_part, int err, int max_nnz, const int *order,
-                         const int *sorted_cnt, cudaStream_t st)
+                         const int *sorted_cnt, cudaStream_t st, int first0 = 0)
 {
+    // the launch covers columns order[first0 .. first0 + cols) (first0 > 0: the warp kernel took the shorter ones)
+    if (sorted_cnt) sorted_cnt += first0;
     // shared-memory staging of one column: (KP + 2) floats per nonzero; columns longer than cap run on global arrays
     // set on every launch: the attribute is per device, and one process may drive several GPUs (one handle each)
     const int smem_budget = 200 * 1024;
@@ -83,7 +85,7 @@ static void kl_launch_nt(const int *ptr, const int *idx, const float *val, float
         if (cap_short < 4) cap_short = 4;
     }
     for (int part = 0; part < 2; ++part) {
-        const int first = part == 0 ? 0 : n_long;
+        const int first = first0 + (part == 0 ? 0 : n_long);
         const int count = part == 0 ? (cap_short == cap ? cols : n_long) : cols - n_long;
         if (part == 1 && cap_short == cap) break;
         if (count <= 0) continue;
@@ -95,15 +97,84 @@ static void kl_launch_nt(const int *ptr, const int *idx, const float *val, float
                                                       sweeps, kl_part, sq_part, err, cap_l, order, first);
     }
 }
+// ---- scd_kl_warp_kernel: one warp per column, 12 bytes of shared memory per nonzero
+constexpr int KLW_CAP_MAX = 2048;     // longer columns stay with the block kernel
+static int klw_blocks_per_sm(int cap)
+{
+    const size_t smem = (size_t)(KLW_THREADS / 32) * (3 * (size_t)cap + KP) * sizeof(float);
+    int b = (int)((216 * 1024) / (smem + 1024));
+    return b < 1 ? 1 : (b > 8 ? 8 : b);           // 8 blocks of 4 warps: beyond 32 warps per SM the kernel is issue-bound anyway
+}
+static void kl_warp_launch(const int *ptr, const int *idx, const float *val, float *X, const float *Y, const float *Yt, size_t ld,
+                           const float *sumY, float b0, float b1, float b2, int k, int max_iter, float rel_tol,
+                           unsigned long long *sweeps, double *kl_part, double *sq_part, int err, const int *order,
+                           const int *sorted_cnt, int first0, int cols, cudaStream_t st)
+{
+    if (cols <= 0) return;
+    constexpr int WPB = KLW_THREADS / 32;
+    cudaFuncSetAttribute(scd_kl_warp_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const int *cnt = sorted_cnt + first0;          // descending
+    int cap_all = (cnt[0] + 3) & ~3;
+    if (cap_all < 4) cap_all = 4;
+    // two classes as in kl_launch_nt: the longer columns with the buffer of the longest, the rest with a buffer that lets
+    // more blocks share an SM; the cut minimises the number of block rounds
+    const int p_all = klw_blocks_per_sm(cap_all);
+    int n_long = 0, cap_short = cap_all;
+    double best = (double)cols / (148.0 * p_all);
+    for (int P = p_all + 1; P <= 8 && cols > 148 * WPB; ++P) {
+        const long per_warp_floats = ((216 * 1024) / P - 1024) / WPB / (long)sizeof(float);
+        int cap_p = (int)((per_warp_floats - KP) / 3) & ~3;
+        if (cap_p < 4) break;
+        int lo = 0, hi = cols;
+        while (lo < hi) { const int mid = (lo + hi) / 2; if (cnt[mid] > cap_p) lo = mid + 1; else hi = mid; }
+        const double rounds = (double)lo / (148.0 * p_all) + (double)(cols - lo) / (148.0 * P);
+        if (lo < cols && rounds < best) { best = rounds; n_long = lo; cap_short = (cnt[lo] + 3) & ~3; }
+    }
+    if (cap_short < 4) cap_short = 4;
+    for (int part = 0; part < 2; ++part) {
+        const bool split = cap_short != cap_all;
+        if (part == 1 && !split) break;
+        const int first = first0 + (part == 0 ? 0 : n_long);
+        const int count = part == 0 ? (split ? n_long : cols) : cols - n_long;
+        if (count <= 0) continue;
+        const int cap_l = part == 0 ? cap_all : cap_short;
+        const size_t smem = (size_t)WPB * (3 * (size_t)cap_l + KP) * sizeof(float);
+        const int bps = klw_blocks_per_sm(cap_l);
+        int grid = (count + WPB - 1) / WPB;
+        if (grid > 148 * bps) grid = 148 * bps;
+        scd_kl_warp_kernel<KP><<<grid, KLW_THREADS, smem, st>>>(ptr, idx, val, X, Y, Yt, ld, sumY, b0, b1, b2, k, count, max_iter,
+                                                                rel_tol, sweeps, kl_part, sq_part, err, cap_l, order, first);
+    }
+}
 void kl_l(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y, const float *sumY, float b0,
           float b1, float b2, int k, int cols, int max_iter, float rel_tol, unsigned long long *sweeps, double *kl_part,
-          double *sq_part, int err, int max_nnz, int avg_nnz, const int *order, const int *sorted_cnt, cudaStream_t st)
+          double *sq_part, int err, int max_nnz, int avg_nnz, const int *order, const int *sorted_cnt, const float *Yt, size_t ld,
+          cudaStream_t st)
 {
+    // Columns of up to KLW_CAP_MAX nonzeros: one warp per column (scd_kl_warp_kernel); the longer ones: one block per column.
+    // A warp walks its column alone (14-20 nonzeros per lane and coordinate at cfg2), so the warp kernel needs many more columns
+    // than warp slots to win: with 3000 columns (cfg2) it has 20 warps per SM running one column each and takes 440 us per
+    // iteration against the block kernel's 234; it is used from 2 x 32 warps per SM upward.  SWNE_KL_WARP=0 / 1 (debug
+    // knob, read at launch) forces the block / warp kernel.
+    const char *warp_e = getenv("SWNE_KL_WARP");
+    const bool warp_want = warp_e ? atoi(warp_e) != 0 : cols >= 148 * 64;
+    const bool warp_on = Yt && order && sorted_cnt && cols > 0 && warp_want;
+    int n_big = 0;      // columns [0, n_big) of the sorted order are longer than KLW_CAP_MAX
+    if (warp_on) {
+        int lo = 0, hi = cols;
+        while (lo < hi) { const int mid = (lo + hi) / 2; if (sorted_cnt[mid] > KLW_CAP_MAX) lo = mid + 1; else hi = mid; }
+        n_big = lo;
+        kl_warp_launch(ptr, idx, val, X, Y, Yt, ld, sumY, b0, b1, b2, k, max_iter, rel_tol, sweeps, kl_part, sq_part, err, order,
+                       sorted_cnt, n_big, cols - n_big, st);
+        if (n_big == 0) return;
+        cols = n_big;
+    }
     // Threads per column.  Every warp of the block pays the per-coordinate reduction (two butterflies, a barrier, the Newton
     // step) whatever the column length, so a thread should own several nonzeros: at cfg2 (456 / 684 nonzeros per column,
     // k = 16) 512 threads per column executed ~150 warp instructions per 32 nonzero-coordinates and ran issue-bound (65 %
     // issue slots, ncu); measured per iteration, both sides: NT 512 / 256 / 128 / 64 = 307 / 239 / 232 / 308 us.
     int nt = avg_nnz > 2048 ? 512 : (avg_nnz > 1024 ? 256 : (avg_nnz > 96 ? 128 : 64));
+    if (warp_on) nt = 512;                        // only the long columns are left
     const char *nt_e = getenv("SWNE_KL_NT");     // debug knob, read at launch: threads per column
     if (nt_e) nt = atoi(nt_e);
 #define KL_NT_CASE(NTV)                                                                                                         \
@@ -125,11 +196,15 @@ void kl_shard_init_l(const int *ptr, const int *idx, float *ajt, const float *X,
 {
     kl_shard_init_kernel<KP><<<cols < 148 * 8 ? cols : 148 * 8, 256, 0, st>>>(ptr, idx, ajt, X, Y, k, cols, dprev, sumX, active);
 }
-void kl_shard_accum_l(const int *ptr, const int *idx, const float *val, float *ajt, const float *Y, const float *dprev,
+void kl_shard_transpose_l(const float *Y, int rows, float *Yt, size_t ld, cudaStream_t st)
+{
+    if (rows > 0) kl_shard_transpose_kernel<KP><<<(rows + 31) / 32, 256, 0, st>>>(Y, rows, Yt, ld);
+}
+void kl_shard_accum_l(const int *ptr, const int *idx, const float *val, float *ajt, const float *Yt, size_t ld, const float *dprev,
                       const int *active, int kk, int kprev, int cols, float *part, cudaStream_t st)
 {
-    kl_shard_accum_kernel<KP><<<cols < 148 * 8 ? cols : 148 * 8, 256, 0, st>>>(ptr, idx, val, ajt, Y, dprev, active, kk, kprev, cols,
-                                                                               reinterpret_cast<float2 *>(part));
+    kl_shard_accum_kernel<KP><<<cols < 148 * 8 ? cols : 148 * 8, 256, 0, st>>>(ptr, idx, val, ajt, Yt, ld, dprev, active, kk, kprev,
+                                                                               cols, reinterpret_cast<float2 *>(part));
 }
 void kl_shard_update_l(const float *part, float *X, const float *sumY, float *sumX, float *dprev, int *active, float b0, float b1,
                        float b2, int kk, int cols, float rel_tol, int flags, cudaStream_t st)
@@ -169,7 +244,7 @@ void ica_step_l(const float *Y, int rows, int nc, const float *R, double *out, i
 
 #define KP_OPS_NAME2(v) kp_ops_table_##v
 #define KP_OPS_NAME(v) KP_OPS_NAME2(v)
-extern const KpOps KP_OPS_NAME(KP_VALUE) = {gram_l, contract_cells_l, contract_genes_l, solve_l, kl_l, kl_shard_init_l, kl_shard_accum_l,
+extern const KpOps KP_OPS_NAME(KP_VALUE) = {gram_l, contract_cells_l, contract_genes_l, solve_l, kl_l, kl_shard_init_l, kl_shard_transpose_l, kl_shard_accum_l,
                                             kl_shard_update_l, kl_shard_sweep_end_l, kl_trace_l,
                                             recon_error_l, right_multiply_l, ica_step_l};
 }  // namespace swne

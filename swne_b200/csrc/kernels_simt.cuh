@@ -681,6 +681,137 @@ __global__ void __launch_bounds__(NT) scd_kl_kernel(const int *__restrict__ ptr,
 }
 
 // ----------------------------------------------------------------------------------------------
+// SCD KL update, one WARP per column (scd_kl_update) -- the kernel for columns of up to a few thousand
+// nonzeros.  scd_kl_kernel stages the gathered rows of the fixed factor ((KP + 2) floats per nonzero), which caps an SM at
+// 3-4 columns in flight, and pays a block-wide reduction per coordinate in every warp (ncu: 65 % issue slots at 137 warp
+// instructions of overhead per warp and coordinate).  Here a column costs 12 bytes of shared memory per nonzero (A-hat, the
+// value, the row index), the coordinate step reads column kk of the fixed factor from its factor-major copy Yt[kk][row]
+// (the rows of a column ascend, so a warp's gather touches a few L1-resident lines), and the reduction is one butterfly
+// with no barrier: 16-32 columns per SM in flight and ~3x fewer instructions per nonzero-coordinate.
+//   X [cols][KP] in/out;  Y [rows][KP] the fixed factor, Yt [KP][ld] its factor-major copy;  the launcher guarantees
+//   nz <= cap for every column of the launch;  err as in scd_kl_kernel
+// ----------------------------------------------------------------------------------------------
+constexpr int KLW_THREADS = 128;
+template <int KP>
+__global__ void __launch_bounds__(KLW_THREADS) scd_kl_warp_kernel(
+    const int *__restrict__ ptr, const int *__restrict__ idx, const float *__restrict__ val, float *__restrict__ X,
+    const float *__restrict__ Y, const float *__restrict__ Yt, size_t ld, const float *__restrict__ sumY, float b0, float b1,
+    float b2, int k, int count, int max_iter, float rel_tol, unsigned long long *sweeps, double *kl_part, double *sq_part,
+    int err, int cap, const int *__restrict__ order, int first)
+{
+    extern __shared__ __align__(16) float klw_dyn[];   // per warp: aj[cap] | av[cap] | ix[cap] | h[KP]
+    constexpr int WPB = KLW_THREADS / 32;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float *aj = klw_dyn + (size_t)wib * (3 * (size_t)cap + KP);
+    float *av = aj + cap;
+    int *ix = reinterpret_cast<int *>(av + cap);
+    float *hs = reinterpret_cast<float *>(ix + cap);
+    const int gw = blockIdx.x * WPB + wib, nw = gridDim.x * WPB;
+    unsigned long long its = 0;
+    double klp = 0.0, sqp = 0.0;
+    for (int t = gw; t < count; t += nw) {
+        const int j = order ? order[first + t] : first + t;
+        const int b = ptr[j], nz = ptr[j + 1] - b;
+        __syncwarp();
+        for (int f = lane; f < KP; f += 32) hs[f] = X[(size_t)j * KP + f];
+        __syncwarp();
+        float sumH = 0.f;
+        for (int f = 0; f < k; ++f) sumH += hs[f];
+        // stage the column: A-hat = (row of Y) . h on the support, the values, the row indices
+        for (int q = lane; q < nz; q += 32) {
+            const int r = idx[b + q];
+            const float4 *y4 = reinterpret_cast<const float4 *>(Y + (size_t)r * KP);
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < KP / 4; ++c) {
+                const float4 y = __ldg(y4 + c);
+                const float4 hh = *reinterpret_cast<const float4 *>(hs + 4 * c);
+                s = fmaf(y.x, hh.x, s); s = fmaf(y.y, hh.y, s); s = fmaf(y.z, hh.z, s); s = fmaf(y.w, hh.w, s);
+            }
+            aj[q] = s; av[q] = val[b + q]; ix[q] = r;
+        }
+        __syncwarp();
+        int it = 0;
+        bool again = true;
+        float d_prev = 0.f;      // the A-hat update of the previous coordinate, applied on the way into the next one
+        int k_prev = 0;
+        for (; it < max_iter && again; ++it) {
+            again = false;
+            for (int kk = 0; kk < k; ++kk) {
+                const float hk = hs[kk];
+                const float *__restrict__ yk = Yt + (size_t)kk * ld;
+                float a2 = 0.f, bb = 0.f;
+                if (d_prev != 0.f) {       // warp-uniform
+                    const float *__restrict__ yp = Yt + (size_t)k_prev * ld;
+#pragma unroll 4
+                    for (int q = lane; q < nz; q += 32) {
+                        const int r = ix[q];
+                        // exact arithmetic keeps A-hat >= 0 (d >= -h_kk); fp32 rounding may not: clamp
+                        const float a = fmaxf(fmaf(d_prev, __ldg(yp + r), aj[q]), 0.f);
+                        aj[q] = a;
+                        const float mu = __fdividef(__ldg(yk + r), a + TINY_NUM_F);
+                        const float v = av[q];
+                        a2 = fmaf(v * mu, mu, a2);
+                        bb = fmaf(v, mu, bb);
+                    }
+                } else {
+#pragma unroll 4
+                    for (int q = lane; q < nz; q += 32) {
+                        const float mu = __fdividef(__ldg(yk + ix[q]), aj[q] + TINY_NUM_F);
+                        const float v = av[q];
+                        a2 = fmaf(v * mu, mu, a2);
+                        bb = fmaf(v, mu, bb);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                    bb += __shfl_xor_sync(0xffffffffu, bb, o);
+                }
+                bb -= sumY[kk];
+                float a2h;     // the two readings of NNLM's step with an L2 penalty: see kl_column
+                if (err & KL_L2_LATE) { a2h = a2 * hk; a2 += b0; }
+                else { a2 += b0; a2h = a2 * hk; }
+                bb += a2h - b2 - b1 * (sumH - hk);
+                float tmp = bb / (a2 + TINY_NUM_F);
+                if (!(tmp > 0.f)) tmp = 0.f;
+                d_prev = tmp - hk;
+                k_prev = kk;
+                if (tmp != hk) {
+                    again |= (2.f * fabsf(d_prev) > rel_tol * (tmp + hk + TINY_NUM_F));
+                    sumH += d_prev;
+                    if (lane == 0) hs[kk] = tmp;
+                }
+                __syncwarp();
+            }
+        }
+        its += (unsigned long long)it;
+        if (err & KL_ERR) {
+            // A-hat recomputed from the final h (see kl_column)
+            for (int q = lane; q < nz; q += 32) {
+                const float *y = Y + (size_t)ix[q] * KP;
+                float s = 0.f;
+                for (int f = 0; f < k; ++f) s = fmaf(__ldg(y + f), hs[f], s);
+                const double a = (double)av[q], ah = (double)s;
+                klp += a * log(ah + TINY_NUM_D);
+                sqp += a * a - 2.0 * a * ah;
+            }
+        }
+        __syncwarp();
+        for (int f = lane; f < KP; f += 32) X[(size_t)j * KP + f] = hs[f];
+    }
+    if (lane == 0 && its) atomicAdd(sweeps, its);
+    if (err & KL_ERR) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            klp += __shfl_xor_sync(0xffffffffu, klp, o);
+            sqp += __shfl_xor_sync(0xffffffffu, sqp, o);
+        }
+        if (lane == 0) { atomicAdd(kl_part, klp); atomicAdd(sq_part, sqp); }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // SCD KL update of the gene side when the cells are sharded over ranks (scd_kl_update).
 // A gene's row of A is spread over all ranks, so one coordinate step is split at the point where the Newton sums are
 // complete:   kl_shard_accum (the rank's part of sum a mu^2, sum a mu on its own nonzeros, with the A-hat update of the
@@ -720,13 +851,36 @@ __global__ void __launch_bounds__(256) kl_shard_init_kernel(const int *__restric
     }
 }
 
+// Yt[f][r] = Y[r][f]: the fixed factor in factor-major order (row stride ld).  A coordinate step only needs column kk of Y,
+// and the nonzeros of a by-gene row come in ascending cell order, so the gathers of the step walk one dense vector almost
+// in order (a few 128-byte lines per warp) instead of touching one 4 KP-byte row of Y per nonzero.
+template <int KP>
+__global__ void __launch_bounds__(256) kl_shard_transpose_kernel(const float *__restrict__ Y, int rows, float *__restrict__ Yt,
+                                                                 size_t ld)
+{
+    __shared__ float tile[32][KP + 1];
+    const int r0 = blockIdx.x * 32;
+    for (int t = threadIdx.x; t < 32 * KP; t += 256) {
+        const int r = t / KP, f = t % KP;
+        tile[r][f] = (r0 + r < rows) ? Y[(size_t)(r0 + r) * KP + f] : 0.f;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 32 * KP; t += 256) {
+        const int f = t / 32, r = t % 32;
+        if (r0 + r < rows) Yt[(size_t)f * ld + r0 + r] = tile[r][f];
+    }
+}
+
 template <int KP>
 __global__ void __launch_bounds__(256) kl_shard_accum_kernel(const int *__restrict__ ptr, const int *__restrict__ idx,
                                                              const float *__restrict__ val, float *__restrict__ ajt,
-                                                             const float *__restrict__ Y, const float *__restrict__ dprev,
+                                                             const float *__restrict__ Yt, size_t ld,
+                                                             const float *__restrict__ dprev,
                                                              const int *__restrict__ active, int kk, int kprev, int cols,
                                                              float2 *__restrict__ part)
 {
+    const float *__restrict__ yk = Yt + (size_t)kk * ld;
+    const float *__restrict__ yp = Yt + (size_t)kprev * ld;
     __shared__ float red[2][8];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int j = blockIdx.x; j < cols; j += gridDim.x) {
@@ -738,13 +892,13 @@ __global__ void __launch_bounds__(256) kl_shard_accum_kernel(const int *__restri
         const float d = dprev[j];
         float a2 = 0.f, bb = 0.f;
         for (int q = tid; q < nz; q += 256) {
-            const float *y = Y + (size_t)idx[b + q] * KP;
+            const int r = idx[b + q];
             float a = ajt[b + q];
             if (d != 0.f) {
-                a = fmaxf(fmaf(d, __ldg(y + kprev), a), 0.f);
+                a = fmaxf(fmaf(d, __ldg(yp + r), a), 0.f);
                 ajt[b + q] = a;
             }
-            const float w = __ldg(y + kk), v = val[b + q];
+            const float w = __ldg(yk + r), v = val[b + q];
             const float mu = __fdividef(w, a + TINY_NUM_F);
             a2 = fmaf(v * mu, mu, a2);
             bb = fmaf(v, mu, bb);

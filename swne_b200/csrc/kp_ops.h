@@ -20,13 +20,14 @@ struct KpOps {
     void (*kl)(const int *ptr, const int *idx, const float *val, float *ajt, float *X, const float *Y, const float *sumY,
                float b0, float b1, float b2, int k, int cols, int max_iter, float rel_tol, unsigned long long *sweeps,
                double *kl_part, double *sq_part, int err, int max_nnz, int avg_nnz, const int *order, const int *sorted_cnt_host,
-               cudaStream_t st);
+               const float *Yt, size_t ld, cudaStream_t st);   // Yt: factor-major copy of Y (kl_shard_transpose) or null
     // gene side of the KL update with the cells sharded over ranks (kernels_simt.cuh, kl_shard_*): init of A-hat and the
     // per-gene state, the rank's partial Newton sums of coordinate kk (part: float2 per gene), the replicated step, sweep end
     void (*kl_shard_init)(const int *ptr, const int *idx, float *ajt, const float *X, const float *Y, int k, int cols, float *dprev,
                           float *sumX, int *active, cudaStream_t st);
-    void (*kl_shard_accum)(const int *ptr, const int *idx, const float *val, float *ajt, const float *Y, const float *dprev,
-                           const int *active, int kk, int kprev, int cols, float *part, cudaStream_t st);
+    void (*kl_shard_transpose)(const float *Y, int rows, float *Yt, size_t ld, cudaStream_t st);   // Yt[f][r] = Y[r][f]
+    void (*kl_shard_accum)(const int *ptr, const int *idx, const float *val, float *ajt, const float *Yt, size_t ld,
+                           const float *dprev, const int *active, int kk, int kprev, int cols, float *part, cudaStream_t st);
     void (*kl_shard_update)(const float *part, float *X, const float *sumY, float *sumX, float *dprev, int *active, float b0,
                             float b1, float b2, int kk, int cols, float rel_tol, int flags, cudaStream_t st);
     void (*kl_shard_sweep_end)(int *active, int cols, unsigned long long *sweeps, unsigned *n_active, cudaStream_t st);

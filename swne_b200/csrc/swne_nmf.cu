@@ -159,6 +159,7 @@ struct swne_nmf_handle_s {
     swne::PeerXchg xchg;                               // NVLink peer-memory exchange of the fused engine's per-iteration sums
     std::vector<cudaEvent_t> ev_slab;           // [2 s] contraction of slab s done, [2 s + 1] its solve done
     swne::DevBuf<float> kls_f;       // sharded KL gene side: Newton partials (2 n), pending delta (n), row sums of W (n)
+    swne::DevBuf<float> kls_yt;      // ... the fixed factor in factor-major order [KP][rows padded to 32]
     swne::DevBuf<int> kls_i;         // ... active / again flags (2 n) and the count of genes still sweeping
     int kl_flags = 0;                // KL_L2_LATE when the fit asks for the alternative reading of NNLM's KL step
     int last_KPv = 0;                // row stride of Wt / H as the last fit left them on the device
@@ -481,9 +482,20 @@ static void launch_kl(swne_nmf_handle_s *h, int k, int KPv, const int *ptr, cons
     const bool by_cell = ptr == h->sp.cptr.p;
     const int max_nnz = by_cell ? h->sp.cmax : h->sp.gmax;
     const int avg_nnz = (int)(h->sp.nnz / (size_t)std::max(1, by_cell ? h->m : h->n));
+    // the fixed factor in factor-major order for the warp-per-column kernel (its coordinate steps read one column of it); the
+    // kernel is chosen by column count (kernels_kp.cu, kl_l: the same rule), so the copy is only made when it will be read
+    const int rows = by_cell ? h->n : h->m;
+    const size_t ld = (size_t)round_up(std::max(rows, 1), 32);
+    const char *warp_e = getenv("SWNE_KL_WARP");
+    const bool warp_want = warp_e ? atoi(warp_e) != 0 : cols >= 148 * 64;
+    if (warp_want) {
+        h->kls_yt.reserve((size_t)KPv * ld);
+        ops_of(KPv).kl_shard_transpose(Y, rows, h->kls_yt.p, ld, h->stream);
+    }
     ops_of(KPv).kl(ptr, idx, val, h->sp.ajt.p, X, Y, sumY, (float)pen[0], (float)pen[1], (float)pen[2], k, cols, max_iter,
                    rel_tol, sweeps, &sc->kl_part, &sc->sq_part, err | h->kl_flags, max_nnz, avg_nnz,
-                   by_cell ? h->sp.corder.p : h->sp.gorder.p, by_cell ? h->sp.ccnt_sorted.data() : h->sp.gcnt_sorted.data(), h->stream);
+                   by_cell ? h->sp.corder.p : h->sp.gorder.p, by_cell ? h->sp.ccnt_sorted.data() : h->sp.gcnt_sorted.data(),
+                   warp_want ? h->kls_yt.p : nullptr, ld, h->stream);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -491,8 +503,8 @@ static void allreduce(swne_nmf_handle_s *h, float *f, size_t nf, double *d, size
 // Gene side of the KL update when the cells are sharded over ranks: a gene's Newton sums run over all cells, so every
 // coordinate step is   partial sums on the rank's nonzeros -> all-reduce of 2 n floats -> the step, replicated
 // (k all-reduces per sweep; NNLM runs one sweep per outer iteration for mkl).  Returns the number of kernel launches.
-static int launch_kl_sharded(swne_nmf_handle_s *h, int k, int KPv, float *X, const float *Y, const float *sumY, const double *pen,
-                             int cols, int max_iter, float rel_tol, unsigned long long *sweeps)
+static int launch_kl_sharded(swne_nmf_handle_s *h, int k, int KPv, float *X, const float *Y, int rows, const float *sumY,
+                             const double *pen, int cols, int max_iter, float rel_tol, unsigned long long *sweeps)
 {
     const KpOps &o = ops_of(KPv);
     cudaStream_t st = h->stream;
@@ -502,11 +514,15 @@ static int launch_kl_sharded(swne_nmf_handle_s *h, int k, int KPv, float *X, con
     float *part = h->kls_f.p, *dprev = part + 2 * (size_t)cols, *sumX = dprev + cols;
     int *active = h->kls_i.p;
     unsigned *n_active = reinterpret_cast<unsigned *>(active + 2 * (size_t)cols);
-    int launches = 1;
+    const size_t ld = (size_t)round_up(std::max(rows, 1), 32);
+    h->kls_yt.reserve((size_t)KPv * ld);
+    int launches = 2;
+    o.kl_shard_transpose(Y, rows, h->kls_yt.p, ld, st);
     o.kl_shard_init(sp.gptr.p, sp.gidx.p, sp.ajt.p, X, Y, k, cols, dprev, sumX, active, st);
     for (int it = 0; it < max_iter; ++it) {
         for (int kk = 0; kk < k; ++kk) {
-            o.kl_shard_accum(sp.gptr.p, sp.gidx.p, sp.gval.p, sp.ajt.p, Y, dprev, active, kk, (kk + k - 1) % k, cols, part, st);
+            o.kl_shard_accum(sp.gptr.p, sp.gidx.p, sp.gval.p, sp.ajt.p, h->kls_yt.p, ld, dprev, active, kk, (kk + k - 1) % k, cols, part,
+                             st);
             allreduce(h, part, 2 * (size_t)cols, nullptr, 0, nullptr, 0);
             o.kl_shard_update(part, X, sumY, sumX, dprev, active, (float)pen[0], (float)pen[1], (float)pen[2], kk, cols, rel_tol,
                               h->kl_flags, st);
@@ -524,6 +540,14 @@ static int launch_kl_sharded(swne_nmf_handle_s *h, int k, int KPv, float *X, con
         }
     }
     return launches;
+}
+
+static bool mse_loss_of(const swne_nmf_params_t &p) { return p.loss == SWNE_LOSS_MSE; }
+// mean gene row of the by-gene view longer than scd_kl_kernel's shared-memory staging (200 KB / (KP + 2) floats per nonzero)
+static bool kl_rows_too_long(const swne_nmf_handle_s *h, int KPv)
+{
+    const size_t cap_max = (200 * 1024) / ((size_t)(KPv + 2) * sizeof(float));
+    return h->sp.ready && h->n > 0 && h->sp.nnz / (size_t)h->n > cap_max;
 }
 
 static void upload_factor_cellmajor(swne_nmf_handle_s *h, const double *src, float *dst, int k, int KPv, size_t cols,
@@ -796,7 +820,10 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
     const bool tcx_solve_simt = getenv("SWNE_TCX_SOLVE_SIMT") != nullptr;   // debug knob, read once per fit
     // mkl with cells sharded over ranks: the gene side runs coordinate by coordinate around an all-reduce (launch_kl_sharded);
     // SWNE_KL_SHARD_STEP takes the same kernels on one GPU (tests)
-    const bool kl_sharded = h->nranks > 1 || getenv("SWNE_KL_SHARD_STEP") != nullptr;
+    // ... and the gene side of one GPU takes them too when a mean gene row is longer than the one-block-per-gene kernel can
+    // stage in shared memory (it would run on the global arrays, measured 1.4-1.5x slower at 3000 x 20 000 / 100 000 cells)
+    const bool kl_sharded = h->nranks > 1 || getenv("SWNE_KL_SHARD_STEP") != nullptr ||
+                            (!mse_loss_of(p) && kl_rows_too_long(h, KPv));
     const bool slab_timeline = getenv("SWNE_TCX_TIMELINE") != nullptr;
     const bool three_streams = getenv("SWNE_TCX_STREAMS2") == nullptr;     // debug knob: both contractions on one stream
     const int genes_regions = getenv("SWNE_TCX_REGIONS") ? atoi(getenv("SWNE_TCX_REGIONS")) : 1;   // debug knob: 2 = double-buffered accumulators
@@ -1122,7 +1149,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             launch_finalize_gram(h, k, KPv, h->G64h.p, h->pack.p, 0.0, 0.0);
             int kl_launches = 1;
             if (kl_sharded)
-                kl_launches = launch_kl_sharded(h, k, KPv, h->Wt.p, h->H.p, pack_colsum(h->pack.p, KPv), p.alpha, n, p.inner_max_iter,
+                kl_launches = launch_kl_sharded(h, k, KPv, h->Wt.p, h->H.p, m, pack_colsum(h->pack.p, KPv), p.alpha, n, p.inner_max_iter,
                                                 inner_tol, &h->dscal.p->sweeps_w);
             else
                 launch_kl(h, k, KPv, h->sp.gptr.p, h->sp.gidx.p, h->sp.gval.p, h->Wt.p, h->H.p, pack_colsum(h->pack.p, KPv), p.alpha, n,
@@ -1132,11 +1159,11 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
             launch_gram(h, KPv, h->Wt.p, n, h->G64w.p);
             launch_finalize_gram(h, k, KPv, h->G64w.p, h->pack.p, 0.0, 0.0);
             prof.end(4, 2);
-            prof.begin(5);
+            prof.begin(1);
             launch_kl(h, k, KPv, h->sp.cptr.p, h->sp.cidx.p, h->sp.cval.p, h->H.p, h->Wt.p, pack_colsum(h->pack.p, KPv), p.beta, m,
                       p.inner_max_iter, inner_tol, &h->dscal.p->sweeps_h, h->dscal.p,
                       (i % p.trace == 0 || i == p.max_iter - 1) ? 1 : 0);
-            prof.end(5, 1);
+            prof.end(1, 1);
             prof.begin(4);
             launch_gram(h, KPv, h->H.p, m, h->G64h.p);
             prof.end(4, 1);
@@ -1250,8 +1277,8 @@ static int nnlm_impl(swne_nmf_handle_s *h, int side, int k, const double *X, dou
         if (side == 0)
             launch_kl(h, k, KPv, h->sp.cptr.p, h->sp.cidx.p, h->sp.cval.p, solve, fixed, pack_colsum(h->pack.p, KPv), pen, cols, max_iter,
                       (float)rel_tol, &h->dscal.p->sweeps_h, h->dscal.p, 0);
-        else if (h->nranks > 1 || getenv("SWNE_KL_SHARD_STEP"))
-            launch_kl_sharded(h, k, KPv, solve, fixed, pack_colsum(h->pack.p, KPv), pen, cols, max_iter, (float)rel_tol,
+        else if (h->nranks > 1 || getenv("SWNE_KL_SHARD_STEP") || kl_rows_too_long(h, KPv))
+            launch_kl_sharded(h, k, KPv, solve, fixed, fixed_rows, pack_colsum(h->pack.p, KPv), pen, cols, max_iter, (float)rel_tol,
                               &h->dscal.p->sweeps_h);
         else
             launch_kl(h, k, KPv, h->sp.gptr.p, h->sp.gidx.p, h->sp.gval.p, solve, fixed, pack_colsum(h->pack.p, KPv), pen, cols, max_iter,

@@ -211,6 +211,36 @@ def test_mkl_sharded_gene_side_kernels_on_one_gpu(handle):
         del os.environ["SWNE_KL_SHARD_STEP"]
 
 
+def test_mkl_warp_per_column_kernel_vs_oracle(handle):
+    """scd_kl_warp_kernel (one warp per column, factor-major gathers) is chosen by column count (>= 9472 columns); SWNE_KL_WARP=1
+    forces it on a small case and on the golden fixtures' shapes: same bars against the oracle as the block kernel, with all
+    three penalties on both sides, the alternative reading of the L2 step, and nnlm on both sides."""
+    from oracle import nnmf_ref, nnlm_ref
+    A = small_matrix(300, 500, 6, 4)
+    W0, H0 = seeded_init(A, 8, 4)
+    handle.set_matrix(A)
+    os.environ["SWNE_KL_WARP"] = "1"
+    try:
+        for late in (False, True):
+            kw = dict(loss="mkl", alpha=[0.2, 0.01, 0.02], beta=[0.1, 0, 0.05], max_iter=30, trace=1, rel_tol=-1.0)
+            ref = nnmf_ref(A, 8, W0, H0, kl_l2_late=late, **kw)
+            r = handle.fit(8, W0, H0, kl_l2_late=late, **kw)
+            within("warp-kernel mkl target_loss, max rel (kl_l2_late=%d)" % late, max_rel(r["target_loss"], ref["target_loss"]), LOSS_TOL)
+            within("warp-kernel mse of the mkl fit, max rel (kl_l2_late=%d)" % late, max_rel(r["mse"], ref["mse"]), LOSS_TOL)
+            within("warp-kernel W rel Frobenius (kl_l2_late=%d)" % late, rel_fro(r["W"], ref["W"]), FACTOR_TOL)
+            within("warp-kernel H rel Frobenius (kl_l2_late=%d)" % late, rel_fro(r["H"], ref["H"]), FACTOR_TOL)
+            within("warp-kernel average_epochs, max rel", max_rel(r["average_epochs"], ref["average_epochs"]), 0.05)
+        Hfix = np.random.default_rng(4).gamma(0.5, 1.0, size=(6, 500))
+        refW = nnlm_ref(Hfix.T, A.T, loss="mkl", init=np.full((6, 300), 0.005), max_iter=200)["coefficients"].T
+        rW = handle.nnlm(1, Hfix, init=np.full((300, 6), 0.005), loss="mkl", max_iter=200)["coefficients"]
+        within("warp-kernel nnlm gene side (mkl)", rel_fro(rW, refW), FACTOR_TOL)
+        refH = nnlm_ref(refW, A, loss="mkl", init=np.full((6, 500), 0.005), max_iter=200)["coefficients"]
+        rH = handle.nnlm(0, refW, init=np.full((6, 500), 0.005), loss="mkl", max_iter=200)["coefficients"]
+        within("warp-kernel nnlm cell side (mkl)", rel_fro(rH, refH), FACTOR_TOL)
+    finally:
+        del os.environ["SWNE_KL_WARP"]
+
+
 def _match_components(S, Sref):
     """|correlation| of every reference component with its best match among S (components are defined up to sign/order)"""
     S = (S - S.mean(axis=1, keepdims=True)); Sref = (Sref - Sref.mean(axis=1, keepdims=True))
