@@ -205,7 +205,9 @@ int swne_ica_init(swne_nmf_handle_t h, int k, int ica_fast, uint64_t seed, doubl
 /* x < eps -> 0 in place; returns the number of zeros so the caller can draw its runif()s */
 int swne_zero_replace(double *x, size_t len, double eps, const double *fill, size_t n_fill, size_t *n_zero);
 
-/* ---- consumers of H */
+/* ---- consumers of H.  H = NULL: the H the most recent swne_nmf_fit / swne_run_nmf of this handle left on the device
+ * ("while H is still resident"; k and m must be that fit's; any other call that works on the handle's
+ * factors -- nnlm, recon_error, a seed, set_matrix -- ends the residency).  Identical results to passing the returned H. */
 int swne_sample_coords(swne_nmf_handle_t h, const double *H, int k, int m, const double *H_coords /* k x 2 col-major */,
                        double alpha_exp, int n_pull, double *out /* m x 2 col-major */);
 /* distance: 0 cosine (1 - cos), 1 pearson sqrt(2(1-r)), 2 euclidean; out k x k */

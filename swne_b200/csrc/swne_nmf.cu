@@ -163,6 +163,7 @@ struct swne_nmf_handle_s {
     swne::DevBuf<int> kls_i;         // ... active / again flags (2 n) and the count of genes still sweeping
     int kl_flags = 0;                // KL_L2_LATE when the fit asks for the alternative reading of NNLM's KL step
     int last_KPv = 0;                // row stride of Wt / H as the last fit left them on the device
+    int last_k = 0;                  // k of the fit whose H is still in h->H (0: none -- another call has used the buffer since)
 };
 
 namespace swne {
@@ -220,6 +221,7 @@ static void begin_matrix(swne_nmf_handle_s *h, int n, int m, bool alloc)
     if (n < 1 || m < 1) FAIL(SWNE_ERR_BAD_ARG, "matrix must have at least one row and one column");
     h->sp.ready = false;
     h->tc.ready = false;
+    h->last_k = 0;
     h->n = n; h->m = m;
     h->ldA = round_up_sz((size_t)n, 4);
     if (alloc) {
@@ -718,6 +720,7 @@ typedef std::function<void(int, double, double)> DeviceInitFn;
 static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W, double *H, double *mse_tr, double *mkl_tr,
                     double *terr_tr, double *epo_tr, int trace_len, swne_nmf_result_t *res, const DeviceInitFn *device_init = nullptr)
 {
+    h->last_k = 0;     // set again when this fit has left its H on the device
     if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident: call swne_nmf_set_matrix_* first");
     if (!pp || ((!W || !H) && !device_init)) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
     swne_nmf_params_t p = *pp;
@@ -1203,6 +1206,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
 
     // ---- results (a device-seeded fit may leave them on the device: FindNumFactors only needs the errors)
     h->last_KPv = KPv;
+    h->last_k = k;
     if (W) download_factor_colmajor(h, h->Wt.p, W, k, KPv, n);
     if (H) download_factor_cellmajor(h, h->H.p, H, k, KPv, (size_t)m);
     cudaEventRecord(e4, st);
@@ -1227,6 +1231,7 @@ static int fit_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, double *W
 static int nnlm_impl(swne_nmf_handle_s *h, int side, int k, const double *X, double *coef, const double *alpha3, int loss,
                      int max_iter, double rel_tol, long long *sweeps)
 {
+    h->last_k = 0;     // h->H is about to be reused
     if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident");
     if (!X || !coef) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
     if (k < 1 || k > SWNE_MAX_K) FAIL(SWNE_ERR_BAD_ARG, "k must be in 1..%d", SWNE_MAX_K);
@@ -1480,6 +1485,7 @@ static void nnsvd_split_device(swne_nmf_handle_s *h, const RsvdResult &r, int k,
 static int nnsvd_impl(swne_nmf_handle_s *h, int k, int oversample, int power_iters, uint64_t seed, double *W, double *H,
                       double *sv)
 {
+    h->last_k = 0;     // h->H is about to be reused
     if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident");
     if (!W || !H) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
     const int n = h->n, m = h->m;
@@ -1697,6 +1703,7 @@ static int run_nmf_impl(swne_nmf_handle_s *h, const swne_nmf_params_t *pp, int i
 // ica_init (R/nmf.R:56-66) as a stand-alone call: the signed W (n x k) and H (k x m), before RunNMF's zero replacement
 static int ica_init_impl(swne_nmf_handle_s *h, int k, int ica_fast, uint64_t seed, double *W, double *H)
 {
+    h->last_k = 0;     // h->H is about to be reused
     if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident");
     if (!W || !H) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
     if (k < 1 || k > SWNE_MAX_K) FAIL(SWNE_ERR_BAD_ARG, "k must be in 1..%d", SWNE_MAX_K);
@@ -1743,6 +1750,7 @@ __global__ void fnf_repad_kernel(const float *src, size_t src_ld, float *dst, si
 static int find_num_factors_impl(swne_nmf_handle_s *h, const int *k_range, int nk, int loss_metric, int max_iter, uint64_t seed,
                                  int engine, double *k_err, int *k_pick, double *err_diff)
 {
+    struct Invalidate { swne_nmf_handle_s *h; ~Invalidate() { h->last_k = 0; } } invalidate_resident_h{h};   // the last fit is of the permuted matrix
     if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident");
     if (!k_range || !k_err) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
     // R/nmf.R:158's rule belongs to the selection; a replica that only wants the errors of its share of k.range (k_pick and
@@ -1852,10 +1860,22 @@ __global__ void gram64_kernel(const double *__restrict__ H, int k, int m, double
     if (threadIdx.x == 0) G[pr] = s;
 }
 
+// H == NULL: the H the most recent fit left on this handle's device (fp32 [cell][KP]); widened to the kernels' fp64 [cell][k]
+// layout on the device -- the same values the host copy of that H holds, so the results are identical, without the upload
+static void resident_h_to_f64(swne_nmf_handle_s *h, int k, int m, double *dH)
+{
+    if (h->last_k == 0 || !h->H.p) FAIL(SWNE_ERR_BAD_ARG, "H is NULL and no fit has left its H on the device (or another call has reused the buffer since)");
+    if (k != h->last_k || m != h->m)
+        FAIL(SWNE_ERR_BAD_ARG, "H is NULL: k and m must be those of the resident fit (k = %d, m = %d)", h->last_k, h->m);
+    const size_t tot = (size_t)m * k;
+    factor_out_cellmajor_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->H.p, dH, k, h->last_KPv, (size_t)m);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 static int sample_coords_impl(swne_nmf_handle_s *h, const double *H, int k, int m, const double *coords, double alpha,
                               int n_pull, double *out)
 {
-    if (!H || !coords || !out) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    if (!coords || !out) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
     if (k < 1 || k > 64 || m < 1) FAIL(SWNE_ERR_BAD_ARG, "bad k or m");
     // R/swne_plotting.R:71-72
     if (n_pull > 0 && n_pull < 3) n_pull = 3;
@@ -1863,7 +1883,8 @@ static int sample_coords_impl(swne_nmf_handle_s *h, const double *H, int k, int 
     cudaStream_t st = h->stream;
     DevBuf<double> dH, dC, dO;
     dH.reserve((size_t)k * m); dC.reserve(2 * k); dO.reserve(2 * (size_t)m);
-    CUDA_CHECK(cudaMemcpyAsync(dH.p, H, sizeof(double) * (size_t)k * m, cudaMemcpyHostToDevice, st));
+    if (H) CUDA_CHECK(cudaMemcpyAsync(dH.p, H, sizeof(double) * (size_t)k * m, cudaMemcpyHostToDevice, st));
+    else resident_h_to_f64(h, k, m, dH.p);
     CUDA_CHECK(cudaMemcpyAsync(dC.p, coords, sizeof(double) * 2 * k, cudaMemcpyHostToDevice, st));
     sample_coords_kernel<<<(m + 127) / 128, 128, 2 * k * sizeof(double), st>>>(dH.p, k, m, dC.p, alpha, n_pull, dO.p);
     CUDA_CHECK(cudaGetLastError());
@@ -1875,13 +1896,16 @@ static int sample_coords_impl(swne_nmf_handle_s *h, const double *H, int k, int 
 
 static int factor_distance_impl(swne_nmf_handle_s *h, const double *H, int k, int m, int distance, double *out)
 {
-    if (!H || !out) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
+    if (!out) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
     if (k < 1 || k > 64 || m < 1) FAIL(SWNE_ERR_BAD_ARG, "bad k or m");
     if (distance < 0 || distance > 2) FAIL(SWNE_ERR_BAD_ARG, "distance must be 0 cosine, 1 pearson or 2 euclidean");
+    // the distance runs over ALL cells: a rank of a sharded fit only holds its own (gather H on the host and pass it)
+    if (!H && h->nranks > 1) FAIL(SWNE_ERR_UNSUPPORTED, "factor distance from the resident H needs all cells on one GPU");
     cudaStream_t st = h->stream;
     DevBuf<double> dH, dG;
     dH.reserve((size_t)k * m); dG.reserve(k * k + k);
-    CUDA_CHECK(cudaMemcpyAsync(dH.p, H, sizeof(double) * (size_t)k * m, cudaMemcpyHostToDevice, st));
+    if (H) CUDA_CHECK(cudaMemcpyAsync(dH.p, H, sizeof(double) * (size_t)k * m, cudaMemcpyHostToDevice, st));
+    else resident_h_to_f64(h, k, m, dH.p);
     gram64_kernel<<<k * k + k, 256, 0, st>>>(dH.p, k, m, dG.p);
     CUDA_CHECK(cudaGetLastError());
     std::vector<double> G(k * k + k);
@@ -1908,6 +1932,7 @@ static int factor_distance_impl(swne_nmf_handle_s *h, const double *H, int k, in
 
 static int recon_error_impl(swne_nmf_handle_s *h, const double *W, const double *H, int k, double *mse, double *kl)
 {
+    h->last_k = 0;     // h->H is about to be reused
     if (!h->dA || h->n == 0) FAIL(SWNE_ERR_NO_MATRIX, "no matrix resident");
     if (!W || !H) FAIL(SWNE_ERR_BAD_ARG, "NULL argument");
     if (k < 1 || k > SWNE_MAX_K) FAIL(SWNE_ERR_BAD_ARG, "k out of range");

@@ -240,14 +240,21 @@ class NMFHandle:
         return mse.value, kl.value
 
     def sample_coords(self, H, H_coords, alpha=1.0, n_pull=None):
-        H = np.asfortranarray(H, dtype=np.float64); Hc = np.asfortranarray(H_coords, dtype=np.float64)
-        k, m = H.shape
+        """get_sample_coords (R/swne_plotting.R:70-84).  H = None: the H the last fit left on the device."""
+        Hc = np.asfortranarray(H_coords, dtype=np.float64)
+        if H is None:
+            k, m, hp = Hc.shape[0], self.m, None
+        else:
+            H = np.asfortranarray(H, dtype=np.float64)
+            (k, m), hp = H.shape, C.dptr(H)
         out = np.zeros((m, 2), order="F")
-        C.check(self._lib.swne_sample_coords(self._h, C.dptr(H), k, m, C.dptr(Hc), float(alpha),
+        C.check(self._lib.swne_sample_coords(self._h, hp, k, m, C.dptr(Hc), float(alpha),
                                              0 if n_pull is None else int(n_pull), C.dptr(out)))
         return out
 
-    def factor_distance(self, H, distance="cosine"):
+    def factor_distance(self, H, distance="cosine", k=None):
+        """the k x k distance block of get_factor_coords (R/swne_plotting.R:43-52).  H = None (with k): the H the last fit left
+        on the device."""
         d = distance.lower()
         if d in ("cor", "correlation"):
             d = "pearson"
@@ -255,10 +262,15 @@ class NMFHandle:
             raise C.SwneError(C.SWNE_ERR_UNSUPPORTED, "IC (randomised KDE mutual information) is not on the device path")
         if d not in ("pearson", "cosine", "euclidean"):
             raise ValueError("Distance must be one of: pearson, IC, cosine, euclidean")
-        H = np.asfortranarray(H, dtype=np.float64)
-        k, m = H.shape
+        if H is None:
+            if k is None:
+                raise ValueError("k is needed with H = None")
+            k, m, hp = int(k), self.m, None
+        else:
+            H = np.asfortranarray(H, dtype=np.float64)
+            (k, m), hp = H.shape, C.dptr(H)
         out = np.zeros((k, k), order="F")
-        C.check(self._lib.swne_factor_distance(self._h, C.dptr(H), k, m, {"cosine": 0, "pearson": 1, "euclidean": 2}[d],
+        C.check(self._lib.swne_factor_distance(self._h, hp, k, m, {"cosine": 0, "pearson": 1, "euclidean": 2}[d],
                                                C.dptr(out)))
         return out
 

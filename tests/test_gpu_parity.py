@@ -428,6 +428,28 @@ def test_sample_coords_and_distances_vs_golden(handle):
         handle.factor_distance(Hnz, "IC")
 
 
+def test_consumers_of_the_resident_h(handle):
+    """get_sample_coords and the factor distance of get_factor_coords straight from the H the fit left on the
+    device (H = NULL in the C-ABI) -- identical to passing the returned H back in (the host copy holds the same fp32 values),
+    for the fp32 and the tcgen05 engine; any later use of the handle's factor buffers ends the residency, loudly."""
+    from swne_b200._capi import SwneError
+    A = small_matrix(400, 700, 6, 12)
+    W0, H0 = seeded_init(A, 7, 12)
+    handle.set_matrix(A)
+    coords = np.random.default_rng(2).uniform(size=(7, 2))
+    for engine in ("simt", "tc"):
+        r = handle.fit(7, W0, H0, max_iter=15, engine=engine)
+        sc_res = handle.sample_coords(None, coords, alpha=1.3, n_pull=4)
+        for dist in ("cosine", "pearson", "euclidean"):
+            assert np.array_equal(handle.factor_distance(None, dist, k=7), handle.factor_distance(r.H, dist))
+        assert np.array_equal(sc_res, handle.sample_coords(r.H, coords, alpha=1.3, n_pull=4))
+        with pytest.raises(SwneError):
+            handle.sample_coords(None, coords[:5], alpha=1.3, n_pull=4)          # k of another fit
+    handle.recon_error(r.W, r.H)                                              # reuses the factor buffers
+    with pytest.raises(SwneError):
+        handle.sample_coords(None, coords)
+
+
 def test_embed_swne_vs_oracle(handle):
     from oracle import get_factor_coords_ref, get_sample_coords_ref
     from swne_b200 import EmbedSWNE
