@@ -1,6 +1,6 @@
 ## r/R/nmf_cuda.R -- drop-in overlay for R/nmf.R (RunNMF :96-134, FindNumFactors :157-205, ProjectFeatures :222-225,
 ## ProjectSamples :241-249, nnsvd_init :12-47, ica_init :56-66) and for the two hot helpers of R/swne_plotting.R
-## (get_sample_coords :70-84, the distance block of get_factor_coords :43-52).  COMPILE-UNTESTED here (no R in the image).
+## (get_sample_coords :70-84, get_factor_coords :32-64 with its distance block on the device).  COMPILE-UNTESTED here (no R in the image).
 ## Same formals and return layouts; only the NNLM / ica / irlba calls are replaced by the CUDA path.  n.cores is accepted
 ## and ignored.  options(swne.cuda.device = 0) selects the GPU.  R's own RNG only provides one seed per call (the device
 ## generator is keyed by it), so set.seed() still makes runs reproducible.
@@ -103,4 +103,33 @@ get_sample_coords <- function(H, H.coords, alpha, n_pull) {
   sample.coords <- swne_sample_coords_cuda(as.matrix(H), as.matrix(H.coords), alpha, as.integer(n_pull), .swne_dev())
   colnames(sample.coords) <- c("x", "y"); rownames(sample.coords) <- colnames(H)
   return(sample.coords)
+}
+
+## get_factor_coords (R/swne_plotting.R:32-64): the k x k factor distance over all cells on the device (cosine, pearson,
+## euclidean); the mutual-information distance ("IC": randomised KDE, R/swne_plotting.R:44) keeps the original code; the
+## Sammon mapping of the k x k matrix stays MASS::sammon
+get_factor_coords <- function(H, method, distance, n.neighbors, min.dist) {
+  distance <- tolower(distance)
+  if (distance == "cor" || distance == "correlation") distance <- "pearson"
+  if (distance == "mutual" || distance == "information" || distance == "mutual information" || distance == "ic") distance <- "IC"
+  if (!distance %in% c("pearson", "IC", "cosine", "euclidean")) {
+    stop(paste(c("Distance must be one of:", paste(c("pearson", "IC", "cosine", "euclidean"), collapse = ", ")), collapse = " "))
+  }
+  if (method == "sammon") {
+    if (distance == "IC") {
+      Ht <- t(H)
+      H.dist <- sqrt(2 * (1 - as.matrix(usedist::dist_make(t(Ht), distance_fcn = MutualInf, method = "IC"))))
+    } else {
+      H.dist <- swne_factor_distance_cuda(as.matrix(H), c(cosine = 0L, pearson = 1L, euclidean = 2L)[[distance]], .swne_dev())
+      dimnames(H.dist) <- list(rownames(H), rownames(H))
+      if (distance != "pearson") H.dist <- stats::as.dist(H.dist)       # proxy::simil / proxy::dist return dist objects
+    }
+    H.coords <- MASS::sammon(H.dist, k = 2, niter = 250)$points
+    rownames(H.coords) <- rownames(H)
+  } else {
+    stop("Invalid factor projection method")
+  }
+  H.coords <- apply(H.coords, 2, normalize_vector, method = "bounded")
+  colnames(H.coords) <- c("x", "y")
+  return(H.coords)
 }

@@ -404,6 +404,7 @@ def test_r_overlay_keeps_the_reference_formals():
                 'ProjectFeatures <- function(newdata, H, alpha = rep(0, 3), loss = "mse", n.cores = 1)',
                 'ProjectSamples <- function(newdata, W, features.use = NULL, alpha = rep(0, 3), loss = "mse", n.cores = 1)',
                 'get_sample_coords <- function(H, H.coords, alpha, n_pull)',
+                'get_factor_coords <- function(H, method, distance, n.neighbors, min.dist)',
                 'nnsvd_init <- function(A, k, LINPACK)',
                 'ica_init <- function(A, k, ica.fast = F)'):
         assert squeeze(sig) in squeeze(src), sig
