@@ -24,7 +24,7 @@ def _check_against(res, ref, loss_tol=LOSS_TOL, factor_tol=FACTOR_TOL, key="targ
     within("H rel Frobenius", rel_fro(res["H"], ref["H"]), factor_tol)
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "mse*.npz"))))
+@pytest.mark.parametrize("path", sorted(f for f in glob.glob(os.path.join(GOLD, "mse*.npz")) if not f.endswith(".nnlm.npz")))
 def test_golden_mse(handle, path):
     g = np.load(path)
     handle.set_matrix(g["A"])
@@ -35,7 +35,24 @@ def test_golden_mse(handle, path):
     assert max_rel(r["mkl"], g["mkl"]) < LOSS_TOL
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "mkl*.npz"))))
+def test_true_nnlm_goldens(handle):
+    """The CUDA path against outputs of the real NNLM package (tests/golden/<name>.nnlm.npz, written by tools/make_golden.R
+    where R + NNLM exist).  None are committed -- neither can run in the build image -- so parity is UNPINNED and this test
+    skips saying so; with the files present it holds the CUDA path to the north-star bars directly against NNLM."""
+    files = sorted(glob.glob(os.path.join(GOLD, "*.nnlm.npz")))
+    if not files:
+        pytest.skip("parity unpinned: no true NNLM goldens (run tools/make_golden.R where R + NNLM exist)")
+    for f in files:
+        t, g = np.load(f), np.load(f.replace(".nnlm.npz", ".npz"))
+        handle.set_matrix(g["A"])
+        r = handle.fit(int(g["k"]), g["W0"], g["H0"], alpha=g["alpha"], beta=g["beta"], loss=str(g["loss"]),
+                       max_iter=int(g["max_iter"]), trace=int(g["trace"]), rel_tol=-1.0)
+        within("true NNLM golden: loss trace, max rel", max_rel(r["target_loss"], t["target_loss"]), LOSS_TOL)
+        within("true NNLM golden: W rel Frobenius", rel_fro(r["W"], t["W"]), FACTOR_TOL)
+        within("true NNLM golden: H rel Frobenius", rel_fro(r["H"], t["H"]), FACTOR_TOL)
+
+
+@pytest.mark.parametrize("path", sorted(f for f in glob.glob(os.path.join(GOLD, "mkl*.npz")) if not f.endswith(".nnlm.npz")))
 def test_golden_mkl(handle, path):
     g = np.load(path)
     handle.set_matrix(g["A"])

@@ -186,7 +186,7 @@ def test_factor_distance_and_sammon():
     assert C.min() == 0.0 and C.max() == 1.0 and C.shape == (6, 2)
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "m*.npz"))))
+@pytest.mark.parametrize("path", sorted(f for f in glob.glob(os.path.join(GOLD, "m*.npz")) if not f.endswith(".nnlm.npz")))
 def test_oracle_reproduces_golden(path):
     g = np.load(path)
     r = nnmf_ref(g["A"], int(g["k"]), g["W0"], g["H0"], alpha=g["alpha"], beta=g["beta"], loss=str(g["loss"]),
@@ -357,3 +357,20 @@ def test_c_oracle_matches_independent_python_restatement(loss, alpha, beta, inne
     np.testing.assert_allclose(ref["mkl"], py["mkl"], rtol=1e-10)
     np.testing.assert_allclose(ref["target_loss"], py["target"], rtol=1e-10)
     np.testing.assert_allclose(ref["average_epochs"], py["epochs"], rtol=0, atol=1e-12)
+
+
+def test_true_nnlm_goldens_pin_the_oracle():
+    """tools/make_golden.R (needs R + NNLM: not available in the build image) writes tests/golden/<name>.nnlm.npz with the
+    real package's outputs for the committed fixtures.  When such files exist the oracle is held to them (1e-8: both are
+    fp64 with the same operation order per column); until then parity stays UNPINNED and this test says so."""
+    import glob
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.nnlm.npz")))
+    if not files:
+        pytest.skip("parity unpinned: no true NNLM goldens (run tools/make_golden.R where R + NNLM exist)")
+    for f in files:
+        t, g = np.load(f), np.load(f.replace(".nnlm.npz", ".npz"))
+        assert int(t["n_iteration"]) == int(g["n_iteration"])
+        for key in ("target_loss", "mse", "mkl"):
+            assert np.max(np.abs(t[key] - g[key]) / np.maximum(np.abs(g[key]), 1e-300)) < 1e-8, (f, key)
+        for key in ("W", "H"):
+            assert np.linalg.norm(t[key] - g[key]) / np.linalg.norm(g[key]) < 1e-8, (f, key)
