@@ -114,9 +114,11 @@ int swne_nmf_create(swne_nmf_handle_t *out, int device);
 int swne_nmf_destroy(swne_nmf_handle_t h);
 int swne_nmf_set_progress(swne_nmf_handle_t h, swne_nmf_progress_fn fn, void *user);
 
-/* ---- multi-GPU: cells sharded over ranks, one ncclAllReduce of {A H' (n x k), H H' (k x k), loss
- * partials} per outer iteration.  id is an ncclUniqueId (128 bytes) made by rank 0 and sent to the
- * other ranks by the caller (torch.distributed / MPI / R parallel). */
+/* ---- multi-GPU: cells sharded over ranks.  loss = mse: one exchange of {A H' (n x k), H H' (k x k), loss partials} per
+ * outer iteration (NVLink peer memory or ncclAllReduce, see swne_nmf_comm_info).  loss = mkl: the cell side is local, the
+ * gene side takes one ncclAllReduce of 2 n floats per coordinate (k per sweep) plus H H' / row sums per iteration.  W is
+ * replicated bit for bit on all ranks.  id is an ncclUniqueId (128 bytes) made by rank 0 and sent to the other ranks by
+ * the caller (torch.distributed / MPI / R parallel). */
 int swne_nmf_comm_unique_id(void *id128);
 int swne_nmf_comm_init(swne_nmf_handle_t h, const void *id128, int rank, int nranks);
 /* rank / number of ranks of the handle, and whether the per-iteration sums of the fused engine travel over NVLink peer
