@@ -374,3 +374,47 @@ def test_true_nnlm_goldens_pin_the_oracle():
             assert np.max(np.abs(t[key] - g[key]) / np.maximum(np.abs(g[key]), 1e-300)) < 1e-8, (f, key)
         for key in ("W", "H"):
             assert np.linalg.norm(t[key] - g[key]) / np.linalg.norm(g[key]) < 1e-8, (f, key)
+
+
+def test_kl_nnlm_fixed_point_is_the_kl_nnls_optimum():
+    """Independent pin of scd_kl_update (the mkl analogue of the scipy.optimize.nnls check): run to convergence, every column
+    of nnlm(loss = "mkl") must satisfy the KKT conditions of  min_{h >= 0} sum(W h - a log(W h))  -- gradient zero on the
+    support, nonnegative off it -- and reach the objective value scipy's L-BFGS-B finds for the same problem."""
+    rng = np.random.default_rng(3)
+    A = small_matrix(60, 40, 4, 5)
+    W = rng.gamma(0.5, 1.0, size=(60, 8)) + 0.01
+    W[:, 5] = 0.7 * W[:, 1] + 0.3 * W[:, 2] + 0.02 * rng.uniform(size=60)       # near-collinear columns: some coefficients end at 0
+    H = nnlm_ref(W, A, loss="mkl", init=np.full((8, 40), 0.05), max_iter=50000, rel_tol=1e-13)["coefficients"]
+    T = 1e-16
+    scale = np.abs(W.sum(axis=0)).max()
+    n_zero = 0
+    for j in range(40):
+        a, h = A[:, j], H[:, j]
+        g = W.T @ (1.0 - a / (W @ h + T))
+        on = h > 1e-9
+        n_zero += int((~on).sum())
+        assert np.all(np.abs(g[on]) < 1e-8 * scale)
+        assert np.all(g[~on] > -1e-8 * scale)
+        f = lambda x: float(np.sum(W @ x - a * np.log(W @ x + T)))
+        res = scipy.optimize.minimize(f, np.full(8, 0.05), jac=lambda x: W.T @ (1.0 - a / (W @ x + T)), bounds=[(0, None)] * 8,
+                                      method="L-BFGS-B", options=dict(ftol=1e-15, gtol=1e-12, maxiter=5000))
+        assert f(h) <= res.fun + 1e-9 * max(1.0, abs(res.fun))
+    assert n_zero > 0                  # the active-set branch (clamp at 0) was exercised
+
+
+def test_mkl_trace_is_the_generalised_kl_divergence_and_beats_multiplicative_updates():
+    """External anchors for the mkl path (sklearn is a loose sanity check, not a parity oracle -- different sweep
+    schedule): (1) the oracle's `mkl` trace times N equals scikit-learn's generalised KL divergence of the same (A, W, H);
+    (2) from the same start, 60 iterations of NNLM's sequential coordinate descent end at a KL objective no worse than 60
+    multiplicative updates of sklearn's NMF(beta_loss = "kullback-leibler")."""
+    sk = pytest.importorskip("sklearn.decomposition")
+    from sklearn.decomposition._nmf import _beta_divergence
+    A = small_matrix(80, 120, 4, 9)
+    W0, H0 = seeded_init(A, 5, 9)
+    r = nnmf_ref(A, 5, W0, H0, loss="mkl", max_iter=60, trace=1, rel_tol=-1.0)
+    div = _beta_divergence(A, r["W"], r["H"], 1)
+    assert abs(r["mkl"][-1] * A.size - div) < 1e-8 * max(1.0, div)
+    mu = sk.NMF(n_components=5, init="custom", solver="mu", beta_loss="kullback-leibler", max_iter=60, tol=0.0)
+    Wm = mu.fit_transform(A, W=np.ascontiguousarray(W0), H=np.ascontiguousarray(H0))
+    div_mu = _beta_divergence(A, Wm, mu.components_, 1)
+    assert div <= div_mu * (1.0 + 1e-6)
